@@ -1,0 +1,388 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle and the golden fixtures.
+
+Bars (BASELINE.json north_star): bit-exact for cluster index, coarse edge_index, edge ordering and
+TopK-driven relabelling; rtol 1e-5 (fp32) / 2e-2 (bf16) for pooled features, edge weights, losses
+and gradients.
+"""
+import math
+
+import pytest
+import torch
+
+import tgp_b200 as T
+from tgp_b200 import functional as F_
+from oracle import ref_path as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+FP32 = dict(rtol=1e-5, atol=1e-6)
+BF16 = dict(rtol=2e-2, atol=2e-2)
+
+
+def _flags(name):
+    return {p[:-1]: bool(int(p[-1])) for p in name.split("_") if p[:-1] in ("dn", "ewn", "rsl", "t")}
+
+
+def _cu(t):
+    return None if t is None else t.to(DEV)
+
+
+def test_native_library_is_loaded():
+    from tgp_b200 import _lib as L
+
+    L.load()
+    maps = open("/proc/self/maps").read()
+    assert "libtgp_b200.so" in maps
+
+
+# --------------------------------------------------------------------------- #
+# primitives through build_csr (scan + stable radix sort)
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("nnz,K", [(0, 3), (1, 1), (31, 5), (4096, 7), (4097, 300), (100_003, 65_537), (1_000_000, 17),
+                                   (2_000_000, 1_100_000)])
+def test_build_csr_matches_stable_argsort(nnz, K):
+    g = torch.Generator().manual_seed(nnz + K)
+    c = torch.randint(0, K, (nnz,), generator=g)
+    order, ptr = F_.build_csr(c.to(DEV), K)
+    exp_order = torch.sort(c, stable=True)[1].to(torch.int32)
+    exp_ptr = torch.zeros(K + 1, dtype=torch.int32)
+    exp_ptr[1:] = torch.bincount(c, minlength=K).cumsum(0)
+    assert torch.equal(ptr.cpu(), exp_ptr)
+    assert torch.equal(order.cpu()[:nnz], exp_order)
+
+
+# --------------------------------------------------------------------------- #
+# sparse reduce
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("op", ["sum", "mean", "max", "min"])
+@pytest.mark.parametrize("F", [1, 3, 64, 128, 200])
+def test_segment_reduce_fp32(op, F):
+    g = torch.Generator().manual_seed(F)
+    N, K = 500, 130
+    sel = torch.randperm(N, generator=g)[:400]
+    cluster = torch.randint(0, K - 5, (400,), generator=g)  # last 5 clusters empty
+    w = torch.rand(400, generator=g) + 0.5
+    x = torch.randn(N, F, generator=g)
+    if op in ("max", "min"):  # create exact ties
+        x[sel[1]] = x[sel[0]]
+        cluster[1] = cluster[0]
+        w[1] = w[0]
+    so_c = R.OracleSelectOutput(node_index=sel, num_nodes=N, cluster_index=cluster, num_supernodes=K, weight=w)
+    xc = x.clone().requires_grad_(True)
+    wc = so_c.s.values().clone().requires_grad_(True)
+    so_c2 = R.OracleSelectOutput(s=torch.sparse_coo_tensor(so_c.s.indices(), wc, so_c.s.shape, is_coalesced=True))
+    exp, _ = (R.base_reduce(xc, so_c2) if op == "sum" else R.aggr_reduce(xc, so_c2, op))
+    gout = torch.randn(K, F, generator=g)
+    (exp * gout).sum().backward()
+
+    xg = x.to(DEV).requires_grad_(True)
+    wg = so_c.s.values().to(DEV).requires_grad_(True)
+    so_g = T.SelectOutput(s=torch.sparse_coo_tensor(so_c.s.indices().to(DEV), wg, so_c.s.shape, is_coalesced=True))
+    got, _ = T.B200Reduce(op)(xg, so_g)
+    (got * gout.to(DEV)).sum().backward()
+    if op == "sum":
+        assert torch.equal(got.detach().cpu(), exp.detach()), "fp32 sums are sequential and must be bit-identical"
+    torch.testing.assert_close(got.detach().cpu(), exp.detach(), **FP32)
+    torch.testing.assert_close(xg.grad.cpu(), xc.grad, **FP32)
+    torch.testing.assert_close(wg.grad.cpu(), wc.grad, rtol=1e-4, atol=1e-5)
+    assert torch.all(got[K - 5:] == 0)
+
+
+def test_segment_reduce_bf16():
+    g = torch.Generator().manual_seed(3)
+    N, K, F = 300, 90, 128
+    cluster = torch.randint(0, K, (N,), generator=g)
+    x = torch.randn(N, F, generator=g).bfloat16()
+    w = (torch.rand(N, generator=g) + 0.5).bfloat16()
+    so_c = R.OracleSelectOutput(cluster_index=cluster, num_supernodes=K, weight=w.float())
+    exp, _ = R.base_reduce(x.float(), so_c)
+    so_g = T.SelectOutput(cluster_index=cluster.to(DEV), num_supernodes=K, weight=w.to(DEV))
+    xg = x.to(DEV).requires_grad_(True)
+    got, _ = T.B200Reduce()(xg, so_g)
+    assert got.dtype == torch.bfloat16
+    torch.testing.assert_close(got.float().cpu(), exp, **BF16)
+    got.float().sum().backward()
+    assert xg.grad.dtype == torch.bfloat16 and torch.isfinite(xg.grad.float()).all()
+
+
+def test_reduce_batch_and_readout():
+    g = torch.Generator().manual_seed(5)
+    N, K = 64, 20
+    batch = torch.sort(torch.randint(0, 4, (N,), generator=g))[0]
+    sel = torch.randperm(N, generator=g)[:30]
+    cluster = torch.randint(0, K, (30,), generator=g)
+    so_c = R.OracleSelectOutput(node_index=sel, num_nodes=N, cluster_index=cluster, num_supernodes=K)
+    so_g = T.SelectOutput(node_index=sel.to(DEV), num_nodes=N, cluster_index=cluster.to(DEV), num_supernodes=K)
+    assert torch.equal(T.Reduce.reduce_batch(so_g, batch.to(DEV)).cpu(), R.reduce_batch(so_c, batch))
+    x = torch.randn(N, 6, generator=g)
+    for op in ("sum", "mean", "max", "min"):
+        exp, eb = R.readout(x, op, batch)
+        got, gb = T.B200Reduce(op)(x.to(DEV), None, batch=batch.to(DEV))
+        torch.testing.assert_close(got.cpu(), exp, **FP32)
+        assert torch.equal(gb.cpu(), eb)
+    x3 = torch.tensor([[[1.0, 2.0], [3.0, 4.0], [5.0, 6.0]], [[-1.0, 0.0], [0.0, 1.0], [2.0, -2.0]]])
+    got, _ = T.B200Reduce("max")(x3.to(DEV), None)
+    assert torch.equal(got.cpu(), torch.tensor([[5.0, 6.0], [2.0, 1.0]]))  # tests/reduce/test_global_reduce.py:9-37
+
+
+# --------------------------------------------------------------------------- #
+# golden fixtures generated by the reference's own files
+# --------------------------------------------------------------------------- #
+def test_golden_topk_cases(golden):
+    names = sorted(k for k in golden if k.startswith("topk_"))
+    assert len(names) == 16
+    for name in names:
+        c, f = golden[name], _flags(name)
+        x = c["x"].to(DEV).requires_grad_(True)
+        sw = c["weight"].to(DEV).requires_grad_(True)
+        w = None if c["edge_weight"] is None else c["edge_weight"].to(DEV).requires_grad_(True)
+        idx = torch.stack([c["node_index"], c["cluster_index"]]).to(DEV)
+        so = T.SelectOutput(s=torch.sparse_coo_tensor(idx, sw, (c["num_nodes"], c["num_supernodes"]), is_coalesced=True))
+        xp, ei, ew, bp = T.sparse_pool(x, c["edge_index"].to(DEV), so, edge_weight=w, batch=c["batch"].to(DEV),
+                                       remove_self_loops=f["rsl"], degree_norm=f["dn"], edge_weight_norm=f["ewn"])
+        assert torch.equal(ei.cpu(), c["edge_index_out"]), name
+        assert ei.is_contiguous() and ei.dtype == torch.long
+        assert torch.equal(bp.cpu(), c["batch_pool"]), name
+        torch.testing.assert_close(xp.detach().cpu(), c["x_pool"], **FP32)
+        if c["edge_weight_out"] is None:
+            assert ew is None, name
+        else:
+            torch.testing.assert_close(ew.detach().cpu(), c["edge_weight_out"], **FP32)
+        loss = xp.square().sum()
+        if ew is not None and ew.requires_grad:
+            loss = loss + (ew * torch.arange(1, ew.numel() + 1, device=DEV)).sum()
+        loss.backward()
+        # grad wrt x in the fixture includes the path through the TopK score; compare the reduce part
+        # by replaying the oracle with detached select weights
+        xo = c["x"].clone().requires_grad_(True)
+        swo = c["weight"].clone().requires_grad_(True)
+        so_o = R.OracleSelectOutput(s=torch.sparse_coo_tensor(idx.cpu(), swo, (c["num_nodes"], c["num_supernodes"]),
+                                                              is_coalesced=True))
+        wo = None if c["edge_weight"] is None else c["edge_weight"].clone().requires_grad_(True)
+        xpo, eio, ewo, _ = R.topk_pool(xo, c["edge_index"], wo, so_o, batch=c["batch"], remove_self_loops=f["rsl"],
+                                       degree_norm=f["dn"], edge_weight_norm=f["ewn"])
+        lo = xpo.square().sum()
+        if ewo is not None and ewo.requires_grad:
+            lo = lo + (ewo * torch.arange(1, ewo.numel() + 1)).sum()
+        lo.backward()
+        torch.testing.assert_close(x.grad.cpu(), xo.grad, **FP32)
+        torch.testing.assert_close(sw.grad.cpu(), swo.grad, rtol=1e-4, atol=1e-5)
+        if w is not None:
+            torch.testing.assert_close(w.grad.cpu(), c["grad_w"], rtol=1e-4, atol=1e-5, msg=name)
+
+
+def test_golden_cluster_cases(golden):
+    names = sorted(k for k in golden if k.startswith("cluster_"))
+    assert len(names) == 40
+    for name in names:
+        c, f = golden[name], _flags(name)
+        op = name.split("_")[1]
+        x = c["x"].to(DEV).requires_grad_(True)
+        w = None if c["edge_weight"] is None else c["edge_weight"].to(DEV).requires_grad_(True)
+        so = T.SelectOutput(cluster_index=c["cluster"].to(DEV), num_nodes=x.size(0), num_supernodes=c["num_supernodes"])
+        xp, bp = T.B200Reduce()(x, so, batch=c["batch"].to(DEV))
+        conn = T.B200SparseConnect(op, f["rsl"], f["ewn"], f["dn"])
+        ei, ew = conn(c["edge_index"].to(DEV), so, edge_weight=w, batch_pooled=c["batch_pooled"].to(DEV))
+        assert torch.equal(ei.cpu(), c["edge_index_out"]), name
+        assert torch.equal(bp.cpu(), c["batch_pool"]), name
+        torch.testing.assert_close(xp.detach().cpu(), c["x_pool"], **FP32)
+        if c["edge_weight_out"] is None:
+            assert ew is None, name
+        else:
+            torch.testing.assert_close(ew.detach().cpu(), c["edge_weight_out"], **FP32, msg=name)
+        loss = xp.square().sum()
+        if ew is not None and ew.requires_grad:
+            loss = loss + (ew * torch.arange(1, ew.numel() + 1, device=DEV)).sum()
+        loss.backward()
+        torch.testing.assert_close(x.grad.cpu(), c["grad_x"], **FP32)
+        if w is not None and op != "mul":
+            torch.testing.assert_close(w.grad.cpu(), c["grad_w"], rtol=1e-4, atol=1e-5, msg=name)
+
+
+def test_golden_dense_cases(golden):
+    names = sorted(k for k in golden if k.startswith("dense_"))
+    assert len(names) == 16
+    for name in names:
+        c, f = golden[name], _flags(name)
+        sr = c["s_raw"].to(DEV).requires_grad_(True)
+        x = c["x"].to(DEV).requires_grad_(True)
+        a = c["adj"].to(DEV).requires_grad_(True)
+        mask = c["mask"].to(DEV)
+        s = torch.softmax(sr, -1) * mask[..., None]
+        kw = dict(remove_self_loops=f["rsl"], degree_norm=f["dn"], adj_transpose=f["t"], edge_weight_norm=f["ewn"])
+        xp, post, lm = T.mincut_pool(x, a, s, **kw)
+        _, post2, ld = T.diff_pool(x, a, s, num_nodes=int(mask.sum()), normalize_loss=False, **kw)
+        _, _, ldn = T.diff_pool(x, a, s, num_nodes=int(mask.sum()), normalize_loss=True, **kw)
+        raw = T.B200DenseConnect().dense_connect(a, s)
+        for got, key in ((xp, "x_pool"), (raw, "adj_pool_raw"), (post, "adj_pool"), (post2, "adj_pool"),
+                         (lm["cut_loss"], "cut"), (lm["ortho_loss"], "ortho"), (ld["link_loss"], "link"),
+                         (ldn["link_loss"], "link_norm"), (ld["entropy_loss"], "ent")):
+            torch.testing.assert_close(got.detach().cpu(), c[key], **FP32, msg=f"{name}:{key}")
+        wts = (torch.arange(1, post.numel() + 1, dtype=torch.float, device=DEV).view_as(post) / post.numel())
+        total = (xp.square().sum() + (post * wts).sum() + lm["cut_loss"] + lm["ortho_loss"] + 0.5 * ld["link_loss"]
+                 + 0.25 * ld["entropy_loss"])
+        total.backward()
+        # the fixture total used x_pool/post from one forward; ours reuses xp/post from mincut_pool only
+        torch.testing.assert_close(sr.grad.cpu(), c["grad_s_raw"], rtol=1e-4, atol=1e-5, msg=name)
+        torch.testing.assert_close(x.grad.cpu(), c["grad_x"], **FP32, msg=name)
+        torch.testing.assert_close(a.grad.cpu(), c["grad_adj"], rtol=1e-4, atol=1e-5, msg=name)
+
+
+# --------------------------------------------------------------------------- #
+# sparse connect at larger random sizes (bit-exact indices vs oracle)
+# --------------------------------------------------------------------------- #
+def _random_graph(g, n, e, weighted=True):
+    ei = torch.randint(0, n, (2, e), generator=g)
+    order = torch.argsort(ei[0] * n + ei[1], stable=True)
+    ei = ei[:, order]
+    ew = (torch.rand(e, generator=g) + 0.5) if weighted else None
+    return ei, ew
+
+
+@pytest.mark.parametrize("weighted", [True, False])
+@pytest.mark.parametrize("dn,ewn", [(False, False), (True, True)])
+def test_kept_node_connect_large(weighted, dn, ewn):
+    g = torch.Generator().manual_seed(11)
+    n, e = 50_000, 400_000
+    ei, ew = _random_graph(g, n, e, weighted)
+    score = torch.randn(n, generator=g)
+    batch = torch.sort(torch.randint(0, 16, (n,), generator=g))[0]
+    so_c = R.topk_select(score, None, 0.5, batch, act=torch.tanh)
+    bp_c = R.reduce_batch(so_c, batch)
+    eo, wo = R.sparse_connect_so(ei, so_c, edge_weight=ew, batch_pooled=bp_c, degree_norm=dn, edge_weight_norm=ewn)
+    so_g = T.SelectOutput(s=so_c.s.to(DEV))
+    bp_g = T.Reduce.reduce_batch(so_g, batch.to(DEV))
+    assert torch.equal(bp_g.cpu(), bp_c)
+    eg, wg = T.B200SparseConnect(degree_norm=dn, edge_weight_norm=ewn)(ei.to(DEV), so_g, edge_weight=_cu(ew),
+                                                                        batch_pooled=bp_g)
+    assert torch.equal(eg.cpu(), eo)
+    if wo is None:
+        assert wg is None
+    else:
+        torch.testing.assert_close(wg.cpu(), wo, **FP32)
+
+
+@pytest.mark.parametrize("weighted", [True, False])
+@pytest.mark.parametrize("K", [300, 40_000, 90_000])  # 32-bit and 64-bit key paths
+def test_cluster_connect_large(weighted, K):
+    g = torch.Generator().manual_seed(K)
+    n, e = 100_000, 600_000
+    ei, ew = _random_graph(g, n, e, weighted)
+    cluster = torch.randint(0, K, (n,), generator=g)
+    so_c = R.OracleSelectOutput(cluster_index=cluster, num_supernodes=K)
+    eo, wo = R.sparse_connect_so(ei, so_c, edge_weight=ew, degree_norm=True)
+    so_g = T.SelectOutput(cluster_index=cluster.to(DEV), num_supernodes=K)
+    eg, wg = T.B200SparseConnect(degree_norm=True)(ei.to(DEV), so_g, edge_weight=_cu(ew))
+    assert torch.equal(eg.cpu(), eo)
+    torch.testing.assert_close(wg.cpu(), wo, **FP32)
+    key = eg[0] * K + eg[1]
+    assert bool((key[1:] > key[:-1]).all())  # lexicographic, duplicate-free
+
+
+def test_connect_edge_cases():
+    so = T.SelectOutput(cluster_index=torch.tensor([0, 1, 0, 2], device=DEV), num_supernodes=4)
+    empty = torch.empty((2, 0), dtype=torch.long, device=DEV)
+    ei, ew = T.B200SparseConnect()(empty, so)
+    assert ei.shape == (2, 0) and ew is None
+    ei, ew = T.B200SparseConnect()(empty, so, edge_weight=torch.empty(0, device=DEV))
+    assert ei.shape == (2, 0) and ew.shape == (0,)
+    # all edges intra-cluster -> all removed as self loops
+    e2 = torch.tensor([[0, 2], [2, 0]], device=DEV)
+    ei, ew = T.B200SparseConnect()(e2, so, edge_weight=torch.ones(2, device=DEV))
+    assert ei.shape == (2, 0)
+    # tiny weights dropped (tests/utils/test_ops.py:254-269)
+    e3 = torch.tensor([[0, 1], [1, 0]], device=DEV)
+    ei, ew = T.B200SparseConnect(remove_self_loops=False)(e3, so, edge_weight=torch.tensor([0.0, 1.0], device=DEV))
+    assert ei.shape == (2, 1) and torch.equal(ew.cpu(), torch.tensor([1.0]))
+    # [E,1] weights flatten, [E,2] raise (tests/poolers/test_graclus.py:50-74)
+    ei, ew = T.B200SparseConnect()(e3, so, edge_weight=torch.ones(2, 1, device=DEV))
+    assert ew.dim() == 1
+    with pytest.raises(RuntimeError):
+        T.B200SparseConnect()(e3, so, edge_weight=torch.ones(2, 2, device=DEV))
+    with pytest.raises(ValueError):
+        T.B200SparseConnect()(e3.to(torch.int32), so)
+    # torch COO in -> coalesced torch COO out, weights None (base_conn.py:103-110)
+    coo = torch.sparse_coo_tensor(torch.tensor([[0, 1, 3], [1, 3, 0]], device=DEV), torch.tensor([1.0, 2.0, 3.0], device=DEV), (4, 4))
+    out, w = T.B200SparseConnect()(coo, so)
+    exp, _ = R.sparse_connect_so(coo.cpu(), R.OracleSelectOutput(cluster_index=torch.tensor([0, 1, 0, 2]), num_supernodes=4))
+    assert w is None and out.is_sparse
+    assert torch.equal(out.indices().cpu(), exp.indices()) and torch.allclose(out.values().cpu(), exp.values())
+
+
+def test_determinism_run_twice():
+    g = torch.Generator().manual_seed(7)
+    n, e, K = 20_000, 300_000, 5_000
+    ei, ew = _random_graph(g, n, e)
+    cluster = torch.randint(0, K, (n,), generator=g)
+    x = torch.randn(n, 64, generator=g).to(DEV)
+    outs = []
+    for _ in range(2):
+        so = T.SelectOutput(cluster_index=cluster.to(DEV), num_supernodes=K)
+        xp, _ = T.B200Reduce("mean")(x, so)
+        eo, wo = T.B200SparseConnect()(ei.to(DEV), so, edge_weight=ew.to(DEV))
+        outs.append((xp, eo, wo))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+
+
+# --------------------------------------------------------------------------- #
+# dense path at non-trivial shapes
+# --------------------------------------------------------------------------- #
+def _dense_inputs(g, B, N, K, F, p=0.1):
+    a = (torch.rand(B, N, N, generator=g) < p).float()
+    a = torch.triu(a, 1)
+    a = a + a.transpose(1, 2)
+    s_raw = torch.randn(B, N, K, generator=g)
+    x = torch.randn(B, N, F, generator=g)
+    return a, s_raw, x
+
+
+@pytest.mark.parametrize("B,N,K,F", [(4, 100, 16, 33), (3, 256, 64, 128), (2, 64, 16, 256)])
+@pytest.mark.parametrize("kind", ["mincut", "diff"])
+def test_dense_pool_fp32_vs_oracle(B, N, K, F, kind):
+    g = torch.Generator().manual_seed(B * N + K)
+    a, s_raw, x = _dense_inputs(g, B, N, K, F)
+    gx = torch.randn(B, K, F, generator=g)
+    ga = torch.randn(B, K, K, generator=g)
+
+    def run(mod, dev):
+        sr = s_raw.to(dev).requires_grad_(True)
+        xx = x.to(dev).requires_grad_(True)
+        aa = a.to(dev).requires_grad_(True)
+        s = torch.softmax(sr, -1)
+        fn = mod.mincut_pool if kind == "mincut" else mod.diff_pool
+        xp, ap, loss = fn(xx, aa, s)
+        tot = (xp * gx.to(dev)).sum() + (ap * ga.to(dev)).sum() + sum(loss.values())
+        tot.backward()
+        return [t.detach().cpu() for t in (xp, ap, *loss.values(), sr.grad, xx.grad, aa.grad)]
+
+    exp = run(R, "cpu")
+    got = run(T, DEV)
+    names = ["x_pool", "adj_pool", "loss0", "loss1", "grad_s", "grad_x", "grad_adj"]
+    for n_, e_, g_ in zip(names, exp, got):
+        tol = FP32 if not n_.startswith("grad") else dict(rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(g_, e_, **tol, msg=f"{kind} {n_}")
+
+
+def test_dense_pool_bf16_vs_oracle():
+    g = torch.Generator().manual_seed(21)
+    B, N, K, F = 3, 128, 32, 64
+    a, s_raw, x = _dense_inputs(g, B, N, K, F)
+    s = torch.softmax(s_raw, -1).bfloat16()
+    xb, ab = x.bfloat16(), a.bfloat16()
+    exp = R.diff_pool(xb.float(), ab.float(), s.float())
+    got = T.diff_pool(xb.to(DEV), ab.to(DEV), s.to(DEV))
+    assert got[0].dtype == torch.bfloat16 and got[1].dtype == torch.bfloat16
+    torch.testing.assert_close(got[0].float().cpu(), exp[0], **BF16)
+    torch.testing.assert_close(got[1].float().cpu(), exp[1], **BF16)
+    for k in exp[2]:
+        torch.testing.assert_close(got[2][k].float().cpu(), exp[2][k], **BF16)
+
+
+def test_dense_connect_hand_matrix():
+    # tests/connect/test_dense_conn.py:210-232
+    s = torch.tensor([[1.0, 0.0], [0.0, 1.0], [1.0, 0.0]], device=DEV)
+    adj = torch.tensor([[0.0, 1.0, 2.0], [1.0, 0.0, 3.0], [2.0, 3.0, 0.0]], device=DEV)
+    out = T.B200DenseConnect().dense_connect(adj=adj, s=s)
+    assert out.shape == (1, 2, 2)
+    assert torch.equal(out[0].cpu(), torch.tensor([[4.0, 4.0], [4.0, 0.0]]))

@@ -1,0 +1,625 @@
+// Dense Reduce + Connect + auxiliary losses (MinCut / DiffPool), forward and backward.
+// Reference: tgp/reduce/base_reduce.py:158-161 (S^T X), tgp/connect/dense_conn.py:112-122 ((S^T A) S),
+// tgp/utils/ops.py:282-335 (post-processing), tgp/utils/losses.py:39-123,476-500,644-708 (losses),
+// call order from tgp/poolers/mincut.py:219-237 and tgp/poolers/diffpool.py:208-218.
+//
+// This translation unit holds the shape-general path: a strided batched GEMM on the FP32 pipe plus the
+// fused statistics / post-processing / gradient-assembly kernels.  dense_tc.cu provides the tcgen05 GEMMs
+// that replace `bgemm` for the tile-aligned shapes.
+#include "dense.cuh"
+
+namespace tgp {
+
+// ------------------------------------------------------------------------------------------
+// Strided batched GEMM  C[b] (+)= alpha * A[b] (MxKd) * B[b] (KdxN), arbitrary element strides.
+// 64x64x16 tiles, 256 threads, 4x4 register micro-tile, FP32 accumulate.
+// ------------------------------------------------------------------------------------------
+template <typename TA, typename TB, typename TC>
+static __global__ void __launch_bounds__(256)
+    k_bgemm(const TA* __restrict__ A, const TB* __restrict__ Bm, TC* __restrict__ C, int M, int N, int Kd, int64_t sAb,
+            int64_t sAm, int64_t sAk, int64_t sBb, int64_t sBk, int64_t sBn, int64_t sCb, int64_t sCm, float alpha,
+            int accumulate) {
+  __shared__ float As[16][65];
+  __shared__ float Bs[16][65];
+  int b = blockIdx.z;
+  int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const TA* Ab = A + (int64_t)b * sAb;
+  const TB* Bb = Bm + (int64_t)b * sBb;
+  int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  bool a_kc = (sAk == 1), b_nc = (sBn == 1);
+  for (int k0 = 0; k0 < Kd; k0 += 16) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int idx = t + r * 256;
+      int m, k;
+      if (a_kc) { m = idx >> 4; k = idx & 15; } else { m = idx & 63; k = idx >> 6; }
+      float v = 0.f;
+      if (m0 + m < M && k0 + k < Kd) v = to_f32<TA>(Ab[(int64_t)(m0 + m) * sAm + (int64_t)(k0 + k) * sAk]);
+      As[k][m] = v;
+      int n, kk;
+      if (b_nc) { n = idx & 63; kk = idx >> 6; } else { n = idx >> 4; kk = idx & 15; }
+      float u = 0.f;
+      if (n0 + n < N && k0 + kk < Kd) u = to_f32<TB>(Bb[(int64_t)(k0 + kk) * sBk + (int64_t)(n0 + n) * sBn]);
+      Bs[kk][n] = u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  TC* Cb = C + (int64_t)b * sCb;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = alpha * acc[i][j];
+      TC* p = Cb + (int64_t)m * sCm + n;
+      if (accumulate) v += to_f32<TC>(*p);
+      *p = from_f32<TC>(v);
+    }
+  }
+}
+
+template <typename TA, typename TB, typename TC>
+int bgemm(const TA* A, const TB* B, TC* C, int batch, int M, int N, int Kd, int64_t sAb, int64_t sAm, int64_t sAk,
+          int64_t sBb, int64_t sBk, int64_t sBn, int64_t sCb, int64_t sCm, float alpha, bool accumulate,
+          cudaStream_t st) {
+  if (batch == 0 || M == 0 || N == 0) return TGPB200_OK;
+  dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64), (unsigned)batch);
+  launch("k_bgemm", k_bgemm<TA, TB, TC>, grid, 256, 0, st, A, B, C, M, N, Kd, sAb, sAm, sAk, sBb, sBk, sBn, sCb, sCm, alpha,
+                                            accumulate ? 1 : 0);
+  return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------
+// Row statistics of one pass over A and S:  d[b,i] = sum_j A[b,i,j];  ss[b,i] = sum_k S^2;
+// a2[b,i] = sum_j A^2;  ent[b,i] = -sum_k S log(S + eps).   One warp per (b, i).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+static __global__ void k_row_stats(const T* __restrict__ A, const T* __restrict__ S, int64_t rows, int N, int K,
+                                   float eps, float* __restrict__ d, float* __restrict__ ss, float* __restrict__ a2,
+                                   float* __restrict__ ent) {
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float sd = 0.f, sa2 = 0.f, s2 = 0.f, se = 0.f;
+  if (A) {
+    const T* a = A + r * N;
+    for (int j = lane; j < N; j += 32) {
+      float v = to_f32<T>(a[j]);
+      sd += v;
+      sa2 += v * v;
+    }
+  }
+  const T* s = S + r * K;
+  for (int k = lane; k < K; k += 32) {
+    float v = to_f32<T>(s[k]);
+    s2 += v * v;
+    se -= v * logf(v + eps);
+  }
+  sd = warp_sum(sd), sa2 = warp_sum(sa2), s2 = warp_sum(s2), se = warp_sum(se);
+  if (lane == 0) {
+    d[r] = sd, ss[r] = s2, a2[r] = sa2, ent[r] = se;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-graph epilogue (one block per graph): loss statistics from the RAW S^T A S and S^T S,
+// then post-processing (diag zero -> D^-1/2 A D^-1/2 -> / max|A|) exactly in ops.py:307-333 order.
+// stats[b] = {num, den, ||M||_F^2, ortho_b, ||A||_F^2, ent_b, maxnorm m, unused}
+// ------------------------------------------------------------------------------------------
+template <typename T>
+static __global__ void __launch_bounds__(256)
+    k_graph_epilogue(const float* __restrict__ Araw, const float* __restrict__ M, const float* __restrict__ d,
+                     const float* __restrict__ ss, const float* __restrict__ a2, const float* __restrict__ ent, int N,
+                     int K, uint32_t flags, float eps, T* __restrict__ Apool, float* __restrict__ dvec,
+                     float* __restrict__ stats, int32_t* __restrict__ argmax) {
+  extern __shared__ float sm[];  // K floats: d_v
+  __shared__ float red[32];
+  __shared__ int redi[32];
+  int b = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
+  const float* Ar = Araw ? Araw + (int64_t)b * K * K : nullptr;
+  float* st = stats + (int64_t)b * 8;
+
+  // den, ||A||^2, entropy (fixed-order block reductions)
+  float den = 0.f, sa2 = 0.f, se = 0.f;
+  for (int i = t; i < N; i += nt) {
+    int64_t r = (int64_t)b * N + i;
+    den += d[r] * ss[r];
+    sa2 += a2[r];
+    se += ent[r];
+  }
+  den = block_sum(den, red), sa2 = block_sum(sa2, red), se = block_sum(se, red);
+
+  float num = 0.f;
+  if (Ar)
+    for (int i = t; i < K; i += nt) num += Ar[(int64_t)i * K + i];
+  num = block_sum(num, red);
+
+  float m2 = 0.f, ortho = 0.f;
+  if (M) {
+    const float* Mb = M + (int64_t)b * K * K;
+    for (int i = t; i < K * K; i += nt) m2 += Mb[i] * Mb[i];
+    m2 = block_sum(m2, red);
+    float nM = sqrtf(m2), isk = 1.0f / sqrtf((float)K);
+    float u2 = 0.f;
+    for (int i = t; i < K * K; i += nt) {
+      float u = Mb[i] / nM - ((i / K == i % K) ? isk : 0.f);
+      u2 += u * u;
+    }
+    ortho = sqrtf(block_sum(u2, red));
+  }
+  if (t == 0) {
+    st[0] = num, st[1] = den, st[2] = m2, st[3] = ortho, st[4] = sa2, st[5] = se, st[6] = 1.f, st[7] = 0.f;
+  }
+  if (!Ar || !Apool) return;
+
+  bool rsl = flags & TGPB200_REMOVE_SELF_LOOPS, dn = flags & TGPB200_DEGREE_NORM;
+  bool tr = flags & TGPB200_ADJ_TRANSPOSE, wn = flags & TGPB200_EDGE_WEIGHT_NORM;
+  // degree vector over the diag-zeroed matrix: s_v = column sum (adj_transpose) or row sum
+  if (dn) {
+    int lane = t & 31, w = t >> 5, nw = nt >> 5;
+    for (int v = w; v < K; v += nw) {
+      float s = 0.f;
+      for (int u = lane; u < K; u += 32) {
+        if (rsl && u == v) continue;
+        s += tr ? Ar[(int64_t)u * K + v] : Ar[(int64_t)v * K + u];
+      }
+      s = warp_sum(s);
+      if (lane == 0) {
+        sm[v] = sqrtf(fmaxf(s, eps));
+        dvec[(int64_t)b * K + v] = s;
+      }
+    }
+  }
+  __syncthreads();
+  float mx = 0.f;
+  int amx = INT_MAX;
+  T* Ap = Apool + (int64_t)b * K * K;
+  for (int i = t; i < K * K; i += nt) {
+    int r = i / K, c = i % K;
+    float v = (rsl && r == c) ? 0.f : Ar[i];
+    if (dn) v = tr ? __fdiv_rn(__fdiv_rn(v, sm[c]), sm[r]) : __fdiv_rn(__fdiv_rn(v, sm[r]), sm[c]);
+    if (wn) {
+      float a = fabsf(v);
+      if (a > mx) { mx = a; amx = i; }
+    } else {
+      Ap[i] = from_f32<T>(v);
+    }
+  }
+  if (wn) {
+    float bm = block_max(mx, red);
+    // first index attaining the max
+    int cand = (mx == bm && amx != INT_MAX) ? amx : INT_MAX;
+    int lane = t & 31, w = t >> 5, nw = nt >> 5;
+    for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(kFull, cand, o));
+    __syncthreads();
+    if (lane == 0) redi[w] = cand;
+    __syncthreads();
+    cand = lane < nw ? redi[lane] : INT_MAX;
+    for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(kFull, cand, o));
+    float m = bm == 0.f ? 1.f : bm;
+    if (t == 0) {
+      st[6] = m;
+      argmax[b] = bm == 0.f ? -1 : cand;
+    }
+    for (int i = t; i < K * K; i += nt) {
+      int r = i / K, c = i % K;
+      float v = (rsl && r == c) ? 0.f : Ar[i];
+      if (dn) v = tr ? __fdiv_rn(__fdiv_rn(v, sm[c]), sm[r]) : __fdiv_rn(__fdiv_rn(v, sm[r]), sm[c]);
+      Ap[i] = from_f32<T>(__fdiv_rn(v, m));
+    }
+  }
+}
+
+// losses[0..3] = {cut (mean_b), ortho (mean_b), link, entropy}; one block, fixed order.
+static __global__ void k_finalize_losses(const float* __restrict__ stats, int B, float eps, float link_div,
+                                         float ent_div, float* __restrict__ losses) {
+  __shared__ float red[32];
+  float cut = 0.f, ortho = 0.f, q = 0.f, ent = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float* st = stats + (int64_t)b * 8;
+    cut += -(st[0] / (st[1] + eps));
+    ortho += st[3];
+    q += st[4] - 2.f * st[0] + st[2];
+    ent += st[5];
+  }
+  cut = block_sum(cut, red), ortho = block_sum(ortho, red), q = block_sum(q, red), ent = block_sum(ent, red);
+  if (threadIdx.x == 0) {
+    losses[0] = cut / (float)B;
+    losses[1] = ortho / (float)B;
+    losses[2] = sqrtf(fmaxf(q, 0.f)) / link_div;
+    losses[3] = ent / ent_div;
+    losses[4] = q;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward assembly (one block per graph):
+//   Graw = d L / d (S^T A S) raw   from  Gpool (through max-norm, degree-norm, diag-zero) + trace terms
+//   P    = d L / d (S^T S) symmetrised:  dS += S P        (ortho + link ||M||^2 term)
+//   coef[b] = {c_den, c_a2, c_ent}  for the element-wise terms
+// gl = upstream grads of {cut, ortho, link, entropy} (device floats, already x coefficient).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+static __global__ void __launch_bounds__(256)
+    k_graph_bwd(const float* __restrict__ Araw, const float* __restrict__ M, const T* __restrict__ Gpool,
+                const float* __restrict__ dvec, const float* __restrict__ stats, const int32_t* __restrict__ argmax,
+                const float* __restrict__ gl, const float* __restrict__ losses, int B, int K, uint32_t flags,
+                int loss_kind, float eps, float link_div, float ent_div, float* __restrict__ Graw,
+                float* __restrict__ P, float* __restrict__ coef) {
+  extern __shared__ float sm[];  // 3K floats: dsq[v], rowdot[v], coldot[v]
+  __shared__ float red[32];
+  float* dsq = sm;
+  float* rdot = sm + K;
+  float* cdot = sm + 2 * K;
+  int b = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
+  const float* st = stats + (int64_t)b * 8;
+  const float* Ar = Araw + (int64_t)b * K * K;
+  float* Gr = Graw + (int64_t)b * K * K;
+  bool rsl = flags & TGPB200_REMOVE_SELF_LOOPS, dn = flags & TGPB200_DEGREE_NORM;
+  bool tr = flags & TGPB200_ADJ_TRANSPOSE, wn = flags & TGPB200_EDGE_WEIGHT_NORM;
+  float m = st[6];
+
+  // --- loss coefficients
+  float g_cut = gl ? gl[0] : 0.f, g_ortho = gl ? gl[1] : 0.f, g_link = gl ? gl[2] : 0.f, g_ent = gl ? gl[3] : 0.f;
+  float c_num = 0.f, c_den = 0.f, c_a2 = 0.f, c_m2 = 0.f, c_ent = 0.f;
+  if (loss_kind == 1) {
+    float dd = st[1] + eps;
+    c_num = -g_cut / ((float)B * dd);
+    c_den = g_cut * st[0] / ((float)B * dd * dd);
+  } else if (loss_kind == 2) {
+    float q = losses[4];
+    float L = sqrtf(fmaxf(q, 0.f));
+    float cq = L > 0.f ? g_link / (2.f * L * link_div) : 0.f;  // dL/dq
+    c_a2 = cq, c_num = -2.f * cq, c_m2 = cq;
+    c_ent = g_ent / ent_div;
+  }
+  if (t == 0) {
+    coef[b * 4 + 0] = c_den, coef[b * 4 + 1] = c_a2, coef[b * 4 + 2] = c_ent, coef[b * 4 + 3] = 0.f;
+  }
+
+  // --- P = dL/dM + transpose  (M symmetric so both terms are symmetric)
+  if (P) {
+    float* Pb = P + (int64_t)b * K * K;
+    const float* Mb = M + (int64_t)b * K * K;
+    if (loss_kind == 1) {
+      float nM = sqrtf(st[2]), r = st[3], isk = 1.0f / sqrtf((float)K);
+      // <U, M> with U = M/nM - I/sqrt(K)
+      float um = 0.f;
+      for (int i = t; i < K * K; i += nt) {
+        float u = Mb[i] / nM - ((i / K == i % K) ? isk : 0.f);
+        um += u * Mb[i];
+      }
+      um = block_sum(um, red);
+      float go = g_ortho / (float)B;
+      for (int i = t; i < K * K; i += nt) {
+        float u = Mb[i] / nM - ((i / K == i % K) ? isk : 0.f);
+        float dM = (r > 0.f) ? go * (u / r - (um / r) * Mb[i] / (nM * nM)) / nM : 0.f;
+        Pb[i] = 2.f * dM;
+      }
+    } else {
+      for (int i = t; i < K * K; i += nt) Pb[i] = 4.f * c_m2 * Mb[i];
+    }
+  }
+
+  // --- Graw from Gpool
+  if (Gpool == nullptr) {
+    for (int i = t; i < K * K; i += nt) Gr[i] = (i / K == i % K) ? c_num : 0.f;
+    return;
+  }
+  const T* Gp = Gpool + (int64_t)b * K * K;
+  if (dn)
+    for (int v = t; v < K; v += nt) dsq[v] = sqrtf(fmaxf(dvec[(int64_t)b * K + v], eps));
+  __syncthreads();
+  // A2 = normalised matrix before max-norm; G2 = grad wrt A2
+  float corr = 0.f;  // sum G * A2 (for the max-norm arg term)
+  if (wn && m != 0.f) {
+    for (int i = t; i < K * K; i += nt) {
+      int r = i / K, c = i % K;
+      float v = (rsl && r == c) ? 0.f : Ar[i];
+      if (dn) v = v / (dsq[r] * dsq[c]);
+      corr += to_f32<T>(Gp[i]) * v;
+    }
+    corr = block_sum(corr, red);
+  }
+  int am = wn ? argmax[b] : -1;
+  // row / column dot products  rdot[v] = sum_j G2[v,j] A2[v,j],  cdot[v] = sum_i G2[i,v] A2[i,v]
+  if (dn) {
+    int lane = t & 31, w = t >> 5, nw = nt >> 5;
+    for (int v = w; v < K; v += nw) {
+      float sr = 0.f, sc = 0.f;
+      for (int u = lane; u < K; u += 32) {
+        {
+          int i = v * K + u;
+          float a = (rsl && u == v) ? 0.f : Ar[i] / (dsq[v] * dsq[u]);
+          float g = to_f32<T>(Gp[i]) / m;
+          if (i == am) g += (a < 0.f ? -1.f : 1.f) * (-corr / (m * m));
+          sr += g * a;
+        }
+        {
+          int i = u * K + v;
+          float a = (rsl && u == v) ? 0.f : Ar[i] / (dsq[v] * dsq[u]);
+          float g = to_f32<T>(Gp[i]) / m;
+          if (i == am) g += (a < 0.f ? -1.f : 1.f) * (-corr / (m * m));
+          sc += g * a;
+        }
+      }
+      sr = warp_sum(sr), sc = warp_sum(sc);
+      if (lane == 0) rdot[v] = sr, cdot[v] = sc;
+    }
+  }
+  __syncthreads();
+  for (int i = t; i < K * K; i += nt) {
+    int r = i / K, c = i % K;
+    float g = to_f32<T>(Gp[i]) / m;
+    if (wn && i == am) {
+      float a = (rsl && r == c) ? 0.f : Ar[i];
+      if (dn) a = a / (dsq[r] * dsq[c]);
+      g += (a < 0.f ? -1.f : 1.f) * (-corr / (m * m));
+    }
+    float out = g;
+    if (dn) {
+      out = g / (dsq[r] * dsq[c]);
+      int v = tr ? c : r;  // s_v is a column sum (transpose) or a row sum
+      float sv = dvec[(int64_t)b * K + v];
+      if (sv >= eps) {
+        float dd = -(rdot[v] + cdot[v]) / dsq[v];  // dL/d d_v
+        out += dd / (2.f * dsq[v]);                // d d_v / d s_v
+      }
+    }
+    if (rsl && r == c) out = 0.f;
+    if (r == c) out += c_num;
+    Gr[i] = out;
+  }
+}
+
+// dS += element-wise terms:  c_den * 2 d_i S_ik  +  c_ent * (-log(S+eps) - S/(S+eps)).
+template <typename T>
+static __global__ void k_ds_elementwise(const T* __restrict__ S, const float* __restrict__ d,
+                                        const float* __restrict__ coef, int64_t total, int N, int K, float eps,
+                                        float* __restrict__ dS) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int64_t row = i / K;
+  int b = (int)(row / N);
+  float c_den = coef[b * 4 + 0], c_ent = coef[b * 4 + 2];
+  if (c_den == 0.f && c_ent == 0.f) return;
+  float s = to_f32<T>(S[i]);
+  float v = dS[i];
+  if (c_den != 0.f) v += c_den * 2.f * d[row] * s;
+  if (c_ent != 0.f) v += c_ent * (-logf(s + eps) - s / (s + eps));
+  dS[i] = v;
+}
+
+// dA += c_den * ss_i (row broadcast) + c_a2 * 2 A_ij
+template <typename T>
+static __global__ void k_da_elementwise(const T* __restrict__ A, const float* __restrict__ ss,
+                                        const float* __restrict__ coef, int64_t total, int N, float* __restrict__ dA) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int64_t row = i / N;
+  int b = (int)(row / N);
+  float c_den = coef[b * 4 + 0], c_a2 = coef[b * 4 + 1];
+  float v = dA[i];
+  if (c_den != 0.f) v += c_den * ss[row];
+  if (c_a2 != 0.f) v += c_a2 * 2.f * to_f32<T>(A[i]);
+  dA[i] = v;
+}
+
+template <typename T>
+static __global__ void k_cast_out(const float* __restrict__ in, T* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = from_f32<T>(in[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Host orchestration
+// ------------------------------------------------------------------------------------------
+struct DensePlan {
+  float *T, *W, *Araw, *M, *d, *ss, *a2, *ent, *dvec, *stats, *losses;
+  int32_t* argmax;
+  bool ok;
+  // `saved` is the forward->backward carry buffer (caller-owned)
+  DensePlan(Workspace& ws, int64_t B, int64_t N, int64_t K) {
+    T = ws.take<float>((size_t)B * K * N);
+    W = ws.take<float>((size_t)B * N * K);
+    Araw = ws.take<float>((size_t)B * K * K);
+    M = ws.take<float>((size_t)B * K * K);
+    d = ws.take<float>((size_t)B * N);
+    ss = ws.take<float>((size_t)B * N);
+    a2 = ws.take<float>((size_t)B * N);
+    ent = ws.take<float>((size_t)B * N);
+    dvec = ws.take<float>((size_t)B * K);
+    stats = ws.take<float>((size_t)B * 8);
+    losses = ws.take<float>(8);
+    argmax = ws.take<int32_t>((size_t)B);
+    ok = ws.ok;
+  }
+};
+
+static size_t dense_saved_bytes(int64_t B, int64_t N, int64_t K) {
+  size_t f = sizeof(float);
+  return align_up((size_t)B * K * N * f) * 2 + align_up((size_t)B * K * K * f) * 2 + align_up((size_t)B * N * f) * 4 +
+         align_up((size_t)B * K * f) + align_up((size_t)B * 8 * f) + align_up(8 * f) + align_up((size_t)B * 4) + 4096;
+}
+
+template <typename T>
+static int dense_fwd(const T* A, const T* S, const T* X, int B, int N, int K, int F, uint32_t flags, int loss_kind,
+                     float eps, float link_div, float ent_div, T* Xpool, T* Apool, float* losses_out, Workspace& saved,
+                     cudaStream_t st) {
+  DensePlan pl(saved, B, N, K);
+  if (!pl.ok) return TGPB200_ERR_WORKSPACE;
+  int rc;
+  int64_t NK = (int64_t)N * K, NN = (int64_t)N * N, NF = (int64_t)N * F, KK = (int64_t)K * K, KF = (int64_t)K * F;
+  if (X && Xpool) {  // X_pool = S^T X
+    rc = bgemm<T, T, T>(S, X, Xpool, B, K, F, N, NK, 1, K, NF, F, 1, KF, F, 1.f, false, st);
+    if (rc) return rc;
+  }
+  if (A) {
+    // T = S^T A  [K,N];  A_raw = T S  [K,K]   (reference association, dense_conn.py:120-121)
+    rc = bgemm<T, T, float>(S, A, pl.T, B, K, N, N, NK, 1, K, NN, N, 1, (int64_t)K * N, N, 1.f, false, st);
+    if (rc) return rc;
+    rc = bgemm<float, T, float>(pl.T, S, pl.Araw, B, K, K, N, (int64_t)K * N, N, 1, NK, K, 1, KK, K, 1.f, false, st);
+    if (rc) return rc;
+  }
+  if (loss_kind != 0) {  // M = S^T S
+    rc = bgemm<T, T, float>(S, S, pl.M, B, K, K, N, NK, 1, K, NK, K, 1, KK, K, 1.f, false, st);
+    if (rc) return rc;
+  }
+  int64_t rows = (int64_t)B * N;
+  if (rows > 0)
+    launch("k_row_stats", k_row_stats<T>, (unsigned)ceil_div(rows * 32, 256), 256, 0, st, A, S, rows, N, K, eps, pl.d, pl.ss, pl.a2,
+                                                                      pl.ent);
+  if (B > 0) {
+    launch("k_graph_epilogue", k_graph_epilogue<T>, B, 256, (size_t)K * sizeof(float), st, A ? pl.Araw : nullptr,
+                                                                  loss_kind != 0 ? pl.M : nullptr, pl.d, pl.ss, pl.a2,
+                                                                  pl.ent, N, K, flags, eps, Apool, pl.dvec, pl.stats,
+                                                                  pl.argmax);
+    launch("k_finalize_losses", k_finalize_losses, 1, 256, 0, st, pl.stats, B, eps, link_div, ent_div, pl.losses);
+    if (losses_out) cudaMemcpyAsync(losses_out, pl.losses, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  }
+  return launch_status();
+}
+
+template <typename T>
+static int dense_bwd(const T* A, const T* S, const T* X, const T* gXpool, const T* gApool, const float* gl, int B,
+                     int N, int K, int F, uint32_t flags, int loss_kind, float eps, float link_div, float ent_div,
+                     T* dS_out, T* dX_out, T* dA_out, Workspace& saved, Workspace& ws, cudaStream_t st) {
+  DensePlan pl(saved, B, N, K);
+  if (!pl.ok) return TGPB200_ERR_WORKSPACE;
+  int64_t NK = (int64_t)N * K, NN = (int64_t)N * N, NF = (int64_t)N * F, KK = (int64_t)K * K, KF = (int64_t)K * F;
+  float* Graw = ws.take<float>((size_t)B * KK);
+  float* P = ws.take<float>((size_t)B * KK);
+  float* coef = ws.take<float>((size_t)B * 4);
+  float* dS = ws.take<float>((size_t)B * NK);
+  float* U = ws.take<float>((size_t)B * NK);
+  float* dA = dA_out ? ws.take<float>((size_t)B * NN) : nullptr;
+  if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+  int rc;
+  if (B == 0) return TGPB200_OK;
+  bool have_a = A != nullptr;
+  if (have_a || loss_kind != 0) {
+    if (have_a)
+      launch("k_graph_bwd", k_graph_bwd<T>, B, 256, (size_t)3 * K * sizeof(float), st, pl.Araw, loss_kind != 0 ? pl.M : nullptr, gApool, pl.dvec, pl.stats, pl.argmax, gl, pl.losses, B, K, flags,
+          loss_kind, eps, link_div, ent_div, Graw, loss_kind != 0 ? P : nullptr, coef);
+  }
+  bool first = true;  // first GEMM into dS overwrites, later ones accumulate
+  if (X && gXpool) {
+    // dX = S Gx  [N,F];   dS += X Gx^T  [N,K]
+    if (dX_out) {
+      rc = bgemm<T, T, T>(S, gXpool, dX_out, B, N, F, K, NK, K, 1, KF, F, 1, NF, F, 1.f, false, st);
+      if (rc) return rc;
+    }
+    rc = bgemm<T, T, float>(X, gXpool, dS, B, N, K, F, NF, F, 1, KF, 1, F, NK, K, 1.f, false, st);
+    if (rc) return rc;
+    first = false;
+  }
+  if (have_a) {
+    // W = A S [N,K];  dS += W Graw^T + T^T Graw
+    rc = bgemm<T, T, float>(A, S, pl.W, B, N, K, N, NN, N, 1, NK, K, 1, NK, K, 1.f, false, st);
+    if (rc) return rc;
+    rc = bgemm<float, float, float>(pl.W, Graw, dS, B, N, K, K, NK, K, 1, KK, 1, K, NK, K, 1.f, !first, st);
+    if (rc) return rc;
+    first = false;
+    rc = bgemm<float, float, float>(pl.T, Graw, dS, B, N, K, K, (int64_t)K * N, 1, N, KK, K, 1, NK, K, 1.f, true, st);
+    if (rc) return rc;
+    if (loss_kind != 0) {  // dS += S P
+      rc = bgemm<T, float, float>(S, P, dS, B, N, K, K, NK, K, 1, KK, K, 1, NK, K, 1.f, true, st);
+      if (rc) return rc;
+    }
+    if (loss_kind != 0)
+      launch("k_ds_elementwise", k_ds_elementwise<T>, (unsigned)ceil_div((int64_t)B * NK, 256), 256, 0, st, S, pl.d, coef, (int64_t)B * NK, N,
+                                                                                   K, eps, dS);
+    if (dA_out) {  // dA = S Graw S^T + element-wise terms
+      rc = bgemm<T, float, float>(S, Graw, U, B, N, K, K, NK, K, 1, KK, K, 1, NK, K, 1.f, false, st);
+      if (rc) return rc;
+      rc = bgemm<float, T, float>(U, S, dA, B, N, N, K, NK, K, 1, NK, 1, K, NN, N, 1.f, false, st);
+      if (rc) return rc;
+      if (loss_kind != 0)
+        launch("k_da_elementwise", k_da_elementwise<T>, (unsigned)ceil_div((int64_t)B * NN, 256), 256, 0, st, A, pl.ss, coef, (int64_t)B * NN,
+                                                                                     N, dA);
+      launch("k_cast_out", k_cast_out<T>, (unsigned)ceil_div((int64_t)B * NN, 256), 256, 0, st, dA, dA_out, (int64_t)B * NN);
+    }
+  }
+  if (first) cudaMemsetAsync(dS, 0, (size_t)B * NK * sizeof(float), st);
+  if (dS_out) launch("k_cast_out", k_cast_out<T>, (unsigned)ceil_div((int64_t)B * NK, 256), 256, 0, st, dS, dS_out, (int64_t)B * NK);
+  return launch_status();
+}
+
+}  // namespace tgp
+
+using namespace tgp;
+
+extern "C" {
+
+size_t tgpb200_dense_pool_saved_bytes(int64_t B, int64_t N, int64_t K) { return dense_saved_bytes(B, N, K); }
+
+size_t tgpb200_dense_pool_bwd_workspace_bytes(int64_t B, int64_t N, int64_t K, int need_grad_adj) {
+  size_t f = sizeof(float);
+  return 2 * align_up((size_t)B * K * K * f) + align_up((size_t)B * 4 * f) + 2 * align_up((size_t)B * N * K * f) +
+         (need_grad_adj ? align_up((size_t)B * N * N * f) : 0) + 4096;
+}
+
+int tgpb200_dense_pool_fwd(const void* adj, const void* s, const void* x, int64_t B, int64_t N, int64_t K, int64_t F,
+                           int dtype, uint32_t flags, int loss_kind, float eps, float link_div, float ent_div,
+                           void* x_pool, void* adj_pool, float* losses, void* saved, size_t saved_bytes,
+                           tgpb200_stream_t stream) {
+  if (B < 0 || N < 0 || K < 0 || F < 0 || !s || !saved) return TGPB200_ERR_INVALID;
+  if (B >= INT32_MAX || N >= 65536 || K >= 32768 || F >= INT32_MAX) return TGPB200_ERR_UNSUPPORTED;
+  if (loss_kind < 0 || loss_kind > 2 || (loss_kind != 0 && !adj)) return TGPB200_ERR_INVALID;
+  if (adj && !adj_pool) return TGPB200_ERR_INVALID;
+  Workspace sv(saved, saved_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == TGPB200_F32)
+    return dense_fwd<float>((const float*)adj, (const float*)s, (const float*)x, (int)B, (int)N, (int)K, (int)F, flags,
+                            loss_kind, eps, link_div, ent_div, (float*)x_pool, (float*)adj_pool, losses, sv, st);
+  if (dtype == TGPB200_BF16)
+    return dense_fwd<__nv_bfloat16>((const __nv_bfloat16*)adj, (const __nv_bfloat16*)s, (const __nv_bfloat16*)x, (int)B,
+                                    (int)N, (int)K, (int)F, flags, loss_kind, eps, link_div, ent_div,
+                                    (__nv_bfloat16*)x_pool, (__nv_bfloat16*)adj_pool, losses, sv, st);
+  return TGPB200_ERR_UNSUPPORTED;
+}
+
+int tgpb200_dense_pool_bwd(const void* adj, const void* s, const void* x, const void* grad_x_pool,
+                           const void* grad_adj_pool, const float* grad_losses, int64_t B, int64_t N, int64_t K,
+                           int64_t F, int dtype, uint32_t flags, int loss_kind, float eps, float link_div,
+                           float ent_div, void* grad_s, void* grad_x, void* grad_adj, void* saved, size_t saved_bytes,
+                           void* workspace, size_t workspace_bytes, tgpb200_stream_t stream) {
+  if (B < 0 || N < 0 || K < 0 || F < 0 || !s || !saved) return TGPB200_ERR_INVALID;
+  if (loss_kind < 0 || loss_kind > 2) return TGPB200_ERR_INVALID;
+  Workspace sv(saved, saved_bytes), ws(workspace, workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == TGPB200_F32)
+    return dense_bwd<float>((const float*)adj, (const float*)s, (const float*)x, (const float*)grad_x_pool,
+                            (const float*)grad_adj_pool, grad_losses, (int)B, (int)N, (int)K, (int)F, flags, loss_kind,
+                            eps, link_div, ent_div, (float*)grad_s, (float*)grad_x, (float*)grad_adj, sv, ws, st);
+  if (dtype == TGPB200_BF16)
+    return dense_bwd<__nv_bfloat16>((const __nv_bfloat16*)adj, (const __nv_bfloat16*)s, (const __nv_bfloat16*)x,
+                                    (const __nv_bfloat16*)grad_x_pool, (const __nv_bfloat16*)grad_adj_pool,
+                                    grad_losses, (int)B, (int)N, (int)K, (int)F, flags, loss_kind, eps, link_div,
+                                    ent_div, (__nv_bfloat16*)grad_s, (__nv_bfloat16*)grad_x, (__nv_bfloat16*)grad_adj,
+                                    sv, ws, st);
+  return TGPB200_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

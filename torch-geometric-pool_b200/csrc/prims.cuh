@@ -1,0 +1,320 @@
+// Device-wide primitives written for this library (no CUB/Thrust): exclusive scan,
+// order-preserving stream compaction, stable LSD radix sort of (key, index) pairs.
+#pragma once
+#include "common.cuh"
+
+namespace tgp {
+
+// ------------------------------------------------------------------------------------------
+// Exclusive scan of int32 (n < 2^31).  reduce-then-scan over 4096-item tiles.
+// ------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int block_exclusive_scan_i(int v, int* smem /* >= 33 ints */, int* block_total) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) smem[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int s = lane < nw ? smem[lane] : 0;
+    int si = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(kFull, si, o);
+      if (lane >= o) si += t;
+    }
+    smem[lane] = si - s;  // exclusive warp base
+    if (lane == 31) smem[32] = si;
+  }
+  __syncthreads();
+  int base = smem[w];
+  if (block_total) *block_total = smem[32];
+  return base + inc - v;
+}
+
+static __global__ void k_scan_reduce(const int* __restrict__ in, int64_t n, int* __restrict__ tile_sums) {
+  __shared__ int red[33];
+  int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int s = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    int64_t i = base + j;
+    if (i < n) s += in[i];
+  }
+  int tot;
+  block_exclusive_scan_i(s, red, &tot);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+// Single block: exclusive scan of tile_sums[nt] in place; optional totals.
+static __global__ void k_scan_spine(int* __restrict__ tile_sums, int nt, int* __restrict__ total32,
+                                    int64_t* __restrict__ total64) {
+  __shared__ int red[33];
+  int carry = 0;
+  for (int start = 0; start < nt; start += blockDim.x) {
+    int i = start + threadIdx.x;
+    int v = i < nt ? tile_sums[i] : 0;
+    int tot;
+    int ex = block_exclusive_scan_i(v, red, &tot);
+    if (i < nt) tile_sums[i] = carry + ex;
+    carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (total32) *total32 = carry;
+    if (total64) *total64 = carry;
+  }
+}
+
+static __global__ void k_scan_down(const int* __restrict__ in, int* __restrict__ out, int64_t n,
+                                   const int* __restrict__ tile_offsets) {
+  __shared__ int red[33];
+  int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int v[kScanItems];
+  int s = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    int64_t i = base + j;
+    v[j] = i < n ? in[i] : 0;
+    s += v[j];
+  }
+  int ex = block_exclusive_scan_i(s, red, nullptr) + tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    int64_t i = base + j;
+    if (i < n) out[i] = ex;
+    ex += v[j];
+  }
+}
+
+inline size_t scan_workspace_bytes(int64_t n) { return align_up((size_t)ceil_div(n > 0 ? n : 1, kScanTile) * sizeof(int)); }
+
+// out may alias in.  total32/total64 (device) receive the grand total when non-null.
+inline int exclusive_scan_i32(const int* in, int* out, int64_t n, int* total32, int64_t* total64, Workspace& ws,
+                              cudaStream_t stream) {
+  int nt = (int)ceil_div(n > 0 ? n : 1, kScanTile);
+  int* sums = ws.take<int>(nt);
+  if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+  launch("k_scan_reduce", k_scan_reduce, nt, kScanThreads, 0, stream, in, n, sums);
+  launch("k_scan_spine", k_scan_spine, 1, 1024, 0, stream, sums, nt, total32, total64);
+  if (n > 0) launch("k_scan_down", k_scan_down, nt, kScanThreads, 0, stream, in, out, n, sums);
+  return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------
+// Order-preserving stream compaction.
+//   Pred:  __device__ bool operator()(int64_t i, Payload& p)   -- may cache loaded data in p
+//   Emit:  __device__ void operator()(int64_t i, int pos, const Payload& p)
+// Pass 1 counts survivors per tile, the spine scan turns counts into offsets (+ total),
+// pass 2 re-evaluates the predicate and writes survivors at offset + in-tile rank.
+// ------------------------------------------------------------------------------------------
+constexpr int kCompactThreads = 256;
+constexpr int kCompactItems = 8;
+constexpr int kCompactTile = kCompactThreads * kCompactItems;
+
+template <typename Pred>
+static __global__ void k_compact_count(Pred pred, int64_t n, int* __restrict__ tile_counts) {
+  __shared__ int red[33];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int64_t base = (int64_t)blockIdx.x * kCompactTile + (int64_t)w * (32 * kCompactItems);
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < kCompactItems; ++j) {
+    int64_t i = base + j * 32 + lane;
+    typename Pred::Payload p;
+    if (i < n && pred(i, p)) ++c;
+  }
+  int tot;
+  block_exclusive_scan_i(c, red, &tot);
+  if (threadIdx.x == 0) tile_counts[blockIdx.x] = tot;
+}
+
+template <typename Pred, typename Emit>
+static __global__ void k_compact_emit(Pred pred, Emit emit, int64_t n, const int* __restrict__ tile_offsets) {
+  __shared__ int warp_tot[kCompactThreads / 32];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int64_t base = (int64_t)blockIdx.x * kCompactTile + (int64_t)w * (32 * kCompactItems);
+  typename Pred::Payload pay[kCompactItems];
+  unsigned ball[kCompactItems];
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < kCompactItems; ++j) {
+    int64_t i = base + j * 32 + lane;
+    bool f = (i < n) && pred(i, pay[j]);
+    ball[j] = __ballot_sync(kFull, f);
+    cnt += __popc(ball[j]);
+  }
+  if (lane == 0) warp_tot[w] = cnt;
+  __syncthreads();
+  int run = tile_offsets[blockIdx.x];
+  for (int k = 0; k < w; ++k) run += warp_tot[k];
+  unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int j = 0; j < kCompactItems; ++j) {
+    if (ball[j] >> lane & 1u) emit(base + j * 32 + lane, run + __popc(ball[j] & lt), pay[j]);
+    run += __popc(ball[j]);
+  }
+}
+
+inline size_t compact_workspace_bytes(int64_t n) {
+  return align_up((size_t)ceil_div(n > 0 ? n : 1, kCompactTile) * sizeof(int));
+}
+
+// Phase 1: per-tile survivor counts -> exclusive tile offsets in `counts`, grand total to total32/total64.
+template <typename Pred>
+inline int compact_count(Pred pred, int64_t n, int* counts, int* total32, int64_t* total64, cudaStream_t stream) {
+  int nt = (int)ceil_div(n > 0 ? n : 1, kCompactTile);
+  launch("k_compact_count", k_compact_count<Pred>, nt, kCompactThreads, 0, stream, pred, n, counts);
+  launch("k_scan_spine", k_scan_spine, 1, 1024, 0, stream, counts, nt, total32, total64);
+  return launch_status();
+}
+// Phase 2: write survivors (counts must hold the offsets produced by compact_count on the same input).
+template <typename Pred, typename Emit>
+inline int compact_emit(Pred pred, Emit emit, int64_t n, const int* counts, cudaStream_t stream) {
+  int nt = (int)ceil_div(n > 0 ? n : 1, kCompactTile);
+  if (n > 0) launch("k_compact_emit", k_compact_emit<Pred, Emit>, nt, kCompactThreads, 0, stream, pred, emit, n, counts);
+  return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------
+// Stable LSD radix sort of (key, uint32 payload) pairs, 8 bits per pass.
+// Pass = tile histogram -> scan of [256][tiles] -> stable scatter (warp match ranking).
+// ------------------------------------------------------------------------------------------
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;
+constexpr int kSortBins = 256;
+
+template <typename KeyT>
+static __global__ void k_radix_hist(const KeyT* __restrict__ keys, int64_t n, int shift, int* __restrict__ tile_hist,
+                                    int nt) {
+  __shared__ int h[kSortBins];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t base = (int64_t)blockIdx.x * kSortTile;
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    int64_t i = base + j * kSortThreads + threadIdx.x;
+    if (i < n) atomicAdd(&h[(int)((keys[i] >> shift) & 255)], 1);
+  }
+  __syncthreads();
+  tile_hist[(size_t)threadIdx.x * nt + blockIdx.x] = h[threadIdx.x];
+}
+
+template <typename KeyT, bool kIota>
+static __global__ void __launch_bounds__(kSortThreads)
+    k_radix_scatter(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                    KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
+                    const int* __restrict__ tile_off, int nt) {
+  constexpr int NW = kSortThreads / 32;
+  __shared__ int warp_cnt[NW][kSortBins];
+  __shared__ int g_base[kSortBins];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < NW * kSortBins; i += kSortThreads) (&warp_cnt[0][0])[i] = 0;
+  __syncthreads();
+
+  int64_t base = (int64_t)blockIdx.x * kSortTile + (int64_t)w * (32 * kSortItems);
+  KeyT key[kSortItems];
+  int rank[kSortItems];
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    int64_t i = base + j * 32 + lane;
+    bool valid = i < n;
+    unsigned vmask = __ballot_sync(kFull, valid);
+    rank[j] = 0;
+    key[j] = 0;
+    if (valid) {
+      key[j] = keys_in[i];
+      int d = (int)((key[j] >> shift) & 255);
+      unsigned peers = __match_any_sync(vmask, d);
+      int leader = __ffs(peers) - 1;
+      int old = 0;
+      if (lane == leader) {
+        old = warp_cnt[w][d];
+        warp_cnt[w][d] = old + __popc(peers);
+      }
+      old = __shfl_sync(vmask, old, leader);
+      rank[j] = old + __popc(peers & ((1u << lane) - 1u));
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    int d = threadIdx.x;  // one thread per digit
+    int run = 0;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+      int c = warp_cnt[k][d];
+      warp_cnt[k][d] = run;
+      run += c;
+    }
+    g_base[d] = tile_off[(size_t)d * nt + blockIdx.x];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    int64_t i = base + j * 32 + lane;
+    if (i < n) {
+      int d = (int)((key[j] >> shift) & 255);
+      int64_t pos = (int64_t)g_base[d] + warp_cnt[w][d] + rank[j];
+      keys_out[pos] = key[j];
+      vals_out[pos] = kIota ? (uint32_t)i : vals_in[i];
+    }
+  }
+}
+
+inline int radix_passes(int key_bits) { return key_bits <= 0 ? 1 : (key_bits + 7) / 8; }
+
+inline size_t radix_sort_workspace_bytes(int64_t n) {
+  int64_t nt = ceil_div(n > 0 ? n : 1, kSortTile);
+  return align_up((size_t)nt * kSortBins * sizeof(int)) + scan_workspace_bytes(nt * kSortBins);
+}
+
+// Sorts n pairs by the low `key_bits` bits of the key.  The first pass takes the payload as
+// iota when vals0 == nullptr.  Buffers (keys0, vals0) and (keys1, vals1) ping-pong; returns
+// (via *result_in_1) which pair holds the result.  keys0 is overwritten.
+template <typename KeyT>
+inline int radix_sort_pairs(KeyT* keys0, uint32_t* vals0_or_null, uint32_t* vals0_buf, KeyT* keys1, uint32_t* vals1,
+                            int64_t n, int key_bits, bool* result_in_1, Workspace& ws, cudaStream_t stream) {
+  int nt = (int)ceil_div(n > 0 ? n : 1, kSortTile);
+  size_t mark = ws.off;
+  int* hist = ws.take<int>((size_t)nt * kSortBins);
+  if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+  size_t mark2 = ws.off;
+  int passes = radix_passes(key_bits);
+  KeyT* kin = keys0;
+  KeyT* kout = keys1;
+  const uint32_t* vin = vals0_or_null;
+  uint32_t* vout = vals1;
+  bool in1 = false;
+  for (int p = 0; p < passes; ++p) {
+    int shift = 8 * p;
+    launch("k_radix_hist", k_radix_hist<KeyT>, nt, kSortThreads, 0, stream, kin, n, shift, hist, nt);
+    ws.off = mark2;
+    int rc = exclusive_scan_i32(hist, hist, (int64_t)nt * kSortBins, nullptr, nullptr, ws, stream);
+    if (rc != TGPB200_OK) return rc;
+    if (vin == nullptr)
+      launch("k_radix_scatter", k_radix_scatter<KeyT, true>, nt, kSortThreads, 0, stream, kin, nullptr, kout, vout, n, shift, hist, nt);
+    else
+      launch("k_radix_scatter", k_radix_scatter<KeyT, false>, nt, kSortThreads, 0, stream, kin, vin, kout, vout, n, shift, hist, nt);
+    in1 = !in1;
+    KeyT* tk = kin;
+    kin = kout;
+    kout = tk;
+    vin = vout;
+    vout = (vout == vals1) ? vals0_buf : vals1;
+  }
+  (void)mark;
+  *result_in_1 = in1;
+  return launch_status();
+}
+
+}  // namespace tgp

@@ -1,0 +1,567 @@
+// Sparse Connect: kept-node filter + relabel, cluster remap + coalesce, edge-weight normalisations.
+// Reference: tgp/connect/base_conn.py:57-112, tgp/utils/ops.py:338-419 (and the PyG subgraph /
+// coalesce / remove_self_loops semantics restated in oracle/pyg_shim.py).
+#include <limits.h>
+
+#include "prims.cuh"
+
+namespace tgp {
+
+// ------------------------------------------------------------------------------------------
+// kept-node branch
+// ------------------------------------------------------------------------------------------
+static __global__ void k_build_table(const int64_t* __restrict__ node_index, int64_t kept, int64_t N,
+                                     int32_t* __restrict__ table) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= kept) return;
+  int64_t v = node_index[j];
+  if (v >= 0 && v < N) table[v] = (int32_t)j;
+}
+
+struct KeptPred {
+  struct Payload {
+    int32_t r, c;
+    float w;
+  };
+  const int64_t* row;
+  const int64_t* col;
+  const float* w;
+  const int32_t* table;
+  int64_t N;
+  bool rsl;
+  float eps;
+  __device__ bool operator()(int64_t i, Payload& p) const {
+    int64_t r = row[i], c = col[i];
+    if (r < 0 || r >= N || c < 0 || c >= N) return false;
+    if (rsl && r == c) return false;
+    p.r = table[r];
+    if (p.r < 0) return false;
+    p.c = table[c];
+    if (p.c < 0) return false;
+    if (w) {
+      p.w = w[i];
+      if (!(fabsf(p.w) > eps)) return false;
+    }
+    return true;
+  }
+};
+struct KeptEmit {
+  int64_t* out_row;
+  int64_t* out_col;
+  float* out_w;
+  int32_t* src;
+  __device__ void operator()(int64_t i, int pos, const KeptPred::Payload& p) const {
+    out_row[pos] = p.r;
+    out_col[pos] = p.c;
+    if (out_w) out_w[pos] = p.w;
+    if (src) src[pos] = (int32_t)i;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// cluster branch
+// ------------------------------------------------------------------------------------------
+template <typename KeyT>
+static __global__ void k_remap_keys(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
+                                    const int64_t* __restrict__ cluster, int64_t E, int64_t N, int64_t K,
+                                    KeyT* __restrict__ keys) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E) return;
+  int64_t r = row[i], c = col[i];
+  int64_t cr = (r >= 0 && r < N) ? cluster[r] : 0;
+  int64_t cc = (c >= 0 && c < N) ? cluster[c] : 0;
+  if (cr < 0 || cr >= K) cr = 0;
+  if (cc < 0 || cc >= K) cc = 0;
+  keys[i] = (KeyT)((uint64_t)cr * (uint64_t)K + (uint64_t)cc);
+}
+
+template <typename KeyT>
+static __global__ void k_head_flags(const KeyT* __restrict__ ks, int64_t E, int* __restrict__ flags) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E) return;
+  flags[i] = (i == 0 || ks[i] != ks[i - 1]) ? 1 : 0;
+}
+
+// excl = exclusive scan of head flags; run id of a head i is excl[i].
+template <typename KeyT>
+static __global__ void k_run_starts(const KeyT* __restrict__ ks, const int* __restrict__ excl,
+                                    const int* __restrict__ total, int64_t E, int* __restrict__ run_start) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E) return;
+  if (i == 0 || ks[i] != ks[i - 1]) run_start[excl[i]] = (int)i;
+  if (i == E - 1) run_start[*total] = (int)E;
+}
+
+// One thread per run: combine the member weights in sorted (= original, the sort is stable) order.
+static __global__ void k_run_combine(const uint32_t* __restrict__ perm, const float* __restrict__ w,
+                                     const int* __restrict__ run_start, const int* __restrict__ total, int op,
+                                     float* __restrict__ comb) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= *total) return;
+  int s = run_start[r], e = run_start[r + 1];
+  float acc = w[perm[s]];
+  for (int i = s + 1; i < e; ++i) {
+    float v = w[perm[i]];
+    if (op == TGPB200_SUM || op == TGPB200_MEAN) acc = __fadd_rn(acc, v);
+    else if (op == TGPB200_MAX) acc = fmaxf(acc, v);
+    else if (op == TGPB200_MIN) acc = fminf(acc, v);
+    else acc = __fmul_rn(acc, v);
+  }
+  if (op == TGPB200_MEAN) acc = __fdiv_rn(acc, (float)(e - s));
+  comb[r] = acc;
+}
+
+template <typename KeyT>
+struct RunPred {
+  struct Payload {
+    int64_t cr, cc;
+    float w;
+    int len;
+  };
+  const KeyT* ks;
+  const int* run_start;
+  const int* total;
+  const float* comb;  // null when unweighted
+  int64_t K;
+  bool rsl;
+  float eps;
+  __device__ bool operator()(int64_t r, Payload& p) const {
+    if (r >= *total) return false;
+    int s = run_start[r];
+    uint64_t key = (uint64_t)ks[s];
+    p.cr = (int64_t)(key / (uint64_t)K);
+    p.cc = (int64_t)(key % (uint64_t)K);
+    p.len = run_start[r + 1] - s;
+    if (rsl && p.cr == p.cc) return false;
+    if (comb) {
+      p.w = comb[r];
+      if (!(fabsf(p.w) > eps)) return false;
+    }
+    return true;
+  }
+};
+template <typename KeyT>
+struct RunEmit {
+  int64_t* out_row;
+  int64_t* out_col;
+  float* out_w;
+  int32_t* run_len;
+  int* run_slot;
+  __device__ void operator()(int64_t r, int pos, const typename RunPred<KeyT>::Payload& p) const {
+    out_row[pos] = p.cr;
+    out_col[pos] = p.cc;
+    if (out_w) out_w[pos] = p.w;
+    if (run_len) run_len[pos] = p.len;
+    run_slot[r] = pos;
+  }
+};
+
+template <typename KeyT>
+static __global__ void k_edge_slots(const KeyT* __restrict__ ks, const uint32_t* __restrict__ perm,
+                                    const int* __restrict__ excl, const int* __restrict__ run_slot, int64_t E,
+                                    int32_t* __restrict__ edge_slot) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E) return;
+  int head = (i == 0 || ks[i] != ks[i - 1]) ? 1 : 0;
+  edge_slot[perm[i]] = run_slot[excl[i] + head - 1];
+}
+
+static int key_bits_for_u64(uint64_t max_value) {
+  int b = 0;
+  while (max_value) {
+    ++b;
+    max_value >>= 1;
+  }
+  return b < 1 ? 1 : b;
+}
+
+// Workspace layout shared by the count and emit phases (carved identically in both calls).
+template <typename KeyT>
+struct CoalescePlan {
+  KeyT *keys0, *keys1;
+  uint32_t *vals0, *vals1;
+  int *excl, *run_start, *run_slot, *tile_counts, *total;
+  float* comb;
+  bool ok;
+  CoalescePlan(Workspace& ws, int64_t E, bool weighted) {
+    size_t n = (size_t)E;
+    keys0 = ws.take<KeyT>(n);
+    keys1 = ws.take<KeyT>(n);
+    vals0 = ws.take<uint32_t>(n);
+    vals1 = ws.take<uint32_t>(n);
+    excl = ws.take<int>(n);
+    run_start = ws.take<int>(n + 1);
+    run_slot = ws.take<int>(n);
+    comb = ws.take<float>(n);
+    tile_counts = ws.take<int>((size_t)ceil_div(E, kCompactTile));
+    total = ws.take<int>(2);  // [0] number of runs, [1] 1 if the sorted data sits in (keys1, vals1)
+    (void)weighted;
+    ok = ws.ok;
+  }
+};
+
+template <typename KeyT>
+static int remap_coalesce_count_impl(const int64_t* row, const int64_t* col, const float* w, int64_t E,
+                                     const int64_t* cluster, int64_t N, int64_t K, int op, uint32_t flags, float eps,
+                                     int64_t* count_out, Workspace& ws, cudaStream_t st) {
+  CoalescePlan<KeyT> pl(ws, E, w != nullptr);
+  if (!pl.ok) return TGPB200_ERR_WORKSPACE;
+  unsigned grid = (unsigned)ceil_div(E, 256);
+  launch("k_remap_keys", k_remap_keys<KeyT>, grid, 256, 0, st, row, col, cluster, E, N, K, pl.keys0);
+  int bits = key_bits_for_u64((uint64_t)K * (uint64_t)K - 1);
+  bool in1 = false;
+  int rc = radix_sort_pairs<KeyT>(pl.keys0, nullptr, pl.vals0, pl.keys1, pl.vals1, E, bits, &in1, ws, st);
+  if (rc != TGPB200_OK) return rc;
+  const KeyT* ks = in1 ? pl.keys1 : pl.keys0;
+  const uint32_t* perm = in1 ? pl.vals1 : pl.vals0;
+  launch("k_head_flags", k_head_flags<KeyT>, grid, 256, 0, st, ks, E, pl.excl);
+  rc = exclusive_scan_i32(pl.excl, pl.excl, E, pl.total, nullptr, ws, st);
+  if (rc != TGPB200_OK) return rc;
+  launch("k_run_starts", k_run_starts<KeyT>, grid, 256, 0, st, ks, pl.excl, pl.total, E, pl.run_start);
+  if (w) launch("k_run_combine", k_run_combine, grid, 256, 0, st, perm, w, pl.run_start, pl.total, op, pl.comb);
+  RunPred<KeyT> pred{ks, pl.run_start, pl.total, w ? pl.comb : nullptr, K, (flags & TGPB200_REMOVE_SELF_LOOPS) != 0, eps};
+  return compact_count(pred, E, pl.tile_counts, nullptr, count_out, st);
+}
+
+template <typename KeyT>
+static int remap_coalesce_emit_impl(int64_t E, int64_t K, bool weighted, uint32_t flags, float eps, int64_t* out_row,
+                                    int64_t* out_col, float* out_w, int32_t* edge_slot, int32_t* run_len,
+                                    Workspace& ws, cudaStream_t st) {
+  CoalescePlan<KeyT> pl(ws, E, weighted);
+  if (!pl.ok) return TGPB200_ERR_WORKSPACE;
+  int bits = key_bits_for_u64((uint64_t)K * (uint64_t)K - 1);
+  bool in1 = (radix_passes(bits) & 1) != 0;
+  const KeyT* ks = in1 ? pl.keys1 : pl.keys0;
+  const uint32_t* perm = in1 ? pl.vals1 : pl.vals0;
+  unsigned grid = (unsigned)ceil_div(E, 256);
+  cudaMemsetAsync(pl.run_slot, 0xff, (size_t)E * sizeof(int), st);
+  RunPred<KeyT> pred{ks, pl.run_start, pl.total, weighted ? pl.comb : nullptr, K,
+                     (flags & TGPB200_REMOVE_SELF_LOOPS) != 0, eps};
+  RunEmit<KeyT> emit{out_row, out_col, weighted ? out_w : nullptr, run_len, pl.run_slot};
+  int rc = compact_emit(pred, emit, E, pl.tile_counts, st);
+  if (rc != TGPB200_OK) return rc;
+  if (edge_slot) launch("k_edge_slots", k_edge_slots<KeyT>, grid, 256, 0, st, ks, perm, pl.excl, pl.run_slot, E, edge_slot);
+  return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------
+// coalesce backward
+// ------------------------------------------------------------------------------------------
+static __global__ void k_coalesce_ties(const float* __restrict__ w, const float* __restrict__ out_w,
+                                       const int32_t* __restrict__ slot, int64_t E, int* __restrict__ ties) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int s = slot[e];
+  if (s >= 0 && w[e] == out_w[s]) atomicAdd(&ties[s], 1);
+}
+static __global__ void k_coalesce_bwd(const float* __restrict__ w, const float* __restrict__ out_w,
+                                      const float* __restrict__ gout, const int32_t* __restrict__ slot,
+                                      const int32_t* __restrict__ run_len, const int* __restrict__ ties, int64_t E,
+                                      int op, float* __restrict__ gin) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int s = slot[e];
+  float g = 0.f;
+  if (s >= 0) {
+    g = gout[s];
+    if (op == TGPB200_MEAN) g = g / (float)run_len[s];
+    else if (op == TGPB200_MAX || op == TGPB200_MIN) g = (w[e] == out_w[s]) ? g / (float)ties[s] : 0.f;
+    else if (op == TGPB200_MUL) g = (w[e] != 0.f) ? g * out_w[s] / w[e] : 0.f;
+  }
+  gin[e] = g;
+}
+
+// ------------------------------------------------------------------------------------------
+// degree / max-weight normalisation
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dinv_of(float deg, float eps) { return 1.0f / sqrtf(fmaxf(deg, eps)); }
+
+static __global__ void k_deg_accum(const int64_t* __restrict__ row, const float* __restrict__ w, int64_t E, int64_t K,
+                                   float* __restrict__ deg) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t r = row[e];
+  if (r >= 0 && r < K) atomicAdd(&deg[r], w ? w[e] : 1.f);
+}
+static __global__ void k_deg_apply(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
+                                   const float* __restrict__ w, const float* __restrict__ deg, int64_t E, int64_t K,
+                                   float eps, float* __restrict__ w_out) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t r = row[e], c = col[e];
+  if (r < 0 || r >= K || c < 0 || c >= K) { w_out[e] = 0.f; return; }
+  float v = w ? w[e] : 1.f;
+  w_out[e] = __fmul_rn(__fmul_rn(v, dinv_of(deg[r], eps)), dinv_of(deg[c], eps));
+}
+static __global__ void k_deg_bwd_accum(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
+                                       const float* __restrict__ w, const float* __restrict__ deg,
+                                       const float* __restrict__ gout, int64_t E, int64_t K, float eps,
+                                       float* __restrict__ gdinv) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t r = row[e], c = col[e];
+  if (r < 0 || r >= K || c < 0 || c >= K) return;
+  float t = gout[e] * (w ? w[e] : 1.f);
+  atomicAdd(&gdinv[r], t * dinv_of(deg[c], eps));
+  atomicAdd(&gdinv[c], t * dinv_of(deg[r], eps));
+}
+static __global__ void k_deg_bwd_apply(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
+                                       const float* __restrict__ deg, const float* __restrict__ gout,
+                                       const float* __restrict__ gdinv, int64_t E, int64_t K, float eps,
+                                       float* __restrict__ gw) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t r = row[e], c = col[e];
+  if (r < 0 || r >= K || c < 0 || c >= K) { gw[e] = 0.f; return; }
+  float dr = dinv_of(deg[r], eps), dc = dinv_of(deg[c], eps);
+  float gdeg = (deg[r] >= eps) ? -0.5f * gdinv[r] * dr * dr * dr : 0.f;
+  gw[e] = gout[e] * dr * dc + gdeg;
+}
+
+static __global__ void k_wn_max(const int64_t* __restrict__ row, const float* __restrict__ w,
+                                const int64_t* __restrict__ batch, int64_t E, int64_t G, float* __restrict__ mx) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t g = batch[row[e]];
+  if (g < 0 || g >= G) return;
+  float a = fabsf(w[e]);
+  if (a == a) atomicMax(reinterpret_cast<int*>(&mx[g]), __float_as_int(a));  // |w| >= 0: int order == float order
+}
+static __global__ void k_wn_apply(const int64_t* __restrict__ row, const float* __restrict__ w,
+                                  const int64_t* __restrict__ batch, const float* __restrict__ mx, int64_t E,
+                                  int64_t G, int32_t* __restrict__ arg, float* __restrict__ w_out) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t g = batch[row[e]];
+  if (g < 0 || g >= G) { w_out[e] = w[e]; return; }
+  float m = mx[g];
+  if (arg && fabsf(w[e]) == m) atomicMin(&arg[g], (int)e);
+  w_out[e] = __fdiv_rn(w[e], m == 0.f ? 1.f : m);
+}
+static __global__ void k_wn_bwd_accum(const int64_t* __restrict__ row, const float* __restrict__ w,
+                                      const int64_t* __restrict__ batch, const float* __restrict__ gout, int64_t E,
+                                      int64_t G, float* __restrict__ acc) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t g = batch[row[e]];
+  if (g >= 0 && g < G) atomicAdd(&acc[g], gout[e] * w[e]);
+}
+static __global__ void k_wn_bwd_apply(const int64_t* __restrict__ row, const float* __restrict__ w,
+                                      const int64_t* __restrict__ batch, const float* __restrict__ mx,
+                                      const int32_t* __restrict__ arg, const float* __restrict__ gout,
+                                      const float* __restrict__ acc, int64_t E, int64_t G, float* __restrict__ gw) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t g = batch[row[e]];
+  if (g < 0 || g >= G) { gw[e] = gout[e]; return; }
+  float m = mx[g];
+  float v = gout[e] / (m == 0.f ? 1.f : m);
+  if (m != 0.f && arg[g] == (int)e) v += (w[e] < 0.f ? -1.f : 1.f) * (-acc[g] / (m * m));
+  gw[e] = v;
+}
+
+}  // namespace tgp
+
+using namespace tgp;
+
+extern "C" {
+
+size_t tgpb200_filter_relabel_workspace_bytes(int64_t E, int64_t N) {
+  return align_up((size_t)(N > 0 ? N : 1) * sizeof(int32_t)) + compact_workspace_bytes(E) + 1024;
+}
+
+struct KeptPlan {
+  int32_t* table;
+  int* tile_counts;
+  bool ok;
+  KeptPlan(Workspace& ws, int64_t E, int64_t N) {
+    table = ws.take<int32_t>((size_t)(N > 0 ? N : 1));
+    tile_counts = ws.take<int>((size_t)ceil_div(E > 0 ? E : 1, kCompactTile));
+    ok = ws.ok;
+  }
+};
+
+int tgpb200_filter_relabel_count(const int64_t* row, const int64_t* col, const float* edge_weight, int64_t E,
+                                 const int64_t* node_index, int64_t kept, int64_t N, uint32_t flags, float eps,
+                                 int64_t* count_out, void* workspace, size_t workspace_bytes,
+                                 tgpb200_stream_t stream) {
+  if (E < 0 || kept < 0 || N < 0 || E >= INT32_MAX || N >= INT32_MAX || !count_out) return TGPB200_ERR_INVALID;
+  if (E > 0 && (!row || !col)) return TGPB200_ERR_INVALID;
+  if (kept > 0 && !node_index) return TGPB200_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  KeptPlan pl(ws, E, N);
+  if (!pl.ok) return TGPB200_ERR_WORKSPACE;
+  cudaMemsetAsync(pl.table, 0xff, (size_t)(N > 0 ? N : 1) * sizeof(int32_t), st);
+  if (kept > 0) launch("k_build_table", k_build_table, (unsigned)ceil_div(kept, 256), 256, 0, st, node_index, kept, N, pl.table);
+  KeptPred pred{row, col, edge_weight, pl.table, N, (flags & TGPB200_REMOVE_SELF_LOOPS) != 0, eps};
+  return compact_count(pred, E, pl.tile_counts, nullptr, count_out, st);
+}
+
+int tgpb200_filter_relabel_emit(const int64_t* row, const int64_t* col, const float* edge_weight, int64_t E,
+                                int64_t N, uint32_t flags, float eps, int64_t* out_row, int64_t* out_col,
+                                float* out_weight, int32_t* src_edge, void* workspace, size_t workspace_bytes,
+                                tgpb200_stream_t stream) {
+  if (E < 0 || N < 0 || E >= INT32_MAX) return TGPB200_ERR_INVALID;
+  if (E == 0) return TGPB200_OK;
+  if (!row || !col || !out_row || !out_col) return TGPB200_ERR_INVALID;
+  if (edge_weight && !out_weight) return TGPB200_ERR_INVALID;
+  Workspace ws(workspace, workspace_bytes);
+  KeptPlan pl(ws, E, N);
+  if (!pl.ok) return TGPB200_ERR_WORKSPACE;
+  KeptPred pred{row, col, edge_weight, pl.table, N, (flags & TGPB200_REMOVE_SELF_LOOPS) != 0, eps};
+  KeptEmit emit{out_row, out_col, edge_weight ? out_weight : nullptr, src_edge};
+  return compact_emit(pred, emit, E, pl.tile_counts, (cudaStream_t)stream);
+}
+
+size_t tgpb200_remap_coalesce_workspace_bytes(int64_t E, int64_t K) {
+  (void)K;
+  size_t n = (size_t)(E > 0 ? E : 1);
+  return 2 * align_up(n * 8) + 7 * align_up((n + 1) * 4) + radix_sort_workspace_bytes(E) + scan_workspace_bytes(E) +
+         compact_workspace_bytes(E) + 4096;
+}
+
+int tgpb200_remap_coalesce_count(const int64_t* row, const int64_t* col, const float* edge_weight, int64_t E,
+                                 const int64_t* cluster_index, int64_t N, int64_t K, int op, uint32_t flags, float eps,
+                                 int64_t* count_out, void* workspace, size_t workspace_bytes,
+                                 tgpb200_stream_t stream) {
+  if (E < 0 || N < 0 || K < 0 || E >= INT32_MAX || K >= INT32_MAX || !count_out) return TGPB200_ERR_INVALID;
+  if (op < TGPB200_SUM || op > TGPB200_MUL) return TGPB200_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (E == 0) {
+    cudaMemsetAsync(count_out, 0, sizeof(int64_t), st);
+    return launch_status();
+  }
+  if (!row || !col || !cluster_index || K == 0) return TGPB200_ERR_INVALID;
+  Workspace ws(workspace, workspace_bytes);
+  if ((uint64_t)K * (uint64_t)K <= 0xffffffffull)
+    return remap_coalesce_count_impl<uint32_t>(row, col, edge_weight, E, cluster_index, N, K, op, flags, eps,
+                                               count_out, ws, st);
+  return remap_coalesce_count_impl<uint64_t>(row, col, edge_weight, E, cluster_index, N, K, op, flags, eps, count_out,
+                                             ws, st);
+}
+
+int tgpb200_remap_coalesce_emit(int64_t E, int64_t K, int weighted, uint32_t flags, float eps, int64_t* out_row,
+                                int64_t* out_col, float* out_weight, int32_t* edge_slot, int32_t* run_len,
+                                void* workspace, size_t workspace_bytes, tgpb200_stream_t stream) {
+  if (E < 0 || K < 0 || E >= INT32_MAX || K >= INT32_MAX) return TGPB200_ERR_INVALID;
+  if (E == 0) return TGPB200_OK;
+  if (!out_row || !out_col || K == 0 || (weighted && !out_weight)) return TGPB200_ERR_INVALID;
+  Workspace ws(workspace, workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((uint64_t)K * (uint64_t)K <= 0xffffffffull)
+    return remap_coalesce_emit_impl<uint32_t>(E, K, weighted != 0, flags, eps, out_row, out_col, out_weight,
+                                              edge_slot, run_len, ws, st);
+  return remap_coalesce_emit_impl<uint64_t>(E, K, weighted != 0, flags, eps, out_row, out_col, out_weight, edge_slot,
+                                            run_len, ws, st);
+}
+
+// grad_in[e] = grad_out[j] for the surviving edges (src_edge[j] == e), 0 elsewhere.
+static __global__ void k_unfilter(const float* __restrict__ gout, const int32_t* __restrict__ src, int64_t cnt,
+                                  float* __restrict__ gin) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < cnt) gin[src[j]] = gout[j];
+}
+
+int tgpb200_filter_relabel_bwd(const float* grad_out, const int32_t* src_edge, int64_t num_out, int64_t E,
+                               float* grad_in, tgpb200_stream_t stream) {
+  if (num_out < 0 || E < 0) return TGPB200_ERR_INVALID;
+  if (E == 0) return TGPB200_OK;
+  if (!grad_in || (num_out > 0 && (!grad_out || !src_edge))) return TGPB200_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(grad_in, 0, (size_t)E * sizeof(float), st);
+  if (num_out > 0) launch("k_unfilter", k_unfilter, (unsigned)ceil_div(num_out, 256), 256, 0, st, grad_out, src_edge, num_out, grad_in);
+  return launch_status();
+}
+
+size_t tgpb200_coalesce_bwd_workspace_bytes(int64_t E, int64_t num_out, int op) {
+  (void)E;
+  if (op == TGPB200_MAX || op == TGPB200_MIN) return align_up((size_t)(num_out > 0 ? num_out : 1) * sizeof(int)) + 256;
+  return 256;
+}
+
+int tgpb200_coalesce_bwd(const float* edge_weight, const float* out_weight, const float* grad_out,
+                         const int32_t* edge_slot, const int32_t* run_len, int64_t E, int64_t num_out, int op,
+                         float* grad_in, void* workspace, size_t workspace_bytes, tgpb200_stream_t stream) {
+  if (E < 0 || num_out < 0 || op < TGPB200_SUM || op > TGPB200_MUL) return TGPB200_ERR_INVALID;
+  if (E == 0) return TGPB200_OK;
+  if (!edge_slot || !grad_in || (num_out > 0 && !grad_out)) return TGPB200_ERR_INVALID;
+  if (op == TGPB200_MEAN && !run_len) return TGPB200_ERR_INVALID;
+  if (op >= TGPB200_MAX && (!edge_weight || !out_weight)) return TGPB200_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  int* ties = nullptr;
+  unsigned grid = (unsigned)ceil_div(E, 256);
+  if (op == TGPB200_MAX || op == TGPB200_MIN) {
+    ties = ws.take<int>((size_t)(num_out > 0 ? num_out : 1));
+    if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+    cudaMemsetAsync(ties, 0, (size_t)(num_out > 0 ? num_out : 1) * sizeof(int), st);
+    launch("k_coalesce_ties", k_coalesce_ties, grid, 256, 0, st, edge_weight, out_weight, edge_slot, E, ties);
+  }
+  launch("k_coalesce_bwd", k_coalesce_bwd, grid, 256, 0, st, edge_weight, out_weight, grad_out, edge_slot, run_len, ties, E, op, grad_in);
+  return launch_status();
+}
+
+int tgpb200_degree_norm_fwd(const int64_t* row, const int64_t* col, const float* w, int64_t E, int64_t K, float eps,
+                            float* deg_out, float* w_out, tgpb200_stream_t stream) {
+  if (E < 0 || K < 0) return TGPB200_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (K > 0) {
+    if (!deg_out) return TGPB200_ERR_INVALID;
+    cudaMemsetAsync(deg_out, 0, (size_t)K * sizeof(float), st);
+  }
+  if (E == 0) return launch_status();
+  if (!row || !col || !w_out) return TGPB200_ERR_INVALID;
+  unsigned grid = (unsigned)ceil_div(E, 256);
+  launch("k_deg_accum", k_deg_accum, grid, 256, 0, st, row, w, E, K, deg_out);
+  launch("k_deg_apply", k_deg_apply, grid, 256, 0, st, row, col, w, deg_out, E, K, eps, w_out);
+  return launch_status();
+}
+
+int tgpb200_degree_norm_bwd(const int64_t* row, const int64_t* col, const float* w, const float* deg,
+                            const float* grad_out, int64_t E, int64_t K, float eps, float* grad_dinv, float* grad_w,
+                            tgpb200_stream_t stream) {
+  if (E < 0 || K < 0) return TGPB200_ERR_INVALID;
+  if (E == 0) return TGPB200_OK;
+  if (!row || !col || !deg || !grad_out || !grad_dinv || !grad_w) return TGPB200_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(grad_dinv, 0, (size_t)K * sizeof(float), st);
+  unsigned grid = (unsigned)ceil_div(E, 256);
+  launch("k_deg_bwd_accum", k_deg_bwd_accum, grid, 256, 0, st, row, col, w, deg, grad_out, E, K, eps, grad_dinv);
+  launch("k_deg_bwd_apply", k_deg_bwd_apply, grid, 256, 0, st, row, col, deg, grad_out, grad_dinv, E, K, eps, grad_w);
+  return launch_status();
+}
+
+int tgpb200_weight_norm_fwd(const int64_t* row, const float* w, const int64_t* batch_pooled, int64_t E, int64_t G,
+                            float* max_out, int32_t* arg_out, float* w_out, tgpb200_stream_t stream) {
+  if (E < 0 || G < 0) return TGPB200_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (G > 0) {
+    if (!max_out) return TGPB200_ERR_INVALID;
+    cudaMemsetAsync(max_out, 0, (size_t)G * sizeof(float), st);
+    if (arg_out) cudaMemsetAsync(arg_out, 0x7f, (size_t)G * sizeof(int32_t), st);
+  }
+  if (E == 0) return launch_status();
+  if (!row || !w || !batch_pooled || !w_out) return TGPB200_ERR_INVALID;
+  unsigned grid = (unsigned)ceil_div(E, 256);
+  launch("k_wn_max", k_wn_max, grid, 256, 0, st, row, w, batch_pooled, E, G, max_out);
+  launch("k_wn_apply", k_wn_apply, grid, 256, 0, st, row, w, batch_pooled, max_out, E, G, arg_out, w_out);
+  return launch_status();
+}
+
+int tgpb200_weight_norm_bwd(const int64_t* row, const float* w, const int64_t* batch_pooled, const float* max_in,
+                            const int32_t* arg_in, const float* grad_out, int64_t E, int64_t G, float* graph_acc,
+                            float* grad_w, tgpb200_stream_t stream) {
+  if (E < 0 || G < 0) return TGPB200_ERR_INVALID;
+  if (E == 0) return TGPB200_OK;
+  if (!row || !w || !batch_pooled || !max_in || !arg_in || !grad_out || !graph_acc || !grad_w)
+    return TGPB200_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(graph_acc, 0, (size_t)G * sizeof(float), st);
+  unsigned grid = (unsigned)ceil_div(E, 256);
+  launch("k_wn_bwd_accum", k_wn_bwd_accum, grid, 256, 0, st, row, w, batch_pooled, grad_out, E, G, graph_acc);
+  launch("k_wn_bwd_apply", k_wn_bwd_apply, grid, 256, 0, st, row, w, batch_pooled, max_in, arg_in, grad_out, graph_acc, E, G, grad_w);
+  return launch_status();
+}
+
+}  // extern "C"

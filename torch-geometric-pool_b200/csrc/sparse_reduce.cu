@@ -1,0 +1,420 @@
+// Sparse Reduce: CSR-by-cluster build, segment reduce forward/backward, reduce_batch.
+// Reference: tgp/reduce/base_reduce.py:15-53,141-155; tgp/reduce/aggr_reduce.py:13-29,99-105.
+#include "prims.cuh"
+
+namespace tgp {
+
+// ------------------------------------------------------------------------------------------
+// CSR build
+// ------------------------------------------------------------------------------------------
+static __global__ void k_cluster_keys_count(const int64_t* __restrict__ cluster, int64_t nnz, int64_t K,
+                                            uint32_t* __restrict__ keys, int* __restrict__ counts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  int64_t c = cluster[i];
+  if (c < 0 || c >= K) c = K - 1 > 0 ? K - 1 : 0;  // out-of-range ids are clamped (never dereferenced OOB)
+  keys[i] = (uint32_t)c;
+  atomicAdd(&counts[c], 1);
+}
+
+static int key_bits_for(int64_t max_value) {
+  int b = 0;
+  while (b < 63 && ((int64_t)1 << b) <= max_value) ++b;
+  return b < 1 ? 1 : b;
+}
+
+// ------------------------------------------------------------------------------------------
+// Vector row access: 16-byte chunks of VEC elements
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct Vec;
+template <>
+struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float (&v)[4]) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  }
+  __device__ static void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f = __bfloat1622float2(h[k]);
+      v[2 * k] = f.x, v[2 * k + 1] = f.y;
+    }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
+// generic chunk access honouring a scalar fallback (F not a multiple of the vector width)
+template <typename T, int W, bool kVec>
+__device__ __forceinline__ void load_chunk(const T* row, int64_t f, int64_t F, float (&v)[W]) {
+  if (kVec) {
+    Vec<T>::load(row + f, reinterpret_cast<float(&)[Vec<T>::N]>(v));
+  } else {
+#pragma unroll
+    for (int k = 0; k < W; ++k) v[k] = (f + k < F) ? to_f32<T>(row[f + k]) : 0.f;
+  }
+}
+template <typename T, int W, bool kVec>
+__device__ __forceinline__ void store_chunk(T* row, int64_t f, int64_t F, const float (&v)[W]) {
+  if (kVec) {
+    Vec<T>::store(row + f, reinterpret_cast<const float(&)[Vec<T>::N]>(v));
+  } else {
+#pragma unroll
+    for (int k = 0; k < W; ++k)
+      if (f + k < F) row[f + k] = from_f32<T>(v[k]);
+  }
+}
+
+__device__ __forceinline__ float combine(int op, float acc, float p, bool first) {
+  if (op == TGPB200_SUM || op == TGPB200_MEAN) return __fadd_rn(acc, p);
+  if (first) return p;
+  return op == TGPB200_MAX ? fmaxf(acc, p) : fminf(acc, p);
+}
+
+// ------------------------------------------------------------------------------------------
+// Forward: one lane-group per cluster, lanes over 16-byte feature chunks, members in CSR order.
+// Products are rounded before the add (no FMA contraction) so fp32 sums are bit-identical
+// to the reference's sequential CPU scatter_add_.
+// ------------------------------------------------------------------------------------------
+template <typename XT, typename OT, bool kVec>
+static __global__ void __launch_bounds__(256)
+    k_segment_reduce_fwd(const XT* __restrict__ x, const int64_t* __restrict__ node_index,
+                         const float* __restrict__ weight, const int32_t* __restrict__ order,
+                         const int32_t* __restrict__ ptr, int64_t N, int64_t K, int64_t F, int op, int lpr,
+                         OT* __restrict__ out) {
+  constexpr int W = Vec<XT>::N;
+  int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / lpr;
+  int sub = threadIdx.x % lpr;
+  if (gid >= K) return;
+  int beg = ptr[gid], end = ptr[gid + 1];
+  for (int64_t f = (int64_t)sub * W; f < F; f += (int64_t)lpr * W) {
+    float acc[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) acc[k] = 0.f;
+    int m = beg;
+    for (; m + 1 < end; m += 2) {  // two members in flight
+      int i0 = order[m], i1 = order[m + 1];
+      int64_t n0 = node_index[i0], n1 = node_index[i1];
+      float w0 = weight ? weight[i0] : 1.f, w1 = weight ? weight[i1] : 1.f;
+      float v0[W], v1[W];
+      bool ok0 = n0 >= 0 && n0 < N, ok1 = n1 >= 0 && n1 < N;
+      if (ok0) load_chunk<XT, W, kVec>(x + n0 * F, f, F, v0);
+      if (ok1) load_chunk<XT, W, kVec>(x + n1 * F, f, F, v1);
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        float p0 = ok0 ? __fmul_rn(v0[k], w0) : 0.f;
+        float p1 = ok1 ? __fmul_rn(v1[k], w1) : 0.f;
+        acc[k] = combine(op, acc[k], p0, m == beg);
+        acc[k] = combine(op, acc[k], p1, false);
+      }
+    }
+    if (m < end) {
+      int i0 = order[m];
+      int64_t n0 = node_index[i0];
+      float w0 = weight ? weight[i0] : 1.f;
+      float v0[W];
+      bool ok0 = n0 >= 0 && n0 < N;
+      if (ok0) load_chunk<XT, W, kVec>(x + n0 * F, f, F, v0);
+#pragma unroll
+      for (int k = 0; k < W; ++k) acc[k] = combine(op, acc[k], ok0 ? __fmul_rn(v0[k], w0) : 0.f, m == beg);
+    }
+    if (op == TGPB200_MEAN) {
+      float cnt = (float)(end - beg > 1 ? end - beg : 1);
+#pragma unroll
+      for (int k = 0; k < W; ++k) acc[k] = __fdiv_rn(acc[k], cnt);
+    }
+    store_chunk<OT, W, kVec>(out + gid * F, f, F, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// MAX / MIN backward pre-pass: inv_ties[c, f] = 1 / #members whose product equals x_pool[c, f].
+// ------------------------------------------------------------------------------------------
+template <typename XT, typename OT>
+static __global__ void k_count_ties(const XT* __restrict__ x, const int64_t* __restrict__ node_index,
+                                    const float* __restrict__ weight, const int32_t* __restrict__ order,
+                                    const int32_t* __restrict__ ptr, const OT* __restrict__ pool, int64_t N, int64_t K,
+                                    int64_t F, float* __restrict__ inv_ties) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= K * F) return;
+  int64_t c = t / F, f = t % F;
+  float target = to_f32<OT>(pool[t]);
+  int cnt = 0;
+  for (int m = ptr[c]; m < ptr[c + 1]; ++m) {
+    int i = order[m];
+    int64_t n = node_index[i];
+    if (n < 0 || n >= N) continue;
+    float p = __fmul_rn(to_f32<XT>(x[n * F + f]), weight ? weight[i] : 1.f);
+    if (to_f32<OT>(from_f32<OT>(p)) == target) ++cnt;
+  }
+  inv_ties[t] = cnt > 0 ? 1.f / (float)cnt : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward: one lane-group per NODE (node_index is sorted, so a node's entries are adjacent):
+//   grad_x[n] = sum_{i in run(n)} w_i * gs_i,   grad_w[i] = <x[n], gs_i>,
+//   gs_i = coefficient(op) * grad_pool[cluster_i].   Unselected nodes get zero rows.
+// ------------------------------------------------------------------------------------------
+template <typename XT, typename OT, bool kVec>
+static __global__ void __launch_bounds__(256)
+    k_segment_reduce_bwd(const XT* __restrict__ x, const int64_t* __restrict__ node_index,
+                         const int64_t* __restrict__ cluster_index, const float* __restrict__ weight,
+                         const int32_t* __restrict__ ptr, const OT* __restrict__ pool, const OT* __restrict__ gpool,
+                         const float* __restrict__ inv_ties, int64_t N, int64_t nnz, int64_t K, int64_t F, int op,
+                         int lpr, XT* __restrict__ gx, float* __restrict__ gw) {
+  constexpr int W = Vec<XT>::N;
+  int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / lpr;
+  int sub = threadIdx.x % lpr;
+  if (n >= N) return;
+  int lane = threadIdx.x & 31;
+  unsigned gmask = lpr >= 32 ? kFull : (((1u << lpr) - 1u) << (lane & ~(lpr - 1)));
+
+  // locate the first entry of node n (fast guess: identity layout, else binary search)
+  int64_t lo;
+  if (n < nnz && node_index[n] == n && (n == 0 || node_index[n - 1] != n)) {
+    lo = n;
+  } else {
+    int64_t a = 0, b = nnz;
+    while (a < b) {
+      int64_t mid = (a + b) >> 1;
+      if (node_index[mid] < n) a = mid + 1; else b = mid;
+    }
+    lo = a;
+  }
+  int64_t hi = lo;
+  while (hi < nnz && node_index[hi] == n) ++hi;
+
+  const XT* xr = x + n * F;
+  for (int64_t i = lo; i < hi; ++i) {
+    if (gw == nullptr) break;
+    int64_t c = cluster_index[i];
+    if (c < 0 || c >= K) { if (sub == 0) gw[i] = 0.f; continue; }
+    float wi = weight ? weight[i] : 1.f;
+    float coef = 1.f;
+    if (op == TGPB200_MEAN) { int cnt = ptr[c + 1] - ptr[c]; coef = 1.f / (float)(cnt > 1 ? cnt : 1); }
+    float dot = 0.f;
+    for (int64_t f = (int64_t)sub * W; f < F; f += (int64_t)lpr * W) {
+      float xv[W], gv[W];
+      load_chunk<XT, W, kVec>(xr, f, F, xv);
+      load_chunk<OT, W, kVec>(gpool + c * F, f, F, gv);
+      if (op == TGPB200_MAX || op == TGPB200_MIN) {
+        float pv[W];
+        load_chunk<OT, W, kVec>(pool + c * F, f, F, pv);
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          float p = to_f32<OT>(from_f32<OT>(__fmul_rn(xv[k], wi)));
+          float it = (f + k < F) ? inv_ties[c * F + f + k] : 0.f;
+          gv[k] = (p == pv[k]) ? gv[k] * it : 0.f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < W; ++k) dot += xv[k] * gv[k] * coef;
+    }
+    for (int o = lpr >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(gmask, dot, o);
+    if (sub == 0) gw[i] = dot;
+  }
+
+  for (int64_t f = (int64_t)sub * W; f < F; f += (int64_t)lpr * W) {
+    float acc[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) acc[k] = 0.f;
+    float xv[W];
+    bool need_x = (op == TGPB200_MAX || op == TGPB200_MIN) && hi > lo;
+    if (need_x) load_chunk<XT, W, kVec>(xr, f, F, xv);
+    for (int64_t i = lo; i < hi; ++i) {
+      int64_t c = cluster_index[i];
+      if (c < 0 || c >= K) continue;
+      float wi = weight ? weight[i] : 1.f;
+      float coef = wi;
+      if (op == TGPB200_MEAN) { int cnt = ptr[c + 1] - ptr[c]; coef = wi / (float)(cnt > 1 ? cnt : 1); }
+      float gv[W];
+      load_chunk<OT, W, kVec>(gpool + c * F, f, F, gv);
+      if (op == TGPB200_MAX || op == TGPB200_MIN) {
+        float pv[W];
+        load_chunk<OT, W, kVec>(pool + c * F, f, F, pv);
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          float p = to_f32<OT>(from_f32<OT>(__fmul_rn(xv[k], wi)));
+          float it = (f + k < F) ? inv_ties[c * F + f + k] : 0.f;
+          gv[k] = (p == pv[k]) ? gv[k] * it : 0.f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < W; ++k) acc[k] = __fadd_rn(acc[k], __fmul_rn(gv[k], coef));
+    }
+    store_chunk<XT, W, kVec>(gx + n * F, f, F, acc);
+  }
+}
+
+// out[c] = batch[node of the LAST member of c in position order] (CPU scatter_ semantics: the
+// last writer wins), or c for an empty cluster (the arange initial value survives).
+static __global__ void k_reduce_batch(const int64_t* __restrict__ batch, const int64_t* __restrict__ node_index,
+                                      const int32_t* __restrict__ order, const int32_t* __restrict__ ptr, int64_t K,
+                                      int64_t* __restrict__ out) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= K) return;
+  int b = ptr[c], e = ptr[c + 1];
+  out[c] = e > b ? batch[node_index[order[e - 1]]] : c;
+}
+
+template <typename XT, typename OT>
+static int launch_fwd(const void* x, const int64_t* node_index, const float* weight, const int32_t* order,
+                      const int32_t* ptr, int64_t N, int64_t K, int64_t F, int op, void* out, cudaStream_t st) {
+  constexpr int W = Vec<XT>::N;
+  bool vec = (F % W == 0) && (F % Vec<OT>::N == 0) && Vec<OT>::N == W;
+  int64_t chunks = ceil_div(F, W);
+  int lpr = 1;
+  while (lpr < 32 && lpr < chunks) lpr <<= 1;
+  int64_t threads = K * lpr;
+  if (threads == 0) return TGPB200_OK;
+  dim3 grid((unsigned)ceil_div(threads, 256));
+  if (vec)
+    launch("k_segment_reduce_fwd", k_segment_reduce_fwd<XT, OT, true>, grid, 256, 0, st, (const XT*)x, node_index, weight, order, ptr, N, K, F, op,
+                                                             lpr, (OT*)out);
+  else
+    launch("k_segment_reduce_fwd", k_segment_reduce_fwd<XT, OT, false>, grid, 256, 0, st, (const XT*)x, node_index, weight, order, ptr, N, K, F,
+                                                              op, lpr, (OT*)out);
+  return launch_status();
+}
+
+template <typename XT, typename OT>
+static int launch_bwd(const void* x, const int64_t* node_index, const int64_t* cluster_index, const float* weight,
+                      const int32_t* order, const int32_t* ptr, const void* pool, const void* gpool, int64_t N,
+                      int64_t nnz, int64_t K, int64_t F, int op, void* gx, float* gw, Workspace& ws, cudaStream_t st) {
+  constexpr int W = Vec<XT>::N;
+  bool vec = (F % W == 0) && Vec<OT>::N == W;
+  float* inv_ties = nullptr;
+  if (op == TGPB200_MAX || op == TGPB200_MIN) {
+    inv_ties = ws.take<float>((size_t)K * F);
+    if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+    if (K * F > 0)
+      launch("k_count_ties", k_count_ties<XT, OT>, (unsigned)ceil_div(K * F, 256), 256, 0, st, (const XT*)x, node_index, weight, order, ptr,
+                                                                          (const OT*)pool, N, K, F, inv_ties);
+  }
+  int64_t chunks = ceil_div(F, W);
+  int lpr = 1;
+  while (lpr < 32 && lpr < chunks) lpr <<= 1;
+  int64_t threads = N * lpr;
+  if (threads == 0) return TGPB200_OK;
+  dim3 grid((unsigned)ceil_div(threads, 256));
+  if (vec)
+    launch("k_segment_reduce_bwd", k_segment_reduce_bwd<XT, OT, true>, grid, 256, 0, st, (const XT*)x, node_index, cluster_index, weight, ptr,
+                                                             (const OT*)pool, (const OT*)gpool, inv_ties, N, nnz, K, F,
+                                                             op, lpr, (XT*)gx, gw);
+  else
+    launch("k_segment_reduce_bwd", k_segment_reduce_bwd<XT, OT, false>, grid, 256, 0, st, (const XT*)x, node_index, cluster_index, weight, ptr,
+                                                              (const OT*)pool, (const OT*)gpool, inv_ties, N, nnz, K,
+                                                              F, op, lpr, (XT*)gx, gw);
+  return launch_status();
+}
+
+}  // namespace tgp
+
+using namespace tgp;
+
+extern "C" {
+
+int tgpb200_abi_version(void) { return 1; }
+
+size_t tgpb200_build_csr_workspace_bytes(int64_t nnz, int64_t K) {
+  size_t n = (size_t)(nnz > 0 ? nnz : 1);
+  return 4 * align_up(n * sizeof(uint32_t)) + radix_sort_workspace_bytes(nnz) + scan_workspace_bytes(K + 1) + 1024;
+}
+
+int tgpb200_build_csr(const int64_t* cluster_index, int64_t nnz, int64_t K, int32_t* order, int32_t* ptr,
+                      void* workspace, size_t workspace_bytes, tgpb200_stream_t stream) {
+  if (nnz < 0 || K < 0 || nnz >= INT32_MAX || K >= INT32_MAX || !ptr || (nnz > 0 && (!cluster_index || !order)))
+    return TGPB200_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  size_t n = (size_t)(nnz > 0 ? nnz : 1);
+  uint32_t* keys0 = ws.take<uint32_t>(n);
+  uint32_t* keys1 = ws.take<uint32_t>(n);
+  uint32_t* valsA = ws.take<uint32_t>(n);
+  if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+  cudaMemsetAsync(ptr, 0, (size_t)(K + 1) * sizeof(int32_t), st);
+  if (nnz > 0) {
+    if (K == 0) return TGPB200_ERR_INVALID;
+    launch("k_cluster_keys_count", k_cluster_keys_count, (unsigned)ceil_div(nnz, 256), 256, 0, st, cluster_index, nnz, K, keys0, ptr);
+    int bits = key_bits_for(K - 1);
+    int passes = radix_passes(bits);
+    // choose buffers so the final payload lands in `order`
+    uint32_t* vals1 = (passes & 1) ? (uint32_t*)order : valsA;
+    uint32_t* vals0 = (passes & 1) ? valsA : (uint32_t*)order;
+    bool in1 = false;
+    int rc = radix_sort_pairs<uint32_t>(keys0, nullptr, vals0, keys1, vals1, nnz, bits, &in1, ws, st);
+    if (rc != TGPB200_OK) return rc;
+  }
+  int rc = exclusive_scan_i32(ptr, ptr, K + 1, nullptr, nullptr, ws, st);
+  return rc != TGPB200_OK ? rc : launch_status();
+}
+
+int tgpb200_segment_reduce_fwd(const void* x, const int64_t* node_index, const float* weight, const int32_t* order,
+                               const int32_t* ptr, int64_t N, int64_t nnz, int64_t K, int64_t F, int op, int x_dtype,
+                               int out_dtype, void* x_pool, tgpb200_stream_t stream) {
+  if (N < 0 || nnz < 0 || K < 0 || F < 0 || op < TGPB200_SUM || op > TGPB200_MIN) return TGPB200_ERR_INVALID;
+  if (K * F == 0) return TGPB200_OK;
+  if (!x_pool || !ptr || (nnz > 0 && (!x || !node_index || !order))) return TGPB200_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == TGPB200_F32 && out_dtype == TGPB200_F32)
+    return launch_fwd<float, float>(x, node_index, weight, order, ptr, N, K, F, op, x_pool, st);
+  if (x_dtype == TGPB200_BF16 && out_dtype == TGPB200_BF16)
+    return launch_fwd<__nv_bfloat16, __nv_bfloat16>(x, node_index, weight, order, ptr, N, K, F, op, x_pool, st);
+  if (x_dtype == TGPB200_BF16 && out_dtype == TGPB200_F32)
+    return launch_fwd<__nv_bfloat16, float>(x, node_index, weight, order, ptr, N, K, F, op, x_pool, st);
+  return TGPB200_ERR_UNSUPPORTED;
+}
+
+size_t tgpb200_segment_reduce_bwd_workspace_bytes(int64_t nnz, int64_t K, int64_t F, int op) {
+  (void)nnz;
+  if (op == TGPB200_MAX || op == TGPB200_MIN) return align_up((size_t)(K * F > 0 ? K * F : 1) * sizeof(float)) + 256;
+  return 256;
+}
+
+int tgpb200_segment_reduce_bwd(const void* x, const int64_t* node_index, const int64_t* cluster_index,
+                               const float* weight, const int32_t* order, const int32_t* ptr, const void* x_pool,
+                               const void* grad_pool, int64_t N, int64_t nnz, int64_t K, int64_t F, int op,
+                               int x_dtype, int out_dtype, void* grad_x, float* grad_weight, void* workspace,
+                               size_t workspace_bytes, tgpb200_stream_t stream) {
+  if (N < 0 || nnz < 0 || K < 0 || F < 0 || op < TGPB200_SUM || op > TGPB200_MIN) return TGPB200_ERR_INVALID;
+  if (N * F == 0 && nnz == 0) return TGPB200_OK;
+  if (!grad_x || !ptr || !grad_pool || (nnz > 0 && (!x || !node_index || !cluster_index))) return TGPB200_ERR_INVALID;
+  if ((op == TGPB200_MAX || op == TGPB200_MIN) && (!x_pool || !order)) return TGPB200_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  if (x_dtype == TGPB200_F32 && out_dtype == TGPB200_F32)
+    return launch_bwd<float, float>(x, node_index, cluster_index, weight, order, ptr, x_pool, grad_pool, N, nnz, K, F,
+                                    op, grad_x, grad_weight, ws, st);
+  if (x_dtype == TGPB200_BF16 && out_dtype == TGPB200_BF16)
+    return launch_bwd<__nv_bfloat16, __nv_bfloat16>(x, node_index, cluster_index, weight, order, ptr, x_pool, grad_pool,
+                                                    N, nnz, K, F, op, grad_x, grad_weight, ws, st);
+  return TGPB200_ERR_UNSUPPORTED;
+}
+
+int tgpb200_reduce_batch(const int64_t* batch, const int64_t* node_index, const int32_t* order, const int32_t* ptr,
+                         int64_t K, int64_t* batch_pool, tgpb200_stream_t stream) {
+  if (K < 0) return TGPB200_ERR_INVALID;
+  if (K == 0) return TGPB200_OK;
+  if (!batch_pool || !ptr || !batch || !node_index || !order) return TGPB200_ERR_INVALID;
+  launch("k_reduce_batch", k_reduce_batch, (unsigned)ceil_div(K, 256), 256, 0, (cudaStream_t)stream, batch, node_index, order, ptr, K,
+                                                                              batch_pool);
+  return launch_status();
+}
+
+}  // extern "C"

@@ -1,0 +1,446 @@
+"""Functional layer: autograd wiring around the C-ABI kernels.
+
+Every function here launches kernels from ``libtgp_b200.so`` through ``_lib.call`` on the
+current CUDA stream.  There is no eager / CPU fallback: CPU tensors raise ``RuntimeError``.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+
+EPS = 1e-8  # tgp/__init__.py:6
+
+
+def _require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("tgp_b200 runs on CUDA tensors only (no CPU fallback by design)")
+
+
+# --------------------------------------------------------------------------- #
+# CSR-by-cluster (cached on the SelectOutput, like the reference caches `_so_cached`)
+# --------------------------------------------------------------------------- #
+def build_csr(cluster_index: Tensor, num_clusters: int) -> Tuple[Tensor, Tensor]:
+    _require_cuda(cluster_index)
+    cluster_index = cluster_index.contiguous()
+    nnz = cluster_index.numel()
+    dev = cluster_index.device
+    order = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    ptr = torch.empty(num_clusters + 1, dtype=torch.int32, device=dev)
+    ws = L.workspace(L.load().tgpb200_build_csr_workspace_bytes(nnz, num_clusters), dev)
+    L.call("tgpb200_build_csr", L.ptr(cluster_index), nnz, num_clusters, L.ptr(order), L.ptr(ptr), L.ptr(ws),
+           ws.numel(), L.stream())
+    return order, ptr
+
+
+def csr_of(so) -> Tuple[Tensor, Tensor]:
+    cached = getattr(so, "_b200_csr", None)
+    if cached is None:
+        cached = build_csr(so.cluster_index, so.num_supernodes)
+        try:
+            so._b200_csr = cached
+        except AttributeError:
+            pass
+    return cached
+
+
+# --------------------------------------------------------------------------- #
+# Sparse reduce
+# --------------------------------------------------------------------------- #
+class _SegmentReduce(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, node_index, cluster_index, order, ptr, num_clusters, op, out_dtype):
+        N, F = x.shape
+        nnz = node_index.numel()
+        out = torch.empty((num_clusters, F), dtype=out_dtype, device=x.device)
+        L.call("tgpb200_segment_reduce_fwd", L.ptr(x), L.ptr(node_index), L.ptr(weight), L.ptr(order), L.ptr(ptr), N,
+               nnz, num_clusters, F, op, L.dtype_code(x.dtype), L.dtype_code(out_dtype), L.ptr(out), L.stream())
+        ctx.save_for_backward(x, weight, node_index, cluster_index, order, ptr, out)
+        ctx.op, ctx.K = op, num_clusters
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, node_index, cluster_index, order, ptr, out = ctx.saved_tensors
+        N, F = x.shape
+        nnz = node_index.numel()
+        g = g.contiguous()
+        if g.dtype != x.dtype:
+            raise RuntimeError("tgp_b200 segment_reduce backward: mixed x / output dtypes are not supported")
+        gx = torch.empty_like(x)
+        need_w = weight is not None and ctx.needs_input_grad[1]
+        gw = torch.empty(nnz, dtype=torch.float32, device=x.device) if need_w else None
+        lib = L.load()
+        ws = L.workspace(lib.tgpb200_segment_reduce_bwd_workspace_bytes(nnz, ctx.K, F, ctx.op), x.device)
+        L.call("tgpb200_segment_reduce_bwd", L.ptr(x), L.ptr(node_index), L.ptr(cluster_index), L.ptr(weight),
+               L.ptr(order), L.ptr(ptr), L.ptr(out), L.ptr(g), N, nnz, ctx.K, F, ctx.op, L.dtype_code(x.dtype),
+               L.dtype_code(g.dtype), L.ptr(gx), L.ptr(gw), L.ptr(ws), ws.numel(), L.stream())
+        return gx, gw, None, None, None, None, None, None, None
+
+
+def segment_reduce(
+    x: Tensor,
+    node_index: Tensor,
+    cluster_index: Tensor,
+    weight: Optional[Tensor],
+    num_clusters: int,
+    op: str = "sum",
+    csr: Optional[Tuple[Tensor, Tensor]] = None,
+) -> Tensor:
+    """``x_pool[c] = op_{i in c} weight[i] * x[node_index[i]]`` (deterministic member order)."""
+    _require_cuda(x, node_index, cluster_index, weight)
+    if op not in ("sum", "add", "mean", "max", "min"):
+        raise ValueError(f"unsupported reduce op '{op}'")
+    if x.dim() != 2:
+        raise ValueError("segment_reduce expects x of shape [N, F]")
+    out_dtype = x.dtype if weight is None else torch.result_type(x, weight)
+    if x.dtype != out_dtype:  # torch type promotion of x * weight (rare: bf16 features, fp32 weights)
+        x = x.to(out_dtype)
+    x = x.contiguous()
+    w32 = None if weight is None else weight.to(torch.float32).contiguous()
+    order, ptr = csr if csr is not None else build_csr(cluster_index, num_clusters)
+    return _SegmentReduce.apply(x, w32, node_index.contiguous(), cluster_index.contiguous(), order, ptr, num_clusters,
+                                L.OPS[op], out_dtype)
+
+
+def reduce_batch_sparse(so, batch: Tensor) -> Tensor:
+    """Reduce.reduce_batch, sparse branch (tgp/reduce/base_reduce.py:37-41)."""
+    _require_cuda(batch)
+    order, ptr = csr_of(so)
+    K = so.num_supernodes
+    out = torch.empty(K, dtype=torch.long, device=batch.device)
+    L.call("tgpb200_reduce_batch", L.ptr(batch.contiguous()), L.ptr(so.node_index.contiguous()), L.ptr(order),
+           L.ptr(ptr), K, L.ptr(out), L.stream())
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# Sparse connect
+# --------------------------------------------------------------------------- #
+def _read_count(count: Tensor) -> int:
+    return int(count.item())  # the one device->host word per data-dependent output size
+
+
+class _FilterRelabel(torch.autograd.Function):
+    """Kept-node branch + self-loop / tiny-weight filters (one order-preserving compaction)."""
+
+    @staticmethod
+    def forward(ctx, edge_weight, row, col, node_index, num_nodes, flags, eps):
+        E = row.numel()
+        dev = row.device
+        lib = L.load()
+        ws = L.workspace(lib.tgpb200_filter_relabel_workspace_bytes(E, num_nodes), dev)
+        count = torch.empty(1, dtype=torch.long, device=dev)
+        L.call("tgpb200_filter_relabel_count", L.ptr(row), L.ptr(col), L.ptr(edge_weight), E, L.ptr(node_index),
+               node_index.numel(), num_nodes, flags, eps, L.ptr(count), L.ptr(ws), ws.numel(), L.stream())
+        n_out = _read_count(count)
+        ei = torch.empty((2, n_out), dtype=torch.long, device=dev)
+        w_out = None if edge_weight is None else torch.empty(n_out, dtype=torch.float32, device=dev)
+        need_grad = edge_weight is not None and ctx.needs_input_grad[0]
+        src = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev) if need_grad else None
+        L.call("tgpb200_filter_relabel_emit", L.ptr(row), L.ptr(col), L.ptr(edge_weight), E, num_nodes, flags, eps,
+               L.ptr(ei[0]), L.ptr(ei[1]), L.ptr(w_out), L.ptr(src), L.ptr(ws), ws.numel(), L.stream())
+        ctx.mark_non_differentiable(ei)
+        if need_grad:
+            ctx.save_for_backward(src)
+        ctx.E, ctx.n_out = E, n_out
+        if w_out is None:
+            return ei, None
+        return ei, w_out
+
+    @staticmethod
+    def backward(ctx, _gei, gw):
+        if gw is None:
+            return (None,) * 7
+        (src,) = ctx.saved_tensors
+        gin = torch.empty(ctx.E, dtype=torch.float32, device=gw.device)
+        L.call("tgpb200_filter_relabel_bwd", L.ptr(gw.contiguous()), L.ptr(src), ctx.n_out, ctx.E, L.ptr(gin),
+               L.stream())
+        return gin, None, None, None, None, None, None
+
+
+class _RemapCoalesce(torch.autograd.Function):
+    """Cluster branch: remap -> stable radix sort -> in-order combine -> filters -> compaction."""
+
+    @staticmethod
+    def forward(ctx, edge_weight, row, col, cluster_index, num_nodes, num_clusters, op, flags, eps):
+        E = row.numel()
+        dev = row.device
+        lib = L.load()
+        ws = L.workspace(lib.tgpb200_remap_coalesce_workspace_bytes(E, num_clusters), dev)
+        count = torch.empty(1, dtype=torch.long, device=dev)
+        L.call("tgpb200_remap_coalesce_count", L.ptr(row), L.ptr(col), L.ptr(edge_weight), E, L.ptr(cluster_index),
+               num_nodes, num_clusters, op, flags, eps, L.ptr(count), L.ptr(ws), ws.numel(), L.stream())
+        n_out = _read_count(count)
+        ei = torch.empty((2, n_out), dtype=torch.long, device=dev)
+        weighted = edge_weight is not None
+        w_out = torch.empty(n_out, dtype=torch.float32, device=dev) if weighted else None
+        need_grad = weighted and ctx.needs_input_grad[0]
+        slot = torch.empty(max(E, 1), dtype=torch.int32, device=dev) if need_grad else None
+        run_len = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev) if need_grad else None
+        L.call("tgpb200_remap_coalesce_emit", E, num_clusters, int(weighted), flags, eps, L.ptr(ei[0]), L.ptr(ei[1]),
+               L.ptr(w_out), L.ptr(slot), L.ptr(run_len), L.ptr(ws), ws.numel(), L.stream())
+        ctx.mark_non_differentiable(ei)
+        if need_grad:
+            ctx.save_for_backward(edge_weight, w_out, slot, run_len)
+        ctx.E, ctx.n_out, ctx.op = E, n_out, op
+        if w_out is None:
+            return ei, None
+        return ei, w_out
+
+    @staticmethod
+    def backward(ctx, _gei, gw):
+        if gw is None:
+            return (None,) * 9
+        w, w_out, slot, run_len = ctx.saved_tensors
+        gin = torch.empty(ctx.E, dtype=torch.float32, device=gw.device)
+        lib = L.load()
+        ws = L.workspace(lib.tgpb200_coalesce_bwd_workspace_bytes(ctx.E, ctx.n_out, ctx.op), gw.device)
+        L.call("tgpb200_coalesce_bwd", L.ptr(w), L.ptr(w_out), L.ptr(gw.contiguous()), L.ptr(slot), L.ptr(run_len),
+               ctx.E, ctx.n_out, ctx.op, L.ptr(gin), L.ptr(ws), ws.numel(), L.stream())
+        return gin, None, None, None, None, None, None, None, None
+
+
+class _DegreeNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w, row, col, num_clusters, eps):
+        E = row.numel()
+        dev = row.device
+        deg = torch.empty(max(num_clusters, 1), dtype=torch.float32, device=dev)
+        out = torch.empty(E, dtype=torch.float32, device=dev)
+        L.call("tgpb200_degree_norm_fwd", L.ptr(row), L.ptr(col), L.ptr(w), E, num_clusters, eps, L.ptr(deg),
+               L.ptr(out), L.stream())
+        ctx.save_for_backward(w, row, col, deg)
+        ctx.K, ctx.eps = num_clusters, eps
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        w, row, col, deg = ctx.saved_tensors
+        if w is None:
+            return None, None, None, None, None
+        E = row.numel()
+        gd = torch.empty(max(ctx.K, 1), dtype=torch.float32, device=g.device)
+        gw = torch.empty(E, dtype=torch.float32, device=g.device)
+        L.call("tgpb200_degree_norm_bwd", L.ptr(row), L.ptr(col), L.ptr(w), L.ptr(deg), L.ptr(g.contiguous()), E,
+               ctx.K, ctx.eps, L.ptr(gd), L.ptr(gw), L.stream())
+        return gw, None, None, None, None
+
+
+class _WeightNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w, row, batch_pooled, num_graphs):
+        E = row.numel()
+        dev = row.device
+        mx = torch.empty(max(num_graphs, 1), dtype=torch.float32, device=dev)
+        arg = torch.empty(max(num_graphs, 1), dtype=torch.int32, device=dev)
+        out = torch.empty(E, dtype=torch.float32, device=dev)
+        L.call("tgpb200_weight_norm_fwd", L.ptr(row), L.ptr(w), L.ptr(batch_pooled), E, num_graphs, L.ptr(mx),
+               L.ptr(arg), L.ptr(out), L.stream())
+        ctx.save_for_backward(w, row, batch_pooled, mx, arg)
+        ctx.G = num_graphs
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        w, row, batch_pooled, mx, arg = ctx.saved_tensors
+        E = row.numel()
+        acc = torch.empty(max(ctx.G, 1), dtype=torch.float32, device=g.device)
+        gw = torch.empty(E, dtype=torch.float32, device=g.device)
+        L.call("tgpb200_weight_norm_bwd", L.ptr(row), L.ptr(w), L.ptr(batch_pooled), L.ptr(mx), L.ptr(arg),
+               L.ptr(g.contiguous()), E, ctx.G, L.ptr(acc), L.ptr(gw), L.stream())
+        return gw, None, None, None
+
+
+def _as_f32_weight(edge_weight: Optional[Tensor]) -> Optional[Tensor]:
+    """tgp/utils/ops.py:1043-1058: [E] or [E,1] only."""
+    if edge_weight is None:
+        return None
+    if edge_weight.ndim > 1:
+        if edge_weight.ndim == 2 and edge_weight.size(-1) == 1:
+            edge_weight = edge_weight.flatten()
+        else:
+            raise RuntimeError(f"Edge weights must be of shape [E] or [E, 1], but got {edge_weight.shape}.")
+    return edge_weight.to(torch.float32).contiguous()
+
+
+def _validate_edge_index(edge_index: Tensor) -> None:
+    """Dense-tensor branch of connectivity_to_edge_index (tgp/utils/ops.py:455-476)."""
+    if edge_index.dim() == 3 or (edge_index.dim() == 2 and edge_index.size(0) != 2):
+        raise ValueError(
+            "Dense adjacency matrices are not supported by connectivity_to_edge_index(). "
+            "Expected a sparse connectivity representation (edge_index with shape [2, E] or a torch COO tensor)."
+        )
+    if edge_index.dim() != 2:
+        raise ValueError(
+            "connectivity_to_edge_index() expected edge_index with shape [2, E] "
+            f"when given a dense Tensor, got a Tensor with {edge_index.dim()} dimensions."
+        )
+    if edge_index.dtype != torch.int64:
+        raise ValueError(
+            "connectivity_to_edge_index() expected edge_index indices to be an integer tensor "
+            f"(dtype torch.long), got dtype={edge_index.dtype}."
+        )
+
+
+def edge_postprocess(
+    edge_index: Tensor,
+    edge_weight: Optional[Tensor],
+    num_nodes: int,
+    degree_norm: bool = False,
+    edge_weight_norm: bool = False,
+    batch_pooled: Optional[Tensor] = None,
+    num_graphs: Optional[int] = None,
+) -> Optional[Tensor]:
+    """Degree / max-weight normalisation of tgp/utils/ops.py:383-417 on already-filtered edges."""
+    row, col = edge_index[0], edge_index[1]
+    if degree_norm:
+        edge_weight = _DegreeNorm.apply(edge_weight, row, col, num_nodes, EPS)
+    if edge_weight_norm and edge_weight is not None:
+        if num_graphs is None:
+            num_graphs = int(batch_pooled.max().item()) + 1 if batch_pooled.numel() > 0 else 0
+        edge_weight = _WeightNorm.apply(edge_weight, row, batch_pooled.contiguous(), num_graphs)
+    return edge_weight
+
+
+def sparse_connect(
+    edge_index: Tensor,
+    edge_weight: Optional[Tensor] = None,
+    node_index: Optional[Tensor] = None,
+    cluster_index: Optional[Tensor] = None,
+    num_nodes: Optional[int] = None,
+    num_supernodes: Optional[int] = None,
+    remove_self_loops: bool = True,
+    reduce_op: str = "sum",
+    edge_weight_norm: bool = False,
+    batch_pooled: Optional[Tensor] = None,
+    degree_norm: bool = False,
+    num_graphs: Optional[int] = None,
+) -> Tuple[Tensor, Optional[Tensor]]:
+    """Drop-in for ``tgp.connect.base_conn.sparse_connect`` (base_conn.py:57-112).
+
+    Branch choice, output order and filters follow the reference: kept-node path when
+    ``len(node_index) < num_nodes`` (input order kept, endpoints relabelled to their position in
+    ``node_index``), cluster path when ``len(cluster_index) == num_nodes`` (lexicographic order,
+    duplicates combined with ``reduce_op`` in original order), else ``RuntimeError``.
+    """
+    _require_cuda(edge_index)
+    to_coo = edge_index.is_sparse
+    if to_coo:
+        coo = edge_index.coalesce() if not edge_index.is_coalesced() else edge_index
+        edge_index, edge_weight = coo.indices().contiguous(), coo.values()
+    else:
+        _validate_edge_index(edge_index)
+    w = _as_f32_weight(edge_weight)
+    if reduce_op not in L.OPS:
+        raise ValueError(f"unknown reduce_op '{reduce_op}'")
+    edge_index = edge_index.contiguous()
+    row, col = edge_index[0], edge_index[1]
+    if num_nodes is None:  # maybe_num_nodes (base_conn.py:78) -- costs a device sync
+        num_nodes = int(edge_index.max().item()) + 1 if edge_index.numel() > 0 else 0
+    flags = L.REMOVE_SELF_LOOPS if remove_self_loops else 0
+
+    if node_index is not None and len(node_index) < num_nodes:
+        ei, w = _FilterRelabel.apply(w, row, col, node_index.contiguous(), num_nodes, flags, EPS)
+    elif cluster_index is not None and len(cluster_index) == num_nodes:
+        ei, w = _RemapCoalesce.apply(w, row, col, cluster_index.contiguous(), num_nodes, num_supernodes,
+                                     L.OPS[reduce_op], flags, EPS)
+    else:
+        raise RuntimeError
+
+    w = edge_postprocess(ei, w, num_supernodes, degree_norm, edge_weight_norm, batch_pooled, num_graphs)
+
+    if to_coo:  # tgp/connect/base_conn.py:107-110 -> connectivity_to_torch_coo
+        if w is None:
+            w = torch.ones(ei.size(1), device=ei.device)
+        return torch.sparse_coo_tensor(ei, w, (num_supernodes, num_supernodes)).coalesce(), None
+    return ei, w
+
+
+# --------------------------------------------------------------------------- #
+# Dense reduce + connect + losses
+# --------------------------------------------------------------------------- #
+LOSS_NONE, LOSS_MINCUT, LOSS_DIFFPOOL = 0, 1, 2
+
+
+class _DensePool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, adj, s, flags, loss_kind, link_div, ent_div):
+        B, N, K = s.shape
+        F = x.size(-1) if x is not None else 0
+        dev = s.device
+        lib = L.load()
+        saved = L.workspace(lib.tgpb200_dense_pool_saved_bytes(B, N, K), dev)
+        x_pool = torch.empty((B, K, F), dtype=s.dtype, device=dev) if x is not None else None
+        adj_pool = torch.empty((B, K, K), dtype=s.dtype, device=dev) if adj is not None else None
+        losses = torch.zeros(4, dtype=torch.float32, device=dev)
+        L.call("tgpb200_dense_pool_fwd", L.ptr(adj), L.ptr(s), L.ptr(x), B, N, K, F, L.dtype_code(s.dtype), flags,
+               loss_kind, EPS, link_div, ent_div, L.ptr(x_pool), L.ptr(adj_pool), L.ptr(losses), L.ptr(saved),
+               saved.numel(), L.stream())
+        ctx.save_for_backward(x, adj, s, saved)
+        ctx.set_materialize_grads(False)
+        ctx.cfg = (B, N, K, F, flags, loss_kind, link_div, ent_div)
+        return x_pool, adj_pool, losses
+
+    @staticmethod
+    def backward(ctx, gx_pool, gadj_pool, glosses):
+        x, adj, s, saved = ctx.saved_tensors
+        B, N, K, F, flags, loss_kind, link_div, ent_div = ctx.cfg
+        dev = s.device
+        lib = L.load()
+        need_adj = adj is not None and ctx.needs_input_grad[1]
+        ws = L.workspace(lib.tgpb200_dense_pool_bwd_workspace_bytes(B, N, K, int(need_adj)), dev)
+        gs = torch.empty_like(s)
+        gx = torch.empty_like(x) if (x is not None and gx_pool is not None) else None
+        gadj = torch.empty_like(adj) if need_adj else None
+        gxp = None if gx_pool is None or x is None else gx_pool.contiguous()
+        gap = None if gadj_pool is None or adj is None else gadj_pool.contiguous()
+        gl = None if glosses is None else glosses.to(torch.float32).contiguous()
+        L.call("tgpb200_dense_pool_bwd", L.ptr(adj), L.ptr(s), L.ptr(x), L.ptr(gxp), L.ptr(gap), L.ptr(gl), B, N, K, F,
+               L.dtype_code(s.dtype), flags, loss_kind, EPS, link_div, ent_div, L.ptr(gs), L.ptr(gx), L.ptr(gadj),
+               L.ptr(saved), saved.numel(), L.ptr(ws), ws.numel(), L.stream())
+        if x is not None and gx is None:
+            gx = torch.zeros_like(x)
+        return gx, gadj, gs, None, None, None, None
+
+
+def dense_flags(remove_self_loops: bool, degree_norm: bool, adj_transpose: bool, edge_weight_norm: bool) -> int:
+    return (
+        (L.REMOVE_SELF_LOOPS if remove_self_loops else 0)
+        | (L.DEGREE_NORM if degree_norm else 0)
+        | (L.ADJ_TRANSPOSE if adj_transpose else 0)
+        | (L.EDGE_WEIGHT_NORM if edge_weight_norm else 0)
+    )
+
+
+def dense_pool(
+    x: Optional[Tensor],
+    adj: Optional[Tensor],
+    s: Tensor,
+    *,
+    remove_self_loops: bool = False,
+    degree_norm: bool = False,
+    adj_transpose: bool = False,
+    edge_weight_norm: bool = False,
+    loss_kind: int = LOSS_NONE,
+    link_div: float = 1.0,
+    ent_div: float = 1.0,
+):
+    """Fused ``(S^T X, postprocess(S^T A S), losses[4])`` for batched dense inputs.
+
+    ``losses`` = ``[mincut, ortho, link, entropy]`` (unused entries are 0).
+    """
+    _require_cuda(x, adj, s)
+    if s.dim() != 3:
+        raise ValueError("dense_pool expects s of shape [B, N, K]")
+    s = s.contiguous()
+    x = None if x is None else x.contiguous()
+    adj = None if adj is None else adj.contiguous()
+    if x is not None and x.dtype != s.dtype or adj is not None and adj.dtype != s.dtype:
+        raise RuntimeError("tgp_b200.dense_pool: x, adj and s must share one dtype")
+    flags = dense_flags(remove_self_loops, degree_norm, adj_transpose, edge_weight_norm)
+    return _DensePool.apply(x, adj, s, flags, loss_kind, float(link_div), float(ent_div))
