@@ -159,7 +159,7 @@ def run_reference(args, w):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample = 32
+    sample = min(w["B"], 512)  # the full C2 batch per step (bounded for the larger workloads)
     ws = dict(w, B=sample)
     a, s, x = make_inputs(ws, "cpu", 123)
     a, s, x = a.float(), s.float(), x.float()

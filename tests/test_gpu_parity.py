@@ -302,7 +302,8 @@ def test_connect_edge_cases():
     with pytest.raises(ValueError):
         T.B200SparseConnect()(e3.to(torch.int32), so)
     # torch COO in -> coalesced torch COO out, weights None (base_conn.py:103-110)
-    coo = torch.sparse_coo_tensor(torch.tensor([[0, 1, 3], [1, 3, 0]], device=DEV), torch.tensor([1.0, 2.0, 3.0], device=DEV), (4, 4))
+    coo = torch.sparse_coo_tensor(torch.tensor([[0, 1, 3], [1, 3, 0]], device=DEV),
+                                  torch.tensor([1.0, 2.0, 3.0], device=DEV), (4, 4)).coalesce()
     out, w = T.B200SparseConnect()(coo, so)
     exp, _ = R.sparse_connect_so(coo.cpu(), R.OracleSelectOutput(cluster_index=torch.tensor([0, 1, 0, 2]), num_supernodes=4))
     assert w is None and out.is_sparse
@@ -345,19 +346,21 @@ def test_dense_pool_fp32_vs_oracle(B, N, K, F, kind):
     gx = torch.randn(B, K, F, generator=g)
     ga = torch.randn(B, K, K, generator=g)
 
-    def run(mod, dev):
-        sr = s_raw.to(dev).requires_grad_(True)
-        xx = x.to(dev).requires_grad_(True)
-        aa = a.to(dev).requires_grad_(True)
+    def run(mod, dev, dt):
+        sr = s_raw.detach().clone().to(dev, dt).requires_grad_(True)
+        xx = x.detach().clone().to(dev, dt).requires_grad_(True)
+        aa = a.detach().clone().to(dev, dt).requires_grad_(True)
         s = torch.softmax(sr, -1)
         fn = mod.mincut_pool if kind == "mincut" else mod.diff_pool
         xp, ap, loss = fn(xx, aa, s)
-        tot = (xp * gx.to(dev)).sum() + (ap * ga.to(dev)).sum() + sum(loss.values())
+        tot = (xp * gx.to(dev, dt)).sum() + (ap * ga.to(dev, dt)).sum() + sum(loss.values())
         tot.backward()
-        return [t.detach().cpu() for t in (xp, ap, *loss.values(), sr.grad, xx.grad, aa.grad)]
+        return [t.detach().cpu().float() for t in (xp, ap, *loss.values(), sr.grad, xx.grad, aa.grad)]
 
-    exp = run(R, "cpu")
-    got = run(T, DEV)
+    # The oracle is evaluated in float64: the reference's own fp32 CPU value of the batch-global Frobenius
+    # norm (link loss) carries ~1e-5 of summation error at these sizes, i.e. as much as the tolerance.
+    exp = run(R, "cpu", torch.float64)
+    got = run(T, DEV, torch.float32)
     names = ["x_pool", "adj_pool", "loss0", "loss1", "grad_s", "grad_x", "grad_adj"]
     for n_, e_, g_ in zip(names, exp, got):
         tol = FP32 if not n_.startswith("grad") else dict(rtol=1e-4, atol=1e-5)

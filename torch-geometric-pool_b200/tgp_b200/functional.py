@@ -142,8 +142,9 @@ class _FilterRelabel(torch.autograd.Function):
         w_out = None if edge_weight is None else torch.empty(n_out, dtype=torch.float32, device=dev)
         need_grad = edge_weight is not None and ctx.needs_input_grad[0]
         src = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev) if need_grad else None
-        L.call("tgpb200_filter_relabel_emit", L.ptr(row), L.ptr(col), L.ptr(edge_weight), E, num_nodes, flags, eps,
-               L.ptr(ei[0]), L.ptr(ei[1]), L.ptr(w_out), L.ptr(src), L.ptr(ws), ws.numel(), L.stream())
+        if n_out > 0:
+            L.call("tgpb200_filter_relabel_emit", L.ptr(row), L.ptr(col), L.ptr(edge_weight), E, num_nodes, flags, eps,
+                   L.ptr(ei[0]), L.ptr(ei[1]), L.ptr(w_out), L.ptr(src), L.ptr(ws), ws.numel(), L.stream())
         ctx.mark_non_differentiable(ei)
         if need_grad:
             ctx.save_for_backward(src)
@@ -182,8 +183,11 @@ class _RemapCoalesce(torch.autograd.Function):
         need_grad = weighted and ctx.needs_input_grad[0]
         slot = torch.empty(max(E, 1), dtype=torch.int32, device=dev) if need_grad else None
         run_len = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev) if need_grad else None
-        L.call("tgpb200_remap_coalesce_emit", E, num_clusters, int(weighted), flags, eps, L.ptr(ei[0]), L.ptr(ei[1]),
-               L.ptr(w_out), L.ptr(slot), L.ptr(run_len), L.ptr(ws), ws.numel(), L.stream())
+        if n_out > 0:
+            L.call("tgpb200_remap_coalesce_emit", E, num_clusters, int(weighted), flags, eps, L.ptr(ei[0]),
+                   L.ptr(ei[1]), L.ptr(w_out), L.ptr(slot), L.ptr(run_len), L.ptr(ws), ws.numel(), L.stream())
+        elif slot is not None:
+            slot.fill_(-1)
         ctx.mark_non_differentiable(ei)
         if need_grad:
             ctx.save_for_backward(edge_weight, w_out, slot, run_len)
