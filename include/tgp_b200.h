@@ -188,6 +188,22 @@ int tgpb200_dense_pool_bwd(const void* adj, const void* s, const void* x, const 
                            float ent_div, void* grad_s, void* grad_x, void* grad_adj, void* saved, size_t saved_bytes,
                            void* workspace, size_t workspace_bytes, tgpb200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core batched product (tcgen05 / TMEM / TMA), the engine under the dense path; exported for tests
+ * and for callers that need a raw S^T X / S^T A S style contraction:
+ *   out[b] (M x N) = alpha * A[b] (M x Kd) * B[b] (Kd x N)  (+ out[b] when accumulate)
+ * Operand layouts per batch item (cols contiguous):  K-major  = [MN extent rows][Kd cols],
+ *                                                     MN-major = [Kd rows][MN extent cols].
+ * fp32 operands run as error-compensated 3xTF32 (fp32-level accuracy), bf16 as a single pass; fp32 accumulate.
+ * Returns TGPB200_ERR_UNSUPPORTED when a TMA constraint fails (16-byte aligned strides; an MN-major extent
+ * must be a multiple of 32 fp32 / 64 bf16 elements).
+ * ------------------------------------------------------------------------------------------ */
+int tgpb200_tc_gemm(const void* a, const void* b, void* out, int64_t batch, int64_t M, int64_t N, int64_t Kd,
+                    int64_t a_batch_stride, int64_t a_row_stride, int a_mn_major, int64_t b_batch_stride,
+                    int64_t b_row_stride, int b_mn_major, int64_t out_batch_stride, int64_t out_row_stride,
+                    int64_t out_col_stride, int in_dtype, int out_dtype, float alpha, int accumulate,
+                    tgpb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

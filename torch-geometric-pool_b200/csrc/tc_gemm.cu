@@ -1,0 +1,518 @@
+// tcgen05 / TMEM / TMA batched GEMM engine (see tc_gemm.cuh for the contract).
+#include "tc_gemm.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace tgp {
+namespace tc {
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint64_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1ull << 26)) {
+      printf("[tgp_b200] mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool kTf32>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  if (kTf32) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, 128B swizzle (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
+//   [46,48) version = 1, [61,64) layout type = 2 (SWIZZLE_128B)
+//   32-bit MN-major operands need the 32-byte-atom variant: layout type = 1 (SWIZZLE_128B_BASE32B, 4-row atoms),
+//   loaded by TMA with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (plain SWIZZLE_128B MN-major tf32 yields zeros).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = 2) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel
+// ------------------------------------------------------------------------------------------
+struct KernelParams {
+  CUtensorMap map_a[kMaxPairs];
+  CUtensorMap map_b[kMaxPairs];
+  int kd[kMaxPairs];
+  int a_mn[kMaxPairs], b_mn[kMaxPairs];
+  int num_pairs;
+  int batch, M, N, BN;
+  int m_tiles, n_tiles, num_items;
+  int stages;
+  uint32_t tmem_cols;
+  void* out;
+  int64_t out_bs, out_rs, out_cs;
+  float alpha;
+  int accumulate, out_bf16;
+  int skip_lo_b_mask;
+};
+
+constexpr int kThreads = 320;
+
+template <bool kF32>
+__global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__ KernelParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int ES = kF32 ? 4 : 2;           // operand element size
+  constexpr int EPB = kStageRowBytes / ES;   // elements per 128-byte line (= BK)
+  constexpr int BK = EPB;
+  constexpr int UMMA_K = 32 / ES;            // 8 (tf32) or 16 (bf16): 32 bytes of K per instruction
+  constexpr int KSTEPS = BK / UMMA_K;        // 4
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int BN = P.BN;
+  const uint32_t a_bytes = BM * kStageRowBytes, b_bytes = (uint32_t)BN * kStageRowBytes;
+  const uint32_t stage_bytes = (a_bytes + b_bytes) * (kF32 ? 2 : 1);
+  const int stages = P.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stage_bytes * stages);
+  // barrier layout: full[stages], lo[stages], empty[stages], tmem_full[2], tmem_empty[2]
+  const uint32_t bar_base = smem_u32(bars);
+  auto bar_full = [&](int s) { return bar_base + 8u * s; };
+  auto bar_lo = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto bar_empty = [&](int s) { return bar_base + 8u * (2 * stages + s); };
+  auto bar_tfull = [&](int i) { return bar_base + 8u * (3 * stages + i); };
+  auto bar_tempty = [&](int i) { return bar_base + 8u * (3 * stages + 2 + i); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_lo(s), 128);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull(i), 1);
+      mbar_init(bar_tempty(i), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // total k-blocks per item (same for every item)
+  int kblocks[kMaxPairs];
+  for (int p = 0; p < kMaxPairs; ++p) kblocks[p] = p < P.num_pairs ? (P.kd[p] + BK - 1) / BK : 0;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < P.num_items; item += gridDim.x) {
+        int nt = item % P.n_tiles, mt = (item / P.n_tiles) % P.m_tiles, b = item / (P.n_tiles * P.m_tiles);
+        int m0 = mt * BM, n0 = nt * BN;
+        for (int p = 0; p < P.num_pairs; ++p) {
+          for (int kb = 0; kb < kblocks[p]; ++kb) {
+            mbar_wait(bar_empty(s), ph ^ 1);
+            uint32_t sa = smem_base + (uint32_t)s * stage_bytes, sb = sa + a_bytes;
+            mbar_arrive_expect_tx(bar_full(s), a_bytes + b_bytes);
+            int k0 = kb * BK;
+            // K-major: one box [rows x 128 B].  MN-major: one box [BK k-rows x 128 B] per 128-byte block of
+            // the MN extent, laid out block after block (the canonical UMMA MN-major SW128 layout, LBO = BK*128 B).
+            if (P.a_mn[p]) {
+              for (int blk = 0; blk < BM / EPB; ++blk)
+                tma_load_3d(sa + blk * (BK * kStageRowBytes), &P.map_a[p], bar_full(s), m0 + blk * EPB, k0, b);
+            } else {
+              tma_load_3d(sa, &P.map_a[p], bar_full(s), k0, m0, b);
+            }
+            if (P.b_mn[p]) {
+              for (int blk = 0; blk < BN / EPB; ++blk)
+                tma_load_3d(sb + blk * (BK * kStageRowBytes), &P.map_b[p], bar_full(s), n0 + blk * EPB, k0, b);
+            } else {
+              tma_load_3d(sb, &P.map_b[p], bar_full(s), k0, n0, b);
+            }
+            if (++s == stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: c=F32 (1<<4), a/b format, a/b major, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t fmt = kF32 ? 2u : 1u;  // TF32 : BF16
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
+        int ab = it & 1;
+        uint32_t aph = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(bar_tempty(ab), aph ^ 1);
+        tc_fence_after();
+        uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
+        uint32_t accum = 0;
+        for (int p = 0; p < P.num_pairs; ++p) {
+          const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)P.a_mn[p] << 15) |
+                                 ((uint32_t)P.b_mn[p] << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+          const uint32_t a_lbo = P.a_mn[p] ? BK * kStageRowBytes : 16, b_lbo = P.b_mn[p] ? BK * kStageRowBytes : 16;
+          const uint32_t a_step = P.a_mn[p] ? UMMA_K * kStageRowBytes : 32, b_step = P.b_mn[p] ? UMMA_K * kStageRowBytes : 32;
+          const bool skip_lo_b = kF32 && ((P.skip_lo_b_mask >> p) & 1);
+          for (int kb = 0; kb < kblocks[p]; ++kb) {
+            mbar_wait(bar_full(s), ph);
+            if (kF32) mbar_wait(bar_lo(s), ph);
+            tc_fence_after();
+            uint32_t sa = smem_base + (uint32_t)s * stage_bytes, sb = sa + a_bytes;
+            uint32_t sa_lo = sb + b_bytes, sb_lo = sa_lo + a_bytes;
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+              // fp32 MN-major tiles use 4-row (512 B) swizzle atoms, everything else 8-row (1024 B) atoms
+              const uint32_t a_sbo = (kF32 && P.a_mn[p]) ? 512 : 1024, b_sbo = (kF32 && P.b_mn[p]) ? 512 : 1024;
+              const uint32_t a_lt = (kF32 && P.a_mn[p]) ? 1 : 2, b_lt = (kF32 && P.b_mn[p]) ? 1 : 2;
+              uint64_t da = make_desc(sa + kk * a_step, a_lbo, a_sbo, a_lt);
+              uint64_t db = make_desc(sb + kk * b_step, b_lbo, b_sbo, b_lt);
+              if (kF32) {
+                uint64_t da_lo = make_desc(sa_lo + kk * a_step, a_lbo, a_sbo, a_lt);
+                uint64_t db_lo = make_desc(sb_lo + kk * b_step, b_lbo, b_sbo, b_lt);
+                umma<true>(d_tmem, da_lo, db, idesc, accum);
+                accum = 1;
+                if (!skip_lo_b) umma<true>(d_tmem, da, db_lo, idesc, accum);
+                umma<true>(d_tmem, da, db, idesc, accum);
+              } else {
+                umma<false>(d_tmem, da, db, idesc, accum);
+                accum = 1;
+              }
+            }
+            umma_commit(bar_empty(s));
+            if (++s == stages) { s = 0; ph ^= 1; }
+          }
+        }
+        umma_commit(bar_tfull(ab));
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== operand split (fp32 only): lo = x - trunc_tf32(x) =====================
+    if (kF32) {
+      const int t = threadIdx.x - 64;  // 0..127
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t raw_bytes = a_bytes + b_bytes;
+      for (int item = blockIdx.x; item < P.num_items; item += gridDim.x) {
+        for (int p = 0; p < P.num_pairs; ++p) {
+          for (int kb = 0; kb < kblocks[p]; ++kb) {
+            mbar_wait(bar_full(s), ph);
+            const float4* raw = reinterpret_cast<const float4*>(smem + (size_t)s * stage_bytes);
+            float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + raw_bytes);
+            for (uint32_t i = t; i < raw_bytes / 16; i += 128) {
+              float4 v = raw[i];
+              float4 r;
+              r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+              r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+              r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+              r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+              lo[i] = r;
+            }
+            fence_proxy_async();
+            mbar_arrive(bar_lo(s));
+            if (++s == stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
+      int nt = item % P.n_tiles, mt = (item / P.n_tiles) % P.m_tiles, b = item / (P.n_tiles * P.m_tiles);
+      int ab = it & 1;
+      uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(bar_tfull(ab), aph);
+      tc_fence_after();
+      const int m = mt * BM + quad * 32 + lane;
+      const int64_t obase = (int64_t)b * P.out_bs + (int64_t)m * P.out_rs;
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN + c0);
+        tmem_ld32(taddr, v);
+        const int n0 = nt * BN + c0;
+        if (m < P.M && n0 < P.N) {
+          if (P.out_bf16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (n0 + j < P.N) {
+                int64_t idx = obase + (int64_t)(n0 + j) * P.out_cs;
+                float r = P.alpha * v[j];
+                if (P.accumulate) r += __bfloat162float(o[idx]);
+                o[idx] = __float2bfloat16_rn(r);
+              }
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(P.out);
+            const bool vec = P.out_cs == 1 && n0 + 32 <= P.N && (((obase + n0) & 3) == 0);
+            if (vec) {
+              float4* o4 = reinterpret_cast<float4*>(o + obase + n0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 r = make_float4(P.alpha * v[4 * j], P.alpha * v[4 * j + 1], P.alpha * v[4 * j + 2],
+                                       P.alpha * v[4 * j + 3]);
+                if (P.accumulate) {
+                  float4 c = o4[j];
+                  r.x += c.x, r.y += c.y, r.z += c.z, r.w += c.w;
+                }
+                o4[j] = r;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (n0 + j < P.N) {
+                  int64_t idx = obase + (int64_t)(n0 + j) * P.out_cs;
+                  float r = P.alpha * v[j];
+                  if (P.accumulate) r += o[idx];
+                  o[idx] = r;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty(ab));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side: tensor maps and launch
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Operand [batch][rows][cols] (cols contiguous).  K-major: rows = MN extent, cols = K extent, box {BK, box_mn, 1}.
+// MN-major: rows = K extent, cols = MN extent, box {EPB, BK, 1} (one load per 128-byte block of the MN extent).
+static bool make_map(CUtensorMap* map, const OperandDesc& op, bool bf16, int batch, int mn_extent, int k_extent,
+                     int box_mn) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const int es = bf16 ? 2 : 4, epb = kStageRowBytes / es;
+  CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
+  cuuint32_t rank;
+  // a stride of 0 is not encodable: a single batch item gets a dummy (never used) batch stride
+  cuuint64_t bstride = (cuuint64_t)(op.batch_stride > 0 ? op.batch_stride : (int64_t)op.row_stride * (op.mn_major ? k_extent : mn_extent)) * es;
+  if (!op.mn_major) {
+    rank = 3;
+    dims[0] = (cuuint64_t)k_extent, dims[1] = (cuuint64_t)mn_extent, dims[2] = (cuuint64_t)batch;
+    strides[0] = (cuuint64_t)op.row_stride * es, strides[1] = bstride;
+    box[0] = epb, box[1] = box_mn, box[2] = 1;
+  } else {
+    rank = 3;
+    dims[0] = (cuuint64_t)mn_extent, dims[1] = (cuuint64_t)k_extent, dims[2] = (cuuint64_t)batch;
+    strides[0] = (cuuint64_t)op.row_stride * es, strides[1] = bstride;
+    box[0] = epb, box[1] = epb /* BK rows */, box[2] = 1;
+    (void)box_mn;
+  }
+  CUtensorMapSwizzle sw = (!bf16 && op.mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = fn(map, dt, rank, const_cast<void*>(op.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static int pick_bn(const GemmProblem& p) {
+  int cap = p.in_bf16 ? 256 : 128;
+  int bn = 64;
+  while (bn < cap && bn < p.N) bn <<= 1;
+  return bn;
+}
+
+bool gemm_supported(const GemmProblem& p) {
+  if (p.batch <= 0 || p.M <= 0 || p.N <= 0 || p.num_pairs < 1 || p.num_pairs > kMaxPairs) return false;
+  const int es = p.in_bf16 ? 2 : 4, epb = kStageRowBytes / es;
+  for (int i = 0; i < p.num_pairs; ++i) {
+    if (p.kd[i] <= 0) return false;
+    const OperandDesc* ops[2] = {&p.a[i], &p.b[i]};
+    const int mn[2] = {p.M, p.N};
+    for (int j = 0; j < 2; ++j) {
+      const OperandDesc& o = *ops[j];
+      if (((uintptr_t)o.ptr & 15) != 0) return false;
+      if ((o.row_stride * es) % 16 != 0 || (o.batch_stride * es) % 16 != 0) return false;
+      (void)mn;
+    }
+  }
+  return encode_fn() != nullptr;
+}
+
+int gemm(const GemmProblem& p, cudaStream_t stream) {
+  if (!gemm_supported(p)) return TGPB200_ERR_UNSUPPORTED;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+    cudaFuncSetAttribute(k_tc_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_tc_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }
+  KernelParams P;
+  memset(&P, 0, sizeof(P));
+  const bool bf16 = p.in_bf16 != 0;
+  P.BN = pick_bn(p);
+  P.num_pairs = p.num_pairs;
+  P.batch = p.batch, P.M = p.M, P.N = p.N;
+  P.m_tiles = (p.M + BM - 1) / BM, P.n_tiles = (p.N + P.BN - 1) / P.BN;
+  P.num_items = p.batch * P.m_tiles * P.n_tiles;
+  for (int i = 0; i < p.num_pairs; ++i) {
+    P.kd[i] = p.kd[i];
+    P.a_mn[i] = p.a[i].mn_major, P.b_mn[i] = p.b[i].mn_major;
+    if (!make_map(&P.map_a[i], p.a[i], bf16, p.batch, p.M, p.kd[i], BM)) return TGPB200_ERR_UNSUPPORTED;
+    if (!make_map(&P.map_b[i], p.b[i], bf16, p.batch, p.N, p.kd[i], P.BN)) return TGPB200_ERR_UNSUPPORTED;
+  }
+  const size_t stage_bytes = (size_t)(BM + P.BN) * kStageRowBytes * (bf16 ? 1 : 2);
+  const size_t budget = 200 * 1024;
+  int stages = (int)(budget / stage_bytes);
+  if (stages > 6) stages = 6;
+  if (stages < 2) return TGPB200_ERR_UNSUPPORTED;
+  P.stages = stages;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * P.BN)) cols <<= 1;
+  P.tmem_cols = cols;
+  P.out = p.out, P.out_bs = p.out_batch_stride, P.out_rs = p.out_row_stride, P.out_cs = p.out_col_stride;
+  P.alpha = p.alpha, P.accumulate = p.accumulate, P.out_bf16 = p.out_bf16;
+  P.skip_lo_b_mask = p.skip_lo_b_mask;
+  const size_t smem = stage_bytes * stages + (3 * stages + 4) * 8 + 16 + 1024;
+  int grid = P.num_items < num_sms ? P.num_items : num_sms;
+  if (bf16)
+    launch("k_tc_gemm_bf16", k_tc_gemm<false>, grid, kThreads, smem, stream, P);
+  else
+    launch("k_tc_gemm_3xtf32", k_tc_gemm<true>, grid, kThreads, smem, stream, P);
+  return launch_status();
+}
+
+}  // namespace tc
+}  // namespace tgp
+
+// Test / integration entry point: one batched product with explicit operand layouts.
+extern "C" int tgpb200_tc_gemm(const void* a, const void* b, void* out, int64_t batch, int64_t M, int64_t N, int64_t Kd,
+                               int64_t a_batch_stride, int64_t a_row_stride, int a_mn_major, int64_t b_batch_stride,
+                               int64_t b_row_stride, int b_mn_major, int64_t out_batch_stride, int64_t out_row_stride,
+                               int64_t out_col_stride, int in_dtype, int out_dtype, float alpha, int accumulate,
+                               tgpb200_stream_t stream) {
+  tgp::tc::GemmProblem p;
+  memset(&p, 0, sizeof(p));
+  p.batch = (int)batch, p.M = (int)M, p.N = (int)N, p.num_pairs = 1, p.kd[0] = (int)Kd;
+  p.a[0] = {a, a_batch_stride, a_row_stride, a_mn_major};
+  p.b[0] = {b, b_batch_stride, b_row_stride, b_mn_major};
+  p.out = out, p.out_batch_stride = out_batch_stride, p.out_row_stride = out_row_stride, p.out_col_stride = out_col_stride;
+  p.alpha = alpha, p.accumulate = accumulate, p.out_bf16 = out_dtype == TGPB200_BF16, p.in_bf16 = in_dtype == TGPB200_BF16;
+  return tgp::tc::gemm(p, (cudaStream_t)stream);
+}

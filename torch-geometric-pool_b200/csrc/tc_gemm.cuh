@@ -1,0 +1,58 @@
+// tcgen05 / TMEM / TMA batched GEMM engine for sm_100a.
+//
+//   D[b] (M x N)  =  alpha * sum_{p < P}  A_p[b] (M x Kp) * B_p[b] (Kp x N)     (+ C[b] when accumulate)
+//
+// * operands arrive by TMA (cp.async.bulk.tensor, 128B swizzle) into a multi-stage shared-memory ring,
+// * one elected thread issues tcgen05.mma (cta_group::1, M = 128) with the accumulator in TMEM
+//   (double-buffered so the epilogue of tile t overlaps the main loop of tile t+1),
+// * fp32 inputs use the error-compensated 3xTF32 scheme (hi*hi + hi*lo + lo*hi, kind::tf32): the tensor core
+//   reads the raw fp32 tile as `hi` (it ignores the low 13 mantissa bits) and four "split" warps write
+//   lo = x - trunc_tf32(x) next to it; bf16 inputs are a single kind::f16 pass,
+// * either operand may be K-major or MN-major in global memory (no transposes are materialised),
+// * the epilogue reads TMEM with tcgen05.ld and writes fp32 or bf16 with arbitrary output strides.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator,
+// warps 2-5 = operand split (fp32 only), warps 6-9 = epilogue.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace tgp {
+namespace tc {
+
+constexpr int kMaxPairs = 4;
+constexpr int BM = 128;
+constexpr int kStageRowBytes = 128;  // every smem tile row is one 128-byte swizzle line
+
+struct OperandDesc {
+  // how the MMA operand is stored in global memory, per batch item:
+  //   K-major : rows = M (or N) extent, cols = K extent, cols contiguous
+  //   MN-major: rows = K extent, cols = M (or N) extent, cols contiguous
+  const void* ptr;
+  int64_t batch_stride;  // elements
+  int64_t row_stride;    // elements (cols are contiguous)
+  int mn_major;          // 0 = K-major, 1 = MN-major
+};
+
+struct GemmProblem {
+  int batch, M, N;
+  int num_pairs;
+  int kd[kMaxPairs];
+  OperandDesc a[kMaxPairs], b[kMaxPairs];
+  void* out;             // fp32 or bf16
+  int64_t out_batch_stride, out_row_stride, out_col_stride;  // elements
+  float alpha;
+  int accumulate;        // D += existing out
+  int out_bf16;
+  int in_bf16;           // operand element type: 0 = fp32 (3xTF32), 1 = bf16
+  int skip_lo_b_mask;    // bit p set: B_p is exactly representable in tf32 (lo pass skipped) -- optional hint
+};
+
+// Enqueue on `stream`.  Returns TGPB200_ERR_UNSUPPORTED when the shape violates the TMA / UMMA constraints
+// (the caller then uses the shape-general FP32-pipe path).
+int gemm(const GemmProblem& p, cudaStream_t stream);
+bool gemm_supported(const GemmProblem& p);
+
+}  // namespace tc
+}  // namespace tgp

@@ -50,6 +50,10 @@ SIGNATURES = {
     "tgpb200_degree_norm_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _F, _P, _P, _P]),
     "tgpb200_weight_norm_fwd": (_INT, [_P, _P, _P, _I64, _I64, _P, _P, _P, _P]),
     "tgpb200_weight_norm_bwd": (_INT, [_P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P]),
+    "tgpb200_tc_gemm": (
+        _INT,
+        [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _INT, _I64, _I64, _INT, _I64, _I64, _I64, _INT, _INT, _F, _INT, _P],
+    ),
     "tgpb200_dense_pool_saved_bytes": (_SZ, [_I64, _I64, _I64]),
     "tgpb200_dense_pool_bwd_workspace_bytes": (_SZ, [_I64, _I64, _I64, _INT]),
     "tgpb200_dense_pool_fwd": (
