@@ -6,7 +6,12 @@
 // This translation unit holds the shape-general path: a strided batched GEMM on the FP32 pipe plus the
 // fused statistics / post-processing / gradient-assembly kernels.  dense_tc.cu provides the tcgen05 GEMMs
 // that replace `bgemm` for the tile-aligned shapes.
+#include <string.h>
+
+#include <type_traits>
+
 #include "dense.cuh"
+#include "tc_gemm.cuh"
 
 namespace tgp {
 
@@ -208,8 +213,18 @@ static __global__ void __launch_bounds__(256)
   }
   if (wn) {
     float bm = block_max(mx, red);
-    // first index attaining the max
-    int cand = (mx == bm && amx != INT_MAX) ? amx : INT_MAX;
+    // Arg of the max for the backward: the FIRST index whose magnitude reaches the max (torch.max rule).
+    // A symmetric adjacency ties (r,c) with (c,r) up to rounding noise of the GEMM, so "reaches" is taken
+    // with a 2e-6 relative slack; the reference then picks the upper-triangle element, and so do we.
+    const float thr = bm * (1.f - 2e-6f);
+    int cand = INT_MAX;
+    for (int i = t; i < K * K; i += nt) {
+      int r = i / K, c = i % K;
+      float v = (rsl && r == c) ? 0.f : Ar[i];
+      if (dn) v = tr ? __fdiv_rn(__fdiv_rn(v, sm[c]), sm[r]) : __fdiv_rn(__fdiv_rn(v, sm[r]), sm[c]);
+      if (fabsf(v) >= thr) { cand = i; break; }
+    }
+    (void)amx;
     int lane = t & 31, w = t >> 5, nw = nt >> 5;
     for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(kFull, cand, o));
     __syncthreads();
@@ -397,7 +412,7 @@ static __global__ void __launch_bounds__(256)
 template <typename T>
 static __global__ void k_ds_elementwise(const T* __restrict__ S, const float* __restrict__ d,
                                         const float* __restrict__ coef, int64_t total, int N, int K, float eps,
-                                        float* __restrict__ dS) {
+                                        T* __restrict__ dS) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int64_t row = i / K;
@@ -405,25 +420,26 @@ static __global__ void k_ds_elementwise(const T* __restrict__ S, const float* __
   float c_den = coef[b * 4 + 0], c_ent = coef[b * 4 + 2];
   if (c_den == 0.f && c_ent == 0.f) return;
   float s = to_f32<T>(S[i]);
-  float v = dS[i];
+  float v = to_f32<T>(dS[i]);
   if (c_den != 0.f) v += c_den * 2.f * d[row] * s;
   if (c_ent != 0.f) v += c_ent * (-logf(s + eps) - s / (s + eps));
-  dS[i] = v;
+  dS[i] = from_f32<T>(v);
 }
 
 // dA += c_den * ss_i (row broadcast) + c_a2 * 2 A_ij
 template <typename T>
 static __global__ void k_da_elementwise(const T* __restrict__ A, const float* __restrict__ ss,
-                                        const float* __restrict__ coef, int64_t total, int N, float* __restrict__ dA) {
+                                        const float* __restrict__ coef, int64_t total, int N, T* __restrict__ dA) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int64_t row = i / N;
   int b = (int)(row / N);
   float c_den = coef[b * 4 + 0], c_a2 = coef[b * 4 + 1];
-  float v = dA[i];
+  if (c_den == 0.f && c_a2 == 0.f) return;
+  float v = to_f32<T>(dA[i]);
   if (c_den != 0.f) v += c_den * ss[row];
   if (c_a2 != 0.f) v += c_a2 * 2.f * to_f32<T>(A[i]);
-  dA[i] = v;
+  dA[i] = from_f32<T>(v);
 }
 
 template <typename T>
@@ -435,14 +451,61 @@ static __global__ void k_cast_out(const float* __restrict__ in, T* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // Host orchestration
 // ------------------------------------------------------------------------------------------
+// A GEMM operand as stored in memory (per batch item, cols contiguous):
+//   K-major : [MN extent rows][K extent cols];   MN-major: [K extent rows][MN extent cols]
+struct Mat {
+  const void* ptr;
+  int64_t bs, rs;
+  int mn;
+};
+
+// D[b] (M x N) = sum_p A_p B_p, written with (row, col) strides.  Tensor-core engine when the layout
+// satisfies the TMA constraints, FP32-pipe batched GEMM otherwise (shape generality, not a second backend:
+// both paths live in this library and compute the same product).
+template <typename T, typename TC>
+static int mm(int batch, int M, int N, int npairs, const int* kd, const Mat* A, const Mat* Bm, TC* out, int64_t obs,
+              int64_t ors, int64_t ocs, cudaStream_t st) {
+  tc::GemmProblem p;
+  memset(&p, 0, sizeof(p));
+  p.batch = batch, p.M = M, p.N = N, p.num_pairs = npairs;
+  for (int i = 0; i < npairs; ++i) {
+    p.kd[i] = kd[i];
+    p.a[i] = {A[i].ptr, A[i].bs, A[i].rs, A[i].mn};
+    p.b[i] = {Bm[i].ptr, Bm[i].bs, Bm[i].rs, Bm[i].mn};
+  }
+  p.out = out, p.out_batch_stride = obs, p.out_row_stride = ors, p.out_col_stride = ocs;
+  p.alpha = 1.f, p.accumulate = 0;
+  p.out_bf16 = std::is_same<TC, __nv_bfloat16>::value;
+  p.in_bf16 = std::is_same<T, __nv_bfloat16>::value;
+  if (tc::gemm_supported(p)) return tc::gemm(p, st);
+  if (ocs != 1) {  // transposed output: D^T = B^T A^T has unit column stride
+    if (ors != 1) return TGPB200_ERR_UNSUPPORTED;
+    return mm<T, TC>(batch, N, M, npairs, kd, Bm, A, out, obs, ocs, ors, st);
+  }
+  for (int i = 0; i < npairs; ++i) {
+    int64_t sAm = A[i].mn ? 1 : A[i].rs, sAk = A[i].mn ? A[i].rs : 1;
+    int64_t sBk = Bm[i].mn ? Bm[i].rs : 1, sBn = Bm[i].mn ? 1 : Bm[i].rs;
+    int rc = bgemm<T, T, TC>((const T*)A[i].ptr, (const T*)Bm[i].ptr, out, batch, M, N, kd[i], A[i].bs, sAm, sAk,
+                             Bm[i].bs, sBk, sBn, obs, ors, 1.f, i > 0, st);
+    if (rc) return rc;
+  }
+  return TGPB200_OK;
+}
+
+template <typename T, typename TC>
+static int mm1(int batch, int M, int N, int kd, Mat A, Mat Bm, TC* out, int64_t obs, int64_t ors, int64_t ocs,
+               cudaStream_t st) {
+  return mm<T, TC>(batch, M, N, 1, &kd, &A, &Bm, out, obs, ors, ocs, st);
+}
+
+template <typename T>
 struct DensePlan {
-  float *T, *W, *Araw, *M, *d, *ss, *a2, *ent, *dvec, *stats, *losses;
+  T* Tt;  // A^T S  [B, N, K]
+  float *Araw, *M, *d, *ss, *a2, *ent, *dvec, *stats, *losses;
   int32_t* argmax;
   bool ok;
-  // `saved` is the forward->backward carry buffer (caller-owned)
   DensePlan(Workspace& ws, int64_t B, int64_t N, int64_t K) {
-    T = ws.take<float>((size_t)B * K * N);
-    W = ws.take<float>((size_t)B * N * K);
+    Tt = ws.take<T>((size_t)B * N * K);
     Araw = ws.take<float>((size_t)B * K * K);
     M = ws.take<float>((size_t)B * K * K);
     d = ws.take<float>((size_t)B * N);
@@ -459,7 +522,7 @@ struct DensePlan {
 
 static size_t dense_saved_bytes(int64_t B, int64_t N, int64_t K) {
   size_t f = sizeof(float);
-  return align_up((size_t)B * K * N * f) * 2 + align_up((size_t)B * K * K * f) * 2 + align_up((size_t)B * N * f) * 4 +
+  return align_up((size_t)B * K * N * f) + align_up((size_t)B * K * K * f) * 2 + align_up((size_t)B * N * f) * 4 +
          align_up((size_t)B * K * f) + align_up((size_t)B * 8 * f) + align_up(8 * f) + align_up((size_t)B * 4) + 4096;
 }
 
@@ -467,34 +530,38 @@ template <typename T>
 static int dense_fwd(const T* A, const T* S, const T* X, int B, int N, int K, int F, uint32_t flags, int loss_kind,
                      float eps, float link_div, float ent_div, T* Xpool, T* Apool, float* losses_out, Workspace& saved,
                      cudaStream_t st) {
-  DensePlan pl(saved, B, N, K);
+  DensePlan<T> pl(saved, B, N, K);
   if (!pl.ok) return TGPB200_ERR_WORKSPACE;
   int rc;
   int64_t NK = (int64_t)N * K, NN = (int64_t)N * N, NF = (int64_t)N * F, KK = (int64_t)K * K, KF = (int64_t)K * F;
-  if (X && Xpool) {  // X_pool = S^T X
-    rc = bgemm<T, T, T>(S, X, Xpool, B, K, F, N, NK, 1, K, NF, F, 1, KF, F, 1.f, false, st);
+  const Mat Smn{S, NK, K, 1};  // S read with the node index as the contraction dim
+  if (X && Xpool) {
+    // X_pool = S^T X.  The larger of (F, K) becomes the 128-row MMA dimension.
+    if (F >= K)  // D[f, k] = sum_i X[i, f] S[i, k], written transposed into X_pool[k, f]
+      rc = mm1<T, T>(B, F, K, N, Mat{X, NF, F, 1}, Smn, Xpool, KF, 1, F, st);
+    else
+      rc = mm1<T, T>(B, K, F, N, Smn, Mat{X, NF, F, 1}, Xpool, KF, F, 1, st);
     if (rc) return rc;
   }
   if (A) {
-    // T = S^T A  [K,N];  A_raw = T S  [K,K]   (reference association, dense_conn.py:120-121)
-    rc = bgemm<T, T, float>(S, A, pl.T, B, K, N, N, NK, 1, K, NN, N, 1, (int64_t)K * N, N, 1.f, false, st);
+    // Tt = A^T S  [N, K]  (= (S^T A)^T);  A_raw = Tt^T S  [K, K]   ((S^T A) S, dense_conn.py:120-121)
+    rc = mm1<T, T>(B, N, K, N, Mat{A, NN, N, 1}, Smn, pl.Tt, NK, K, 1, st);
     if (rc) return rc;
-    rc = bgemm<float, T, float>(pl.T, S, pl.Araw, B, K, K, N, (int64_t)K * N, N, 1, NK, K, 1, KK, K, 1.f, false, st);
+    rc = mm1<T, float>(B, K, K, N, Mat{pl.Tt, NK, K, 1}, Smn, pl.Araw, KK, K, 1, st);
     if (rc) return rc;
   }
   if (loss_kind != 0) {  // M = S^T S
-    rc = bgemm<T, T, float>(S, S, pl.M, B, K, K, N, NK, 1, K, NK, K, 1, KK, K, 1.f, false, st);
+    rc = mm1<T, float>(B, K, K, N, Smn, Smn, pl.M, KK, K, 1, st);
     if (rc) return rc;
   }
   int64_t rows = (int64_t)B * N;
   if (rows > 0)
-    launch("k_row_stats", k_row_stats<T>, (unsigned)ceil_div(rows * 32, 256), 256, 0, st, A, S, rows, N, K, eps, pl.d, pl.ss, pl.a2,
-                                                                      pl.ent);
+    launch("k_row_stats", k_row_stats<T>, (unsigned)ceil_div(rows * 32, 256), 256, 0, st, A, S, rows, N, K, eps, pl.d,
+           pl.ss, pl.a2, pl.ent);
   if (B > 0) {
-    launch("k_graph_epilogue", k_graph_epilogue<T>, B, 256, (size_t)K * sizeof(float), st, A ? pl.Araw : nullptr,
-                                                                  loss_kind != 0 ? pl.M : nullptr, pl.d, pl.ss, pl.a2,
-                                                                  pl.ent, N, K, flags, eps, Apool, pl.dvec, pl.stats,
-                                                                  pl.argmax);
+    launch("k_graph_epilogue", k_graph_epilogue<T>, B, 256, (size_t)K * sizeof(float), st,
+           A ? pl.Araw : (float*)nullptr, loss_kind != 0 ? pl.M : (float*)nullptr, pl.d, pl.ss, pl.a2, pl.ent, N, K,
+           flags, eps, Apool, pl.dvec, pl.stats, pl.argmax);
     launch("k_finalize_losses", k_finalize_losses, 1, 256, 0, st, pl.stats, B, eps, link_div, ent_div, pl.losses);
     if (losses_out) cudaMemcpyAsync(losses_out, pl.losses, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st);
   }
@@ -505,64 +572,73 @@ template <typename T>
 static int dense_bwd(const T* A, const T* S, const T* X, const T* gXpool, const T* gApool, const float* gl, int B,
                      int N, int K, int F, uint32_t flags, int loss_kind, float eps, float link_div, float ent_div,
                      T* dS_out, T* dX_out, T* dA_out, Workspace& saved, Workspace& ws, cudaStream_t st) {
-  DensePlan pl(saved, B, N, K);
+  DensePlan<T> pl(saved, B, N, K);
   if (!pl.ok) return TGPB200_ERR_WORKSPACE;
   int64_t NK = (int64_t)N * K, NN = (int64_t)N * N, NF = (int64_t)N * F, KK = (int64_t)K * K, KF = (int64_t)K * F;
   float* Graw = ws.take<float>((size_t)B * KK);
   float* P = ws.take<float>((size_t)B * KK);
   float* coef = ws.take<float>((size_t)B * 4);
-  float* dS = ws.take<float>((size_t)B * NK);
-  float* U = ws.take<float>((size_t)B * NK);
-  float* dA = dA_out ? ws.take<float>((size_t)B * NN) : nullptr;
+  T* W = ws.take<T>((size_t)B * NK);
+  T* U = ws.take<T>((size_t)B * NK);
+  T* Gt = ws.take<T>((size_t)B * KK);  // Graw / P in the operand dtype (bf16 runs)
+  T* Pt = ws.take<T>((size_t)B * KK);
   if (!ws.ok) return TGPB200_ERR_WORKSPACE;
   int rc;
   if (B == 0) return TGPB200_OK;
-  bool have_a = A != nullptr;
-  if (have_a || loss_kind != 0) {
-    if (have_a)
-      launch("k_graph_bwd", k_graph_bwd<T>, B, 256, (size_t)3 * K * sizeof(float), st, pl.Araw, loss_kind != 0 ? pl.M : nullptr, gApool, pl.dvec, pl.stats, pl.argmax, gl, pl.losses, B, K, flags,
-          loss_kind, eps, link_div, ent_div, Graw, loss_kind != 0 ? P : nullptr, coef);
-  }
-  bool first = true;  // first GEMM into dS overwrites, later ones accumulate
-  if (X && gXpool) {
-    // dX = S Gx  [N,F];   dS += X Gx^T  [N,K]
-    if (dX_out) {
-      rc = bgemm<T, T, T>(S, gXpool, dX_out, B, N, F, K, NK, K, 1, KF, F, 1, NF, F, 1.f, false, st);
-      if (rc) return rc;
-    }
-    rc = bgemm<T, T, float>(X, gXpool, dS, B, N, K, F, NF, F, 1, KF, 1, F, NK, K, 1.f, false, st);
-    if (rc) return rc;
-    first = false;
-  }
+  const bool have_a = A != nullptr;
+  const bool f32 = std::is_same<T, float>::value;
   if (have_a) {
-    // W = A S [N,K];  dS += W Graw^T + T^T Graw
-    rc = bgemm<T, T, float>(A, S, pl.W, B, N, K, N, NN, N, 1, NK, K, 1, NK, K, 1.f, false, st);
-    if (rc) return rc;
-    rc = bgemm<float, float, float>(pl.W, Graw, dS, B, N, K, K, NK, K, 1, KK, 1, K, NK, K, 1.f, !first, st);
-    if (rc) return rc;
-    first = false;
-    rc = bgemm<float, float, float>(pl.T, Graw, dS, B, N, K, K, (int64_t)K * N, 1, N, KK, K, 1, NK, K, 1.f, true, st);
-    if (rc) return rc;
-    if (loss_kind != 0) {  // dS += S P
-      rc = bgemm<T, float, float>(S, P, dS, B, N, K, K, NK, K, 1, KK, K, 1, NK, K, 1.f, true, st);
-      if (rc) return rc;
-    }
-    if (loss_kind != 0)
-      launch("k_ds_elementwise", k_ds_elementwise<T>, (unsigned)ceil_div((int64_t)B * NK, 256), 256, 0, st, S, pl.d, coef, (int64_t)B * NK, N,
-                                                                                   K, eps, dS);
-    if (dA_out) {  // dA = S Graw S^T + element-wise terms
-      rc = bgemm<T, float, float>(S, Graw, U, B, N, K, K, NK, K, 1, KK, K, 1, NK, K, 1.f, false, st);
-      if (rc) return rc;
-      rc = bgemm<float, T, float>(U, S, dA, B, N, N, K, NK, K, 1, NK, 1, K, NN, N, 1.f, false, st);
-      if (rc) return rc;
+    launch("k_graph_bwd", k_graph_bwd<T>, B, 256, (size_t)3 * K * sizeof(float), st, pl.Araw,
+           loss_kind != 0 ? pl.M : (float*)nullptr, gApool, pl.dvec, pl.stats, pl.argmax, gl, pl.losses, B, K, flags,
+           loss_kind, eps, link_div, ent_div, Graw, loss_kind != 0 ? P : (float*)nullptr, coef);
+    if (f32) {
+      Gt = reinterpret_cast<T*>(Graw);
+      Pt = reinterpret_cast<T*>(P);
+    } else {
+      launch("k_cast_out", k_cast_out<T>, (unsigned)ceil_div((int64_t)B * KK, 256), 256, 0, st, Graw, Gt, (int64_t)B * KK);
       if (loss_kind != 0)
-        launch("k_da_elementwise", k_da_elementwise<T>, (unsigned)ceil_div((int64_t)B * NN, 256), 256, 0, st, A, pl.ss, coef, (int64_t)B * NN,
-                                                                                     N, dA);
-      launch("k_cast_out", k_cast_out<T>, (unsigned)ceil_div((int64_t)B * NN, 256), 256, 0, st, dA, dA_out, (int64_t)B * NN);
+        launch("k_cast_out", k_cast_out<T>, (unsigned)ceil_div((int64_t)B * KK, 256), 256, 0, st, P, Pt, (int64_t)B * KK);
     }
   }
-  if (first) cudaMemsetAsync(dS, 0, (size_t)B * NK * sizeof(float), st);
-  if (dS_out) launch("k_cast_out", k_cast_out<T>, (unsigned)ceil_div((int64_t)B * NK, 256), 256, 0, st, dS, dS_out, (int64_t)B * NK);
+  const bool have_x = X && gXpool;
+  if (have_x && dX_out) {  // dX = S Gx  [N, F]
+    rc = mm1<T, T>(B, N, F, K, Mat{S, NK, K, 0}, Mat{gXpool, KF, F, 1}, dX_out, NF, F, 1, st);
+    if (rc) return rc;
+  }
+  if (have_a) {  // W = A S  [N, K]
+    rc = mm1<T, T>(B, N, K, N, Mat{A, NN, N, 0}, Mat{S, NK, K, 1}, W, NK, K, 1, st);
+    if (rc) return rc;
+  }
+  // dS = X Gx^T + W Graw^T + Tt Graw + S P   (one accumulation chain in TMEM)
+  {
+    int kd[4];
+    Mat a[4], b[4];
+    int n = 0;
+    if (have_x) { kd[n] = F; a[n] = Mat{X, NF, F, 0}; b[n] = Mat{gXpool, KF, F, 0}; ++n; }
+    if (have_a) {
+      kd[n] = K; a[n] = Mat{W, NK, K, 0}; b[n] = Mat{Gt, KK, K, 0}; ++n;
+      kd[n] = K; a[n] = Mat{pl.Tt, NK, K, 0}; b[n] = Mat{Gt, KK, K, 1}; ++n;
+      if (loss_kind != 0) { kd[n] = K; a[n] = Mat{S, NK, K, 0}; b[n] = Mat{Pt, KK, K, 1}; ++n; }
+    }
+    if (n > 0) {
+      rc = mm<T, T>(B, N, K, n, kd, a, b, dS_out, NK, K, 1, st);
+      if (rc) return rc;
+    } else {
+      cudaMemsetAsync(dS_out, 0, (size_t)B * NK * sizeof(T), st);
+    }
+  }
+  if (have_a && loss_kind != 0)
+    launch("k_ds_elementwise", k_ds_elementwise<T>, (unsigned)ceil_div((int64_t)B * NK, 256), 256, 0, st, S, pl.d, coef,
+           (int64_t)B * NK, N, K, eps, dS_out);
+  if (have_a && dA_out) {  // dA = (S Graw) S^T + element-wise terms
+    rc = mm1<T, T>(B, N, K, K, Mat{S, NK, K, 0}, Mat{Gt, KK, K, 1}, U, NK, K, 1, st);
+    if (rc) return rc;
+    rc = mm1<T, T>(B, N, N, K, Mat{U, NK, K, 0}, Mat{S, NK, K, 0}, dA_out, NN, N, 1, st);
+    if (rc) return rc;
+    if (loss_kind != 0)
+      launch("k_da_elementwise", k_da_elementwise<T>, (unsigned)ceil_div((int64_t)B * NN, 256), 256, 0, st, A, pl.ss,
+             coef, (int64_t)B * NN, N, dA_out);
+  }
   return launch_status();
 }
 
@@ -576,8 +652,8 @@ size_t tgpb200_dense_pool_saved_bytes(int64_t B, int64_t N, int64_t K) { return 
 
 size_t tgpb200_dense_pool_bwd_workspace_bytes(int64_t B, int64_t N, int64_t K, int need_grad_adj) {
   size_t f = sizeof(float);
-  return 2 * align_up((size_t)B * K * K * f) + align_up((size_t)B * 4 * f) + 2 * align_up((size_t)B * N * K * f) +
-         (need_grad_adj ? align_up((size_t)B * N * N * f) : 0) + 4096;
+  (void)need_grad_adj;
+  return 4 * align_up((size_t)B * K * K * f) + align_up((size_t)B * 4 * f) + 2 * align_up((size_t)B * N * K * f) + 8192;
 }
 
 int tgpb200_dense_pool_fwd(const void* adj, const void* s, const void* x, int64_t B, int64_t N, int64_t K, int64_t F,

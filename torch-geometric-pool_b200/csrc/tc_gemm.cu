@@ -106,6 +106,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 // UMMA shared-memory descriptor, 128B swizzle (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
 //   [46,48) version = 1, [61,64) layout type = 2 (SWIZZLE_128B)
@@ -290,15 +296,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
         for (int p = 0; p < P.num_pairs; ++p) {
           for (int kb = 0; kb < kblocks[p]; ++kb) {
             mbar_wait(bar_full(s), ph);
-            const float4* raw = reinterpret_cast<const float4*>(smem + (size_t)s * stage_bytes);
+            // round-to-nearest split: hi = rna_tf32(x) overwrites the TMA tile in place, lo = x - hi goes next
+            // to it.  (The tensor core truncates its fp32 inputs to tf32; with a truncated hi the residual error
+            // is one-sided and adds up coherently over long sums, with a rounded hi it is ~2^-23 and zero-mean.)
+            float4* raw = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
             float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + raw_bytes);
             for (uint32_t i = t; i < raw_bytes / 16; i += 128) {
               float4 v = raw[i];
-              float4 r;
-              r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-              r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-              r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-              r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+              float4 h, r;
+              h.x = rna_tf32(v.x), h.y = rna_tf32(v.y), h.z = rna_tf32(v.z), h.w = rna_tf32(v.w);
+              r.x = v.x - h.x, r.y = v.y - h.y, r.z = v.z - h.z, r.w = v.w - h.w;
+              raw[i] = h;
               lo[i] = r;
             }
             fence_proxy_async();

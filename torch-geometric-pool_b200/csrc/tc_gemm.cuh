@@ -5,9 +5,9 @@
 // * operands arrive by TMA (cp.async.bulk.tensor, 128B swizzle) into a multi-stage shared-memory ring,
 // * one elected thread issues tcgen05.mma (cta_group::1, M = 128) with the accumulator in TMEM
 //   (double-buffered so the epilogue of tile t overlaps the main loop of tile t+1),
-// * fp32 inputs use the error-compensated 3xTF32 scheme (hi*hi + hi*lo + lo*hi, kind::tf32): the tensor core
-//   reads the raw fp32 tile as `hi` (it ignores the low 13 mantissa bits) and four "split" warps write
-//   lo = x - trunc_tf32(x) next to it; bf16 inputs are a single kind::f16 pass,
+// * fp32 inputs use the error-compensated 3xTF32 scheme (hi*hi + hi*lo + lo*hi, kind::tf32): four "split"
+//   warps rewrite each fp32 tile in shared memory as hi = rna_tf32(x) (in place) and lo = x - hi (next to it);
+//   bf16 inputs are a single kind::f16 pass,
 // * either operand may be K-major or MN-major in global memory (no transposes are materialised),
 // * the epilogue reads TMEM with tcgen05.ld and writes fp32 or bf16 with arbitrary output strides.
 //
