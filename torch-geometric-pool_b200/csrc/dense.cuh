@@ -3,3 +3,11 @@
 #include <limits.h>
 
 #include "common.cuh"
+
+namespace tgp {
+namespace tc {
+// dense_fused.cu: one pass over A, X, S per graph -> Tt = A^T S, X_pool = S^T X, M = S^T S and the row statistics.
+int dense_fwd_fused(const void* A, const void* S, const void* X, int B, int N, int K, int F, bool bf16, float eps,
+                    void* Tt, void* Xp, float* Mm, float* d, float* ss, float* a2, float* ent, cudaStream_t stream);
+}  // namespace tc
+}  // namespace tgp

@@ -500,7 +500,7 @@ static int mm1(int batch, int M, int N, int kd, Mat A, Mat Bm, TC* out, int64_t 
 
 template <typename T>
 struct DensePlan {
-  T* Tt;  // A^T S  [B, N, K]
+  T* Tt;  // T = S^T A  [B, K, N]
   float *Araw, *M, *d, *ss, *a2, *ent, *dvec, *stats, *losses;
   int32_t* argmax;
   bool ok;
@@ -535,29 +535,40 @@ static int dense_fwd(const T* A, const T* S, const T* X, int B, int N, int K, in
   int rc;
   int64_t NK = (int64_t)N * K, NN = (int64_t)N * N, NF = (int64_t)N * F, KK = (int64_t)K * K, KF = (int64_t)K * F;
   const Mat Smn{S, NK, K, 1};  // S read with the node index as the contraction dim
-  if (X && Xpool) {
-    // X_pool = S^T X.  The larger of (F, K) becomes the 128-row MMA dimension.
-    if (F >= K)  // D[f, k] = sum_i X[i, f] S[i, k], written transposed into X_pool[k, f]
-      rc = mm1<T, T>(B, F, K, N, Mat{X, NF, F, 1}, Smn, Xpool, KF, 1, F, st);
-    else
-      rc = mm1<T, T>(B, K, F, N, Smn, Mat{X, NF, F, 1}, Xpool, KF, F, 1, st);
+  bool fused = false;
+  if (A && X && Xpool && B > 0) {
+    // one pass over A, X, S: Tt, X_pool, M and the row statistics (dense_fused.cu)
+    rc = tc::dense_fwd_fused(A, S, X, B, N, K, F, std::is_same<T, __nv_bfloat16>::value, eps, pl.Tt, Xpool, pl.M, pl.d,
+                             pl.ss, pl.a2, pl.ent, st);
+    if (rc == TGPB200_OK) fused = true;
+    else if (rc != TGPB200_ERR_UNSUPPORTED) return rc;
+  }
+  if (!fused) {
+    if (X && Xpool) {
+      // X_pool = S^T X.  The larger of (F, K) becomes the 128-row MMA dimension.
+      if (F >= K)  // D[f, k] = sum_i X[i, f] S[i, k], written transposed into X_pool[k, f]
+        rc = mm1<T, T>(B, F, K, N, Mat{X, NF, F, 1}, Smn, Xpool, KF, 1, F, st);
+      else
+        rc = mm1<T, T>(B, K, F, N, Smn, Mat{X, NF, F, 1}, Xpool, KF, F, 1, st);
+      if (rc) return rc;
+    }
+    if (A) {  // T = S^T A  [K, N], computed as D[j, k] = sum_i A[i, j] S[i, k] and written transposed
+      rc = mm1<T, T>(B, N, K, N, Mat{A, NN, N, 1}, Smn, pl.Tt, NK, 1, N, st);
+      if (rc) return rc;
+    }
+    if (loss_kind != 0) {  // M = S^T S
+      rc = mm1<T, float>(B, K, K, N, Smn, Smn, pl.M, KK, K, 1, st);
+      if (rc) return rc;
+    }
+    int64_t rows = (int64_t)B * N;
+    if (rows > 0)
+      launch("k_row_stats", k_row_stats<T>, (unsigned)ceil_div(rows * 32, 256), 256, 0, st, A, S, rows, N, K, eps, pl.d,
+             pl.ss, pl.a2, pl.ent);
+  }
+  if (A) {  // A_raw = T S  [K, K]   ((S^T A) S, dense_conn.py:120-121)
+    rc = mm1<T, float>(B, K, K, N, Mat{pl.Tt, NK, N, 0}, Smn, pl.Araw, KK, K, 1, st);
     if (rc) return rc;
   }
-  if (A) {
-    // Tt = A^T S  [N, K]  (= (S^T A)^T);  A_raw = Tt^T S  [K, K]   ((S^T A) S, dense_conn.py:120-121)
-    rc = mm1<T, T>(B, N, K, N, Mat{A, NN, N, 1}, Smn, pl.Tt, NK, K, 1, st);
-    if (rc) return rc;
-    rc = mm1<T, float>(B, K, K, N, Mat{pl.Tt, NK, K, 1}, Smn, pl.Araw, KK, K, 1, st);
-    if (rc) return rc;
-  }
-  if (loss_kind != 0) {  // M = S^T S
-    rc = mm1<T, float>(B, K, K, N, Smn, Smn, pl.M, KK, K, 1, st);
-    if (rc) return rc;
-  }
-  int64_t rows = (int64_t)B * N;
-  if (rows > 0)
-    launch("k_row_stats", k_row_stats<T>, (unsigned)ceil_div(rows * 32, 256), 256, 0, st, A, S, rows, N, K, eps, pl.d,
-           pl.ss, pl.a2, pl.ent);
   if (B > 0) {
     launch("k_graph_epilogue", k_graph_epilogue<T>, B, 256, (size_t)K * sizeof(float), st,
            A ? pl.Araw : (float*)nullptr, loss_kind != 0 ? pl.M : (float*)nullptr, pl.d, pl.ss, pl.a2, pl.ent, N, K,
@@ -609,7 +620,7 @@ static int dense_bwd(const T* A, const T* S, const T* X, const T* gXpool, const 
     rc = mm1<T, T>(B, N, K, N, Mat{A, NN, N, 0}, Mat{S, NK, K, 1}, W, NK, K, 1, st);
     if (rc) return rc;
   }
-  // dS = X Gx^T + W Graw^T + Tt Graw + S P   (one accumulation chain in TMEM)
+  // dS = X Gx^T + W Graw^T + T^T Graw + S P   (one accumulation chain in TMEM)
   {
     int kd[4];
     Mat a[4], b[4];
@@ -617,7 +628,7 @@ static int dense_bwd(const T* A, const T* S, const T* X, const T* gXpool, const 
     if (have_x) { kd[n] = F; a[n] = Mat{X, NF, F, 0}; b[n] = Mat{gXpool, KF, F, 0}; ++n; }
     if (have_a) {
       kd[n] = K; a[n] = Mat{W, NK, K, 0}; b[n] = Mat{Gt, KK, K, 0}; ++n;
-      kd[n] = K; a[n] = Mat{pl.Tt, NK, K, 0}; b[n] = Mat{Gt, KK, K, 1}; ++n;
+      kd[n] = K; a[n] = Mat{pl.Tt, NK, N, 1}; b[n] = Mat{Gt, KK, K, 1}; ++n;  // T^T Graw
       if (loss_kind != 0) { kd[n] = K; a[n] = Mat{S, NK, K, 0}; b[n] = Mat{Pt, KK, K, 1}; ++n; }
     }
     if (n > 0) {

@@ -1,5 +1,6 @@
 // tcgen05 / TMEM / TMA batched GEMM engine (see tc_gemm.cuh for the contract).
 #include "tc_gemm.cuh"
+#include "tc_ptx.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -7,126 +8,6 @@
 
 namespace tgp {
 namespace tc {
-
-// ------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Bounded spin: a protocol bug traps (kernel error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  uint64_t spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > (1ull << 26)) {
-      printf("[tgp_b200] mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
-             parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-          dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-template <bool kTf32>
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
-  if (kTf32) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
-// UMMA shared-memory descriptor, 128B swizzle (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
-//   [46,48) version = 1, [61,64) layout type = 2 (SWIZZLE_128B)
-//   32-bit MN-major operands need the 32-byte-atom variant: layout type = 1 (SWIZZLE_128B_BASE32B, 4-row atoms),
-//   loaded by TMA with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (plain SWIZZLE_128B MN-major tf32 yields zeros).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                              uint32_t layout_type = 2) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3fff);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
 
 // ------------------------------------------------------------------------------------------
 // Kernel
@@ -253,25 +134,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
           const uint32_t a_lbo = P.a_mn[p] ? BK * kStageRowBytes : 16, b_lbo = P.b_mn[p] ? BK * kStageRowBytes : 16;
           const uint32_t a_step = P.a_mn[p] ? UMMA_K * kStageRowBytes : 32, b_step = P.b_mn[p] ? UMMA_K * kStageRowBytes : 32;
           const bool skip_lo_b = kF32 && ((P.skip_lo_b_mask >> p) & 1);
+          // fp32 MN-major tiles use 4-row (512 B) swizzle atoms, everything else 8-row (1024 B) atoms
+          const uint64_t desc_a0 = make_desc(smem_base, a_lbo, (kF32 && P.a_mn[p]) ? 512 : 1024, (kF32 && P.a_mn[p]) ? 1 : 2);
+          const uint64_t desc_b0 = make_desc(smem_base, b_lbo, (kF32 && P.b_mn[p]) ? 512 : 1024, (kF32 && P.b_mn[p]) ? 1 : 2);
           for (int kb = 0; kb < kblocks[p]; ++kb) {
             mbar_wait(bar_full(s), ph);
             if (kF32) mbar_wait(bar_lo(s), ph);
             tc_fence_after();
-            uint32_t sa = smem_base + (uint32_t)s * stage_bytes, sb = sa + a_bytes;
-            uint32_t sa_lo = sb + b_bytes, sb_lo = sa_lo + a_bytes;
+            // descriptors differ only in the 14-bit start-address field: build once per pair, then add offsets
+            const uint32_t so = ((uint32_t)s * stage_bytes) >> 4;
+            const uint64_t da0 = desc_a0 + so, db0 = desc_b0 + so + (a_bytes >> 4);
+            const uint32_t lo_off = (a_bytes + b_bytes) >> 4;
 #pragma unroll
             for (int kk = 0; kk < KSTEPS; ++kk) {
-              // fp32 MN-major tiles use 4-row (512 B) swizzle atoms, everything else 8-row (1024 B) atoms
-              const uint32_t a_sbo = (kF32 && P.a_mn[p]) ? 512 : 1024, b_sbo = (kF32 && P.b_mn[p]) ? 512 : 1024;
-              const uint32_t a_lt = (kF32 && P.a_mn[p]) ? 1 : 2, b_lt = (kF32 && P.b_mn[p]) ? 1 : 2;
-              uint64_t da = make_desc(sa + kk * a_step, a_lbo, a_sbo, a_lt);
-              uint64_t db = make_desc(sb + kk * b_step, b_lbo, b_sbo, b_lt);
+              const uint64_t da = da0 + (uint64_t)(kk * (a_step >> 4)), db = db0 + (uint64_t)(kk * (b_step >> 4));
               if (kF32) {
-                uint64_t da_lo = make_desc(sa_lo + kk * a_step, a_lbo, a_sbo, a_lt);
-                uint64_t db_lo = make_desc(sb_lo + kk * b_step, b_lbo, b_sbo, b_lt);
-                umma<true>(d_tmem, da_lo, db, idesc, accum);
+                umma<true>(d_tmem, da + lo_off, db, idesc, accum);
                 accum = 1;
-                if (!skip_lo_b) umma<true>(d_tmem, da, db_lo, idesc, accum);
+                if (!skip_lo_b) umma<true>(d_tmem, da, db + lo_off, idesc, accum);
                 umma<true>(d_tmem, da, db, idesc, accum);
               } else {
                 umma<false>(d_tmem, da, db, idesc, accum);
@@ -299,15 +179,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
             // round-to-nearest split: hi = rna_tf32(x) overwrites the TMA tile in place, lo = x - hi goes next
             // to it.  (The tensor core truncates its fp32 inputs to tf32; with a truncated hi the residual error
             // is one-sided and adds up coherently over long sums, with a rounded hi it is ~2^-23 and zero-mean.)
-            float4* raw = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
-            float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + raw_bytes);
-            for (uint32_t i = t; i < raw_bytes / 16; i += 128) {
-              float4 v = raw[i];
-              float4 h, r;
-              h.x = rna_tf32(v.x), h.y = rna_tf32(v.y), h.z = rna_tf32(v.z), h.w = rna_tf32(v.w);
-              r.x = v.x - h.x, r.y = v.y - h.y, r.z = v.z - h.z, r.w = v.w - h.w;
-              raw[i] = h;
-              lo[i] = r;
+            const uint32_t raw = smem_base + (uint32_t)s * stage_bytes, lo = raw + raw_bytes;
+            const uint32_t nvec = raw_bytes / 16;  // multiple of 512 (BM and BN are multiples of 64 rows)
+            for (uint32_t i0 = t; i0 < nvec; i0 += 128 * 4) {
+              float4 v[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) v[u] = lds128(raw + (i0 + u * 128) * 16);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                float4 h, r;
+                h.x = rna_tf32(v[u].x), h.y = rna_tf32(v[u].y), h.z = rna_tf32(v[u].z), h.w = rna_tf32(v[u].w);
+                r.x = v[u].x - h.x, r.y = v[u].y - h.y, r.z = v[u].z - h.z, r.w = v[u].w - h.w;
+                sts128(raw + (i0 + u * 128) * 16, h);
+                sts128(lo + (i0 + u * 128) * 16, r);
+              }
             }
             fence_proxy_async();
             mbar_arrive(bar_lo(s));
@@ -387,11 +272,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
 // ------------------------------------------------------------------------------------------
 // Host side: tensor maps and launch
 // ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
+EncodeTiledFn encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -403,6 +284,50 @@ static EncodeTiledFn encode_fn() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   }
   return fn;
+}
+
+bool make_map_3d(CUtensorMap* map, const void* ptr, bool bf16, int64_t batch, int64_t rows, int64_t cols,
+                 int64_t row_stride, int64_t batch_stride, int box_rows, bool swizzle32) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const int es = bf16 ? 2 : 4, epb = kStageRowBytes / es;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t bs = (cuuint64_t)(batch_stride > 0 ? batch_stride : row_stride * rows) * es;
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride * es, bs};
+  cuuint32_t box[3] = {(cuuint32_t)epb, (cuuint32_t)box_rows, 1}, estr[3] = {1, 1, 1};
+  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool make_map_blocked(CUtensorMap* map, const void* ptr, bool bf16, int64_t batch, int64_t rows, int64_t cols,
+                      int64_t row_stride, int64_t batch_stride, int box_rows, int box_blocks, bool swizzle32) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const int es = bf16 ? 2 : 4, epb = kStageRowBytes / es;
+  if (cols % epb) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)epb, (cuuint64_t)rows, (cuuint64_t)(cols / epb), (cuuint64_t)batch};
+  cuuint64_t bs = (cuuint64_t)(batch_stride > 0 ? batch_stride : row_stride * rows) * es;
+  cuuint64_t strides[3] = {(cuuint64_t)row_stride * es, (cuuint64_t)kStageRowBytes, bs};
+  cuuint32_t box[4] = {(cuuint32_t)epb, (cuuint32_t)box_rows, (cuuint32_t)box_blocks, 1}, estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+int device_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
 }
 
 // Operand [batch][rows][cols] (cols contiguous).  K-major: rows = MN extent, cols = K extent, box {BK, box_mn, 1}.

@@ -52,6 +52,22 @@ struct GemmProblem {
 // Enqueue on `stream`.  Returns TGPB200_ERR_UNSUPPORTED when the shape violates the TMA / UMMA constraints
 // (the caller then uses the shape-general FP32-pipe path).
 int gemm(const GemmProblem& p, cudaStream_t stream);
+
+// cuTensorMapEncodeTiled resolved through the runtime (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn();
+// 3-D tensor map over an operand stored [batch][rows][cols] (cols contiguous); box = {128 bytes of cols, box_rows, 1}.
+// swizzle32 selects CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (fp32 MN-major operands), else SWIZZLE_128B.
+bool make_map_3d(CUtensorMap* map, const void* ptr, bool bf16, int64_t batch, int64_t rows, int64_t cols,
+                 int64_t row_stride, int64_t batch_stride, int box_rows, bool swizzle32);
+// 4-D "blocked" map of the same operand for MN-major tiles: dims {128 B of cols, rows, column blocks, batch};
+// box {128 B, box_rows, box_blocks, 1} lands in shared memory block after block ([block][row][128 B]), i.e. the
+// canonical UMMA MN-major layout, with ONE TMA instruction per tile.  cols must be a multiple of the block width.
+bool make_map_blocked(CUtensorMap* map, const void* ptr, bool bf16, int64_t batch, int64_t rows, int64_t cols,
+                      int64_t row_stride, int64_t batch_stride, int box_rows, int box_blocks, bool swizzle32);
+int device_sm_count();
 bool gemm_supported(const GemmProblem& p);
 
 }  // namespace tc
