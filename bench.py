@@ -40,6 +40,130 @@ WORKLOADS = {
 }
 
 
+SPARSE_WORKLOADS = {
+    "c1": dict(kind="topk", graphs=128, n_lo=24, n_hi=36, p=0.1, F=64,
+               desc="TopK ratio 0.5 + sum reduce + kept-node connect, 128 ER graphs (~30 nodes, 64 feats), fwd+bwd"),
+    "c4": dict(kind="cluster", N=1_000_000, E=20_000_000, F=128,
+               desc="cluster connect (remap + coalesce sum + self-loop removal) + mean reduce, 1M nodes / 20M edges "
+                    "power-law, 128 feats, matching-style cluster map (K ~ 0.55 N), fwd+bwd"),
+    "c5": dict(kind="topk_big", N=16_000_000, E=400_000_000, F=128,
+               desc="TopK 50% kept-node connect + sum reduce on one 16M-node / 400M-edge graph, 128 feats, fwd"),
+}
+
+
+def powerlaw_graph(n, e, device, seed):
+    """Chung-Lu style power-law graph (exponent 2.3), symmetric, no self loops, sorted by (row, col)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    w = (torch.arange(1, n + 1, device=device, dtype=torch.float32)) ** (-1.0 / 1.3)
+    cdf = torch.cumsum(w.double(), 0)
+    cdf = (cdf / cdf[-1]).float()
+    half = e // 2
+    src = torch.searchsorted(cdf, torch.rand(half, device=device, generator=g)).clamp_(max=n - 1)
+    dst = torch.randint(0, n, (half,), device=device, generator=g)
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    perm = torch.randperm(n, device=device, generator=g)  # hubs are spread over the id range
+    src, dst = perm[src], perm[dst]
+    row = torch.cat([src, dst])
+    col = torch.cat([dst, src])
+    order = torch.argsort(row * n + col)
+    return torch.stack([row[order], col[order]])
+
+
+def run_sparse(args, name):
+    import tgp_b200 as T
+    from tgp_b200 import _lib
+
+    w = SPARSE_WORKLOADS[name]
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    if w["kind"] == "topk":
+        gc = torch.Generator().manual_seed(0)
+        xs, eis, bs, off = [], [], [], 0
+        for gi in range(w["graphs"]):
+            n = int(torch.randint(w["n_lo"], w["n_hi"] + 1, (1,), generator=gc))
+            up = torch.triu(torch.rand(n, n, generator=gc) < w["p"], 1)
+            r, c = up.nonzero(as_tuple=True)
+            eis.append(torch.cat([torch.stack([r, c]), torch.stack([c, r])], 1) + off)
+            bs.append(torch.full((n,), gi))
+            off += n
+        ei = torch.cat(eis, 1)
+        ei = ei[:, torch.argsort(ei[0] * off + ei[1])].to(dev)
+        batch = torch.cat(bs).to(dev)
+        N, units = off, w["graphs"]
+    else:
+        N = w["N"]
+        ei = powerlaw_graph(N, w["E"], dev, 0)
+        batch = None
+        units = 1
+    E = ei.size(1)
+    F = w["F"]
+    x = torch.randn(N, F, device=dev, generator=g).requires_grad_(w["kind"] != "topk_big")
+    ew = (torch.rand(E, device=dev, generator=g) + 0.5).requires_grad_(w["kind"] != "topk_big")
+    if w["kind"] == "cluster":
+        # matching-style map: a random pairing along a permutation, ~45% of the nodes paired -> K ~ 0.55 N
+        perm = torch.randperm(N, device=dev, generator=g)
+        paired = int(0.9 * N) // 2 * 2
+        cl = torch.empty(N, dtype=torch.long, device=dev)
+        cl[perm[:paired]] = torch.arange(paired // 2, device=dev).repeat_interleave(2)
+        cl[perm[paired:]] = torch.arange(paired // 2, paired // 2 + N - paired, device=dev)
+        K = paired // 2 + N - paired
+        so = T.SelectOutput(cluster_index=cl, num_nodes=N, num_supernodes=K)
+        reduce_op = "mean"
+    else:
+        score = torch.tanh(torch.randn(N, device=dev, generator=g))
+        if batch is None:
+            node_index = torch.topk(score, N // 2).indices
+        else:  # per-graph top half (selection is upstream of the path and not timed)
+            order = torch.argsort(batch * 4.0 - score)  # graph asc, score desc
+            ptr = torch.zeros(int(batch.max()) + 2, dtype=torch.long, device=dev)
+            ptr[1:] = torch.bincount(batch).cumsum(0)
+            rank_in = torch.arange(N, device=dev) - ptr[batch[order]]
+            keep = rank_in < ((ptr[1:] - ptr[:-1] + 1) // 2)[batch[order]]
+            node_index = order[keep]
+        K = node_index.numel()
+        so = T.SelectOutput(node_index=node_index, num_nodes=N, cluster_index=torch.arange(K, device=dev),
+                            num_supernodes=K, weight=score[node_index])
+        reduce_op = "sum"
+    T.functional.csr_of(so)  # the CSR is cached on the SelectOutput (pre-coarsened pipelines reuse it)
+    train = w["kind"] != "topk_big"
+
+    def step():
+        x.grad = None
+        ew.grad = None
+        xp, eo, wo, _ = T.sparse_pool(x, ei, so, edge_weight=ew, batch=batch, reduce_op=reduce_op)
+        if train:
+            torch.autograd.backward([xp, wo], [torch.ones_like(xp), torch.ones_like(wo)])
+        return eo.size(1)
+
+    for _ in range(max(args.warmup, 3)):
+        e_out = step()
+    torch.cuda.synchronize()
+    l0 = _lib.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    hbm, _, src = peaks()
+    # algorithmic bytes (SURVEY 8d): edges in (2*8+4) + edges out (2*8+4) + index map + x in + x_pool out, x2 for bwd feats
+    alg = 20 * E + 20 * e_out + 8 * so.node_index.numel() + 4 * F * (so.node_index.numel() + K)
+    if train:
+        alg += 4 * F * (N + K) + 4 * E + 4 * e_out
+    line = {"metric": "coarsened graphs/s (Reduce+Connect fwd+bwd)", "value": units / (ms * 1e-3), "unit": "graphs/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "N": N, "E": E, "K": K, "E_out": e_out},
+            "gpu_launches": _lib.kernel_launches() - l0,
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / hbm, "traffic": None, "kernel": "whole step",
+                         "algorithmic_bytes": alg, "peak_source": src}}
+    print(json.dumps(line), flush=True)
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -190,9 +314,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + sorted(SPARSE_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.workload in SPARSE_WORKLOADS:
+        run_sparse(args, args.workload)
+        return
     w = WORKLOADS[args.workload]
 
     if args.impl == "reference":

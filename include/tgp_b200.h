@@ -155,6 +155,16 @@ int tgpb200_degree_norm_fwd(const int64_t* row, const int64_t* col, const float*
 int tgpb200_degree_norm_bwd(const int64_t* row, const int64_t* col, const float* w, const float* deg,
                             const float* grad_out, int64_t num_edges, int64_t num_clusters, float eps,
                             float* grad_dinv /* [K] scratch, overwritten */, float* grad_w, tgpb200_stream_t stream);
+/* Split forms for the edge-sharded multi-GPU path: accumulate the [K] degree / [G] max partials on
+ * the local edge shard, combine them across ranks (all-reduce sum / max), then apply. */
+int tgpb200_degree_accumulate(const int64_t* row, const float* w, int64_t num_edges, int64_t num_clusters, float* deg,
+                              tgpb200_stream_t stream);
+int tgpb200_degree_apply(const int64_t* row, const int64_t* col, const float* w, const float* deg, int64_t num_edges,
+                         int64_t num_clusters, float eps, float* w_out, tgpb200_stream_t stream);
+int tgpb200_weight_max_accumulate(const int64_t* row, const float* w, const int64_t* batch_pooled, int64_t num_edges,
+                                  int64_t num_graphs, float* max_out, tgpb200_stream_t stream);
+int tgpb200_weight_max_apply(const int64_t* row, const float* w, const int64_t* batch_pooled, const float* max_in,
+                             int64_t num_edges, int64_t num_graphs, float* w_out, tgpb200_stream_t stream);
 int tgpb200_weight_norm_fwd(const int64_t* row, const float* w, const int64_t* batch_pooled, int64_t num_edges,
                             int64_t num_graphs, float* max_out, int32_t* arg_out, float* w_out,
                             tgpb200_stream_t stream);

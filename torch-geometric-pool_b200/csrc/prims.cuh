@@ -209,19 +209,29 @@ static __global__ void k_radix_hist(const KeyT* __restrict__ keys, int64_t n, in
   tile_hist[(size_t)threadIdx.x * nt + blockIdx.x] = h[threadIdx.x];
 }
 
+// Stable scatter of one tile.  Ranking: every warp owns 512 consecutive items and ranks them round by round with
+// __match_any_sync (stable inside the warp); per-digit counts are then prefixed over warps and digits.  The items
+// are first placed in shared memory in tile-local sorted order, so that the final global writes of a digit run are
+// consecutive (full-sector stores) instead of one scattered 8/12-byte write per item.
 template <typename KeyT, bool kIota>
 static __global__ void __launch_bounds__(kSortThreads)
     k_radix_scatter(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                     KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
                     const int* __restrict__ tile_off, int nt) {
   constexpr int NW = kSortThreads / 32;
-  __shared__ int warp_cnt[NW][kSortBins];
-  __shared__ int g_base[kSortBins];
+  extern __shared__ __align__(16) unsigned char radix_smem[];
+  KeyT* s_keys = reinterpret_cast<KeyT*>(radix_smem);                                   // [kSortTile]
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(radix_smem + sizeof(KeyT) * kSortTile);  // [kSortTile]
+  int(*warp_cnt)[kSortBins] = reinterpret_cast<int(*)[kSortBins]>(s_vals + kSortTile);   // [NW][bins]
+  int* dig_base = &warp_cnt[0][0] + NW * kSortBins;                                      // [bins] tile-local start
+  int* g_base = dig_base + kSortBins;                                                    // [bins] global start
+  __shared__ int scan_tmp[33];
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < NW * kSortBins; i += kSortThreads) (&warp_cnt[0][0])[i] = 0;
   __syncthreads();
 
-  int64_t base = (int64_t)blockIdx.x * kSortTile + (int64_t)w * (32 * kSortItems);
+  const int64_t tile0 = (int64_t)blockIdx.x * kSortTile;
+  const int64_t base = tile0 + (int64_t)w * (32 * kSortItems);
   KeyT key[kSortItems];
   int rank[kSortItems];
 #pragma unroll
@@ -247,8 +257,9 @@ static __global__ void __launch_bounds__(kSortThreads)
     __syncwarp();
   }
   __syncthreads();
+  int tot;
   {
-    int d = threadIdx.x;  // one thread per digit
+    int d = threadIdx.x;  // one thread per digit: exclusive prefix over warps, then over digits
     int run = 0;
 #pragma unroll
     for (int k = 0; k < NW; ++k) {
@@ -257,6 +268,8 @@ static __global__ void __launch_bounds__(kSortThreads)
       run += c;
     }
     g_base[d] = tile_off[(size_t)d * nt + blockIdx.x];
+    int ex = block_exclusive_scan_i(run, scan_tmp, &tot);
+    dig_base[d] = ex;
   }
   __syncthreads();
 #pragma unroll
@@ -264,11 +277,24 @@ static __global__ void __launch_bounds__(kSortThreads)
     int64_t i = base + j * 32 + lane;
     if (i < n) {
       int d = (int)((key[j] >> shift) & 255);
-      int64_t pos = (int64_t)g_base[d] + warp_cnt[w][d] + rank[j];
-      keys_out[pos] = key[j];
-      vals_out[pos] = kIota ? (uint32_t)i : vals_in[i];
+      int lp = dig_base[d] + warp_cnt[w][d] + rank[j];
+      s_keys[lp] = key[j];
+      s_vals[lp] = kIota ? (uint32_t)i : vals_in[i];
     }
   }
+  __syncthreads();
+  for (int lp = threadIdx.x; lp < tot; lp += kSortThreads) {
+    KeyT k = s_keys[lp];
+    int d = (int)((k >> shift) & 255);
+    int64_t pos = (int64_t)g_base[d] + (lp - dig_base[d]);
+    keys_out[pos] = k;
+    vals_out[pos] = s_vals[lp];
+  }
+}
+
+template <typename KeyT>
+constexpr size_t radix_scatter_smem() {
+  return (sizeof(KeyT) + 4) * kSortTile + sizeof(int) * (kSortThreads / 32 + 2) * kSortBins;
 }
 
 inline int radix_passes(int key_bits) { return key_bits <= 0 ? 1 : (key_bits + 7) / 8; }
@@ -290,6 +316,14 @@ inline int radix_sort_pairs(KeyT* keys0, uint32_t* vals0_or_null, uint32_t* vals
   if (!ws.ok) return TGPB200_ERR_WORKSPACE;
   size_t mark2 = ws.off;
   int passes = radix_passes(key_bits);
+  static bool smem_attr_set = false;  // per KeyT instantiation: > 48 KB dynamic shared memory needs the opt-in
+  if (!smem_attr_set) {
+    smem_attr_set = true;
+    cudaFuncSetAttribute(k_radix_scatter<KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)radix_scatter_smem<KeyT>());
+    cudaFuncSetAttribute(k_radix_scatter<KeyT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)radix_scatter_smem<KeyT>());
+  }
   KeyT* kin = keys0;
   KeyT* kout = keys1;
   const uint32_t* vin = vals0_or_null;
@@ -302,9 +336,11 @@ inline int radix_sort_pairs(KeyT* keys0, uint32_t* vals0_or_null, uint32_t* vals
     int rc = exclusive_scan_i32(hist, hist, (int64_t)nt * kSortBins, nullptr, nullptr, ws, stream);
     if (rc != TGPB200_OK) return rc;
     if (vin == nullptr)
-      launch("k_radix_scatter", k_radix_scatter<KeyT, true>, nt, kSortThreads, 0, stream, kin, nullptr, kout, vout, n, shift, hist, nt);
+      launch("k_radix_scatter", k_radix_scatter<KeyT, true>, nt, kSortThreads, radix_scatter_smem<KeyT>(), stream, kin,
+             (const uint32_t*)nullptr, kout, vout, n, shift, hist, nt);
     else
-      launch("k_radix_scatter", k_radix_scatter<KeyT, false>, nt, kSortThreads, 0, stream, kin, vin, kout, vout, n, shift, hist, nt);
+      launch("k_radix_scatter", k_radix_scatter<KeyT, false>, nt, kSortThreads, radix_scatter_smem<KeyT>(), stream, kin,
+             vin, kout, vout, n, shift, hist, nt);
     in1 = !in1;
     KeyT* tk = kin;
     kin = kout;

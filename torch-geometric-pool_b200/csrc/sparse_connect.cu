@@ -518,6 +518,58 @@ int tgpb200_degree_norm_fwd(const int64_t* row, const int64_t* col, const float*
   return launch_status();
 }
 
+// Split form of the two normalisations, for the edge-sharded multi-GPU path: accumulate locally, combine the
+// [K] / [G] partials across ranks (NCCL all-reduce, sum / max), then apply.
+int tgpb200_degree_accumulate(const int64_t* row, const float* w, int64_t E, int64_t K, float* deg,
+                              tgpb200_stream_t stream) {
+  if (E < 0 || K < 0) return TGPB200_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (K > 0) {
+    if (!deg) return TGPB200_ERR_INVALID;
+    cudaMemsetAsync(deg, 0, (size_t)K * sizeof(float), st);
+  }
+  if (E > 0) {
+    if (!row) return TGPB200_ERR_INVALID;
+    launch("k_deg_accum", k_deg_accum, (unsigned)ceil_div(E, 256), 256, 0, st, row, w, E, K, deg);
+  }
+  return launch_status();
+}
+
+int tgpb200_degree_apply(const int64_t* row, const int64_t* col, const float* w, const float* deg, int64_t E, int64_t K,
+                         float eps, float* w_out, tgpb200_stream_t stream) {
+  if (E < 0 || K < 0) return TGPB200_ERR_INVALID;
+  if (E == 0) return TGPB200_OK;
+  if (!row || !col || !deg || !w_out) return TGPB200_ERR_INVALID;
+  launch("k_deg_apply", k_deg_apply, (unsigned)ceil_div(E, 256), 256, 0, (cudaStream_t)stream, row, col, w, deg, E, K, eps,
+         w_out);
+  return launch_status();
+}
+
+int tgpb200_weight_max_accumulate(const int64_t* row, const float* w, const int64_t* batch_pooled, int64_t E, int64_t G,
+                                  float* max_out, tgpb200_stream_t stream) {
+  if (E < 0 || G < 0) return TGPB200_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (G > 0) {
+    if (!max_out) return TGPB200_ERR_INVALID;
+    cudaMemsetAsync(max_out, 0, (size_t)G * sizeof(float), st);
+  }
+  if (E > 0) {
+    if (!row || !w || !batch_pooled) return TGPB200_ERR_INVALID;
+    launch("k_wn_max", k_wn_max, (unsigned)ceil_div(E, 256), 256, 0, st, row, w, batch_pooled, E, G, max_out);
+  }
+  return launch_status();
+}
+
+int tgpb200_weight_max_apply(const int64_t* row, const float* w, const int64_t* batch_pooled, const float* max_in,
+                             int64_t E, int64_t G, float* w_out, tgpb200_stream_t stream) {
+  if (E < 0 || G < 0) return TGPB200_ERR_INVALID;
+  if (E == 0) return TGPB200_OK;
+  if (!row || !w || !batch_pooled || !max_in || !w_out) return TGPB200_ERR_INVALID;
+  launch("k_wn_apply", k_wn_apply, (unsigned)ceil_div(E, 256), 256, 0, (cudaStream_t)stream, row, w, batch_pooled, max_in,
+         E, G, (int32_t*)nullptr, w_out);
+  return launch_status();
+}
+
 int tgpb200_degree_norm_bwd(const int64_t* row, const int64_t* col, const float* w, const float* deg,
                             const float* grad_out, int64_t E, int64_t K, float eps, float* grad_dinv, float* grad_w,
                             tgpb200_stream_t stream) {

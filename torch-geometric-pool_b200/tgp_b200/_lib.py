@@ -48,6 +48,10 @@ SIGNATURES = {
     "tgpb200_coalesce_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _INT, _P, _P, _SZ, _P]),
     "tgpb200_degree_norm_fwd": (_INT, [_P, _P, _P, _I64, _I64, _F, _P, _P, _P]),
     "tgpb200_degree_norm_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _F, _P, _P, _P]),
+    "tgpb200_degree_accumulate": (_INT, [_P, _P, _I64, _I64, _P, _P]),
+    "tgpb200_degree_apply": (_INT, [_P, _P, _P, _P, _I64, _I64, _F, _P, _P]),
+    "tgpb200_weight_max_accumulate": (_INT, [_P, _P, _P, _I64, _I64, _P, _P]),
+    "tgpb200_weight_max_apply": (_INT, [_P, _P, _P, _P, _I64, _I64, _P, _P]),
     "tgpb200_weight_norm_fwd": (_INT, [_P, _P, _P, _I64, _I64, _P, _P, _P, _P]),
     "tgpb200_weight_norm_bwd": (_INT, [_P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P]),
     "tgpb200_tc_gemm": (
