@@ -111,8 +111,8 @@ def test_edge_sharded_connect_matches_single_process():
         p.start()
     outs, outs2, outs3, losses = q.get()
     for p in procs:
-        p.join(60)
-        assert p.exitcode == 0
+        p.join(600)
+        assert p.exitcode == 0, f"worker exit code {p.exitcode}"
 
     n, ei, ew, g = _graph(0)
     score = torch.randn(n, generator=g)
