@@ -133,7 +133,7 @@ static __global__ void k_row_stats(const T* __restrict__ A, const T* __restrict_
 // stats[b] = {num, den, ||M||_F^2, ortho_b, ||A||_F^2, ent_b, maxnorm m, unused}
 // ------------------------------------------------------------------------------------------
 template <typename T>
-static __global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(1024)
     k_graph_epilogue(const float* __restrict__ Araw, const float* __restrict__ M, const float* __restrict__ d,
                      const float* __restrict__ ss, const float* __restrict__ a2, const float* __restrict__ ent, int N,
                      int K, uint32_t flags, float eps, T* __restrict__ Apool, float* __restrict__ dvec,
@@ -276,7 +276,7 @@ static __global__ void k_finalize_losses(const float* __restrict__ stats, int B,
 // gl = upstream grads of {cut, ortho, link, entropy} (device floats, already x coefficient).
 // ------------------------------------------------------------------------------------------
 template <typename T>
-static __global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(1024)
     k_graph_bwd(const float* __restrict__ Araw, const float* __restrict__ M, const T* __restrict__ Gpool,
                 const float* __restrict__ dvec, const float* __restrict__ stats, const int32_t* __restrict__ argmax,
                 const float* __restrict__ gl, const float* __restrict__ losses, int B, int K, uint32_t flags,
@@ -462,9 +462,17 @@ struct Mat {
 // D[b] (M x N) = sum_p A_p B_p, written with (row, col) strides.  Tensor-core engine when the layout
 // satisfies the TMA constraints, FP32-pipe batched GEMM otherwise (shape generality, not a second backend:
 // both paths live in this library and compute the same product).
+struct EwHook {  // fused element-wise terms of dS (tc::GemmProblem::ew_*); *applied is set when the engine took it
+  const void* S = nullptr;
+  const float* d = nullptr;
+  const float* coef = nullptr;
+  float eps = 0.f;
+  bool* applied = nullptr;
+};
+
 template <typename T, typename TC>
 static int mm(int batch, int M, int N, int npairs, const int* kd, const Mat* A, const Mat* Bm, TC* out, int64_t obs,
-              int64_t ors, int64_t ocs, cudaStream_t st) {
+              int64_t ors, int64_t ocs, cudaStream_t st, EwHook hook = EwHook()) {
   tc::GemmProblem p;
   memset(&p, 0, sizeof(p));
   p.batch = batch, p.M = M, p.N = N, p.num_pairs = npairs;
@@ -477,7 +485,13 @@ static int mm(int batch, int M, int N, int npairs, const int* kd, const Mat* A, 
   p.alpha = 1.f, p.accumulate = 0;
   p.out_bf16 = std::is_same<TC, __nv_bfloat16>::value;
   p.in_bf16 = std::is_same<T, __nv_bfloat16>::value;
-  if (tc::gemm_supported(p)) return tc::gemm(p, st);
+  if (tc::gemm_supported(p)) {
+    if (hook.S && ocs == 1 && ors == N) {
+      p.ew_S = hook.S, p.ew_d = hook.d, p.ew_coef = hook.coef, p.ew_eps = hook.eps;
+      if (hook.applied) *hook.applied = true;
+    }
+    return tc::gemm(p, st);
+  }
   if (ocs != 1) {  // transposed output: D^T = B^T A^T has unit column stride
     if (ors != 1) return TGPB200_ERR_UNSUPPORTED;
     return mm<T, TC>(batch, N, M, npairs, kd, Bm, A, out, obs, ocs, ors, st);
@@ -570,7 +584,7 @@ static int dense_fwd(const T* A, const T* S, const T* X, int B, int N, int K, in
     if (rc) return rc;
   }
   if (B > 0) {
-    launch("k_graph_epilogue", k_graph_epilogue<T>, B, 256, (size_t)K * sizeof(float), st,
+    launch("k_graph_epilogue", k_graph_epilogue<T>, B, K * K >= 2048 ? 1024 : 256, (size_t)K * sizeof(float), st,
            A ? pl.Araw : (float*)nullptr, loss_kind != 0 ? pl.M : (float*)nullptr, pl.d, pl.ss, pl.a2, pl.ent, N, K,
            flags, eps, Apool, pl.dvec, pl.stats, pl.argmax);
     launch("k_finalize_losses", k_finalize_losses, 1, 256, 0, st, pl.stats, B, eps, link_div, ent_div, pl.losses);
@@ -599,7 +613,7 @@ static int dense_bwd(const T* A, const T* S, const T* X, const T* gXpool, const 
   const bool have_a = A != nullptr;
   const bool f32 = std::is_same<T, float>::value;
   if (have_a) {
-    launch("k_graph_bwd", k_graph_bwd<T>, B, 256, (size_t)3 * K * sizeof(float), st, pl.Araw,
+    launch("k_graph_bwd", k_graph_bwd<T>, B, K * K >= 2048 ? 1024 : 256, (size_t)3 * K * sizeof(float), st, pl.Araw,
            loss_kind != 0 ? pl.M : (float*)nullptr, gApool, pl.dvec, pl.stats, pl.argmax, gl, pl.losses, B, K, flags,
            loss_kind, eps, link_div, ent_div, Graw, loss_kind != 0 ? P : (float*)nullptr, coef);
     if (f32) {
@@ -620,7 +634,9 @@ static int dense_bwd(const T* A, const T* S, const T* X, const T* gXpool, const 
     rc = mm1<T, T>(B, N, K, N, Mat{A, NN, N, 0}, Mat{S, NK, K, 1}, W, NK, K, 1, st);
     if (rc) return rc;
   }
-  // dS = X Gx^T + W Graw^T + T^T Graw + S P   (one accumulation chain in TMEM)
+  // dS = X Gx^T + W Graw^T + T^T Graw + S P   (one accumulation chain in TMEM; the element-wise loss terms
+  // are added in the same epilogue when the tensor-core engine runs the product)
+  bool ew_done = false;
   {
     int kd[4];
     Mat a[4], b[4];
@@ -632,13 +648,17 @@ static int dense_bwd(const T* A, const T* S, const T* X, const T* gXpool, const 
       if (loss_kind != 0) { kd[n] = K; a[n] = Mat{S, NK, K, 0}; b[n] = Mat{Pt, KK, K, 1}; ++n; }
     }
     if (n > 0) {
-      rc = mm<T, T>(B, N, K, n, kd, a, b, dS_out, NK, K, 1, st);
+      EwHook hook;
+      if (have_a && loss_kind != 0) {
+        hook.S = S, hook.d = pl.d, hook.coef = coef, hook.eps = eps, hook.applied = &ew_done;
+      }
+      rc = mm<T, T>(B, N, K, n, kd, a, b, dS_out, NK, K, 1, st, hook);
       if (rc) return rc;
     } else {
       cudaMemsetAsync(dS_out, 0, (size_t)B * NK * sizeof(T), st);
     }
   }
-  if (have_a && loss_kind != 0)
+  if (have_a && loss_kind != 0 && !ew_done)
     launch("k_ds_elementwise", k_ds_elementwise<T>, (unsigned)ceil_div((int64_t)B * NK, 256), 256, 0, st, S, pl.d, coef,
            (int64_t)B * NK, N, K, eps, dS_out);
   if (have_a && dA_out) {  // dA = (S Graw) S^T + element-wise terms

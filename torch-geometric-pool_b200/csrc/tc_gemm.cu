@@ -27,6 +27,10 @@ struct KernelParams {
   float alpha;
   int accumulate, out_bf16;
   int skip_lo_b_mask;
+  const void* ew_S;
+  const float* ew_d;
+  const float* ew_coef;
+  float ew_eps;
 };
 
 constexpr int kThreads = 320;
@@ -211,49 +215,116 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
       uint32_t aph = (uint32_t)(it >> 1) & 1u;
       mbar_wait(bar_tfull(ab), aph);
       tc_fence_after();
-      const int m = mt * BM + quad * 32 + lane;
+      const int m_base = mt * BM + quad * 32;
+      const int m = m_base + lane;
       const int64_t obase = (int64_t)b * P.out_bs + (int64_t)m * P.out_rs;
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
         uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN + c0);
         tmem_ld32(taddr, v);
         const int n0 = nt * BN + c0;
-        if (m < P.M && n0 < P.N) {
-          if (P.out_bf16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out);
+        if (n0 >= P.N || m_base >= P.M) continue;  // warp-uniform
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (n0 + j < P.N) {
-                int64_t idx = obase + (int64_t)(n0 + j) * P.out_cs;
-                float r = P.alpha * v[j];
-                if (P.accumulate) r += __bfloat162float(o[idx]);
-                o[idx] = __float2bfloat16_rn(r);
+        for (int j = 0; j < 32; ++j) v[j] *= P.alpha;
+        if (P.out_cs == 1) {
+          // Row-major destination: every thread owns one row and moves its 32 values as 8 x 128-bit accesses
+          // (fewer instructions than a shared-memory transposition, which measured slower).
+          if (m < P.M) {
+            const bool full = n0 + 32 <= P.N;
+            if (P.ew_S != nullptr) {
+              // fused element-wise gradient terms of the dense backward (see GemmProblem::ew_*)
+              const float c_den = P.ew_coef[b * 4 + 0], c_ent = P.ew_coef[b * 4 + 2];
+              if (c_den != 0.f || c_ent != 0.f) {
+                const float dd = 2.f * c_den * P.ew_d[(int64_t)b * P.M + m];
+                const int64_t si = ((int64_t)b * P.M + m) * P.N + n0;
+                float sv[32];
+                if (kF32 && full && ((si & 3) == 0)) {
+                  const float4* s4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(P.ew_S) + si);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    float4 t4 = __ldg(s4 + j);
+                    sv[4 * j] = t4.x, sv[4 * j + 1] = t4.y, sv[4 * j + 2] = t4.z, sv[4 * j + 3] = t4.w;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    sv[j] = (n0 + j < P.N)
+                                ? (kF32 ? reinterpret_cast<const float*>(P.ew_S)[si + j]
+                                        : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.ew_S)[si + j]))
+                                : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  float add = dd * sv[j];
+                  if (c_ent != 0.f) add += c_ent * (-logf(sv[j] + P.ew_eps) - sv[j] / (sv[j] + P.ew_eps));
+                  v[j] += add;
+                }
               }
             }
-          } else {
-            float* o = reinterpret_cast<float*>(P.out);
-            const bool vec = P.out_cs == 1 && n0 + 32 <= P.N && (((obase + n0) & 3) == 0);
-            if (vec) {
-              float4* o4 = reinterpret_cast<float4*>(o + obase + n0);
+            if (!P.out_bf16 && full && (((obase + n0) & 3) == 0)) {
+              float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + obase + n0);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                float4 r = make_float4(P.alpha * v[4 * j], P.alpha * v[4 * j + 1], P.alpha * v[4 * j + 2],
-                                       P.alpha * v[4 * j + 3]);
+                float4 r4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 if (P.accumulate) {
-                  float4 c = o4[j];
-                  r.x += c.x, r.y += c.y, r.z += c.z, r.w += c.w;
+                  float4 c4 = o4[j];
+                  r4.x += c4.x, r4.y += c4.y, r4.z += c4.z, r4.w += c4.w;
                 }
-                o4[j] = r;
+                o4[j] = r4;
+              }
+            } else if (P.out_bf16 && full && (((obase + n0) & 7) == 0)) {
+              uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + obase + n0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 pk;
+                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+                if (P.accumulate) {
+                  uint4 c4 = o4[j];
+                  const __nv_bfloat162* c2 = reinterpret_cast<const __nv_bfloat162*>(&c4);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    float2 f = __bfloat1622float2(c2[q]);
+                    v[8 * j + 2 * q] += f.x, v[8 * j + 2 * q + 1] += f.y;
+                  }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) h2[q] = __floats2bfloat162_rn(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
+                o4[j] = pk;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 if (n0 + j < P.N) {
-                  int64_t idx = obase + (int64_t)(n0 + j) * P.out_cs;
-                  float r = P.alpha * v[j];
-                  if (P.accumulate) r += o[idx];
-                  o[idx] = r;
+                  const int64_t idx = obase + n0 + j;
+                  float val = v[j];
+                  if (P.out_bf16) {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out);
+                    if (P.accumulate) val += __bfloat162float(o[idx]);
+                    o[idx] = __float2bfloat16_rn(val);
+                  } else {
+                    float* o = reinterpret_cast<float*>(P.out);
+                    if (P.accumulate) val += o[idx];
+                    o[idx] = val;
+                  }
                 }
+              }
+            }
+          }
+        } else if (m < P.M) {
+          // strided destination (e.g. transposed output, out_rs == 1): lanes already walk the contiguous index
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (n0 + j < P.N) {
+              const int64_t idx = obase + (int64_t)(n0 + j) * P.out_cs;
+              float val = v[j];
+              if (P.out_bf16) {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out);
+                if (P.accumulate) val += __bfloat162float(o[idx]);
+                o[idx] = __float2bfloat16_rn(val);
+              } else {
+                float* o = reinterpret_cast<float*>(P.out);
+                if (P.accumulate) val += o[idx];
+                o[idx] = val;
               }
             }
           }
@@ -422,6 +493,7 @@ int gemm(const GemmProblem& p, cudaStream_t stream) {
   P.out = p.out, P.out_bs = p.out_batch_stride, P.out_rs = p.out_row_stride, P.out_cs = p.out_col_stride;
   P.alpha = p.alpha, P.accumulate = p.accumulate, P.out_bf16 = p.out_bf16;
   P.skip_lo_b_mask = p.skip_lo_b_mask;
+  P.ew_S = p.ew_S, P.ew_d = p.ew_d, P.ew_coef = p.ew_coef, P.ew_eps = p.ew_eps;
   const size_t smem = stage_bytes * stages + (3 * stages + 4) * 8 + 16 + 1024;
   int grid = P.num_items < num_sms ? P.num_items : num_sms;
   if (bf16)

@@ -47,6 +47,13 @@ struct GemmProblem {
   int out_bf16;
   int in_bf16;           // operand element type: 0 = fp32 (3xTF32), 1 = bf16
   int skip_lo_b_mask;    // bit p set: B_p is exactly representable in tf32 (lo pass skipped) -- optional hint
+  // Optional fused epilogue of the dense backward (out must be [M, N] row-major, M = nodes, N = clusters):
+  //   out[b, i, k] += c_den[b] * 2 * d[b, i] * S[b, i, k]  +  c_ent[b] * (-log(S + eps) - S / (S + eps))
+  // with coef[b*4 + 0] = c_den, coef[b*4 + 2] = c_ent (the mincut-denominator and entropy-loss gradients).
+  const void* ew_S;      // operand dtype, [batch, M, N]; nullptr = no element-wise term
+  const float* ew_d;     // [batch, M]
+  const float* ew_coef;  // [batch, 4]
+  float ew_eps;
 };
 
 // Enqueue on `stream`.  Returns TGPB200_ERR_UNSUPPORTED when the shape violates the TMA / UMMA constraints
