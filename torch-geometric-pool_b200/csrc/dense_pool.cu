@@ -137,14 +137,29 @@ static __global__ void __launch_bounds__(1024)
     k_graph_epilogue(const float* __restrict__ Araw, const float* __restrict__ M, const float* __restrict__ d,
                      const float* __restrict__ ss, const float* __restrict__ a2, const float* __restrict__ ent, int N,
                      int K, uint32_t flags, float eps, T* __restrict__ Apool, float* __restrict__ dvec,
-                     float* __restrict__ stats, int32_t* __restrict__ argmax) {
-  extern __shared__ float sm[];  // K floats: d_v
+                     float* __restrict__ stats, int32_t* __restrict__ argmax, int stage) {
+  extern __shared__ float sm[];  // K floats: d_v  (+ 2 K^2 floats when the matrices are staged)
   __shared__ float red[32];
   __shared__ int redi[32];
   int b = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
   const float* Ar = Araw ? Araw + (int64_t)b * K * K : nullptr;
+  const float* Mg = M ? M + (int64_t)b * K * K : nullptr;
   float* st = stats + (int64_t)b * 8;
+  if (stage) {  // the kernel is a chain of short block-wide passes: keep the [K,K] operands on chip
+    float* sA = sm + K;
+    float* sM = sA + K * K;
+    for (int i = t; i < K * K; i += nt) {
+      if (Ar) sA[i] = Ar[i];
+      if (Mg) sM[i] = Mg[i];
+    }
+    if (Ar) Ar = sA;
+    if (Mg) Mg = sM;
+    __syncthreads();
+  }
 
+  const int kshift = (K & (K - 1)) == 0 ? __ffs(K) - 1 : -1;
+  auto row_of = [&](int i) { return kshift >= 0 ? (i >> kshift) : (i / K); };
+  auto col_of = [&](int i, int r) { return kshift >= 0 ? (i & (K - 1)) : (i - r * K); };
   // den, ||A||^2, entropy (fixed-order block reductions)
   float den = 0.f, sa2 = 0.f, se = 0.f;
   for (int i = t; i < N; i += nt) {
@@ -162,13 +177,14 @@ static __global__ void __launch_bounds__(1024)
 
   float m2 = 0.f, ortho = 0.f;
   if (M) {
-    const float* Mb = M + (int64_t)b * K * K;
+    const float* Mb = Mg;
     for (int i = t; i < K * K; i += nt) m2 += Mb[i] * Mb[i];
     m2 = block_sum(m2, red);
     float nM = sqrtf(m2), isk = 1.0f / sqrtf((float)K);
     float u2 = 0.f;
     for (int i = t; i < K * K; i += nt) {
-      float u = Mb[i] / nM - ((i / K == i % K) ? isk : 0.f);
+      int r = row_of(i);
+      float u = Mb[i] / nM - ((r == col_of(i, r)) ? isk : 0.f);
       u2 += u * u;
     }
     ortho = sqrtf(block_sum(u2, red));
@@ -201,7 +217,7 @@ static __global__ void __launch_bounds__(1024)
   int amx = INT_MAX;
   T* Ap = Apool + (int64_t)b * K * K;
   for (int i = t; i < K * K; i += nt) {
-    int r = i / K, c = i % K;
+    int r = row_of(i), c = col_of(i, r);
     float v = (rsl && r == c) ? 0.f : Ar[i];
     if (dn) v = tr ? __fdiv_rn(__fdiv_rn(v, sm[c]), sm[r]) : __fdiv_rn(__fdiv_rn(v, sm[r]), sm[c]);
     if (wn) {
@@ -219,7 +235,7 @@ static __global__ void __launch_bounds__(1024)
     const float thr = bm * (1.f - 2e-6f);
     int cand = INT_MAX;
     for (int i = t; i < K * K; i += nt) {
-      int r = i / K, c = i % K;
+      int r = row_of(i), c = col_of(i, r);
       float v = (rsl && r == c) ? 0.f : Ar[i];
       if (dn) v = tr ? __fdiv_rn(__fdiv_rn(v, sm[c]), sm[r]) : __fdiv_rn(__fdiv_rn(v, sm[r]), sm[c]);
       if (fabsf(v) >= thr) { cand = i; break; }
@@ -238,7 +254,7 @@ static __global__ void __launch_bounds__(1024)
       argmax[b] = bm == 0.f ? -1 : cand;
     }
     for (int i = t; i < K * K; i += nt) {
-      int r = i / K, c = i % K;
+      int r = row_of(i), c = col_of(i, r);
       float v = (rsl && r == c) ? 0.f : Ar[i];
       if (dn) v = tr ? __fdiv_rn(__fdiv_rn(v, sm[c]), sm[r]) : __fdiv_rn(__fdiv_rn(v, sm[r]), sm[c]);
       Ap[i] = from_f32<T>(__fdiv_rn(v, m));
@@ -281,8 +297,8 @@ static __global__ void __launch_bounds__(1024)
                 const float* __restrict__ dvec, const float* __restrict__ stats, const int32_t* __restrict__ argmax,
                 const float* __restrict__ gl, const float* __restrict__ losses, int B, int K, uint32_t flags,
                 int loss_kind, float eps, float link_div, float ent_div, float* __restrict__ Graw,
-                float* __restrict__ P, float* __restrict__ coef) {
-  extern __shared__ float sm[];  // 3K floats: dsq[v], rowdot[v], coldot[v]
+                float* __restrict__ P, float* __restrict__ coef, int stage) {
+  extern __shared__ float sm[];  // 3K floats: dsq[v], rowdot[v], coldot[v]  (+ 2 K^2 staged floats)
   __shared__ float red[32];
   float* dsq = sm;
   float* rdot = sm + K;
@@ -290,6 +306,18 @@ static __global__ void __launch_bounds__(1024)
   int b = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
   const float* st = stats + (int64_t)b * 8;
   const float* Ar = Araw + (int64_t)b * K * K;
+  const float* Mst = M ? M + (int64_t)b * K * K : nullptr;
+  if (stage) {
+    float* sA = sm + 3 * K;
+    float* sM = sA + K * K;
+    for (int i = t; i < K * K; i += nt) {
+      sA[i] = Ar[i];
+      if (Mst) sM[i] = Mst[i];
+    }
+    Ar = sA;
+    if (Mst) Mst = sM;
+    __syncthreads();
+  }
   float* Gr = Graw + (int64_t)b * K * K;
   bool rsl = flags & TGPB200_REMOVE_SELF_LOOPS, dn = flags & TGPB200_DEGREE_NORM;
   bool tr = flags & TGPB200_ADJ_TRANSPOSE, wn = flags & TGPB200_EDGE_WEIGHT_NORM;
@@ -313,24 +341,32 @@ static __global__ void __launch_bounds__(1024)
     coef[b * 4 + 0] = c_den, coef[b * 4 + 1] = c_a2, coef[b * 4 + 2] = c_ent, coef[b * 4 + 3] = 0.f;
   }
 
+  // index split without an integer division when K is a power of two (the common case)
+  const int kshift = (K & (K - 1)) == 0 ? __ffs(K) - 1 : -1;
+  auto row_of = [&](int i) { return kshift >= 0 ? (i >> kshift) : (i / K); };
+  auto col_of = [&](int i, int r) { return kshift >= 0 ? (i & (K - 1)) : (i - r * K); };
+
   // --- P = dL/dM + transpose  (M symmetric so both terms are symmetric)
   if (P) {
     float* Pb = P + (int64_t)b * K * K;
-    const float* Mb = M + (int64_t)b * K * K;
+    const float* Mb = Mst;
     if (loss_kind == 1) {
-      float nM = sqrtf(st[2]), r = st[3], isk = 1.0f / sqrtf((float)K);
+      const float nM = sqrtf(st[2]), rr = st[3], isk = 1.0f / sqrtf((float)K), inM = 1.0f / nM;
       // <U, M> with U = M/nM - I/sqrt(K)
       float um = 0.f;
       for (int i = t; i < K * K; i += nt) {
-        float u = Mb[i] / nM - ((i / K == i % K) ? isk : 0.f);
+        int r = row_of(i);
+        float u = Mb[i] * inM - ((r == col_of(i, r)) ? isk : 0.f);
         um += u * Mb[i];
       }
       um = block_sum(um, red);
-      float go = g_ortho / (float)B;
+      const float go = g_ortho / (float)B;
+      // dM = go * (U/r - <U,M>/r * M/nM^2) / nM
+      const float c1 = rr > 0.f ? 2.f * go / (rr * nM) : 0.f, c2 = rr > 0.f ? 2.f * go * um / (rr * nM * nM * nM) : 0.f;
       for (int i = t; i < K * K; i += nt) {
-        float u = Mb[i] / nM - ((i / K == i % K) ? isk : 0.f);
-        float dM = (r > 0.f) ? go * (u / r - (um / r) * Mb[i] / (nM * nM)) / nM : 0.f;
-        Pb[i] = 2.f * dM;
+        int r = row_of(i);
+        float u = Mb[i] * inM - ((r == col_of(i, r)) ? isk : 0.f);
+        Pb[i] = c1 * u - c2 * Mb[i];
       }
     } else {
       for (int i = t; i < K * K; i += nt) Pb[i] = 4.f * c_m2 * Mb[i];
@@ -339,43 +375,52 @@ static __global__ void __launch_bounds__(1024)
 
   // --- Graw from Gpool
   if (Gpool == nullptr) {
-    for (int i = t; i < K * K; i += nt) Gr[i] = (i / K == i % K) ? c_num : 0.f;
+    for (int i = t; i < K * K; i += nt) {
+      int r = row_of(i);
+      Gr[i] = (r == col_of(i, r)) ? c_num : 0.f;
+    }
     return;
   }
   const T* Gp = Gpool + (int64_t)b * K * K;
+  // dsq holds 1 / d_v = 1 / sqrt(clamp(s_v, eps)): the gradient assembly multiplies by reciprocals (the kernel
+  // was bound by IEEE divisions); results agree with the divided form to ~1 ulp.
   if (dn)
-    for (int v = t; v < K; v += nt) dsq[v] = sqrtf(fmaxf(dvec[(int64_t)b * K + v], eps));
+    for (int v = t; v < K; v += nt) dsq[v] = 1.0f / sqrtf(fmaxf(dvec[(int64_t)b * K + v], eps));
   __syncthreads();
+  const float im = 1.0f / m;
   // A2 = normalised matrix before max-norm; G2 = grad wrt A2
   float corr = 0.f;  // sum G * A2 (for the max-norm arg term)
   if (wn && m != 0.f) {
     for (int i = t; i < K * K; i += nt) {
-      int r = i / K, c = i % K;
+      int r = row_of(i), c = col_of(i, r);
       float v = (rsl && r == c) ? 0.f : Ar[i];
-      if (dn) v = v / (dsq[r] * dsq[c]);
+      if (dn) v = v * (dsq[r] * dsq[c]);
       corr += to_f32<T>(Gp[i]) * v;
     }
     corr = block_sum(corr, red);
   }
-  int am = wn ? argmax[b] : -1;
+  const int am = wn ? argmax[b] : -1;
+  const float argterm = -corr * im * im;
   // row / column dot products  rdot[v] = sum_j G2[v,j] A2[v,j],  cdot[v] = sum_i G2[i,v] A2[i,v]
   if (dn) {
     int lane = t & 31, w = t >> 5, nw = nt >> 5;
     for (int v = w; v < K; v += nw) {
       float sr = 0.f, sc = 0.f;
+      const float iv = dsq[v];
       for (int u = lane; u < K; u += 32) {
+        const float ivu = iv * dsq[u];
         {
           int i = v * K + u;
-          float a = (rsl && u == v) ? 0.f : Ar[i] / (dsq[v] * dsq[u]);
-          float g = to_f32<T>(Gp[i]) / m;
-          if (i == am) g += (a < 0.f ? -1.f : 1.f) * (-corr / (m * m));
+          float a = (rsl && u == v) ? 0.f : Ar[i] * ivu;
+          float g = to_f32<T>(Gp[i]) * im;
+          if (i == am) g += (a < 0.f ? -argterm : argterm);
           sr += g * a;
         }
         {
           int i = u * K + v;
-          float a = (rsl && u == v) ? 0.f : Ar[i] / (dsq[v] * dsq[u]);
-          float g = to_f32<T>(Gp[i]) / m;
-          if (i == am) g += (a < 0.f ? -1.f : 1.f) * (-corr / (m * m));
+          float a = (rsl && u == v) ? 0.f : Ar[i] * ivu;
+          float g = to_f32<T>(Gp[i]) * im;
+          if (i == am) g += (a < 0.f ? -argterm : argterm);
           sc += g * a;
         }
       }
@@ -385,22 +430,20 @@ static __global__ void __launch_bounds__(1024)
   }
   __syncthreads();
   for (int i = t; i < K * K; i += nt) {
-    int r = i / K, c = i % K;
-    float g = to_f32<T>(Gp[i]) / m;
+    int r = row_of(i), c = col_of(i, r);
+    float g = to_f32<T>(Gp[i]) * im;
     if (wn && i == am) {
       float a = (rsl && r == c) ? 0.f : Ar[i];
-      if (dn) a = a / (dsq[r] * dsq[c]);
-      g += (a < 0.f ? -1.f : 1.f) * (-corr / (m * m));
+      if (dn) a = a * (dsq[r] * dsq[c]);
+      g += (a < 0.f ? -argterm : argterm);
     }
     float out = g;
     if (dn) {
-      out = g / (dsq[r] * dsq[c]);
+      out = g * (dsq[r] * dsq[c]);
       int v = tr ? c : r;  // s_v is a column sum (transpose) or a row sum
       float sv = dvec[(int64_t)b * K + v];
-      if (sv >= eps) {
-        float dd = -(rdot[v] + cdot[v]) / dsq[v];  // dL/d d_v
-        out += dd / (2.f * dsq[v]);                // d d_v / d s_v
-      }
+      // dL/d d_v = -(rdot + cdot) / d_v ;  d d_v / d s_v = 1 / (2 d_v)   (clamp passes the gradient for s_v >= eps)
+      if (sv >= eps) out += -0.5f * (rdot[v] + cdot[v]) * dsq[v] * dsq[v];
     }
     if (rsl && r == c) out = 0.f;
     if (r == c) out += c_num;
@@ -584,9 +627,16 @@ static int dense_fwd(const T* A, const T* S, const T* X, int B, int N, int K, in
     if (rc) return rc;
   }
   if (B > 0) {
-    launch("k_graph_epilogue", k_graph_epilogue<T>, B, K * K >= 2048 ? 1024 : 256, (size_t)K * sizeof(float), st,
+    const int stage_e = (size_t)(K + 2 * K * K) * sizeof(float) <= 160 * 1024;
+    const size_t smem_e = (size_t)(K + (stage_e ? 2 * K * K : 0)) * sizeof(float);
+    static bool attr_e = false;
+    if (!attr_e) {
+      attr_e = true;
+      cudaFuncSetAttribute(k_graph_epilogue<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024);
+    }
+    launch("k_graph_epilogue", k_graph_epilogue<T>, B, K * K >= 2048 ? 1024 : 256, smem_e, st,
            A ? pl.Araw : (float*)nullptr, loss_kind != 0 ? pl.M : (float*)nullptr, pl.d, pl.ss, pl.a2, pl.ent, N, K,
-           flags, eps, Apool, pl.dvec, pl.stats, pl.argmax);
+           flags, eps, Apool, pl.dvec, pl.stats, pl.argmax, stage_e);
     launch("k_finalize_losses", k_finalize_losses, 1, 256, 0, st, pl.stats, B, eps, link_div, ent_div, pl.losses);
     if (losses_out) cudaMemcpyAsync(losses_out, pl.losses, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st);
   }
@@ -613,9 +663,16 @@ static int dense_bwd(const T* A, const T* S, const T* X, const T* gXpool, const 
   const bool have_a = A != nullptr;
   const bool f32 = std::is_same<T, float>::value;
   if (have_a) {
-    launch("k_graph_bwd", k_graph_bwd<T>, B, K * K >= 2048 ? 1024 : 256, (size_t)3 * K * sizeof(float), st, pl.Araw,
+    const int stage_b = (size_t)(3 * K + 2 * K * K) * sizeof(float) <= 160 * 1024;
+    const size_t smem_b = (size_t)(3 * K + (stage_b ? 2 * K * K : 0)) * sizeof(float);
+    static bool attr_b = false;
+    if (!attr_b) {
+      attr_b = true;
+      cudaFuncSetAttribute(k_graph_bwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024);
+    }
+    launch("k_graph_bwd", k_graph_bwd<T>, B, K * K >= 2048 ? 1024 : 256, smem_b, st, pl.Araw,
            loss_kind != 0 ? pl.M : (float*)nullptr, gApool, pl.dvec, pl.stats, pl.argmax, gl, pl.losses, B, K, flags,
-           loss_kind, eps, link_div, ent_div, Graw, loss_kind != 0 ? P : (float*)nullptr, coef);
+           loss_kind, eps, link_div, ent_div, Graw, loss_kind != 0 ? P : (float*)nullptr, coef, stage_b);
     if (f32) {
       Gt = reinterpret_cast<T*>(Graw);
       Pt = reinterpret_cast<T*>(P);
