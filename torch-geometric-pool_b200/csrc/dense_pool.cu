@@ -198,17 +198,25 @@ static __global__ void __launch_bounds__(1024)
   bool tr = flags & TGPB200_ADJ_TRANSPOSE, wn = flags & TGPB200_EDGE_WEIGHT_NORM;
   // degree vector over the diag-zeroed matrix: s_v = column sum (adj_transpose) or row sum
   if (dn) {
-    int lane = t & 31, w = t >> 5, nw = nt >> 5;
-    for (int v = w; v < K; v += nw) {
-      float s = 0.f;
-      for (int u = lane; u < K; u += 32) {
-        if (rsl && u == v) continue;
-        s += tr ? Ar[(int64_t)u * K + v] : Ar[(int64_t)v * K + u];
-      }
-      s = warp_sum(s);
-      if (lane == 0) {
+    if (tr) {  // column sums: thread v walks column v, lanes read consecutive addresses of each row
+      for (int v = t; v < K; v += nt) {
+        float s = 0.f;
+        for (int u = 0; u < K; ++u)
+          if (!(rsl && u == v)) s += Ar[(int64_t)u * K + v];
         sm[v] = sqrtf(fmaxf(s, eps));
         dvec[(int64_t)b * K + v] = s;
+      }
+    } else {  // row sums: one warp per row
+      int lane = t & 31, w = t >> 5, nw = nt >> 5;
+      for (int v = w; v < K; v += nw) {
+        float s = 0.f;
+        for (int u = lane; u < K; u += 32)
+          if (!(rsl && u == v)) s += Ar[(int64_t)v * K + u];
+        s = warp_sum(s);
+        if (lane == 0) {
+          sm[v] = sqrtf(fmaxf(s, eps));
+          dvec[(int64_t)b * K + v] = s;
+        }
       }
     }
   }
@@ -297,7 +305,7 @@ static __global__ void __launch_bounds__(1024)
                 const float* __restrict__ dvec, const float* __restrict__ stats, const int32_t* __restrict__ argmax,
                 const float* __restrict__ gl, const float* __restrict__ losses, int B, int K, uint32_t flags,
                 int loss_kind, float eps, float link_div, float ent_div, float* __restrict__ Graw,
-                float* __restrict__ P, float* __restrict__ coef, int stage) {
+                float* __restrict__ P, float* __restrict__ coef, int stage, T* __restrict__ Gt, T* __restrict__ Pt) {
   extern __shared__ float sm[];  // 3K floats: dsq[v], rowdot[v], coldot[v]  (+ 2 K^2 staged floats)
   __shared__ float red[32];
   float* dsq = sm;
@@ -367,9 +375,13 @@ static __global__ void __launch_bounds__(1024)
         int r = row_of(i);
         float u = Mb[i] * inM - ((r == col_of(i, r)) ? isk : 0.f);
         Pb[i] = c1 * u - c2 * Mb[i];
+        if (Pt) Pt[(int64_t)b * K * K + i] = from_f32<T>(Pb[i]);
       }
     } else {
-      for (int i = t; i < K * K; i += nt) Pb[i] = 4.f * c_m2 * Mb[i];
+      for (int i = t; i < K * K; i += nt) {
+        Pb[i] = 4.f * c_m2 * Mb[i];
+        if (Pt) Pt[(int64_t)b * K * K + i] = from_f32<T>(Pb[i]);
+      }
     }
   }
 
@@ -378,6 +390,7 @@ static __global__ void __launch_bounds__(1024)
     for (int i = t; i < K * K; i += nt) {
       int r = row_of(i);
       Gr[i] = (r == col_of(i, r)) ? c_num : 0.f;
+      if (Gt) Gt[(int64_t)b * K * K + i] = from_f32<T>(Gr[i]);
     }
     return;
   }
@@ -404,28 +417,30 @@ static __global__ void __launch_bounds__(1024)
   // row / column dot products  rdot[v] = sum_j G2[v,j] A2[v,j],  cdot[v] = sum_i G2[i,v] A2[i,v]
   if (dn) {
     int lane = t & 31, w = t >> 5, nw = nt >> 5;
-    for (int v = w; v < K; v += nw) {
-      float sr = 0.f, sc = 0.f;
+    for (int v = w; v < K; v += nw) {  // row dots: one warp per row
+      float sr = 0.f;
       const float iv = dsq[v];
       for (int u = lane; u < K; u += 32) {
-        const float ivu = iv * dsq[u];
-        {
-          int i = v * K + u;
-          float a = (rsl && u == v) ? 0.f : Ar[i] * ivu;
-          float g = to_f32<T>(Gp[i]) * im;
-          if (i == am) g += (a < 0.f ? -argterm : argterm);
-          sr += g * a;
-        }
-        {
-          int i = u * K + v;
-          float a = (rsl && u == v) ? 0.f : Ar[i] * ivu;
-          float g = to_f32<T>(Gp[i]) * im;
-          if (i == am) g += (a < 0.f ? -argterm : argterm);
-          sc += g * a;
-        }
+        int i = v * K + u;
+        float a = (rsl && u == v) ? 0.f : Ar[i] * (iv * dsq[u]);
+        float g = to_f32<T>(Gp[i]) * im;
+        if (i == am) g += (a < 0.f ? -argterm : argterm);
+        sr += g * a;
       }
-      sr = warp_sum(sr), sc = warp_sum(sc);
-      if (lane == 0) rdot[v] = sr, cdot[v] = sc;
+      sr = warp_sum(sr);
+      if (lane == 0) rdot[v] = sr;
+    }
+    for (int v = t; v < K; v += nt) {  // column dots: thread v walks column v (coalesced across the warp)
+      float sc = 0.f;
+      const float iv = dsq[v];
+      for (int u = 0; u < K; ++u) {
+        int i = u * K + v;
+        float a = (rsl && u == v) ? 0.f : Ar[i] * (iv * dsq[u]);
+        float g = to_f32<T>(Gp[i]) * im;
+        if (i == am) g += (a < 0.f ? -argterm : argterm);
+        sc += g * a;
+      }
+      cdot[v] = sc;
     }
   }
   __syncthreads();
@@ -448,6 +463,7 @@ static __global__ void __launch_bounds__(1024)
     if (rsl && r == c) out = 0.f;
     if (r == c) out += c_num;
     Gr[i] = out;
+    if (Gt) Gt[(int64_t)b * K * K + i] = from_f32<T>(out);
   }
 }
 
@@ -672,14 +688,11 @@ static int dense_bwd(const T* A, const T* S, const T* X, const T* gXpool, const 
     }
     launch("k_graph_bwd", k_graph_bwd<T>, B, K * K >= 2048 ? 1024 : 256, smem_b, st, pl.Araw,
            loss_kind != 0 ? pl.M : (float*)nullptr, gApool, pl.dvec, pl.stats, pl.argmax, gl, pl.losses, B, K, flags,
-           loss_kind, eps, link_div, ent_div, Graw, loss_kind != 0 ? P : (float*)nullptr, coef, stage_b);
+           loss_kind, eps, link_div, ent_div, Graw, loss_kind != 0 ? P : (float*)nullptr, coef, stage_b,
+           f32 ? (T*)nullptr : Gt, (f32 || loss_kind == 0) ? (T*)nullptr : Pt);
     if (f32) {
       Gt = reinterpret_cast<T*>(Graw);
       Pt = reinterpret_cast<T*>(P);
-    } else {
-      launch("k_cast_out", k_cast_out<T>, (unsigned)ceil_div((int64_t)B * KK, 256), 256, 0, st, Graw, Gt, (int64_t)B * KK);
-      if (loss_kind != 0)
-        launch("k_cast_out", k_cast_out<T>, (unsigned)ceil_div((int64_t)B * KK, 256), 256, 0, st, P, Pt, (int64_t)B * KK);
     }
   }
   const bool have_x = X && gXpool;

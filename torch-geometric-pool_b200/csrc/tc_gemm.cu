@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                   float add = dd * sv[j];
-                  if (c_ent != 0.f) add += c_ent * (-logf(sv[j] + P.ew_eps) - sv[j] / (sv[j] + P.ew_eps));
+                  if (c_ent != 0.f) add += c_ent * (-__logf(sv[j] + P.ew_eps) - __fdividef(sv[j], sv[j] + P.ew_eps));
                   v[j] += add;
                 }
               }
