@@ -53,7 +53,7 @@ class OracleSelectOutput:
             cluster_index = cluster_index[perm]
             values = weight[perm] if weight is not None else torch.ones(node_index.numel())
             s = torch.sparse_coo_tensor(
-                torch.stack([node_index, cluster_index]), values, (num_nodes, num_supernodes), is_coalesced=True
+                torch.stack([node_index, cluster_index]), values, (num_nodes, num_supernodes), is_coalesced=True, check_invariants=False
             )
         elif s.is_sparse:
             s = s.coalesce()

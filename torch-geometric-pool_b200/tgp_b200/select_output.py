@@ -34,7 +34,7 @@ def cluster_to_s(
     cluster_index = cluster_index[perm]
     indices = torch.stack([node_index, cluster_index], dim=0)
     values = weight[perm] if weight is not None else torch.ones(indices.size(1), device=indices.device)
-    return torch.sparse_coo_tensor(indices, values, (num_nodes, num_supernodes), is_coalesced=True)
+    return torch.sparse_coo_tensor(indices, values, (num_nodes, num_supernodes), is_coalesced=True, check_invariants=False)
 
 
 class SelectOutput:
