@@ -214,6 +214,19 @@ int tgpb200_tc_gemm(const void* a, const void* b, void* out, int64_t batch, int6
                     int64_t out_col_stride, int in_dtype, int out_dtype, float alpha, int accumulate,
                     tgpb200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * TopK selection (producer of the kept-node SelectOutput):
+ * TopkSelect.forward  tgp/select/topk_select.py:194-203 (PyG topk, ratio mode) + the ascending node sort of
+ * cluster_to_s  tgp/select/base_select.py:56-60.  Per graph the top ceil(ratio * n_g) scores (int(ratio) when
+ * ratio >= 1), descending, ties -> lower node id.  Outputs (capacity N): node_index ascending and
+ * cluster_index[j] = rank of node_index[j] in (graph asc, score desc) order; *count_out = K.
+ * batch may be NULL (one graph).  score is fp32.
+ * ------------------------------------------------------------------------------------------ */
+size_t tgpb200_topk_select_workspace_bytes(int64_t num_nodes, int64_t num_graphs);
+int tgpb200_topk_select(const float* score, const int64_t* batch, int64_t num_nodes, int64_t num_graphs, float ratio,
+                        int64_t* node_index, int64_t* cluster_index, int64_t* count_out, void* workspace,
+                        size_t workspace_bytes, tgpb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -402,3 +402,34 @@ def test_dense_connect_hand_matrix():
     out = T.B200DenseConnect().dense_connect(adj=adj, s=s)
     assert out.shape == (1, 2, 2)
     assert torch.equal(out[0].cpu(), torch.tensor([[4.0, 4.0], [4.0, 0.0]]))
+
+
+# --------------------------------------------------------------------------- #
+# TopK selection (bit-exact)
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("N,G,ratio", [(6, 1, 0.5), (1000, 7, 0.5), (5000, 128, 0.3), (200_000, 1, 0.5), (50_000, 64, 3)])
+def test_topk_select_bit_exact(N, G, ratio):
+    g = torch.Generator().manual_seed(N + G)
+    batch = torch.sort(torch.randint(0, G, (N,), generator=g))[0]
+    batch[0], batch[-1] = 0, G - 1
+    score = torch.tanh(torch.randn(N, generator=g))
+    score[torch.randint(0, N, (N // 10,), generator=g)] = 0.25  # many exact ties
+    score[:3] = torch.tensor([0.0, -0.0, 0.0])[: min(3, N)]
+    so_c = R.topk_select(score, None, ratio, batch, act=lambda v: v)
+    ni, ci = T.topk(score.to(DEV), ratio, batch.to(DEV))
+    assert torch.equal(ni.cpu(), so_c.node_index)
+    assert torch.equal(ci.cpu(), so_c.cluster_index)
+    so_g = T.topk_select(score.to(DEV), None, ratio, batch.to(DEV), act="linear")
+    assert torch.equal(so_g.weight.cpu(), so_c.weight) and so_g.num_supernodes == so_c.num_supernodes
+
+
+def test_topk_reference_pins():
+    # tests/poolers/test_topk.py:22-34 (scores 1..5, ratio .5 -> {2,3,4}) and :60-63 (k = ceil(0.5 * 6) = 3)
+    so = T.topk_select(torch.arange(1.0, 6.0, device=DEV).unsqueeze(-1), None, 0.5, None, act="linear")
+    assert torch.equal(so.node_index.sort(descending=True)[0].cpu(), torch.tensor([4, 3, 2]))
+    x = torch.randn(6, 4, device=DEV)
+    p = torch.randn(1, 4, device=DEV, requires_grad=True)
+    so = T.topk_select(x, p, 0.5)
+    assert so.num_supernodes == 3
+    so.weight.sum().backward()
+    assert p.grad is not None and torch.isfinite(p.grad).all()

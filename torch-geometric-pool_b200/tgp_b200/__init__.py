@@ -3,10 +3,11 @@ from . import functional
 from .connect import B200DenseConnect, B200SparseConnect, Connect, sparse_connect
 from .poolers import diff_pool, mincut_pool, patch_pooler, sparse_pool
 from .reduce import B200Reduce, Reduce
+from .select import topk, topk_select
 from .select_output import SelectOutput, cluster_to_s
 
 __all__ = [
     "functional", "B200Reduce", "B200SparseConnect", "B200DenseConnect", "Reduce", "Connect", "SelectOutput",
-    "cluster_to_s", "sparse_connect", "mincut_pool", "diff_pool", "sparse_pool", "patch_pooler",
+    "cluster_to_s", "topk", "topk_select", "sparse_connect", "mincut_pool", "diff_pool", "sparse_pool", "patch_pooler",
 ]
 __version__ = "0.1.0"

@@ -58,6 +58,8 @@ SIGNATURES = {
         _INT,
         [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _INT, _I64, _I64, _INT, _I64, _I64, _I64, _INT, _INT, _F, _INT, _P],
     ),
+    "tgpb200_topk_select_workspace_bytes": (_SZ, [_I64, _I64]),
+    "tgpb200_topk_select": (_INT, [_P, _P, _I64, _I64, _F, _P, _P, _P, _P, _SZ, _P]),
     "tgpb200_dense_pool_saved_bytes": (_SZ, [_I64, _I64, _I64]),
     "tgpb200_dense_pool_bwd_workspace_bytes": (_SZ, [_I64, _I64, _I64, _INT]),
     "tgpb200_dense_pool_fwd": (
