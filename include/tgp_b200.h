@@ -227,6 +227,41 @@ int tgpb200_topk_select(const float* score, const int64_t* batch, int64_t num_no
                         int64_t* node_index, int64_t* cluster_index, int64_t* count_out, void* workspace,
                         size_t workspace_bytes, tgpb200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Dense -> block-diagonal sparse output:
+ * dense_to_block_diag  tgp/utils/ops.py:53-82  fused with the masking / compact renumbering of
+ * DenseSRCPooling._finalize_sparse_output  tgp/src.py:526-552.
+ * Keeps adj[b, r, c] with |a| > eps and (out_mask == NULL or out_mask[b, r] && out_mask[b, c]) in row-major
+ * (b, r, c) order; endpoints are b*K + r, or the compact id (exclusive scan of out_mask) when a mask is given.
+ * out_mask is a uint8 [B, K] array.  Two phases sharing one workspace; src_pos (int32, optional) records the
+ * flat position of every emitted entry for the backward (grad_adj = scatter of grad_weight, zero elsewhere).
+ * ------------------------------------------------------------------------------------------ */
+size_t tgpb200_block_diag_workspace_bytes(int64_t B, int64_t K);
+int tgpb200_block_diag_count(const void* adj, const uint8_t* out_mask, int64_t B, int64_t K, int dtype, float eps,
+                             int64_t* num_valid_out, int64_t* count_out, void* workspace, size_t workspace_bytes,
+                             tgpb200_stream_t stream);
+int tgpb200_block_diag_emit(const void* adj, const uint8_t* out_mask, int64_t B, int64_t K, int dtype, float eps,
+                            int64_t* out_row, int64_t* out_col, void* out_weight, int32_t* src_pos, void* workspace,
+                            size_t workspace_bytes, tgpb200_stream_t stream);
+int tgpb200_block_diag_bwd(const void* grad_weight, const int32_t* src_pos, int64_t num_edges, int64_t total, int dtype,
+                           void* grad_adj, tgpb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense pre-processing: DenseSRCPooling.preprocessing  tgp/src.py:434-450
+ *   graph_ptr:      ptr[b] = first node of graph b (batch sorted ascending), ptr[B] = N     (PyG cumsum of bincount)
+ *   to_dense_batch: x [N, F] -> [B, Nmax, F] zero padded, mask [B, Nmax] (uint8)            (PyG to_dense_batch)
+ *   to_dense_adj:   edges -> [B, Nmax, Nmax] fp32, duplicates summed, default weight 1.0,
+ *                   transpose != 0 writes A^T (src.py:442-443)                               (PyG to_dense_adj)
+ * ------------------------------------------------------------------------------------------ */
+int tgpb200_graph_ptr(const int64_t* batch, int64_t num_nodes, int64_t num_graphs, int32_t* ptr, void* workspace,
+                      size_t workspace_bytes, tgpb200_stream_t stream);
+int tgpb200_to_dense_batch(const void* x, const int64_t* batch, const int32_t* ptr, int64_t num_nodes, int64_t F,
+                           int64_t num_graphs, int64_t max_nodes, int dtype, void* out, uint8_t* mask,
+                           tgpb200_stream_t stream);
+int tgpb200_to_dense_adj(const int64_t* row, const int64_t* col, const float* w, const int64_t* batch,
+                         const int32_t* ptr, int64_t num_edges, int64_t num_graphs, int64_t max_nodes, int transpose,
+                         float* adj, tgpb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

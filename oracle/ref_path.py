@@ -514,3 +514,54 @@ def diff_pool(
         "entropy_loss": entropy_loss(s, num_nodes) * ent_loss_coeff,
     }
     return x_pool, adj_pool, loss
+
+
+# --------------------------------------------------------------------------- #
+# Sparse output of the dense poolers              tgp/src.py:500-557, tgp/utils/ops.py:85-132
+# --------------------------------------------------------------------------- #
+def out_mask_from_dense_s(s: Tensor) -> Tensor:
+    """get_mask_from_dense_s for [B, N, K] (ops.py:119-121)."""
+    return s.sum(dim=-2) > 0
+
+
+def finalize_sparse_output(x_pool: Tensor, adj_pool: Tensor, batch, batch_pooled, out_mask):
+    """DenseSRCPooling._finalize_sparse_output, src.py:500-557."""
+    B, K = adj_pool.size(0), adj_pool.size(1)
+    x_flat = x_pool.reshape(-1, x_pool.size(-1))
+    if batch_pooled is None and batch is not None:
+        batch_pooled = torch.arange(int(batch.max()) + 1).repeat_interleave(K)
+    if batch_pooled is None and B > 1:
+        batch_pooled = torch.arange(B).repeat_interleave(K)
+    if batch_pooled is None and out_mask is not None:
+        batch_pooled = torch.zeros(B * K, dtype=torch.long)
+    if out_mask is not None:
+        valid_flat = out_mask.reshape(-1)
+        valid_indices = valid_flat.nonzero(as_tuple=True)[0]
+        x_out = x_flat[valid_indices]
+        batch_pooled = batch_pooled[valid_flat]
+        adj_masked = adj_pool * out_mask.unsqueeze(-1).to(adj_pool.dtype) * out_mask.unsqueeze(-2).to(adj_pool.dtype)
+        ei, ew = dense_to_block_diag(adj_masked)
+        old_to_new = torch.full((B * K,), -1, dtype=torch.long)
+        old_to_new[valid_indices] = torch.arange(valid_indices.numel())
+        keep = (old_to_new[ei[0]] >= 0) & (old_to_new[ei[1]] >= 0)
+        ei = torch.stack([old_to_new[ei[0][keep]], old_to_new[ei[1][keep]]], 0)
+        ew = ew[keep]
+    else:
+        ei, ew = dense_to_block_diag(adj_pool)
+        x_out = x_flat
+    return x_out, ei, ew, batch_pooled
+
+
+def dense_connect_forward_unbatched(edge_index, edge_weight, batch, s, batch_pooled=None, remove_self_loops=True,
+                                    degree_norm=True, edge_weight_norm=False, sparse_output=False):
+    """DenseConnect._forward_unbatched_inputs, dense_conn.py:273-354."""
+    batch_size = 1 if batch is None else int(batch.max()) + 1
+    K = s.size(-1)
+    raw = dense_connect_unbatched(edge_index, edge_weight, batch, s, batch_size)
+    if not sparse_output:
+        return postprocess_adj_pool_dense(raw, remove_self_loops=remove_self_loops, degree_norm=degree_norm,
+                                          adj_transpose=False, edge_weight_norm=edge_weight_norm), None
+    ei, ew = dense_to_block_diag(raw)
+    return postprocess_adj_pool_sparse(ei, ew, num_nodes=batch_size * K, remove_self_loops=remove_self_loops,
+                                       degree_norm=degree_norm, edge_weight_norm=edge_weight_norm,
+                                       batch_pooled=batch_pooled)

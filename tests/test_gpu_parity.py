@@ -433,3 +433,93 @@ def test_topk_reference_pins():
     assert so.num_supernodes == 3
     so.weight.sum().backward()
     assert p.grad is not None and torch.isfinite(p.grad).all()
+
+
+# --------------------------------------------------------------------------- #
+# sparse output of dense poolers, dense pre-processing
+# --------------------------------------------------------------------------- #
+def test_block_diag_and_finalize_sparse_output():
+    g = torch.Generator().manual_seed(4)
+    B, N, K, F = 5, 20, 6, 7
+    s = torch.softmax(torch.randn(B, N, K, generator=g), -1)
+    s[:, :, 4] = 0.0          # an empty supernode in every graph
+    s[2, :, 1] = 0.0
+    adj_pool = torch.randn(B, K, K, generator=g)
+    adj_pool[0, 1, 2] = 1e-9  # below eps
+    x_pool = torch.randn(B, K, F, generator=g)
+    mask = R.out_mask_from_dense_s(s)
+    for m in (None, mask):
+        ap = adj_pool.clone().requires_grad_(True)
+        exp = R.finalize_sparse_output(x_pool, ap, None, None, m)
+        (exp[2] * torch.arange(1, exp[2].numel() + 1)).sum().backward()
+        ag = adj_pool.clone().to(DEV).requires_grad_(True)
+        got = F_.finalize_sparse_output(x_pool.to(DEV), ag, None, None, None if m is None else m.to(DEV))
+        (got[2] * torch.arange(1, got[2].numel() + 1, device=DEV)).sum().backward()
+        assert torch.equal(got[1].cpu(), exp[1])
+        assert torch.equal(got[2].detach().cpu(), exp[2].detach())
+        assert torch.equal(got[0].cpu(), exp[0]) and torch.equal(got[3].cpu(), exp[3])
+        assert torch.equal(ag.grad.cpu(), ap.grad)
+    ei, ew = F_.dense_to_block_diag(torch.zeros(2, 3, 3, device=DEV))
+    assert ei.shape == (2, 0) and ew.shape == (0,)
+
+
+def test_dense_preprocessing_matches_pyg_semantics():
+    from oracle import pyg_shim as pyg
+
+    g = torch.Generator().manual_seed(8)
+    sizes = [5, 9, 1, 7]
+    batch = torch.cat([torch.full((n,), i) for i, n in enumerate(sizes)])
+    N = batch.numel()
+    x = torch.randn(N, 6, generator=g)
+    eis, off = [], 0
+    for n in sizes:
+        eis.append(torch.randint(0, n, (2, 3 * n), generator=g) + off)
+        off += n
+    ei = torch.cat(eis, 1)
+    ew = torch.rand(ei.size(1), generator=g)
+    xd, m = pyg.to_dense_batch(x, batch)
+    xg, mg = F_.to_dense_batch(x.to(DEV), batch.to(DEV))
+    assert torch.equal(xg.cpu(), xd) and torch.equal(mg.cpu(), m)
+    for w in (None, ew):
+        ad = pyg.to_dense_adj(ei, batch, w)
+        ag = F_.to_dense_adj(ei.to(DEV), batch.to(DEV), _cu(w))
+        torch.testing.assert_close(ag.cpu(), ad, rtol=1e-6, atol=1e-6)
+        agt = F_.to_dense_adj(ei.to(DEV), batch.to(DEV), _cu(w), transpose=True)
+        torch.testing.assert_close(agt.cpu(), ad.transpose(1, 2), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("sparse_output", [False, True])
+def test_unbatched_dense_mode_matches_oracle_and_batched(sparse_output):
+    # tests/poolers/test_dense_poolers_batched_vs_unbatched.py:36-174: batched == unbatched (rtol 1e-5)
+    g = torch.Generator().manual_seed(12)
+    sizes = [12, 20, 7]
+    K, F = 4, 5
+    batch = torch.cat([torch.full((n,), i) for i, n in enumerate(sizes)])
+    N = batch.numel()
+    eis, off = [], 0
+    for n in sizes:
+        up = torch.triu(torch.rand(n, n, generator=g) < 0.4, 1)
+        r, c = up.nonzero(as_tuple=True)
+        eis.append(torch.cat([torch.stack([r, c]), torch.stack([c, r])], 1) + off)
+        off += n
+    ei = torch.cat(eis, 1)
+    ew = torch.rand(ei.size(1), generator=g) + 0.5
+    s = torch.softmax(torch.randn(N, K, generator=g), -1)
+    x = torch.randn(N, F, generator=g)
+    bp = torch.arange(len(sizes)).repeat_interleave(K)
+    exp_a, exp_w = R.dense_connect_forward_unbatched(ei, ew, batch, s, bp, sparse_output=sparse_output)
+    so = T.SelectOutput(s=s.to(DEV), batch=batch.to(DEV))
+    conn = T.B200DenseConnect(adj_transpose=False, sparse_output=sparse_output)
+    got_a, got_w = conn(ei.to(DEV), so, edge_weight=ew.to(DEV), batch=batch.to(DEV), batch_pooled=bp.to(DEV))
+    if sparse_output:
+        assert torch.equal(got_a.cpu(), exp_a)
+        close32(got_w.cpu(), exp_w, "unbatched sparse weights")
+    else:
+        assert got_w is None
+        close32(got_a.cpu(), exp_a, "unbatched dense adj")
+    exp_x, exp_b = R.base_reduce(x, R.OracleSelectOutput(s=s), batch=batch)
+    got_x, got_b = T.B200Reduce()(x.to(DEV), so, batch=batch.to(DEV))
+    close32(got_x.cpu(), exp_x, "unbatched reduce")
+    assert torch.equal(got_b.cpu(), exp_b)
+    got_xb, _ = T.B200Reduce()(x.to(DEV), so, batch=batch.to(DEV), return_batched=True)
+    assert got_xb.shape == (len(sizes), K, F)

@@ -60,6 +60,13 @@ SIGNATURES = {
     ),
     "tgpb200_topk_select_workspace_bytes": (_SZ, [_I64, _I64]),
     "tgpb200_topk_select": (_INT, [_P, _P, _I64, _I64, _F, _P, _P, _P, _P, _SZ, _P]),
+    "tgpb200_block_diag_workspace_bytes": (_SZ, [_I64, _I64]),
+    "tgpb200_block_diag_count": (_INT, [_P, _P, _I64, _I64, _INT, _F, _P, _P, _P, _SZ, _P]),
+    "tgpb200_block_diag_emit": (_INT, [_P, _P, _I64, _I64, _INT, _F, _P, _P, _P, _P, _P, _SZ, _P]),
+    "tgpb200_block_diag_bwd": (_INT, [_P, _P, _I64, _I64, _INT, _P, _P]),
+    "tgpb200_graph_ptr": (_INT, [_P, _I64, _I64, _P, _P, _SZ, _P]),
+    "tgpb200_to_dense_batch": (_INT, [_P, _P, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P]),
+    "tgpb200_to_dense_adj": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _INT, _P, _P]),
     "tgpb200_dense_pool_saved_bytes": (_SZ, [_I64, _I64, _I64]),
     "tgpb200_dense_pool_bwd_workspace_bytes": (_SZ, [_I64, _I64, _I64, _INT]),
     "tgpb200_dense_pool_fwd": (

@@ -162,10 +162,7 @@ class B200DenseConnect(Connect):
     ):
         s = self._validate_select_output(so)
         if not is_dense_adj(edge_index):
-            raise NotImplementedError(
-                "tgp_b200: DenseConnect on unbatched sparse adjacency (batched=False mode) is not covered yet; "
-                "pass a dense [B, N, N] adjacency."
-            )
+            return self._forward_unbatched_inputs(edge_index, edge_weight, batch, s, batch_pooled)
         s, adj = self._prepare_batched_dense_inputs(s, edge_index)
         _, adj_pool, _ = F_.dense_pool(
             None,
@@ -177,6 +174,54 @@ class B200DenseConnect(Connect):
             edge_weight_norm=self.edge_weight_norm,
         )
         return adj_pool, None
+
+    def _forward_unbatched_inputs(self, edge_index, edge_weight, batch, s, batch_pooled):
+        """Sparse adjacency + dense ``[N, K]`` assignment (dense_conn.py:273-354).  The per-graph
+        ``sparse.mm`` loop of the reference becomes: scatter the edges into a padded ``[B, Nmax, Nmax]`` batch
+        (``to_dense_adj`` kernel) and run the batched tensor-core path; same values as the batched mode."""
+        to_coo = isinstance(edge_index, Tensor) and edge_index.is_sparse
+        if to_coo:
+            coo = edge_index.coalesce()
+            edge_index, edge_weight = coo.indices(), coo.values()
+        if s.dim() == 3:
+            if s.size(0) != 1:
+                raise ValueError(
+                    "[DenseConnect - unbatched]: SelectOutput.s must have shape "
+                    f"[N, K] or [1, N, K], but got {s.size()}."
+                )
+            s = s.squeeze(0)
+        elif s.dim() != 2:
+            raise ValueError(
+                "[DenseConnect - unbatched]: SelectOutput.s must have shape "
+                f"[N, K] or [1, N, K], but got {s.size()}."
+            )
+        num_nodes, K = s.size()
+        B = 1 if batch is None else int(batch.max().item()) + 1
+        b0 = batch if batch is not None else torch.zeros(num_nodes, dtype=torch.long, device=s.device)
+        s3, _ = F_.to_dense_batch(s, b0, B)
+        adj = F_.to_dense_adj(edge_index, b0, edge_weight, num_graphs=B, max_num_nodes=s3.size(1)).to(s.dtype)
+        if not self.sparse_output:
+            _, adj_pool, _ = F_.dense_pool(
+                None, adj, s3, remove_self_loops=self.remove_self_loops, degree_norm=self.degree_norm,
+                adj_transpose=False, edge_weight_norm=self.edge_weight_norm,
+            )
+            return adj_pool, None
+        if self.edge_weight_norm and batch_pooled is None:
+            raise AssertionError(
+                "edge_weight_norm=True but batch_pooled=None. "
+                "batch_pooled parameter is required for per-graph normalization in DenseConnect."
+            )
+        _, raw, _ = F_.dense_pool(None, adj, s3)
+        ei, ew = F_.dense_to_block_diag(raw)
+        n_super = B * K
+        flags = F_.L.REMOVE_SELF_LOOPS if self.remove_self_loops else 0
+        ident = torch.arange(n_super, device=s.device)
+        ei, ew = F_._FilterRelabel.apply(ew.to(torch.float32), ei[0].contiguous(), ei[1].contiguous(), ident, n_super,
+                                         flags, F_.EPS)
+        ew = F_.edge_postprocess(ei, ew, n_super, self.degree_norm, self.edge_weight_norm, batch_pooled)
+        if to_coo:
+            return torch.sparse_coo_tensor(ei, ew, (n_super, n_super)).coalesce(), None
+        return ei, ew
 
     def __repr__(self) -> str:
         return (

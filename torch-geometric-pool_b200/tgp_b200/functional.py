@@ -448,3 +448,136 @@ def dense_pool(
         raise RuntimeError("tgp_b200.dense_pool: x, adj and s must share one dtype")
     flags = dense_flags(remove_self_loops, degree_norm, adj_transpose, edge_weight_norm)
     return _DensePool.apply(x, adj, s, flags, loss_kind, float(link_div), float(ent_div))
+
+
+# --------------------------------------------------------------------------- #
+# Dense -> block-diagonal sparse output, dense pre-processing
+# --------------------------------------------------------------------------- #
+class _BlockDiag(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, adj_pool, out_mask, eps):
+        B, K = adj_pool.size(0), adj_pool.size(1)
+        dev = adj_pool.device
+        lib = L.load()
+        ws = L.workspace(lib.tgpb200_block_diag_workspace_bytes(B, K), dev)
+        counts = torch.zeros(2, dtype=torch.long, device=dev)
+        m8 = None if out_mask is None else out_mask.to(torch.uint8).contiguous()
+        dt = L.dtype_code(adj_pool.dtype)
+        L.call("tgpb200_block_diag_count", L.ptr(adj_pool), L.ptr(m8), B, K, dt, eps, L.ptr(counts[1:]), L.ptr(counts[:1]),
+               L.ptr(ws), ws.numel(), L.stream())
+        n_out = int(counts[0].item())
+        ei = torch.empty((2, n_out), dtype=torch.long, device=dev)
+        w = torch.empty(n_out, dtype=adj_pool.dtype, device=dev)
+        src = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev)
+        if n_out > 0:
+            L.call("tgpb200_block_diag_emit", L.ptr(adj_pool), L.ptr(m8), B, K, dt, eps, L.ptr(ei[0]), L.ptr(ei[1]),
+                   L.ptr(w), L.ptr(src), L.ptr(ws), ws.numel(), L.stream())
+        ctx.mark_non_differentiable(ei)
+        ctx.save_for_backward(src)
+        ctx.shape, ctx.n_out = adj_pool.shape, n_out
+        return ei, w
+
+    @staticmethod
+    def backward(ctx, _gei, gw):
+        (src,) = ctx.saved_tensors
+        gadj = torch.empty(ctx.shape, dtype=gw.dtype, device=gw.device)
+        L.call("tgpb200_block_diag_bwd", L.ptr(gw.contiguous()), L.ptr(src), ctx.n_out, gadj.numel(),
+               L.dtype_code(gw.dtype), L.ptr(gadj), L.stream())
+        return gadj, None, None
+
+
+def dense_to_block_diag(adj_pool: Tensor, out_mask: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """tgp/utils/ops.py:53-82 (+ the masking / compact renumbering of tgp/src.py:526-552 when ``out_mask``
+    [B, K] is given): entries with ``|a| > eps`` in row-major (b, i, j) order as a block-diagonal edge list."""
+    _require_cuda(adj_pool, out_mask)
+    if adj_pool.dim() == 2:
+        adj_pool = adj_pool.unsqueeze(0)
+    if adj_pool.dim() != 3:
+        raise ValueError("adj_pool must have shape [B, K, K] or [K, K].")
+    return _BlockDiag.apply(adj_pool.contiguous(), out_mask, EPS)
+
+
+def finalize_sparse_output(x_pool: Tensor, adj_pool: Tensor, batch: Optional[Tensor], batch_pooled: Optional[Tensor],
+                           out_mask: Optional[Tensor]):
+    """DenseSRCPooling._finalize_sparse_output (tgp/src.py:500-557) given ``so.out_mask``."""
+    B, K = adj_pool.size(0), adj_pool.size(1)
+    x_flat = x_pool.reshape(-1, x_pool.size(-1))
+    if batch_pooled is None and batch is not None and batch.numel() > 0:
+        batch_pooled = torch.arange(int(batch.max().item()) + 1, device=x_pool.device).repeat_interleave(K)
+    if batch_pooled is None and B > 1:
+        batch_pooled = torch.arange(B, device=x_pool.device).repeat_interleave(K)
+    if batch_pooled is None and out_mask is not None:
+        batch_pooled = torch.zeros(B * K, dtype=torch.long, device=x_pool.device)
+    edge_index, edge_weight = dense_to_block_diag(adj_pool, out_mask)
+    if out_mask is not None:
+        valid = out_mask.reshape(-1)
+        x_flat = x_flat[valid]
+        batch_pooled = batch_pooled[valid]
+    return x_flat, edge_index, edge_weight, batch_pooled
+
+
+def graph_ptr(batch: Tensor, num_graphs: int) -> Tensor:
+    ptr = torch.empty(num_graphs + 1, dtype=torch.int32, device=batch.device)
+    ws = L.workspace(4096 + 4 * (num_graphs + 2), batch.device)
+    L.call("tgpb200_graph_ptr", L.ptr(batch.contiguous()), batch.numel(), num_graphs, L.ptr(ptr), L.ptr(ws), ws.numel(),
+           L.stream())
+    return ptr
+
+
+class _ToDenseBatch(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, batch, ptr, B, Nmax):
+        N, F = x.shape
+        out = torch.empty((B, Nmax, F), dtype=x.dtype, device=x.device)
+        mask = torch.empty((B, Nmax), dtype=torch.uint8, device=x.device)
+        L.call("tgpb200_to_dense_batch", L.ptr(x), L.ptr(batch), L.ptr(ptr), N, F, B, Nmax, L.dtype_code(x.dtype),
+               L.ptr(out), L.ptr(mask), L.stream())
+        ctx.save_for_backward(batch, ptr)
+        ctx.Nmax = Nmax
+        ctx.mark_non_differentiable(mask)
+        return out, mask
+
+    @staticmethod
+    def backward(ctx, g, _gm):
+        batch, ptr = ctx.saved_tensors
+        n = batch.numel()
+        idx = batch * ctx.Nmax + (torch.arange(n, device=batch.device) - ptr.long()[batch])
+        return g.reshape(-1, g.size(-1))[idx], None, None, None, None
+
+
+def to_dense_batch(x: Tensor, batch: Tensor, num_graphs: Optional[int] = None, max_num_nodes: Optional[int] = None):
+    """PyG to_dense_batch (tgp/src.py:448-450): ``[N, F]`` + sorted ``batch`` -> zero-padded ``[B, Nmax, F]`` and a
+    bool mask ``[B, Nmax]``."""
+    _require_cuda(x, batch)
+    B = num_graphs if num_graphs is not None else (int(batch.max().item()) + 1 if batch.numel() else 1)
+    ptr = graph_ptr(batch, B)
+    if max_num_nodes is None:
+        max_num_nodes = int((ptr[1:] - ptr[:-1]).max().item())
+    out, mask = _ToDenseBatch.apply(x.contiguous(), batch.contiguous(), ptr, B, max_num_nodes)
+    return out, mask.bool()
+
+
+def to_dense_adj(edge_index: Tensor, batch: Optional[Tensor], edge_weight: Optional[Tensor] = None,
+                 num_graphs: Optional[int] = None, max_num_nodes: Optional[int] = None, transpose: bool = False) -> Tensor:
+    """PyG to_dense_adj (tgp/src.py:434-443): ``[B, Nmax, Nmax]`` fp32, duplicates summed, default weight 1."""
+    _require_cuda(edge_index, batch, edge_weight)
+    dev = edge_index.device
+    if batch is None:
+        n = int(edge_index.max().item()) + 1 if edge_index.numel() else 0
+        batch = torch.zeros(n, dtype=torch.long, device=dev)
+    B = num_graphs if num_graphs is not None else (int(batch.max().item()) + 1 if batch.numel() else 1)
+    ptr = graph_ptr(batch, B)
+    if max_num_nodes is None:
+        max_num_nodes = int((ptr[1:] - ptr[:-1]).max().item()) if batch.numel() else 0
+    adj = torch.empty((B, max_num_nodes, max_num_nodes), dtype=torch.float32, device=dev)
+    w = _as_f32_weight(edge_weight)
+    ei = edge_index.contiguous()
+    L.call("tgpb200_to_dense_adj", L.ptr(ei[0]), L.ptr(ei[1]), L.ptr(None if w is None else w.detach()), L.ptr(batch.contiguous()),
+           L.ptr(ptr), ei.size(1), B, max_num_nodes, int(transpose), L.ptr(adj), L.stream())
+    if w is not None and w.requires_grad:  # d adj / d w is a gather; keep it in autograd with an index_put view
+        b = batch[ei[0]]
+        lr, lc = ei[0] - ptr.long()[b], ei[1] - ptr.long()[b]
+        if transpose:
+            lr, lc = lc, lr
+        adj = adj.detach() + torch.zeros_like(adj).index_put((b, lr, lc), w - w.detach(), accumulate=True)
+    return adj

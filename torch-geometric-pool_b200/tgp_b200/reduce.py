@@ -89,11 +89,14 @@ class B200Reduce(Reduce):
         if so.s.dim() != 2:
             raise ValueError(f"Dense SelectOutput.s must be 2D [N, K] or 3D [B, N, K], got ndim={so.s.dim()}.")
         multi = batch is not None and batch.numel() > 0 and int(batch.min().item()) != int(batch.max().item())
-        if multi:
-            raise NotImplementedError(
-                "tgp_b200: dense [N, K] assignments over a multi-graph batch (batched=False mode) are not "
-                "covered yet; use the batched [B, N, K] representation."
-            )
+        if multi:  # base_reduce.py:170-182: per-graph S_i^T X_i, here as one padded batched product
+            B = int(batch.max().item()) + 1
+            s3, _ = F_.to_dense_batch(so.s, batch, B)
+            x3, _ = F_.to_dense_batch(x, batch, B, s3.size(1))
+            x_pool, _, _ = F_.dense_pool(x3, None, s3)
+            if not return_batched:
+                x_pool = x_pool.reshape(B * so.num_supernodes, -1)
+            return x_pool, self.reduce_batch(so, batch)
         x_pool, _, _ = F_.dense_pool(x.unsqueeze(0), None, so.s.unsqueeze(0))
         x_pool = x_pool if return_batched else x_pool.squeeze(0)
         return x_pool, self.reduce_batch(so, batch)
