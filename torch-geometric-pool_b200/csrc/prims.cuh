@@ -1,6 +1,8 @@
 // Device-wide primitives written for this library (no CUB/Thrust): exclusive scan,
 // order-preserving stream compaction, stable LSD radix sort of (key, index) pairs.
 #pragma once
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tgp {
@@ -185,49 +187,73 @@ inline int compact_emit(Pred pred, Emit emit, int64_t n, const int* counts, cuda
 }
 
 // ------------------------------------------------------------------------------------------
-// Stable LSD radix sort of (key, uint32 payload) pairs, 8 bits per pass.
-// Pass = tile histogram -> scan of [256][tiles] -> stable scatter (warp match ranking).
+// Stable LSD radix sort of (key, uint32 payload) pairs; 8, 10 or 11 bits per pass (fewest passes that cover the key).
+// Pass = tile histogram -> scan of [bins][tiles] -> stable scatter (warp match ranking, smem-staged stores).
 // ------------------------------------------------------------------------------------------
 constexpr int kSortThreads = 256;
 constexpr int kSortItems = 16;
 constexpr int kSortTile = kSortThreads * kSortItems;
-constexpr int kSortBins = 256;
+constexpr int kSortMaxBins = 2048;
 
-template <typename KeyT>
+struct RadixPlan {
+  int bits;    // digit width
+  int passes;  // number of passes
+};
+inline RadixPlan radix_plan(int key_bits) {
+  if (key_bits < 1) key_bits = 1;
+  // Measured on B200 (20 M 39-bit keys): a 10-bit pass costs 1.55x an 8-bit pass (2 KB x 8 warp counters and
+  // the staging buffer halve the occupancy), so 4 x 10-bit passes lose to 5 x 8-bit passes.  8 bits it is; the
+  // wider instantiations stay available through TGPB200_RADIX_BITS for experiments.
+  RadixPlan p;
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("TGPB200_RADIX_BITS");
+    forced = e ? atoi(e) : 0;
+  }
+  p.bits = (forced == 10 || forced == 11) ? forced : 8;
+  p.passes = (key_bits + p.bits - 1) / p.bits;
+  return p;
+}
+inline int radix_passes(int key_bits) { return radix_plan(key_bits).passes; }
+
+template <typename KeyT, int BITS>
 static __global__ void k_radix_hist(const KeyT* __restrict__ keys, int64_t n, int shift, int* __restrict__ tile_hist,
                                     int nt) {
-  __shared__ int h[kSortBins];
-  h[threadIdx.x] = 0;
+  constexpr int BINS = 1 << BITS;
+  __shared__ int h[BINS];
+  for (int d = threadIdx.x; d < BINS; d += kSortThreads) h[d] = 0;
   __syncthreads();
   int64_t base = (int64_t)blockIdx.x * kSortTile;
 #pragma unroll
   for (int j = 0; j < kSortItems; ++j) {
     int64_t i = base + j * kSortThreads + threadIdx.x;
-    if (i < n) atomicAdd(&h[(int)((keys[i] >> shift) & 255)], 1);
+    if (i < n) atomicAdd(&h[(int)((keys[i] >> shift) & (BINS - 1))], 1);
   }
   __syncthreads();
-  tile_hist[(size_t)threadIdx.x * nt + blockIdx.x] = h[threadIdx.x];
+  for (int d = threadIdx.x; d < BINS; d += kSortThreads) tile_hist[(size_t)d * nt + blockIdx.x] = h[d];
 }
 
 // Stable scatter of one tile.  Ranking: every warp owns 512 consecutive items and ranks them round by round with
 // __match_any_sync (stable inside the warp); per-digit counts are then prefixed over warps and digits.  The items
 // are first placed in shared memory in tile-local sorted order, so that the final global writes of a digit run are
 // consecutive (full-sector stores) instead of one scattered 8/12-byte write per item.
-template <typename KeyT, bool kIota>
+template <typename KeyT, int BITS, bool kIota>
 static __global__ void __launch_bounds__(kSortThreads)
     k_radix_scatter(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                     KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
                     const int* __restrict__ tile_off, int nt) {
   constexpr int NW = kSortThreads / 32;
+  constexpr int BINS = 1 << BITS;
+  constexpr int DPT = BINS / kSortThreads;  // digits owned by one thread (consecutive)
   extern __shared__ __align__(16) unsigned char radix_smem[];
-  KeyT* s_keys = reinterpret_cast<KeyT*>(radix_smem);                                   // [kSortTile]
+  KeyT* s_keys = reinterpret_cast<KeyT*>(radix_smem);                                     // [kSortTile]
   uint32_t* s_vals = reinterpret_cast<uint32_t*>(radix_smem + sizeof(KeyT) * kSortTile);  // [kSortTile]
-  int(*warp_cnt)[kSortBins] = reinterpret_cast<int(*)[kSortBins]>(s_vals + kSortTile);   // [NW][bins]
-  int* dig_base = &warp_cnt[0][0] + NW * kSortBins;                                      // [bins] tile-local start
-  int* g_base = dig_base + kSortBins;                                                    // [bins] global start
+  int(*warp_cnt)[BINS] = reinterpret_cast<int(*)[BINS]>(s_vals + kSortTile);              // [NW][bins]
+  int* dig_base = &warp_cnt[0][0] + NW * BINS;                                            // [bins] tile-local start
+  int* g_base = dig_base + BINS;                                                          // [bins] global start
   __shared__ int scan_tmp[33];
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < NW * kSortBins; i += kSortThreads) (&warp_cnt[0][0])[i] = 0;
+  for (int i = threadIdx.x; i < NW * BINS; i += kSortThreads) (&warp_cnt[0][0])[i] = 0;
   __syncthreads();
 
   const int64_t tile0 = (int64_t)blockIdx.x * kSortTile;
@@ -243,7 +269,7 @@ static __global__ void __launch_bounds__(kSortThreads)
     key[j] = 0;
     if (valid) {
       key[j] = keys_in[i];
-      int d = (int)((key[j] >> shift) & 255);
+      int d = (int)((key[j] >> shift) & (BINS - 1));
       unsigned peers = __match_any_sync(vmask, d);
       int leader = __ffs(peers) - 1;
       int old = 0;
@@ -259,24 +285,36 @@ static __global__ void __launch_bounds__(kSortThreads)
   __syncthreads();
   int tot;
   {
-    int d = threadIdx.x;  // one thread per digit: exclusive prefix over warps, then over digits
-    int run = 0;
+    // thread t owns digits [t*DPT, (t+1)*DPT): exclusive prefix over warps per digit, then over digits
+    int dsum[DPT];
+    int tsum = 0;
 #pragma unroll
-    for (int k = 0; k < NW; ++k) {
-      int c = warp_cnt[k][d];
-      warp_cnt[k][d] = run;
-      run += c;
+    for (int q = 0; q < DPT; ++q) {
+      int d = threadIdx.x * DPT + q;
+      int run = 0;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        int c = warp_cnt[k][d];
+        warp_cnt[k][d] = run;
+        run += c;
+      }
+      dsum[q] = run;
+      tsum += run;
+      g_base[d] = tile_off[(size_t)d * nt + blockIdx.x];
     }
-    g_base[d] = tile_off[(size_t)d * nt + blockIdx.x];
-    int ex = block_exclusive_scan_i(run, scan_tmp, &tot);
-    dig_base[d] = ex;
+    int ex = block_exclusive_scan_i(tsum, scan_tmp, &tot);
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+      dig_base[threadIdx.x * DPT + q] = ex;
+      ex += dsum[q];
+    }
   }
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < kSortItems; ++j) {
     int64_t i = base + j * 32 + lane;
     if (i < n) {
-      int d = (int)((key[j] >> shift) & 255);
+      int d = (int)((key[j] >> shift) & (BINS - 1));
       int lp = dig_base[d] + warp_cnt[w][d] + rank[j];
       s_keys[lp] = key[j];
       s_vals[lp] = kIota ? (uint32_t)i : vals_in[i];
@@ -285,62 +323,74 @@ static __global__ void __launch_bounds__(kSortThreads)
   __syncthreads();
   for (int lp = threadIdx.x; lp < tot; lp += kSortThreads) {
     KeyT k = s_keys[lp];
-    int d = (int)((k >> shift) & 255);
+    int d = (int)((k >> shift) & (BINS - 1));
     int64_t pos = (int64_t)g_base[d] + (lp - dig_base[d]);
     keys_out[pos] = k;
     vals_out[pos] = s_vals[lp];
   }
 }
 
-template <typename KeyT>
+template <typename KeyT, int BITS>
 constexpr size_t radix_scatter_smem() {
-  return (sizeof(KeyT) + 4) * kSortTile + sizeof(int) * (kSortThreads / 32 + 2) * kSortBins;
+  return (sizeof(KeyT) + 4) * kSortTile + sizeof(int) * (kSortThreads / 32 + 2) * (1 << BITS);
 }
-
-inline int radix_passes(int key_bits) { return key_bits <= 0 ? 1 : (key_bits + 7) / 8; }
 
 inline size_t radix_sort_workspace_bytes(int64_t n) {
   int64_t nt = ceil_div(n > 0 ? n : 1, kSortTile);
-  return align_up((size_t)nt * kSortBins * sizeof(int)) + scan_workspace_bytes(nt * kSortBins);
+  return align_up((size_t)nt * kSortMaxBins * sizeof(int)) + scan_workspace_bytes(nt * kSortMaxBins);
+}
+
+// NOTE: internal linkage on purpose.  The kernels above are `static` (one copy per translation unit), so the
+// "attribute already set" flag below must be per translation unit too; an `inline` function would share one flag
+// across units and leave the other units' kernel copies without the > 48 KB shared-memory opt-in.
+template <typename KeyT, int BITS>
+static int radix_pass(const KeyT* kin, const uint32_t* vin, KeyT* kout, uint32_t* vout, int64_t n, int shift, int* hist,
+                      int nt, Workspace& ws, cudaStream_t stream) {
+  constexpr int BINS = 1 << BITS;
+  static bool smem_attr_set = false;  // per instantiation: > 48 KB dynamic shared memory needs the opt-in
+  if (!smem_attr_set) {
+    smem_attr_set = true;
+    cudaFuncSetAttribute(k_radix_scatter<KeyT, BITS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)radix_scatter_smem<KeyT, BITS>());
+    cudaFuncSetAttribute(k_radix_scatter<KeyT, BITS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)radix_scatter_smem<KeyT, BITS>());
+  }
+  launch("k_radix_hist", k_radix_hist<KeyT, BITS>, nt, kSortThreads, 0, stream, kin, n, shift, hist, nt);
+  int rc = exclusive_scan_i32(hist, hist, (int64_t)nt * BINS, nullptr, nullptr, ws, stream);
+  if (rc != TGPB200_OK) return rc;
+  if (vin == nullptr)
+    launch("k_radix_scatter", k_radix_scatter<KeyT, BITS, true>, nt, kSortThreads, radix_scatter_smem<KeyT, BITS>(),
+           stream, kin, (const uint32_t*)nullptr, kout, vout, n, shift, hist, nt);
+  else
+    launch("k_radix_scatter", k_radix_scatter<KeyT, BITS, false>, nt, kSortThreads, radix_scatter_smem<KeyT, BITS>(),
+           stream, kin, vin, kout, vout, n, shift, hist, nt);
+  return TGPB200_OK;
 }
 
 // Sorts n pairs by the low `key_bits` bits of the key.  The first pass takes the payload as
 // iota when vals0 == nullptr.  Buffers (keys0, vals0) and (keys1, vals1) ping-pong; returns
 // (via *result_in_1) which pair holds the result.  keys0 is overwritten.
 template <typename KeyT>
-inline int radix_sort_pairs(KeyT* keys0, uint32_t* vals0_or_null, uint32_t* vals0_buf, KeyT* keys1, uint32_t* vals1,
+static int radix_sort_pairs(KeyT* keys0, uint32_t* vals0_or_null, uint32_t* vals0_buf, KeyT* keys1, uint32_t* vals1,
                             int64_t n, int key_bits, bool* result_in_1, Workspace& ws, cudaStream_t stream) {
   int nt = (int)ceil_div(n > 0 ? n : 1, kSortTile);
-  size_t mark = ws.off;
-  int* hist = ws.take<int>((size_t)nt * kSortBins);
+  const RadixPlan plan = radix_plan(key_bits);
+  int* hist = ws.take<int>((size_t)nt * (1 << plan.bits));
   if (!ws.ok) return TGPB200_ERR_WORKSPACE;
   size_t mark2 = ws.off;
-  int passes = radix_passes(key_bits);
-  static bool smem_attr_set = false;  // per KeyT instantiation: > 48 KB dynamic shared memory needs the opt-in
-  if (!smem_attr_set) {
-    smem_attr_set = true;
-    cudaFuncSetAttribute(k_radix_scatter<KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)radix_scatter_smem<KeyT>());
-    cudaFuncSetAttribute(k_radix_scatter<KeyT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)radix_scatter_smem<KeyT>());
-  }
   KeyT* kin = keys0;
   KeyT* kout = keys1;
   const uint32_t* vin = vals0_or_null;
   uint32_t* vout = vals1;
   bool in1 = false;
-  for (int p = 0; p < passes; ++p) {
-    int shift = 8 * p;
-    launch("k_radix_hist", k_radix_hist<KeyT>, nt, kSortThreads, 0, stream, kin, n, shift, hist, nt);
+  for (int p = 0; p < plan.passes; ++p) {
+    int shift = plan.bits * p;
     ws.off = mark2;
-    int rc = exclusive_scan_i32(hist, hist, (int64_t)nt * kSortBins, nullptr, nullptr, ws, stream);
+    int rc;
+    if (plan.bits == 8) rc = radix_pass<KeyT, 8>(kin, vin, kout, vout, n, shift, hist, nt, ws, stream);
+    else if (plan.bits == 10) rc = radix_pass<KeyT, 10>(kin, vin, kout, vout, n, shift, hist, nt, ws, stream);
+    else rc = radix_pass<KeyT, 11>(kin, vin, kout, vout, n, shift, hist, nt, ws, stream);
     if (rc != TGPB200_OK) return rc;
-    if (vin == nullptr)
-      launch("k_radix_scatter", k_radix_scatter<KeyT, true>, nt, kSortThreads, radix_scatter_smem<KeyT>(), stream, kin,
-             (const uint32_t*)nullptr, kout, vout, n, shift, hist, nt);
-    else
-      launch("k_radix_scatter", k_radix_scatter<KeyT, false>, nt, kSortThreads, radix_scatter_smem<KeyT>(), stream, kin,
-             vin, kout, vout, n, shift, hist, nt);
     in1 = !in1;
     KeyT* tk = kin;
     kin = kout;
@@ -348,7 +398,6 @@ inline int radix_sort_pairs(KeyT* keys0, uint32_t* vals0_or_null, uint32_t* vals
     vin = vout;
     vout = (vout == vals1) ? vals0_buf : vals1;
   }
-  (void)mark;
   *result_in_1 = in1;
   return launch_status();
 }

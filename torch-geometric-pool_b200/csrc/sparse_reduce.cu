@@ -185,20 +185,31 @@ static __global__ void __launch_bounds__(256)
   int lane = threadIdx.x & 31;
   unsigned gmask = lpr >= 32 ? kFull : (((1u << lpr) - 1u) << (lane & ~(lpr - 1)));
 
-  // locate the first entry of node n (fast guess: identity layout, else binary search)
-  int64_t lo;
-  if (n < nnz && node_index[n] == n && (n == 0 || node_index[n - 1] != n)) {
-    lo = n;
-  } else {
-    int64_t a = 0, b = nnz;
-    while (a < b) {
-      int64_t mid = (a + b) >> 1;
-      if (node_index[mid] < n) a = mid + 1; else b = mid;
+  // Locate the entries of node n.  The probe loads (neighbouring node ids and the would-be cluster / weight of the
+  // identity layout) are independent of each other, so the common "every node selected once, node_index[n] == n"
+  // case costs one round trip instead of a chain of dependent loads; otherwise binary search + a linear run scan.
+  int64_t lo, hi;
+  {
+    const int64_t a = n < nnz ? node_index[n] : -1;
+    const int64_t pa = (n > 0 && n - 1 < nnz) ? node_index[n - 1] : -1;
+    const int64_t na = n + 1 < nnz ? node_index[n + 1] : -2;
+    if (a == n && pa != n) {
+      lo = n;
+      hi = n + 1;
+      if (na == n) {
+        while (hi < nnz && node_index[hi] == n) ++hi;
+      }
+    } else {
+      int64_t x0 = 0, x1 = nnz;
+      while (x0 < x1) {
+        int64_t mid = (x0 + x1) >> 1;
+        if (node_index[mid] < n) x0 = mid + 1; else x1 = mid;
+      }
+      lo = x0;
+      hi = lo;
+      while (hi < nnz && node_index[hi] == n) ++hi;
     }
-    lo = a;
   }
-  int64_t hi = lo;
-  while (hi < nnz && node_index[hi] == n) ++hi;
 
   const XT* xr = x + n * F;
   for (int64_t i = lo; i < hi; ++i) {
