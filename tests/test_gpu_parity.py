@@ -523,3 +523,45 @@ def test_unbatched_dense_mode_matches_oracle_and_batched(sparse_output):
     assert torch.equal(got_b.cpu(), exp_b)
     got_xb, _ = T.B200Reduce()(x.to(DEV), so, batch=batch.to(DEV), return_batched=True)
     assert got_xb.shape == (len(sizes), K, F)
+
+
+# --------------------------------------------------------------------------- #
+# lift (tgp/lift/base_lift.py:113-123 sparse, dense batched matmul)
+# --------------------------------------------------------------------------- #
+def test_lift_sparse_and_dense():
+    g = torch.Generator().manual_seed(6)
+    N, K, F = 300, 80, 32
+    cluster = torch.randint(0, K, (N,), generator=g)
+    w = torch.rand(N, generator=g) + 0.5
+    xp = torch.randn(K, F, generator=g)
+    xpc, wc = xp.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    exp = xpc[cluster] * wc.view(-1, 1)          # scatter(x_pool[col] * values, row) with row = arange(N)
+    gout = torch.randn(N, F, generator=g)
+    (exp * gout).sum().backward()
+    xpg, wg = xp.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True)
+    so = T.SelectOutput(s=torch.sparse_coo_tensor(torch.stack([torch.arange(N), cluster]).to(DEV), wg, (N, K),
+                                                   is_coalesced=True, check_invariants=False))
+    got = T.B200Lift()(xpg, so)
+    (got * gout.to(DEV)).sum().backward()
+    torch.testing.assert_close(got.detach().cpu(), exp.detach(), **FP32)
+    torch.testing.assert_close(xpg.grad.cpu(), xpc.grad, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(wg.grad.cpu(), wc.grad, rtol=1e-4, atol=1e-5)
+    # TopK-style: only kept nodes receive features, the rest are zero rows
+    keep = torch.sort(torch.randperm(N, generator=g)[:K])[0]
+    so2 = T.SelectOutput(node_index=keep.to(DEV), num_nodes=N, cluster_index=torch.arange(K, device=DEV), num_supernodes=K)
+    lifted = T.B200Lift()(xp.to(DEV), so2).cpu()
+    assert torch.equal(lifted[keep], xp) and float(lifted.abs().sum()) == float(xp.abs().sum())
+    # dense batched: S x_pool
+    B, Nn, Kk, Ff = 3, 128, 32, 64
+    s = torch.softmax(torch.randn(B, Nn, Kk, generator=g), -1)
+    xpd = torch.randn(B, Kk, Ff, generator=g)
+    sc, xc = s.clone().double().requires_grad_(True), xpd.clone().double().requires_grad_(True)
+    ed = sc @ xc
+    gd = torch.randn(B, Nn, Ff, generator=g)
+    (ed * gd.double()).sum().backward()
+    sg, xg = s.to(DEV).requires_grad_(True), xpd.to(DEV).requires_grad_(True)
+    gotd = T.B200Lift()(xg, T.SelectOutput(s=sg))
+    (gotd * gd.to(DEV)).sum().backward()
+    close32(gotd.detach().cpu(), ed.detach().float(), "lift dense")
+    close32(sg.grad.cpu(), sc.grad.float(), "lift dS", rtol=1e-4)
+    close32(xg.grad.cpu(), xc.grad.float(), "lift dXp", rtol=1e-4)
