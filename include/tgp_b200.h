@@ -114,6 +114,14 @@ int tgpb200_filter_relabel_emit(const int64_t* row, const int64_t* col, const fl
                                 int64_t num_nodes, uint32_t flags, float eps, int64_t* out_row, int64_t* out_col,
                                 float* out_weight, int32_t* src_edge, void* workspace, size_t workspace_bytes,
                                 tgpb200_stream_t stream);
+/* Single-pass form (decoupled look-back compaction): the edge list is read once.  The outputs must have capacity
+ * num_edges; *count_out receives the survivor count when the stream has drained. */
+size_t tgpb200_filter_relabel_onepass_workspace_bytes(int64_t num_edges, int64_t num_nodes);
+int tgpb200_filter_relabel_onepass(const int64_t* row, const int64_t* col, const float* edge_weight, int64_t num_edges,
+                                   const int64_t* node_index, int64_t num_kept, int64_t num_nodes, uint32_t flags,
+                                   float eps, int64_t* out_row, int64_t* out_col, float* out_weight, int32_t* src_edge,
+                                   int64_t* count_out, void* workspace, size_t workspace_bytes,
+                                   tgpb200_stream_t stream);
 /* Backward: grad_in[src_edge[j]] = grad_out[j], zero elsewhere. */
 int tgpb200_filter_relabel_bwd(const float* grad_out, const int32_t* src_edge, int64_t num_out, int64_t num_edges,
                                float* grad_in, tgpb200_stream_t stream);

@@ -187,6 +187,106 @@ inline int compact_emit(Pred pred, Emit emit, int64_t n, const int* counts, cuda
 }
 
 // ------------------------------------------------------------------------------------------
+// Single-pass order-preserving compaction (decoupled look-back): the input is read ONCE.  Outputs must have
+// capacity n (the survivor count is only known at the end).  Tiles take a ticket (so a tile's predecessors are
+// always running or done), publish their survivor count as (flag, value) packed in 64 bits, and resolve their
+// exclusive offset by walking back over the published aggregates until they meet an inclusive prefix.
+// tile_state ([tiles] uint64) and ticket (int) must be zero before the launch.  Spins are bounded (trap).
+// ------------------------------------------------------------------------------------------
+template <typename Pred, typename Emit>
+static __global__ void __launch_bounds__(kCompactThreads)
+    k_compact_onepass(Pred pred, Emit emit, int64_t n, unsigned long long* __restrict__ tile_state,
+                      int* __restrict__ ticket, int num_tiles, int64_t* __restrict__ count_out) {
+  __shared__ int warp_tot[kCompactThreads / 32];
+  __shared__ int s_tile, s_excl;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
+  __syncthreads();
+  const int tile = s_tile;
+  int64_t base = (int64_t)tile * kCompactTile + (int64_t)w * (32 * kCompactItems);
+  typename Pred::Payload pay[kCompactItems];
+  unsigned ball[kCompactItems];
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < kCompactItems; ++j) {
+    int64_t i = base + j * 32 + lane;
+    bool f = (i < n) && pred(i, pay[j]);
+    ball[j] = __ballot_sync(kFull, f);
+    cnt += __popc(ball[j]);
+  }
+  if (lane == 0) warp_tot[w] = cnt;
+  __syncthreads();
+  if (w == 0) {
+    // warp 0 resolves the tile's exclusive offset: 32 predecessors per look-back step
+    int total = 0;
+    for (int k = 0; k < kCompactThreads / 32; ++k) total += warp_tot[k];
+    unsigned long long excl = 0;
+    if (tile == 0) {
+      if (lane == 0) atomicExch(&tile_state[0], (2ull << 32) | (unsigned)total);
+    } else {
+      if (lane == 0) atomicExch(&tile_state[tile], (1ull << 32) | (unsigned)total);
+      int t = tile - 1;
+      while (true) {
+        const int idx = t - lane;
+        unsigned long long v = 2ull << 32;  // before tile 0: an inclusive prefix of 0
+        if (idx >= 0) {
+          long long spins = 0;
+          while (((v = *(volatile unsigned long long*)&tile_state[idx]) >> 32) == 0) {
+            if (++spins > (1ll << 26)) __trap();
+          }
+        }
+        const unsigned done = __ballot_sync(kFull, (v >> 32) == 2);
+        // lanes up to (and including) the nearest inclusive prefix contribute
+        const int first = done ? __ffs(done) - 1 : 31;
+        unsigned val = lane <= first ? (unsigned)(v & 0xffffffffull) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(kFull, val, o);
+        excl += val;
+        if (done) break;
+        t -= 32;
+      }
+      if (lane == 0) {
+        __threadfence();
+        atomicExch(&tile_state[tile], (2ull << 32) | (unsigned)(excl + total));
+      }
+    }
+    if (lane == 0) {
+      s_excl = (int)excl;
+      if (tile == num_tiles - 1 && count_out) *count_out = (int64_t)excl + total;
+    }
+  }
+  __syncthreads();
+  int run = s_excl;
+  for (int k = 0; k < w; ++k) run += warp_tot[k];
+  unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int j = 0; j < kCompactItems; ++j) {
+    if (ball[j] >> lane & 1u) emit(base + j * 32 + lane, run + __popc(ball[j] & lt), pay[j]);
+    run += __popc(ball[j]);
+  }
+}
+
+inline size_t compact_onepass_workspace_bytes(int64_t n) {
+  return align_up(((size_t)ceil_div(n > 0 ? n : 1, kCompactTile) + 2) * sizeof(unsigned long long));
+}
+
+template <typename Pred, typename Emit>
+static int compact_onepass(Pred pred, Emit emit, int64_t n, int64_t* count_out, Workspace& ws, cudaStream_t stream) {
+  int nt = (int)ceil_div(n > 0 ? n : 1, kCompactTile);
+  unsigned long long* state = ws.take<unsigned long long>((size_t)nt + 2);
+  if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+  cudaMemsetAsync(state, 0, ((size_t)nt + 2) * sizeof(unsigned long long), stream);
+  int* ticket = reinterpret_cast<int*>(state + nt);
+  if (n <= 0) {
+    if (count_out) cudaMemsetAsync(count_out, 0, sizeof(int64_t), stream);
+    return launch_status();
+  }
+  launch("k_compact_onepass", k_compact_onepass<Pred, Emit>, nt, kCompactThreads, 0, stream, pred, emit, n, state, ticket,
+         nt, count_out);
+  return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------
 // Stable LSD radix sort of (key, uint32 payload) pairs; 8, 10 or 11 bits per pass (fewest passes that cover the key).
 // Pass = tile histogram -> scan of [bins][tiles] -> stable scatter (warp match ranking, smem-staged stores).
 // ------------------------------------------------------------------------------------------

@@ -10,12 +10,17 @@ namespace tgp {
 // ------------------------------------------------------------------------------------------
 // kept-node branch
 // ------------------------------------------------------------------------------------------
+// table[v] = position of v in node_index (-1 if not kept) and a 1-bit-per-node membership mask.  The mask (N/8
+// bytes) stays cache resident, so the two random table reads are only paid by the edges that survive.
 static __global__ void k_build_table(const int64_t* __restrict__ node_index, int64_t kept, int64_t N,
-                                     int32_t* __restrict__ table) {
+                                     int32_t* __restrict__ table, uint32_t* __restrict__ bits) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= kept) return;
   int64_t v = node_index[j];
-  if (v >= 0 && v < N) table[v] = (int32_t)j;
+  if (v >= 0 && v < N) {
+    table[v] = (int32_t)j;
+    atomicOr(&bits[v >> 5], 1u << (v & 31));
+  }
 }
 
 struct KeptPred {
@@ -27,19 +32,20 @@ struct KeptPred {
   const int64_t* col;
   const float* w;
   const int32_t* table;
+  const uint32_t* bits;
   int64_t N;
   bool rsl;
   float eps;
   __device__ bool operator()(int64_t i, Payload& p) const {
-    int64_t r = row[i], c = col[i];
+    // the edge list is touched once: streaming (evict-first) loads keep the mask / table lines in L2
+    int64_t r = __ldcs(row + i), c = __ldcs(col + i);
     if (r < 0 || r >= N || c < 0 || c >= N) return false;
     if (rsl && r == c) return false;
-    p.r = table[r];
-    if (p.r < 0) return false;
-    p.c = table[c];
-    if (p.c < 0) return false;
+    if (!((__ldg(bits + (r >> 5)) >> (r & 31)) & 1u) || !((__ldg(bits + (c >> 5)) >> (c & 31)) & 1u)) return false;
+    p.r = __ldg(table + r);
+    p.c = __ldg(table + c);
     if (w) {
-      p.w = w[i];
+      p.w = __ldcs(w + i);
       if (!(fabsf(p.w) > eps)) return false;
     }
     return true;
@@ -51,10 +57,10 @@ struct KeptEmit {
   float* out_w;
   int32_t* src;
   __device__ void operator()(int64_t i, int pos, const KeptPred::Payload& p) const {
-    out_row[pos] = p.r;
-    out_col[pos] = p.c;
-    if (out_w) out_w[pos] = p.w;
-    if (src) src[pos] = (int32_t)i;
+    __stcs(out_row + pos, (int64_t)p.r);
+    __stcs(out_col + pos, (int64_t)p.c);
+    if (out_w) __stcs(out_w + pos, p.w);
+    if (src) __stcs(src + pos, (int32_t)i);
   }
 };
 
@@ -367,15 +373,18 @@ using namespace tgp;
 extern "C" {
 
 size_t tgpb200_filter_relabel_workspace_bytes(int64_t E, int64_t N) {
-  return align_up((size_t)(N > 0 ? N : 1) * sizeof(int32_t)) + compact_workspace_bytes(E) + 1024;
+  return align_up((size_t)(N > 0 ? N : 1) * sizeof(int32_t)) + align_up((size_t)(N / 32 + 1) * 4) +
+         compact_workspace_bytes(E) + 1024;
 }
 
 struct KeptPlan {
   int32_t* table;
+  uint32_t* bits;
   int* tile_counts;
   bool ok;
   KeptPlan(Workspace& ws, int64_t E, int64_t N) {
     table = ws.take<int32_t>((size_t)(N > 0 ? N : 1));
+    bits = ws.take<uint32_t>((size_t)(N / 32 + 1));
     tile_counts = ws.take<int>((size_t)ceil_div(E > 0 ? E : 1, kCompactTile));
     ok = ws.ok;
   }
@@ -393,8 +402,10 @@ int tgpb200_filter_relabel_count(const int64_t* row, const int64_t* col, const f
   KeptPlan pl(ws, E, N);
   if (!pl.ok) return TGPB200_ERR_WORKSPACE;
   cudaMemsetAsync(pl.table, 0xff, (size_t)(N > 0 ? N : 1) * sizeof(int32_t), st);
-  if (kept > 0) launch("k_build_table", k_build_table, (unsigned)ceil_div(kept, 256), 256, 0, st, node_index, kept, N, pl.table);
-  KeptPred pred{row, col, edge_weight, pl.table, N, (flags & TGPB200_REMOVE_SELF_LOOPS) != 0, eps};
+  cudaMemsetAsync(pl.bits, 0, (size_t)(N / 32 + 1) * sizeof(uint32_t), st);
+  if (kept > 0)
+    launch("k_build_table", k_build_table, (unsigned)ceil_div(kept, 256), 256, 0, st, node_index, kept, N, pl.table, pl.bits);
+  KeptPred pred{row, col, edge_weight, pl.table, pl.bits, N, (flags & TGPB200_REMOVE_SELF_LOOPS) != 0, eps};
   return compact_count(pred, E, pl.tile_counts, nullptr, count_out, st);
 }
 
@@ -409,7 +420,7 @@ int tgpb200_filter_relabel_emit(const int64_t* row, const int64_t* col, const fl
   Workspace ws(workspace, workspace_bytes);
   KeptPlan pl(ws, E, N);
   if (!pl.ok) return TGPB200_ERR_WORKSPACE;
-  KeptPred pred{row, col, edge_weight, pl.table, N, (flags & TGPB200_REMOVE_SELF_LOOPS) != 0, eps};
+  KeptPred pred{row, col, edge_weight, pl.table, pl.bits, N, (flags & TGPB200_REMOVE_SELF_LOOPS) != 0, eps};
   KeptEmit emit{out_row, out_col, edge_weight ? out_weight : nullptr, src_edge};
   return compact_emit(pred, emit, E, pl.tile_counts, (cudaStream_t)stream);
 }
@@ -454,6 +465,35 @@ int tgpb200_remap_coalesce_emit(int64_t E, int64_t K, int weighted, uint32_t fla
                                               edge_slot, run_len, ws, st);
   return remap_coalesce_emit_impl<uint64_t>(E, K, weighted != 0, flags, eps, out_row, out_col, out_weight, edge_slot,
                                             run_len, ws, st);
+}
+
+size_t tgpb200_filter_relabel_onepass_workspace_bytes(int64_t E, int64_t N) {
+  return align_up((size_t)(N > 0 ? N : 1) * sizeof(int32_t)) + align_up((size_t)(N / 32 + 1) * 4) +
+         compact_onepass_workspace_bytes(E) + 1024;
+}
+
+// Single-pass form: the edge list is read once; outputs have capacity E and *count_out gets the survivor count.
+int tgpb200_filter_relabel_onepass(const int64_t* row, const int64_t* col, const float* edge_weight, int64_t E,
+                                   const int64_t* node_index, int64_t kept, int64_t N, uint32_t flags, float eps,
+                                   int64_t* out_row, int64_t* out_col, float* out_weight, int32_t* src_edge,
+                                   int64_t* count_out, void* workspace, size_t workspace_bytes,
+                                   tgpb200_stream_t stream) {
+  if (E < 0 || kept < 0 || N < 0 || E >= INT32_MAX || N >= INT32_MAX || !count_out) return TGPB200_ERR_INVALID;
+  if (E > 0 && (!row || !col || !out_row || !out_col)) return TGPB200_ERR_INVALID;
+  if (edge_weight && E > 0 && !out_weight) return TGPB200_ERR_INVALID;
+  if (kept > 0 && !node_index) return TGPB200_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  int32_t* table = ws.take<int32_t>((size_t)(N > 0 ? N : 1));
+  uint32_t* bits = ws.take<uint32_t>((size_t)(N / 32 + 1));
+  if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+  cudaMemsetAsync(table, 0xff, (size_t)(N > 0 ? N : 1) * sizeof(int32_t), st);
+  cudaMemsetAsync(bits, 0, (size_t)(N / 32 + 1) * sizeof(uint32_t), st);
+  if (kept > 0)
+    launch("k_build_table", k_build_table, (unsigned)ceil_div(kept, 256), 256, 0, st, node_index, kept, N, table, bits);
+  KeptPred pred{row, col, edge_weight, table, bits, N, (flags & TGPB200_REMOVE_SELF_LOOPS) != 0, eps};
+  KeptEmit emit{out_row, out_col, edge_weight ? out_weight : nullptr, src_edge};
+  return compact_onepass(pred, emit, E, count_out, ws, st);
 }
 
 // grad_in[e] = grad_out[j] for the surviving edges (src_edge[j] == e), 0 elsewhere.

@@ -40,6 +40,8 @@ SIGNATURES = {
     "tgpb200_filter_relabel_workspace_bytes": (_SZ, [_I64, _I64]),
     "tgpb200_filter_relabel_count": (_INT, [_P, _P, _P, _I64, _P, _I64, _I64, _U32, _F, _P, _P, _SZ, _P]),
     "tgpb200_filter_relabel_emit": (_INT, [_P, _P, _P, _I64, _I64, _U32, _F, _P, _P, _P, _P, _P, _SZ, _P]),
+    "tgpb200_filter_relabel_onepass_workspace_bytes": (_SZ, [_I64, _I64]),
+    "tgpb200_filter_relabel_onepass": (_INT, [_P, _P, _P, _I64, _P, _I64, _I64, _U32, _F, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "tgpb200_filter_relabel_bwd": (_INT, [_P, _P, _I64, _I64, _P, _P]),
     "tgpb200_remap_coalesce_workspace_bytes": (_SZ, [_I64, _I64]),
     "tgpb200_remap_coalesce_count": (_INT, [_P, _P, _P, _I64, _P, _I64, _I64, _INT, _U32, _F, _P, _P, _SZ, _P]),

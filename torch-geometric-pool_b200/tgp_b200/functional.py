@@ -133,18 +133,25 @@ class _FilterRelabel(torch.autograd.Function):
         E = row.numel()
         dev = row.device
         lib = L.load()
-        ws = L.workspace(lib.tgpb200_filter_relabel_workspace_bytes(E, num_nodes), dev)
+        need_grad = edge_weight is not None and ctx.needs_input_grad[0]
+        # single pass over the edge list (decoupled look-back compaction) into capacity-E buffers, then the survivor
+        # count (the one device->host word) sizes the exact, contiguous outputs
+        ws = L.workspace(lib.tgpb200_filter_relabel_onepass_workspace_bytes(E, num_nodes), dev)
         count = torch.empty(1, dtype=torch.long, device=dev)
-        L.call("tgpb200_filter_relabel_count", L.ptr(row), L.ptr(col), L.ptr(edge_weight), E, L.ptr(node_index),
-               node_index.numel(), num_nodes, flags, eps, L.ptr(count), L.ptr(ws), ws.numel(), L.stream())
+        cap = max(E, 1)
+        row_c = torch.empty(cap, dtype=torch.long, device=dev)
+        col_c = torch.empty(cap, dtype=torch.long, device=dev)
+        w_c = None if edge_weight is None else torch.empty(cap, dtype=torch.float32, device=dev)
+        src_c = torch.empty(cap, dtype=torch.int32, device=dev) if need_grad else None
+        L.call("tgpb200_filter_relabel_onepass", L.ptr(row), L.ptr(col), L.ptr(edge_weight), E, L.ptr(node_index),
+               node_index.numel(), num_nodes, flags, eps, L.ptr(row_c), L.ptr(col_c), L.ptr(w_c), L.ptr(src_c),
+               L.ptr(count), L.ptr(ws), ws.numel(), L.stream())
         n_out = _read_count(count)
         ei = torch.empty((2, n_out), dtype=torch.long, device=dev)
-        w_out = None if edge_weight is None else torch.empty(n_out, dtype=torch.float32, device=dev)
-        need_grad = edge_weight is not None and ctx.needs_input_grad[0]
-        src = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev) if need_grad else None
-        if n_out > 0:
-            L.call("tgpb200_filter_relabel_emit", L.ptr(row), L.ptr(col), L.ptr(edge_weight), E, num_nodes, flags, eps,
-                   L.ptr(ei[0]), L.ptr(ei[1]), L.ptr(w_out), L.ptr(src), L.ptr(ws), ws.numel(), L.stream())
+        ei[0].copy_(row_c[:n_out])
+        ei[1].copy_(col_c[:n_out])
+        w_out = None if edge_weight is None else w_c[:n_out].clone()
+        src = src_c[:max(n_out, 1)].clone() if need_grad else None
         ctx.mark_non_differentiable(ei)
         if need_grad:
             ctx.save_for_backward(src)
