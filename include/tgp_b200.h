@@ -53,6 +53,10 @@ typedef struct CUstream_st* tgpb200_stream_t;
 int tgpb200_abi_version(void);
 /* number of kernels this library has launched in the process so far (diagnostics; bench.py reports it) */
 long long tgpb200_debug_launch_count(void);
+/* Per-kernel timing for bench.py: bracket every kernel whose name contains `filter` with CUDA events on its launch
+ * stream (NULL stops and resets); tgpb200_debug_kernel_time_ms returns the mean duration of the recorded launches. */
+void tgpb200_debug_time_kernel(const char* filter);
+double tgpb200_debug_kernel_time_ms(int* count);
 
 /* ------------------------------------------------------------------------------------------
  * CSR-by-cluster of a sparse assignment (replaces the stable torch.sort in

@@ -23,11 +23,20 @@ inline int launch_status() {
   return e == cudaSuccess ? TGPB200_OK : TGPB200_ERR_CUDA;
 }
 
+// Optional per-kernel timing (bench.py): kernels whose name contains the filter are bracketed by CUDA events on
+// their own launch stream; tgpb200_debug_kernel_time_ms() averages the recorded pairs.
+bool timing_match(const char* name);
+void timing_begin(cudaStream_t st);
+void timing_end(cudaStream_t st);
+
 template <typename... KArgs, typename... Args>
 inline void launch(const char* name, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                    Args... args) {
   ++launch_counter();
+  const bool timed = timing_match(name);
+  if (timed) timing_begin(st);
   kernel<<<grid, block, smem, st>>>(args...);
+  if (timed) timing_end(st);
   if (debug_sync_enabled()) {
     cudaError_t e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaPeekAtLastError();

@@ -28,6 +28,8 @@ _P, _I64, _SZ, _INT, _U32, _F = c_void_p, c_int64, c_size_t, c_int, c_uint32, c_
 SIGNATURES = {
     "tgpb200_abi_version": (_INT, []),
     "tgpb200_debug_launch_count": (ctypes.c_longlong, []),
+    "tgpb200_debug_time_kernel": (None, [ctypes.c_char_p]),
+    "tgpb200_debug_kernel_time_ms": (ctypes.c_double, [ctypes.POINTER(ctypes.c_int)]),
     "tgpb200_build_csr_workspace_bytes": (_SZ, [_I64, _I64]),
     "tgpb200_build_csr": (_INT, [_P, _I64, _I64, _P, _P, _P, _SZ, _P]),
     "tgpb200_segment_reduce_fwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _INT, _INT, _INT, _P, _P]),
@@ -140,6 +142,18 @@ def check(rc: int, what: str) -> None:
 def kernel_launches() -> int:
     """Kernels launched by libtgp_b200.so in this process so far."""
     return int(load().tgpb200_debug_launch_count())
+
+
+def time_kernel(name_filter: Optional[str]) -> None:
+    """Bracket every kernel whose name contains ``name_filter`` with CUDA events (None stops)."""
+    load().tgpb200_debug_time_kernel(None if name_filter is None else name_filter.encode())
+
+
+def kernel_time_ms():
+    """(mean ms, launches) of the kernels recorded since ``time_kernel``."""
+    n = ctypes.c_int(0)
+    ms = load().tgpb200_debug_kernel_time_ms(ctypes.byref(n))
+    return float(ms), int(n.value)
 
 
 def call(name: str, *args) -> None:
