@@ -1,3 +1,4 @@
+"""Per-role clock64 timeline of block 0 of the fused dense forward kernel (tgpb200_debug_fused_timeline)."""
 import sys, os, ctypes
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "torch-geometric-pool_b200"))
 import torch, tgp_b200 as T

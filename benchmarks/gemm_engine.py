@@ -1,3 +1,6 @@
+"""Micro-benchmark of the tcgen05 batched GEMM engine (C2-shaped and large products). Run on a B200:
+    python benchmarks/gemm_engine.py
+"""
 import sys, os
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "torch-geometric-pool_b200"))
 import torch

@@ -127,6 +127,28 @@ static __global__ void k_row_stats(const T* __restrict__ A, const T* __restrict_
   }
 }
 
+// Column reduction over a [K, K] matrix with all warps busy and 128-byte row reads: warp w accumulates rows
+// w, w + nw, ... of a 32-column strip, the partials are summed over warps through shared memory (fixed order).
+// `colred` must hold 33 * 32 floats.  f(u, v) is the addend of row u, column v; out(v, sum) consumes the result.
+template <typename F, typename O>
+__device__ __forceinline__ void block_col_reduce(int K, float* colred, F f, O out) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c0 = 0; c0 < K; c0 += 32) {
+    const int v = c0 + lane;
+    float acc = 0.f;
+    if (v < K)
+      for (int u = w; u < K; u += nw) acc += f(u, v);
+    colred[w * 33 + lane] = acc;
+    __syncthreads();
+    if (w == 0 && v < K) {
+      float s = 0.f;
+      for (int k = 0; k < nw; ++k) s += colred[k * 33 + lane];
+      out(v, s);
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Per-graph epilogue (one block per graph): loss statistics from the RAW S^T A S and S^T S,
 // then post-processing (diag zero -> D^-1/2 A D^-1/2 -> / max|A|) exactly in ops.py:307-333 order.
@@ -141,6 +163,7 @@ static __global__ void __launch_bounds__(1024)
   extern __shared__ float sm[];  // K floats: d_v  (+ 2 K^2 floats when the matrices are staged)
   __shared__ float red[32];
   __shared__ int redi[32];
+  __shared__ float colred[33 * 32];
   int b = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
   const float* Ar = Araw ? Araw + (int64_t)b * K * K : nullptr;
   const float* Mg = M ? M + (int64_t)b * K * K : nullptr;
@@ -198,14 +221,13 @@ static __global__ void __launch_bounds__(1024)
   bool tr = flags & TGPB200_ADJ_TRANSPOSE, wn = flags & TGPB200_EDGE_WEIGHT_NORM;
   // degree vector over the diag-zeroed matrix: s_v = column sum (adj_transpose) or row sum
   if (dn) {
-    if (tr) {  // column sums: thread v walks column v, lanes read consecutive addresses of each row
-      for (int v = t; v < K; v += nt) {
-        float s = 0.f;
-        for (int u = 0; u < K; ++u)
-          if (!(rsl && u == v)) s += Ar[(int64_t)u * K + v];
-        sm[v] = sqrtf(fmaxf(s, eps));
-        dvec[(int64_t)b * K + v] = s;
-      }
+    if (tr) {  // column sums (tiled: every warp reads 128-byte row segments)
+      block_col_reduce(
+          K, colred, [&](int u, int v) { return (rsl && u == v) ? 0.f : Ar[(int64_t)u * K + v]; },
+          [&](int v, float s) {
+            sm[v] = sqrtf(fmaxf(s, eps));
+            dvec[(int64_t)b * K + v] = s;
+          });
     } else {  // row sums: one warp per row
       int lane = t & 31, w = t >> 5, nw = nt >> 5;
       for (int v = w; v < K; v += nw) {
@@ -308,6 +330,7 @@ static __global__ void __launch_bounds__(1024)
                 float* __restrict__ P, float* __restrict__ coef, int stage, T* __restrict__ Gt, T* __restrict__ Pt) {
   extern __shared__ float sm[];  // 3K floats: dsq[v], rowdot[v], coldot[v]  (+ 2 K^2 staged floats)
   __shared__ float red[32];
+  __shared__ float colred[33 * 32];
   float* dsq = sm;
   float* rdot = sm + K;
   float* cdot = sm + 2 * K;
@@ -374,13 +397,13 @@ static __global__ void __launch_bounds__(1024)
       for (int i = t; i < K * K; i += nt) {
         int r = row_of(i);
         float u = Mb[i] * inM - ((r == col_of(i, r)) ? isk : 0.f);
-        Pb[i] = c1 * u - c2 * Mb[i];
-        if (Pt) Pt[(int64_t)b * K * K + i] = from_f32<T>(Pb[i]);
+        const float pv = c1 * u - c2 * Mb[i];
+        if (Pt) Pt[(int64_t)b * K * K + i] = from_f32<T>(pv); else Pb[i] = pv;
       }
     } else {
       for (int i = t; i < K * K; i += nt) {
-        Pb[i] = 4.f * c_m2 * Mb[i];
-        if (Pt) Pt[(int64_t)b * K * K + i] = from_f32<T>(Pb[i]);
+        const float pv = 4.f * c_m2 * Mb[i];
+        if (Pt) Pt[(int64_t)b * K * K + i] = from_f32<T>(pv); else Pb[i] = pv;
       }
     }
   }
@@ -389,8 +412,8 @@ static __global__ void __launch_bounds__(1024)
   if (Gpool == nullptr) {
     for (int i = t; i < K * K; i += nt) {
       int r = row_of(i);
-      Gr[i] = (r == col_of(i, r)) ? c_num : 0.f;
-      if (Gt) Gt[(int64_t)b * K * K + i] = from_f32<T>(Gr[i]);
+      const float gv = (r == col_of(i, r)) ? c_num : 0.f;
+      if (Gt) Gt[(int64_t)b * K * K + i] = from_f32<T>(gv); else Gr[i] = gv;
     }
     return;
   }
@@ -430,18 +453,16 @@ static __global__ void __launch_bounds__(1024)
       sr = warp_sum(sr);
       if (lane == 0) rdot[v] = sr;
     }
-    for (int v = t; v < K; v += nt) {  // column dots: thread v walks column v (coalesced across the warp)
-      float sc = 0.f;
-      const float iv = dsq[v];
-      for (int u = 0; u < K; ++u) {
-        int i = u * K + v;
-        float a = (rsl && u == v) ? 0.f : Ar[i] * (iv * dsq[u]);
-        float g = to_f32<T>(Gp[i]) * im;
-        if (i == am) g += (a < 0.f ? -argterm : argterm);
-        sc += g * a;
-      }
-      cdot[v] = sc;
-    }
+    block_col_reduce(  // column dots (tiled)
+        K, colred,
+        [&](int u, int v) {
+          int i = u * K + v;
+          float a = (rsl && u == v) ? 0.f : Ar[i] * (dsq[v] * dsq[u]);
+          float g = to_f32<T>(Gp[i]) * im;
+          if (i == am) g += (a < 0.f ? -argterm : argterm);
+          return g * a;
+        },
+        [&](int v, float sc) { cdot[v] = sc; });
   }
   __syncthreads();
   for (int i = t; i < K * K; i += nt) {
@@ -462,8 +483,7 @@ static __global__ void __launch_bounds__(1024)
     }
     if (rsl && r == c) out = 0.f;
     if (r == c) out += c_num;
-    Gr[i] = out;
-    if (Gt) Gt[(int64_t)b * K * K + i] = from_f32<T>(out);
+    if (Gt) Gt[(int64_t)b * K * K + i] = from_f32<T>(out); else Gr[i] = out;
   }
 }
 
