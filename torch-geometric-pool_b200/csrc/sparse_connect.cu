@@ -81,96 +81,10 @@ static __global__ void k_remap_keys(const int64_t* __restrict__ row, const int64
   keys[i] = (KeyT)((uint64_t)cr * (uint64_t)K + (uint64_t)cc);
 }
 
-template <typename KeyT>
-static __global__ void k_head_flags(const KeyT* __restrict__ ks, int64_t E, int* __restrict__ flags) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= E) return;
-  flags[i] = (i == 0 || ks[i] != ks[i - 1]) ? 1 : 0;
-}
 
-// excl = exclusive scan of head flags; run id of a head i is excl[i].
-template <typename KeyT>
-static __global__ void k_run_starts(const KeyT* __restrict__ ks, const int* __restrict__ excl,
-                                    const int* __restrict__ total, int64_t E, int* __restrict__ run_start) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= E) return;
-  if (i == 0 || ks[i] != ks[i - 1]) run_start[excl[i]] = (int)i;
-  if (i == E - 1) run_start[*total] = (int)E;
-}
 
-// One thread per run: combine the member weights in sorted (= original, the sort is stable) order.
-static __global__ void k_run_combine(const uint32_t* __restrict__ perm, const float* __restrict__ w,
-                                     const int* __restrict__ run_start, const int* __restrict__ total, int op,
-                                     float* __restrict__ comb) {
-  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= *total) return;
-  int s = run_start[r], e = run_start[r + 1];
-  float acc = w[perm[s]];
-  for (int i = s + 1; i < e; ++i) {
-    float v = w[perm[i]];
-    if (op == TGPB200_SUM || op == TGPB200_MEAN) acc = __fadd_rn(acc, v);
-    else if (op == TGPB200_MAX) acc = fmaxf(acc, v);
-    else if (op == TGPB200_MIN) acc = fminf(acc, v);
-    else acc = __fmul_rn(acc, v);
-  }
-  if (op == TGPB200_MEAN) acc = __fdiv_rn(acc, (float)(e - s));
-  comb[r] = acc;
-}
 
-template <typename KeyT>
-struct RunPred {
-  struct Payload {
-    int64_t cr, cc;
-    float w;
-    int len;
-  };
-  const KeyT* ks;
-  const int* run_start;
-  const int* total;
-  const float* comb;  // null when unweighted
-  int64_t K;
-  bool rsl;
-  float eps;
-  __device__ bool operator()(int64_t r, Payload& p) const {
-    if (r >= *total) return false;
-    int s = run_start[r];
-    uint64_t key = (uint64_t)ks[s];
-    p.cr = (int64_t)(key / (uint64_t)K);
-    p.cc = (int64_t)(key % (uint64_t)K);
-    p.len = run_start[r + 1] - s;
-    if (rsl && p.cr == p.cc) return false;
-    if (comb) {
-      p.w = comb[r];
-      if (!(fabsf(p.w) > eps)) return false;
-    }
-    return true;
-  }
-};
-template <typename KeyT>
-struct RunEmit {
-  int64_t* out_row;
-  int64_t* out_col;
-  float* out_w;
-  int32_t* run_len;
-  int* run_slot;
-  __device__ void operator()(int64_t r, int pos, const typename RunPred<KeyT>::Payload& p) const {
-    out_row[pos] = p.cr;
-    out_col[pos] = p.cc;
-    if (out_w) out_w[pos] = p.w;
-    if (run_len) run_len[pos] = p.len;
-    run_slot[r] = pos;
-  }
-};
 
-template <typename KeyT>
-static __global__ void k_edge_slots(const KeyT* __restrict__ ks, const uint32_t* __restrict__ perm,
-                                    const int* __restrict__ excl, const int* __restrict__ run_slot, int64_t E,
-                                    int32_t* __restrict__ edge_slot) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= E) return;
-  int head = (i == 0 || ks[i] != ks[i - 1]) ? 1 : 0;
-  edge_slot[perm[i]] = run_slot[excl[i] + head - 1];
-}
 
 static int key_bits_for_u64(uint64_t max_value) {
   int b = 0;
@@ -181,27 +95,107 @@ static int key_bits_for_u64(uint64_t max_value) {
   return b < 1 ? 1 : b;
 }
 
+// Fused run handling on the sorted keys: a run head (first position of a key) walks its run, combining the member
+// weights in sorted (= original, the sort is stable) order; the same pass decides whether the coarse edge survives
+// the self-loop / tiny-weight filters.  The count phase stores the combined weight at the head position so that
+// the emit phase does not repeat the random gathers.
+template <typename KeyT>
+struct RunCountPred {
+  struct Payload {};
+  const KeyT* ks;
+  const uint32_t* perm;
+  const float* w;  // null when unweighted
+  float* comb;     // [E] combined weight at head positions
+  int64_t E, K;
+  int op;
+  bool rsl;
+  float eps;
+  __device__ bool operator()(int64_t i, Payload&) const {
+    const KeyT key = ks[i];
+    if (i > 0 && ks[i - 1] == key) return false;
+    const uint64_t k64 = (uint64_t)key;
+    const bool self = (int64_t)(k64 / (uint64_t)K) == (int64_t)(k64 % (uint64_t)K);
+    if (w == nullptr) return !(rsl && self);
+    float acc = w[perm[i]];
+    int64_t j = i + 1;
+    for (; j < E && ks[j] == key; ++j) {
+      const float v = w[perm[j]];
+      if (op == TGPB200_SUM || op == TGPB200_MEAN) acc = __fadd_rn(acc, v);
+      else if (op == TGPB200_MAX) acc = fmaxf(acc, v);
+      else if (op == TGPB200_MIN) acc = fminf(acc, v);
+      else acc = __fmul_rn(acc, v);
+    }
+    if (op == TGPB200_MEAN) acc = __fdiv_rn(acc, (float)(j - i));
+    comb[i] = acc;
+    if (rsl && self) return false;
+    return fabsf(acc) > eps;
+  }
+};
+template <typename KeyT>
+struct RunEmitPred {
+  struct Payload {
+    int64_t cr, cc;
+    float w;
+  };
+  const KeyT* ks;
+  const float* comb;  // null when unweighted
+  int64_t K;
+  bool rsl;
+  float eps;
+  __device__ bool operator()(int64_t i, Payload& p) const {
+    const KeyT key = ks[i];
+    if (i > 0 && ks[i - 1] == key) return false;
+    const uint64_t k64 = (uint64_t)key;
+    p.cr = (int64_t)(k64 / (uint64_t)K);
+    p.cc = (int64_t)(k64 % (uint64_t)K);
+    if (rsl && p.cr == p.cc) return false;
+    if (comb) {
+      p.w = comb[i];
+      if (!(fabsf(p.w) > eps)) return false;
+    }
+    return true;
+  }
+};
+template <typename KeyT>
+struct RunEmit2 {
+  const KeyT* ks;
+  const uint32_t* perm;
+  int64_t E;
+  int64_t* out_row;
+  int64_t* out_col;
+  float* out_w;
+  int32_t* run_len;
+  int32_t* edge_slot;  // pre-filled with -1
+  __device__ void operator()(int64_t i, int pos, const typename RunEmitPred<KeyT>::Payload& p) const {
+    out_row[pos] = p.cr;
+    out_col[pos] = p.cc;
+    if (out_w) out_w[pos] = p.w;
+    if (run_len || edge_slot) {
+      const KeyT key = ks[i];
+      int64_t j = i;
+      for (; j < E && ks[j] == key; ++j)
+        if (edge_slot) edge_slot[perm[j]] = pos;
+      if (run_len) run_len[pos] = (int32_t)(j - i);
+    }
+  }
+};
+
 // Workspace layout shared by the count and emit phases (carved identically in both calls).
 template <typename KeyT>
 struct CoalescePlan {
   KeyT *keys0, *keys1;
   uint32_t *vals0, *vals1;
-  int *excl, *run_start, *run_slot, *tile_counts, *total;
+  int* tile_counts;
   float* comb;
   bool ok;
-  CoalescePlan(Workspace& ws, int64_t E, bool weighted) {
+  CoalescePlan(Workspace& ws, int64_t E) {
     size_t n = (size_t)E;
     keys0 = ws.take<KeyT>(n);
     keys1 = ws.take<KeyT>(n);
     vals0 = ws.take<uint32_t>(n);
     vals1 = ws.take<uint32_t>(n);
-    excl = ws.take<int>(n);
-    run_start = ws.take<int>(n + 1);
-    run_slot = ws.take<int>(n);
     comb = ws.take<float>(n);
     tile_counts = ws.take<int>((size_t)ceil_div(E, kCompactTile));
-    total = ws.take<int>(2);  // [0] number of runs, [1] 1 if the sorted data sits in (keys1, vals1)
-    (void)weighted;
     ok = ws.ok;
   }
 };
@@ -210,7 +204,7 @@ template <typename KeyT>
 static int remap_coalesce_count_impl(const int64_t* row, const int64_t* col, const float* w, int64_t E,
                                      const int64_t* cluster, int64_t N, int64_t K, int op, uint32_t flags, float eps,
                                      int64_t* count_out, Workspace& ws, cudaStream_t st) {
-  CoalescePlan<KeyT> pl(ws, E, w != nullptr);
+  CoalescePlan<KeyT> pl(ws, E);
   if (!pl.ok) return TGPB200_ERR_WORKSPACE;
   unsigned grid = (unsigned)ceil_div(E, 256);
   launch("k_remap_keys", k_remap_keys<KeyT>, grid, 256, 0, st, row, col, cluster, E, N, K, pl.keys0);
@@ -218,14 +212,8 @@ static int remap_coalesce_count_impl(const int64_t* row, const int64_t* col, con
   bool in1 = false;
   int rc = radix_sort_pairs<KeyT>(pl.keys0, nullptr, pl.vals0, pl.keys1, pl.vals1, E, bits, &in1, ws, st);
   if (rc != TGPB200_OK) return rc;
-  const KeyT* ks = in1 ? pl.keys1 : pl.keys0;
-  const uint32_t* perm = in1 ? pl.vals1 : pl.vals0;
-  launch("k_head_flags", k_head_flags<KeyT>, grid, 256, 0, st, ks, E, pl.excl);
-  rc = exclusive_scan_i32(pl.excl, pl.excl, E, pl.total, nullptr, ws, st);
-  if (rc != TGPB200_OK) return rc;
-  launch("k_run_starts", k_run_starts<KeyT>, grid, 256, 0, st, ks, pl.excl, pl.total, E, pl.run_start);
-  if (w) launch("k_run_combine", k_run_combine, grid, 256, 0, st, perm, w, pl.run_start, pl.total, op, pl.comb);
-  RunPred<KeyT> pred{ks, pl.run_start, pl.total, w ? pl.comb : nullptr, K, (flags & TGPB200_REMOVE_SELF_LOOPS) != 0, eps};
+  RunCountPred<KeyT> pred{in1 ? pl.keys1 : pl.keys0, in1 ? pl.vals1 : pl.vals0, w, pl.comb, E, K, op,
+                          (flags & TGPB200_REMOVE_SELF_LOOPS) != 0, eps};
   return compact_count(pred, E, pl.tile_counts, nullptr, count_out, st);
 }
 
@@ -233,21 +221,16 @@ template <typename KeyT>
 static int remap_coalesce_emit_impl(int64_t E, int64_t K, bool weighted, uint32_t flags, float eps, int64_t* out_row,
                                     int64_t* out_col, float* out_w, int32_t* edge_slot, int32_t* run_len,
                                     Workspace& ws, cudaStream_t st) {
-  CoalescePlan<KeyT> pl(ws, E, weighted);
+  CoalescePlan<KeyT> pl(ws, E);
   if (!pl.ok) return TGPB200_ERR_WORKSPACE;
   int bits = key_bits_for_u64((uint64_t)K * (uint64_t)K - 1);
   bool in1 = (radix_passes(bits) & 1) != 0;
   const KeyT* ks = in1 ? pl.keys1 : pl.keys0;
   const uint32_t* perm = in1 ? pl.vals1 : pl.vals0;
-  unsigned grid = (unsigned)ceil_div(E, 256);
-  cudaMemsetAsync(pl.run_slot, 0xff, (size_t)E * sizeof(int), st);
-  RunPred<KeyT> pred{ks, pl.run_start, pl.total, weighted ? pl.comb : nullptr, K,
-                     (flags & TGPB200_REMOVE_SELF_LOOPS) != 0, eps};
-  RunEmit<KeyT> emit{out_row, out_col, weighted ? out_w : nullptr, run_len, pl.run_slot};
-  int rc = compact_emit(pred, emit, E, pl.tile_counts, st);
-  if (rc != TGPB200_OK) return rc;
-  if (edge_slot) launch("k_edge_slots", k_edge_slots<KeyT>, grid, 256, 0, st, ks, perm, pl.excl, pl.run_slot, E, edge_slot);
-  return launch_status();
+  if (edge_slot) cudaMemsetAsync(edge_slot, 0xff, (size_t)E * sizeof(int32_t), st);
+  RunEmitPred<KeyT> pred{ks, weighted ? pl.comb : nullptr, K, (flags & TGPB200_REMOVE_SELF_LOOPS) != 0, eps};
+  RunEmit2<KeyT> emit{ks, perm, E, out_row, out_col, weighted ? out_w : nullptr, run_len, edge_slot};
+  return compact_emit(pred, emit, E, pl.tile_counts, st);
 }
 
 // ------------------------------------------------------------------------------------------
