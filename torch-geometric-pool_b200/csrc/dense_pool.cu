@@ -639,14 +639,19 @@ static int dense_fwd(const T* A, const T* S, const T* X, int B, int N, int K, in
   if (!fused) {
     if (X && Xpool) {
       // X_pool = S^T X.  The larger of (F, K) becomes the 128-row MMA dimension.
-      if (F >= K)  // D[f, k] = sum_i X[i, f] S[i, k], written transposed into X_pool[k, f]
+      // (transposed stores are scalar per element; when K already fills the 128-row tile the natural orientation
+      //  with vectorised row stores is the faster one)
+      if (F >= K && K % 128 != 0)  // D[f, k] = sum_i X[i, f] S[i, k], written transposed into X_pool[k, f]
         rc = mm1<T, T>(B, F, K, N, Mat{X, NF, F, 1}, Smn, Xpool, KF, 1, F, st);
       else
         rc = mm1<T, T>(B, K, F, N, Smn, Mat{X, NF, F, 1}, Xpool, KF, F, 1, st);
       if (rc) return rc;
     }
-    if (A) {  // T = S^T A  [K, N], computed as D[j, k] = sum_i A[i, j] S[i, k] and written transposed
-      rc = mm1<T, T>(B, N, K, N, Mat{A, NN, N, 1}, Smn, pl.Tt, NK, 1, N, st);
+    if (A) {  // T = S^T A  [K, N]
+      if (K % 128 == 0)  // natural orientation: D[k, j] = sum_i S[i, k] A[i, j]
+        rc = mm1<T, T>(B, K, N, N, Smn, Mat{A, NN, N, 1}, pl.Tt, NK, N, 1, st);
+      else  // D[j, k] = sum_i A[i, j] S[i, k], written transposed (no padding of K up to the 128-row tile)
+        rc = mm1<T, T>(B, N, K, N, Mat{A, NN, N, 1}, Smn, pl.Tt, NK, 1, N, st);
       if (rc) return rc;
     }
     if (loss_kind != 0) {  // M = S^T S

@@ -245,6 +245,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
                     float4 t4 = __ldg(s4 + j);
                     sv[4 * j] = t4.x, sv[4 * j + 1] = t4.y, sv[4 * j + 2] = t4.z, sv[4 * j + 3] = t4.w;
                   }
+                } else if (!kF32 && full && ((si & 7) == 0)) {
+                  const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(P.ew_S) + si);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    uint4 t4 = __ldg(s4 + j);
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t4);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                      float2 f2 = __bfloat1622float2(h2[q]);
+                      sv[8 * j + 2 * q] = f2.x, sv[8 * j + 2 * q + 1] = f2.y;
+                    }
+                  }
                 } else {
 #pragma unroll
                   for (int j = 0; j < 32; ++j)
