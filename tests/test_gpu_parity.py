@@ -380,6 +380,46 @@ def test_dense_pool_fp32_vs_oracle(B, N, K, F, kind):
         close32(g_, e_, f"{kind} {n_}", rtol=1e-5 if not n_.startswith("grad") else 1e-4)
 
 
+@pytest.mark.parametrize("elems,stage", [(64, 1), (128, 0), (32768, 1), (600, 0)])
+@pytest.mark.parametrize("K", [6, 12, 32, 128])
+def test_dense_per_graph_kernels_all_strip_plans(monkeypatch, elems, stage, K):
+    """The per-graph epilogue / backward kernels run as clusters of row strips; every plan (cluster size 1..8,
+    staged or not, scalar / 128-bit paths) must give the same answer as the float64 oracle for every flag set."""
+    monkeypatch.setenv("TGPB200_STRIP_ELEMS", str(elems))
+    monkeypatch.setenv("TGPB200_STRIP_STAGE", str(stage))
+    B, N, F = 3, 160, 32
+    g = torch.Generator().manual_seed(1000 + K)
+    a, s_raw, x = _dense_inputs(g, B, N, K, F)
+    a = a + torch.diag_embed(torch.rand(B, N, generator=g))  # self loops so that remove_self_loops matters
+    gx = torch.randn(B, K, F, generator=g)
+    ga = torch.randn(B, K, K, generator=g)
+    ga = ga + ga.transpose(1, 2)
+    for kind in ("mincut", "diff"):
+        for rsl, dn, tr, ewn in [(True, True, True, False), (True, True, False, False), (False, True, True, True),
+                                 (True, False, True, True), (False, False, False, False), (True, True, False, True)]:
+            kw = dict(remove_self_loops=rsl, degree_norm=dn, adj_transpose=tr, edge_weight_norm=ewn)
+
+            def run(mod, dev, dt):
+                sr = s_raw.detach().clone().to(dev, dt).requires_grad_(True)
+                xx = x.detach().clone().to(dev, dt).requires_grad_(True)
+                aa = a.detach().clone().to(dev, dt).requires_grad_(True)
+                s = torch.softmax(sr, -1)
+                fn = mod.mincut_pool if kind == "mincut" else mod.diff_pool
+                xp, ap, loss = fn(xx, aa, s, **kw)
+                tot = (xp * gx.to(dev, dt)).sum() + (ap * ga.to(dev, dt)).sum() + sum(loss.values())
+                tot.backward()
+                ag = aa.grad
+                if ewn:  # only the symmetric part of dA is well defined under max-normalisation (see above)
+                    ag = 0.5 * (ag + ag.transpose(1, 2))
+                return [t.detach().cpu().float() for t in (xp, ap, *loss.values(), sr.grad, xx.grad, ag)]
+
+            exp = run(R, "cpu", torch.float64)
+            got = run(T, DEV, torch.float32)
+            names = ["x_pool", "adj_pool", "loss0", "loss1", "grad_s", "grad_x", "grad_adj"]
+            for n_, e_, g_ in zip(names, exp, got):
+                close32(g_, e_, f"{kind} {kw} {n_}", rtol=1e-5 if not n_.startswith("grad") else 1e-4)
+
+
 def test_dense_pool_bf16_vs_oracle():
     g = torch.Generator().manual_seed(21)
     B, N, K, F = 3, 128, 32, 64

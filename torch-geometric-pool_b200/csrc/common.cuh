@@ -44,6 +44,34 @@ inline void launch(const char* name, void (*kernel)(KArgs...), dim3 grid, dim3 b
   }
 }
 
+// Same as launch() for a kernel that runs as thread-block clusters of `cluster` CTAs along x (grid.x % cluster == 0).
+template <typename... KArgs, typename... Args>
+inline void launch_cluster(const char* name, void (*kernel)(KArgs...), unsigned grid, unsigned block, unsigned cluster,
+                           size_t smem, cudaStream_t st, Args... args) {
+  ++launch_counter();
+  const bool timed = timing_match(name);
+  if (timed) timing_begin(st);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (timed) timing_end(st);
+  if (debug_sync_enabled()) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaPeekAtLastError();
+    if (e != cudaSuccess) report_launch_failure(name, e);
+  }
+}
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // Bump allocator over the caller-provided workspace (the torch shim owns the memory).

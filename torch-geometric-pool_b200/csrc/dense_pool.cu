@@ -6,12 +6,16 @@
 // This translation unit holds the shape-general path: a strided batched GEMM on the FP32 pipe plus the
 // fused statistics / post-processing / gradient-assembly kernels.  dense_tc.cu provides the tcgen05 GEMMs
 // that replace `bgemm` for the tile-aligned shapes.
+#include <cooperative_groups.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <type_traits>
 
 #include "dense.cuh"
 #include "tc_gemm.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace tgp {
 
@@ -127,17 +131,138 @@ static __global__ void k_row_stats(const T* __restrict__ A, const T* __restrict_
   }
 }
 
-// Column reduction over a [K, K] matrix with all warps busy and 128-byte row reads: warp w accumulates rows
-// w, w + nw, ... of a 32-column strip, the partials are summed over warps through shared memory (fixed order).
-// `colred` must hold 33 * 32 floats.  f(u, v) is the addend of row u, column v; out(v, sum) consumes the result.
+// V consecutive elements <-> registers (V = 4: one 128-bit fp32 / 64-bit bf16 access; V = 1: scalar)
+template <int V, typename T>
+__device__ __forceinline__ void ldv(const T* p, float (&a)[V]) {
+  if constexpr (V == 4 && sizeof(T) == 4) {
+    const float4 x = *reinterpret_cast<const float4*>(p);
+    a[0] = x.x, a[1] = x.y, a[2] = x.z, a[3] = x.w;
+  } else if constexpr (V == 4) {
+    const uint2 x = *reinterpret_cast<const uint2*>(p);
+    a[0] = __uint_as_float(x.x << 16), a[1] = __uint_as_float(x.x & 0xffff0000u);
+    a[2] = __uint_as_float(x.y << 16), a[3] = __uint_as_float(x.y & 0xffff0000u);
+  } else {
+    a[0] = to_f32<T>(p[0]);
+  }
+}
+template <int V, typename T>
+__device__ __forceinline__ void stv(T* p, const float (&a)[V]) {
+  if constexpr (V == 4 && sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1], a[2], a[3]);
+  } else if constexpr (V == 4) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a[0], a[1]), hi = __floats2bfloat162_rn(a[2], a[3]);
+    uint2 x;
+    x.x = *reinterpret_cast<uint32_t*>(&lo), x.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = x;
+  } else {
+    p[0] = from_f32<T>(a[0]);
+  }
+}
+// strip copy global -> shared as fp32, several 128-bit loads in flight per thread
+template <int V, typename T>
+__device__ __forceinline__ void stage_strip(float* dst, const T* src, int cnt) {
+#pragma unroll 4
+  for (int i = threadIdx.x * V; i < cnt; i += blockDim.x * V) {
+    float a[V];
+    ldv<V, T>(src + i, a);
+    stv<V, float>(dst + i, a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-graph kernels run as a thread-block CLUSTER per graph: CTA `rank` owns the row strip
+// [rank * rows_per, (rank + 1) * rows_per) of the [K, K] matrices (staged once in its shared memory), and the
+// graph-wide reductions are combined through distributed shared memory in a fixed order (bitwise reproducible).
+// A cluster of one CTA is the small-K case.
+// ------------------------------------------------------------------------------------------
+struct GraphCluster {
+  cg::cluster_group g;
+  unsigned rank, size;
+  float* slots;  // kClusterSlots floats in every CTA's shared memory, one per reduction
+  int next;
+  __device__ GraphCluster(float* s) : g(cg::this_cluster()), slots(s), next(0) {
+    rank = g.block_rank();
+    size = g.num_blocks();
+  }
+  __device__ __forceinline__ void sync() {
+    if (size > 1) g.sync(); else __syncthreads();
+  }
+  // combine a per-CTA value (identical in all threads of the CTA) over the cluster
+  template <typename Op>
+  __device__ __forceinline__ float combine(float v, Op op) {
+    if (size == 1) return v;
+    const int s = next++;
+    if (threadIdx.x == 0) slots[s] = v;
+    g.sync();
+    float r = *g.map_shared_rank(&slots[s], 0);
+    for (unsigned k = 1; k < size; ++k) r = op(r, *g.map_shared_rank(&slots[s], k));
+    return r;
+  }
+  __device__ __forceinline__ float sum(float v, float* red) {
+    return combine(block_sum(v, red), [](float a, float b) { return a + b; });
+  }
+  // n sums with ONE cluster round trip (v[] in/out)
+  template <int NV>
+  __device__ __forceinline__ void sum_n(float (&v)[NV], float* red) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = block_sum(v[j], red);
+    if (size == 1) return;
+    const int s = next;
+    next += NV;
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) slots[s + j] = v[j];
+    }
+    g.sync();
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float r = *g.map_shared_rank(&slots[s + j], 0);
+      for (unsigned k = 1; k < size; ++k) r += *g.map_shared_rank(&slots[s + j], k);
+      v[j] = r;
+    }
+  }
+  __device__ __forceinline__ float max(float v, float* red) {
+    return combine(block_max(v, red), [](float a, float b) { return fmaxf(a, b); });
+  }
+  __device__ __forceinline__ int min_int(int v, int* redi) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) v = ::min(v, __shfl_xor_sync(kFull, v, o));
+    __syncthreads();
+    if (lane == 0) redi[w] = v;
+    __syncthreads();
+    v = lane < nw ? redi[lane] : INT_MAX;
+    for (int o = 16; o > 0; o >>= 1) v = ::min(v, __shfl_xor_sync(kFull, v, o));
+    return __float_as_int(
+        combine(__int_as_float(v), [](float a, float b) { return __int_as_float(::min(__float_as_int(a), __float_as_int(b))); }));
+  }
+  // full[v] = sum over CTAs of part[v]  (part lives at the same shared-memory offset in every CTA)
+  template <typename O>
+  __device__ __forceinline__ void gather_sum(const float* part, int K, O out) {
+    sync();
+    for (int v = threadIdx.x; v < K; v += blockDim.x) {
+      float s = part[v];
+      if (size > 1) {
+        s = *g.map_shared_rank(part + v, 0);
+        for (unsigned k = 1; k < size; ++k) s += *g.map_shared_rank(part + v, k);
+      }
+      out(v, s);
+    }
+    __syncthreads();
+  }
+};
+constexpr int kClusterSlots = 24;
+
+// Column sums over the row strip [u0, u1) with all warps busy and 128-byte row reads: warp w accumulates rows
+// u0 + w, u0 + w + nw, ... of a 32-column strip, the partials are summed over warps through shared memory
+// (fixed order).  `colred` must hold 33 * 32 floats.  f(u, v) is the addend; out(v, sum) consumes the result.
 template <typename F, typename O>
-__device__ __forceinline__ void block_col_reduce(int K, float* colred, F f, O out) {
+__device__ __forceinline__ void block_col_reduce(int K, int u0, int u1, float* colred, F f, O out) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int c0 = 0; c0 < K; c0 += 32) {
     const int v = c0 + lane;
     float acc = 0.f;
     if (v < K)
-      for (int u = w; u < K; u += nw) acc += f(u, v);
+      for (int u = u0 + w; u < u1; u += nw) acc += f(u, v);
     colred[w * 33 + lane] = acc;
     __syncthreads();
     if (w == 0 && v < K) {
@@ -149,147 +274,242 @@ __device__ __forceinline__ void block_col_reduce(int K, float* colred, F f, O ou
   }
 }
 
+// One pass over a row strip with 128-bit accesses: thread t owns columns 4 * (t % TPR) .. + 3 (TPR = K / 4 threads
+// per row, a power of two <= blockDim) and walks rows r0 + t / TPR, + G, ...   f(i, r, c0, p) yields the four addends
+// of the strip-local element i = (r - r0) * K + c0.   colout[v] = sum over the strip's rows (all v), rowout[r] = sum
+// over the columns (rows r0..r1 only); both in a fixed order.
+// colred: 4 * blockDim floats, rowp: (r1 - r0) * max(1, K / 128) floats.
+template <bool COLS, bool ROWS, typename F>
+__device__ __forceinline__ void strip_sums4(int K, int r0, int r1, float* colred, float* rowp, float* colout,
+                                            float* rowout, F f) {
+  const int t = threadIdx.x, nt = blockDim.x, lane = t & 31;
+  const int TPR = K >> 2, tshift = __ffs(TPR) - 1;
+  const int G = nt >> tshift;  // rows in flight
+  const int cx = t & (TPR - 1), g = t >> tshift, c0 = cx << 2;
+  const int wpr = TPR >> 5;  // warps per row when a row spans whole warps
+  float ca[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int rb = r0; rb < r1; rb += G) {
+    const int r = rb + g;
+    const bool on = g < G && r < r1;
+    float p[4] = {0.f, 0.f, 0.f, 0.f};
+    if (on) f((r - r0) * K + c0, r, c0, p);
+    if (COLS) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ca[j] += p[j];
+    }
+    if (ROWS) {
+      float v = (p[0] + p[1]) + (p[2] + p[3]);
+      if (TPR >= 32) {
+        v = warp_sum(v);
+        if (lane == 0 && on) rowp[(r - r0) * wpr + (cx >> 5)] = v;
+      } else {
+        for (int o = TPR >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        if (cx == 0 && on) rowout[r] = v;
+      }
+    }
+  }
+  if (COLS) {
+    if (g < G) *reinterpret_cast<float4*>(colred + g * K + c0) = make_float4(ca[0], ca[1], ca[2], ca[3]);
+    __syncthreads();
+    for (int v = t; v < K; v += nt) {
+      float s = 0.f;
+      for (int k = 0; k < G; ++k) s += colred[k * K + v];
+      colout[v] = s;
+    }
+  }
+  if (ROWS && TPR >= 32) {
+    __syncthreads();
+    for (int r = r0 + t; r < r1; r += nt) {
+      float s = 0.f;
+      for (int k = 0; k < wpr; ++k) s += rowp[(r - r0) * wpr + k];
+      rowout[r] = s;
+    }
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------
-// Per-graph epilogue (one block per graph): loss statistics from the RAW S^T A S and S^T S,
+// Per-graph epilogue (one cluster per graph): loss statistics from the RAW S^T A S and S^T S,
 // then post-processing (diag zero -> D^-1/2 A D^-1/2 -> / max|A|) exactly in ops.py:307-333 order.
 // stats[b] = {num, den, ||M||_F^2, ortho_b, ||A||_F^2, ent_b, maxnorm m, unused}
 // ------------------------------------------------------------------------------------------
-template <typename T>
-static __global__ void __launch_bounds__(1024)
+template <typename T, int V, bool STAGED>
+static __global__ void __launch_bounds__(512)
     k_graph_epilogue(const float* __restrict__ Araw, const float* __restrict__ M, const float* __restrict__ d,
                      const float* __restrict__ ss, const float* __restrict__ a2, const float* __restrict__ ent, int N,
                      int K, uint32_t flags, float eps, T* __restrict__ Apool, float* __restrict__ dvec,
-                     float* __restrict__ stats, int32_t* __restrict__ argmax, int stage) {
-  extern __shared__ float sm[];  // K floats: d_v  (+ 2 K^2 floats when the matrices are staged)
+                     float* __restrict__ stats, int32_t* __restrict__ argmax, int rows_per, int rowp_floats) {
+  // dq[K] (degree scale, all columns), part[K], rowp[rowp_floats]  (+ the two staged row strips)
+  extern __shared__ __align__(16) float sm[];
   __shared__ float red[32];
   __shared__ int redi[32];
-  __shared__ float colred[33 * 32];
-  int b = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
-  const float* Ar = Araw ? Araw + (int64_t)b * K * K : nullptr;
-  const float* Mg = M ? M + (int64_t)b * K * K : nullptr;
+  __shared__ __align__(16) float colred[4 * 512];
+  __shared__ float slots[kClusterSlots];
+  GraphCluster cl(slots);
+  float* dq = sm;
+  float* part = sm + K;
+  float* rowp = sm + 2 * K;
+  const int b = blockIdx.x / cl.size, t = threadIdx.x, nt = blockDim.x;
+  const int r0 = min(K, (int)cl.rank * rows_per), r1 = min(K, r0 + rows_per);
+  const int i0 = r0 * K, cnt = (r1 - r0) * K;  // this CTA's elements are i0 + [0, cnt)
+  const bool hasA = Araw != nullptr, hasM = M != nullptr;
+  const float* Ar = hasA ? Araw + (int64_t)b * K * K + i0 : nullptr;
+  const float* Mg = hasM ? M + (int64_t)b * K * K + i0 : nullptr;
   float* st = stats + (int64_t)b * 8;
-  if (stage) {  // the kernel is a chain of short block-wide passes: keep the [K,K] operands on chip
-    float* sA = sm + K;
-    float* sM = sA + K * K;
-    for (int i = t; i < K * K; i += nt) {
-      if (Ar) sA[i] = Ar[i];
-      if (Mg) sM[i] = Mg[i];
-    }
-    if (Ar) Ar = sA;
-    if (Mg) Mg = sM;
+  if constexpr (STAGED) {  // the kernel is a chain of short passes over the same strip: keep it on chip
+    float* sA = sm + 2 * K + rowp_floats;
+    float* sM = sA + rows_per * K;
+    if (hasA) stage_strip<V, float>(sA, Ar, cnt);
+    if (hasM) stage_strip<V, float>(sM, Mg, cnt);
+    Ar = sA;  // unconditional: the later accesses compile to shared-memory loads
+    Mg = sM;
     __syncthreads();
   }
 
   const int kshift = (K & (K - 1)) == 0 ? __ffs(K) - 1 : -1;
-  auto row_of = [&](int i) { return kshift >= 0 ? (i >> kshift) : (i / K); };
-  auto col_of = [&](int i, int r) { return kshift >= 0 ? (i & (K - 1)) : (i - r * K); };
-  // den, ||A||^2, entropy (fixed-order block reductions)
-  float den = 0.f, sa2 = 0.f, se = 0.f;
-  for (int i = t; i < N; i += nt) {
+  auto row_of = [&](int i) { return r0 + (kshift >= 0 ? (i >> kshift) : (i / K)); };  // i is strip-local
+  auto col_of = [&](int i, int r) { return kshift >= 0 ? (i & (K - 1)) : (i - (r - r0) * K); };
+  // den, ||A||^2, entropy, trace, ||M||^2: fixed-order reductions, one cluster round trip
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = cl.rank * nt + t; i < N; i += nt * cl.size) {
     int64_t r = (int64_t)b * N + i;
-    den += d[r] * ss[r];
-    sa2 += a2[r];
-    se += ent[r];
+    acc[0] += d[r] * ss[r];
+    acc[1] += a2[r];
+    acc[2] += ent[r];
   }
-  den = block_sum(den, red), sa2 = block_sum(sa2, red), se = block_sum(se, red);
-
-  float num = 0.f;
-  if (Ar)
-    for (int i = t; i < K; i += nt) num += Ar[(int64_t)i * K + i];
-  num = block_sum(num, red);
-
-  float m2 = 0.f, ortho = 0.f;
-  if (M) {
-    const float* Mb = Mg;
-    for (int i = t; i < K * K; i += nt) m2 += Mb[i] * Mb[i];
-    m2 = block_sum(m2, red);
-    float nM = sqrtf(m2), isk = 1.0f / sqrtf((float)K);
-    float u2 = 0.f;
-    for (int i = t; i < K * K; i += nt) {
-      int r = row_of(i);
-      float u = Mb[i] / nM - ((r == col_of(i, r)) ? isk : 0.f);
-      u2 += u * u;
+  if (hasA)
+    for (int r = r0 + t; r < r1; r += nt) acc[3] += Ar[(int64_t)(r - r0) * K + r];
+  if (hasM)
+    for (int i = t * V; i < cnt; i += nt * V) {
+      float mv[V];
+      ldv<V, float>(Mg + i, mv);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[4] += mv[j] * mv[j];
     }
-    ortho = sqrtf(block_sum(u2, red));
+  cl.sum_n(acc, red);
+  const float den = acc[0], sa2 = acc[1], se = acc[2], num = acc[3], m2 = acc[4];
+  float ortho = 0.f;
+  if (hasM) {
+    const float nM = sqrtf(m2), isk = 1.0f / sqrtf((float)K), inM = 1.0f / nM;
+    float u2 = 0.f;
+    for (int i = t * V; i < cnt; i += nt * V) {
+      float mv[V];
+      ldv<V, float>(Mg + i, mv);
+      const int r = row_of(i), c = col_of(i, r);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float u = mv[j] * inM - ((r == c + j) ? isk : 0.f);
+        u2 += u * u;
+      }
+    }
+    ortho = sqrtf(cl.sum(u2, red));
   }
-  if (t == 0) {
+  if (t == 0 && cl.rank == 0) {
     st[0] = num, st[1] = den, st[2] = m2, st[3] = ortho, st[4] = sa2, st[5] = se, st[6] = 1.f, st[7] = 0.f;
   }
-  if (!Ar || !Apool) return;
+  if (!hasA || !Apool) {
+    cl.sync();  // no CTA may retire while a peer can still read its slots
+    return;
+  }
 
   bool rsl = flags & TGPB200_REMOVE_SELF_LOOPS, dn = flags & TGPB200_DEGREE_NORM;
   bool tr = flags & TGPB200_ADJ_TRANSPOSE, wn = flags & TGPB200_EDGE_WEIGHT_NORM;
+  constexpr bool kRecip = sizeof(T) == 2;
   // degree vector over the diag-zeroed matrix: s_v = column sum (adj_transpose) or row sum
   if (dn) {
-    if (tr) {  // column sums (tiled: every warp reads 128-byte row segments)
+    for (int v = t; v < K; v += nt) part[v] = 0.f;
+    __syncthreads();
+    if (V == 4 && kshift >= 2 && (K >> 2) <= nt) {  // one vectorised pass
+      auto addends = [&](int i, int r, int c0, float (&p)[4]) {
+        const float4 x = *reinterpret_cast<const float4*>(Ar + i);
+        p[0] = x.x, p[1] = x.y, p[2] = x.z, p[3] = x.w;
+        if (rsl) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (r == c0 + j) p[j] = 0.f;
+        }
+      };
+      if (tr) strip_sums4<true, false>(K, r0, r1, colred, rowp, part, nullptr, addends);
+      else strip_sums4<false, true>(K, r0, r1, colred, rowp, nullptr, part, addends);
+    } else if (tr) {  // column sums of the strip (tiled: every warp reads 128-byte row segments)
       block_col_reduce(
-          K, colred, [&](int u, int v) { return (rsl && u == v) ? 0.f : Ar[(int64_t)u * K + v]; },
-          [&](int v, float s) {
-            sm[v] = sqrtf(fmaxf(s, eps));
-            dvec[(int64_t)b * K + v] = s;
-          });
-    } else {  // row sums: one warp per row
+          K, r0, r1, colred, [&](int u, int v) { return (rsl && u == v) ? 0.f : Ar[(int64_t)(u - r0) * K + v]; },
+          [&](int v, float s) { part[v] = s; });
+    } else {  // row sums: one warp per row (rows of other CTAs stay zero)
       int lane = t & 31, w = t >> 5, nw = nt >> 5;
-      for (int v = w; v < K; v += nw) {
+      for (int v = r0 + w; v < r1; v += nw) {
         float s = 0.f;
         for (int u = lane; u < K; u += 32)
-          if (!(rsl && u == v)) s += Ar[(int64_t)v * K + u];
+          if (!(rsl && u == v)) s += Ar[(int64_t)(v - r0) * K + u];
         s = warp_sum(s);
-        if (lane == 0) {
-          sm[v] = sqrtf(fmaxf(s, eps));
-          dvec[(int64_t)b * K + v] = s;
-        }
+        if (lane == 0) part[v] = s;
       }
     }
+    // fp32 outputs divide twice like ops.py:318-326; bf16 outputs multiply by the reciprocal (the difference is
+    // far below the bf16 rounding of the result)
+    cl.gather_sum(part, K, [&](int v, float s) {
+      const float dv = sqrtf(fmaxf(s, eps));
+      dq[v] = kRecip ? 1.0f / dv : dv;
+      if (cl.rank == 0) dvec[(int64_t)b * K + v] = s;
+    });
   }
   __syncthreads();
-  float mx = 0.f;
-  int amx = INT_MAX;
-  T* Ap = Apool + (int64_t)b * K * K;
-  for (int i = t; i < K * K; i += nt) {
-    int r = row_of(i), c = col_of(i, r);
-    float v = (rsl && r == c) ? 0.f : Ar[i];
-    if (dn) v = tr ? __fdiv_rn(__fdiv_rn(v, sm[c]), sm[r]) : __fdiv_rn(__fdiv_rn(v, sm[r]), sm[c]);
-    if (wn) {
-      float a = fabsf(v);
-      if (a > mx) { mx = a; amx = i; }
-    } else {
-      Ap[i] = from_f32<T>(v);
+  // the V post-processed values starting at strip-local element i (same row)
+  auto values = [&](int i, float (&v)[V]) {
+    ldv<V, float>(Ar + i, v);
+    const int r = row_of(i), c = col_of(i, r);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      if (rsl && r == c + j) v[j] = 0.f;
+      if (dn) {
+        if (kRecip) v[j] = v[j] * (dq[r] * dq[c + j]);
+        else v[j] = tr ? __fdiv_rn(__fdiv_rn(v[j], dq[c + j]), dq[r]) : __fdiv_rn(__fdiv_rn(v[j], dq[r]), dq[c + j]);
+      }
     }
-  }
-  if (wn) {
-    float bm = block_max(mx, red);
+  };
+  T* Ap = Apool + (int64_t)b * K * K + i0;
+  if (!wn) {
+    for (int i = t * V; i < cnt; i += nt * V) {
+      float v[V];
+      values(i, v);
+      stv<V, T>(Ap + i, v);
+    }
+  } else {
+    float mx = 0.f;
+    for (int i = t * V; i < cnt; i += nt * V) {
+      float v[V];
+      values(i, v);
+#pragma unroll
+      for (int j = 0; j < V; ++j) mx = fmaxf(mx, fabsf(v[j]));
+    }
+    const float bm = cl.max(mx, red);
     // Arg of the max for the backward: the FIRST index whose magnitude reaches the max (torch.max rule).
     // A symmetric adjacency ties (r,c) with (c,r) up to rounding noise of the GEMM, so "reaches" is taken
     // with a 2e-6 relative slack; the reference then picks the upper-triangle element, and so do we.
     const float thr = bm * (1.f - 2e-6f);
     int cand = INT_MAX;
-    for (int i = t; i < K * K; i += nt) {
-      int r = row_of(i), c = col_of(i, r);
-      float v = (rsl && r == c) ? 0.f : Ar[i];
-      if (dn) v = tr ? __fdiv_rn(__fdiv_rn(v, sm[c]), sm[r]) : __fdiv_rn(__fdiv_rn(v, sm[r]), sm[c]);
-      if (fabsf(v) >= thr) { cand = i; break; }
+    for (int i = t * V; i < cnt && cand == INT_MAX; i += nt * V) {
+      float v[V];
+      values(i, v);
+#pragma unroll
+      for (int j = V - 1; j >= 0; --j)
+        if (fabsf(v[j]) >= thr) cand = i0 + i + j;
     }
-    (void)amx;
-    int lane = t & 31, w = t >> 5, nw = nt >> 5;
-    for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(kFull, cand, o));
-    __syncthreads();
-    if (lane == 0) redi[w] = cand;
-    __syncthreads();
-    cand = lane < nw ? redi[lane] : INT_MAX;
-    for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(kFull, cand, o));
-    float m = bm == 0.f ? 1.f : bm;
-    if (t == 0) {
+    cand = cl.min_int(cand, redi);
+    const float m = bm == 0.f ? 1.f : bm;
+    if (t == 0 && cl.rank == 0) {
       st[6] = m;
       argmax[b] = bm == 0.f ? -1 : cand;
     }
-    for (int i = t; i < K * K; i += nt) {
-      int r = row_of(i), c = col_of(i, r);
-      float v = (rsl && r == c) ? 0.f : Ar[i];
-      if (dn) v = tr ? __fdiv_rn(__fdiv_rn(v, sm[c]), sm[r]) : __fdiv_rn(__fdiv_rn(v, sm[r]), sm[c]);
-      Ap[i] = from_f32<T>(__fdiv_rn(v, m));
+    for (int i = t * V; i < cnt; i += nt * V) {
+      float v[V];
+      values(i, v);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] = __fdiv_rn(v[j], m);
+      stv<V, T>(Ap + i, v);
     }
   }
+  cl.sync();
 }
 
 // losses[0..3] = {cut (mean_b), ortho (mean_b), link, entropy}; one block, fixed order.
@@ -315,41 +535,62 @@ static __global__ void k_finalize_losses(const float* __restrict__ stats, int B,
 }
 
 // ------------------------------------------------------------------------------------------
-// Backward assembly (one block per graph):
+// Backward assembly (one cluster per graph, row strips as in the epilogue):
 //   Graw = d L / d (S^T A S) raw   from  Gpool (through max-norm, degree-norm, diag-zero) + trace terms
 //   P    = d L / d (S^T S) symmetrised:  dS += S P        (ortho + link ||M||^2 term)
 //   coef[b] = {c_den, c_a2, c_ent}  for the element-wise terms
 // gl = upstream grads of {cut, ortho, link, entropy} (device floats, already x coefficient).
 // ------------------------------------------------------------------------------------------
-template <typename T>
-static __global__ void __launch_bounds__(1024)
+template <typename T, int V, bool STAGED>
+static __global__ void __launch_bounds__(512)
     k_graph_bwd(const float* __restrict__ Araw, const float* __restrict__ M, const T* __restrict__ Gpool,
                 const float* __restrict__ dvec, const float* __restrict__ stats, const int32_t* __restrict__ argmax,
                 const float* __restrict__ gl, const float* __restrict__ losses, int B, int K, uint32_t flags,
                 int loss_kind, float eps, float link_div, float ent_div, float* __restrict__ Graw,
-                float* __restrict__ P, float* __restrict__ coef, int stage, T* __restrict__ Gt, T* __restrict__ Pt) {
-  extern __shared__ float sm[];  // 3K floats: dsq[v], rowdot[v], coldot[v]  (+ 2 K^2 staged floats)
+                float* __restrict__ P, float* __restrict__ coef, int rows_per, int rowp_floats, T* __restrict__ Gt,
+                T* __restrict__ Pt) {
+  // dsq[K] = 1/d_v, part[K], tot[K] = rowdot + coldot, rowv[K], rowp[rowp_floats]  (+ three staged strips)
+  extern __shared__ __align__(16) float sm[];
   __shared__ float red[32];
-  __shared__ float colred[33 * 32];
+  __shared__ __align__(16) float colred[4 * 512];
+  __shared__ float slots[kClusterSlots];
+  GraphCluster cl(slots);
   float* dsq = sm;
-  float* rdot = sm + K;
-  float* cdot = sm + 2 * K;
-  int b = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
+  float* part = sm + K;
+  float* tot = sm + 2 * K;
+  float* rowv = sm + 3 * K;
+  float* rowp = sm + 4 * K;
+  const int b = blockIdx.x / cl.size, t = threadIdx.x, nt = blockDim.x;
+  const int r0 = min(K, (int)cl.rank * rows_per), r1 = min(K, r0 + rows_per);
+  const int i0 = r0 * K, cnt = (r1 - r0) * K;
   const float* st = stats + (int64_t)b * 8;
-  const float* Ar = Araw + (int64_t)b * K * K;
-  const float* Mst = M ? M + (int64_t)b * K * K : nullptr;
-  if (stage) {
-    float* sA = sm + 3 * K;
-    float* sM = sA + K * K;
-    for (int i = t; i < K * K; i += nt) {
-      sA[i] = Ar[i];
-      if (Mst) sM[i] = Mst[i];
-    }
-    Ar = sA;
-    if (Mst) Mst = sM;
+  const bool hasM = M != nullptr, hasG = Gpool != nullptr;
+  const float* Ar = Araw + (int64_t)b * K * K + i0;
+  const float* Mb = hasM ? M + (int64_t)b * K * K + i0 : nullptr;
+  const T* Gp = hasG ? Gpool + (int64_t)b * K * K + i0 : nullptr;
+  const float* Gs = nullptr;  // staged fp32 copy of the upstream gradient strip
+  if constexpr (STAGED) {
+    float* sA = sm + 4 * K + rowp_floats;
+    float* sM = sA + rows_per * K;
+    float* sG = sM + rows_per * K;
+    stage_strip<V, float>(sA, Ar, cnt);
+    if (hasM) stage_strip<V, float>(sM, Mb, cnt);
+    if (hasG) stage_strip<V, T>(sG, Gp, cnt);
+    Ar = sA;  // unconditional: the later accesses compile to shared-memory loads
+    Mb = sM;
+    Gs = sG;
     __syncthreads();
   }
-  float* Gr = Graw + (int64_t)b * K * K;
+  auto gp = [&](int i) {
+    if constexpr (STAGED) return Gs[i]; else return to_f32<T>(Gp[i]);
+  };
+  auto gpv = [&](int i, float (&g)[V]) {
+    if constexpr (STAGED) ldv<V, float>(Gs + i, g); else ldv<V, T>(Gp + i, g);
+  };
+  auto outv = [&](T* ot, float* of, int i, const float (&v)[V]) {  // operand-dtype copy (bf16 runs) or fp32
+    if (ot) stv<V, T>(ot + i, v); else stv<V, float>(of + i, v);
+  };
+  const int64_t o0 = (int64_t)b * K * K + i0;  // output offset of this strip
   bool rsl = flags & TGPB200_REMOVE_SELF_LOOPS, dn = flags & TGPB200_DEGREE_NORM;
   bool tr = flags & TGPB200_ADJ_TRANSPOSE, wn = flags & TGPB200_EDGE_WEIGHT_NORM;
   float m = st[6];
@@ -368,56 +609,58 @@ static __global__ void __launch_bounds__(1024)
     c_a2 = cq, c_num = -2.f * cq, c_m2 = cq;
     c_ent = g_ent / ent_div;
   }
-  if (t == 0) {
+  if (t == 0 && cl.rank == 0) {
     coef[b * 4 + 0] = c_den, coef[b * 4 + 1] = c_a2, coef[b * 4 + 2] = c_ent, coef[b * 4 + 3] = 0.f;
   }
 
-  // index split without an integer division when K is a power of two (the common case)
+  // index split without an integer division when K is a power of two (the common case); i is strip-local
   const int kshift = (K & (K - 1)) == 0 ? __ffs(K) - 1 : -1;
-  auto row_of = [&](int i) { return kshift >= 0 ? (i >> kshift) : (i / K); };
-  auto col_of = [&](int i, int r) { return kshift >= 0 ? (i & (K - 1)) : (i - r * K); };
+  auto row_of = [&](int i) { return r0 + (kshift >= 0 ? (i >> kshift) : (i / K)); };
+  auto col_of = [&](int i, int r) { return kshift >= 0 ? (i & (K - 1)) : (i - (r - r0) * K); };
 
   // --- P = dL/dM + transpose  (M symmetric so both terms are symmetric)
-  if (P) {
-    float* Pb = P + (int64_t)b * K * K;
-    const float* Mb = Mst;
+  if (P && hasM) {
     if (loss_kind == 1) {
       const float nM = sqrtf(st[2]), rr = st[3], isk = 1.0f / sqrtf((float)K), inM = 1.0f / nM;
-      // <U, M> with U = M/nM - I/sqrt(K)
-      float um = 0.f;
-      for (int i = t; i < K * K; i += nt) {
-        int r = row_of(i);
-        float u = Mb[i] * inM - ((r == col_of(i, r)) ? isk : 0.f);
-        um += u * Mb[i];
-      }
-      um = block_sum(um, red);
+      // With U = M/nM - I/sqrt(K) and r = ||U||:  <U, M> = nM * <U, M/nM> = nM * r^2 / 2  (no extra reduction,
+      // and no cancellation near perfect orthogonality).
+      const float um = 0.5f * nM * rr * rr;
       const float go = g_ortho / (float)B;
       // dM = go * (U/r - <U,M>/r * M/nM^2) / nM
       const float c1 = rr > 0.f ? 2.f * go / (rr * nM) : 0.f, c2 = rr > 0.f ? 2.f * go * um / (rr * nM * nM * nM) : 0.f;
-      for (int i = t; i < K * K; i += nt) {
-        int r = row_of(i);
-        float u = Mb[i] * inM - ((r == col_of(i, r)) ? isk : 0.f);
-        const float pv = c1 * u - c2 * Mb[i];
-        if (Pt) Pt[(int64_t)b * K * K + i] = from_f32<T>(pv); else Pb[i] = pv;
+      for (int i = t * V; i < cnt; i += nt * V) {
+        float mv[V], pv[V];
+        ldv<V, float>(Mb + i, mv);
+        const int r = row_of(i), c = col_of(i, r);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          float u = mv[j] * inM - ((r == c + j) ? isk : 0.f);
+          pv[j] = c1 * u - c2 * mv[j];
+        }
+        outv(Pt ? Pt + o0 : nullptr, P + o0, i, pv);
       }
     } else {
-      for (int i = t; i < K * K; i += nt) {
-        const float pv = 4.f * c_m2 * Mb[i];
-        if (Pt) Pt[(int64_t)b * K * K + i] = from_f32<T>(pv); else Pb[i] = pv;
+      for (int i = t * V; i < cnt; i += nt * V) {
+        float mv[V], pv[V];
+        ldv<V, float>(Mb + i, mv);
+#pragma unroll
+        for (int j = 0; j < V; ++j) pv[j] = 4.f * c_m2 * mv[j];
+        outv(Pt ? Pt + o0 : nullptr, P + o0, i, pv);
       }
     }
   }
 
   // --- Graw from Gpool
-  if (Gpool == nullptr) {
-    for (int i = t; i < K * K; i += nt) {
-      int r = row_of(i);
-      const float gv = (r == col_of(i, r)) ? c_num : 0.f;
-      if (Gt) Gt[(int64_t)b * K * K + i] = from_f32<T>(gv); else Gr[i] = gv;
+  if (!hasG) {
+    for (int i = t * V; i < cnt; i += nt * V) {
+      const int r = row_of(i), c = col_of(i, r);
+      float gv[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) gv[j] = (r == c + j) ? c_num : 0.f;
+      outv(Gt ? Gt + o0 : nullptr, Graw + o0, i, gv);
     }
-    return;
+    return;  // no cluster reduction was started on this path
   }
-  const T* Gp = Gpool + (int64_t)b * K * K;
   // dsq holds 1 / d_v = 1 / sqrt(clamp(s_v, eps)): the gradient assembly multiplies by reciprocals (the kernel
   // was bound by IEEE divisions); results agree with the divided form to ~1 ulp.
   if (dn)
@@ -427,64 +670,99 @@ static __global__ void __launch_bounds__(1024)
   // A2 = normalised matrix before max-norm; G2 = grad wrt A2
   float corr = 0.f;  // sum G * A2 (for the max-norm arg term)
   if (wn && m != 0.f) {
-    for (int i = t; i < K * K; i += nt) {
-      int r = row_of(i), c = col_of(i, r);
-      float v = (rsl && r == c) ? 0.f : Ar[i];
-      if (dn) v = v * (dsq[r] * dsq[c]);
-      corr += to_f32<T>(Gp[i]) * v;
-    }
-    corr = block_sum(corr, red);
-  }
-  const int am = wn ? argmax[b] : -1;
-  const float argterm = -corr * im * im;
-  // row / column dot products  rdot[v] = sum_j G2[v,j] A2[v,j],  cdot[v] = sum_i G2[i,v] A2[i,v]
-  if (dn) {
-    int lane = t & 31, w = t >> 5, nw = nt >> 5;
-    for (int v = w; v < K; v += nw) {  // row dots: one warp per row
-      float sr = 0.f;
-      const float iv = dsq[v];
-      for (int u = lane; u < K; u += 32) {
-        int i = v * K + u;
-        float a = (rsl && u == v) ? 0.f : Ar[i] * (iv * dsq[u]);
-        float g = to_f32<T>(Gp[i]) * im;
-        if (i == am) g += (a < 0.f ? -argterm : argterm);
-        sr += g * a;
+    for (int i = t * V; i < cnt; i += nt * V) {
+      float av[V], gv[V];
+      ldv<V, float>(Ar + i, av);
+      gpv(i, gv);
+      const int r = row_of(i), c = col_of(i, r);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float v = (rsl && r == c + j) ? 0.f : av[j];
+        if (dn) v = v * (dsq[r] * dsq[c + j]);
+        corr += gv[j] * v;
       }
-      sr = warp_sum(sr);
-      if (lane == 0) rdot[v] = sr;
     }
-    block_col_reduce(  // column dots (tiled)
-        K, colred,
-        [&](int u, int v) {
-          int i = u * K + v;
-          float a = (rsl && u == v) ? 0.f : Ar[i] * (dsq[v] * dsq[u]);
-          float g = to_f32<T>(Gp[i]) * im;
+  }
+  if (wn) corr = cl.sum(corr, red);
+  const int am = wn ? argmax[b] - i0 : -1;  // strip-local index of the arg-max element (out of range elsewhere)
+  const float argterm = -corr * im * im;
+  // tot[v] = sum_j G2[v,j] A2[v,j] + sum_i G2[i,v] A2[i,v]   (row dot + column dot)
+  if (dn) {
+    for (int v = t; v < K; v += nt) part[v] = 0.f;
+    __syncthreads();
+    if (V == 4 && kshift >= 2 && (K >> 2) <= nt) {  // row and column dots in one vectorised pass
+      strip_sums4<true, true>(K, r0, r1, colred, rowp, part, rowv, [&](int i, int r, int c0, float (&p)[4]) {
+        float av[4], gv[4];
+        ldv<4, float>(Ar + i, av);
+        if constexpr (STAGED) ldv<4, float>(Gs + i, gv); else ldv<4, T>(Gp + i, gv);
+        const float ir = dsq[r];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a = (rsl && r == c0 + j) ? 0.f : av[j] * (ir * dsq[c0 + j]);
+          float g = gv[j] * im;
+          if (i + j == am) g += (a < 0.f ? -argterm : argterm);
+          p[j] = g * a;
+        }
+      });
+      for (int v = r0 + t; v < r1; v += nt) part[v] += rowv[v];
+    } else {
+      block_col_reduce(  // column dots over the strip (tiled)
+          K, r0, r1, colred,
+          [&](int u, int v) {
+            int i = (u - r0) * K + v;
+            float a = (rsl && u == v) ? 0.f : Ar[i] * (dsq[v] * dsq[u]);
+            float g = gp(i) * im;
+            if (i == am) g += (a < 0.f ? -argterm : argterm);
+            return g * a;
+          },
+          [&](int v, float sc) { part[v] = sc; });
+      int lane = t & 31, w = t >> 5, nw = nt >> 5;
+      for (int v = r0 + w; v < r1; v += nw) {  // row dots: one warp per row of the strip
+        float sr = 0.f;
+        const float iv = dsq[v];
+        for (int u = lane; u < K; u += 32) {
+          int i = (v - r0) * K + u;
+          float a = (rsl && u == v) ? 0.f : Ar[i] * (iv * dsq[u]);
+          float g = gp(i) * im;
           if (i == am) g += (a < 0.f ? -argterm : argterm);
-          return g * a;
-        },
-        [&](int v, float sc) { cdot[v] = sc; });
+          sr += g * a;
+        }
+        sr = warp_sum(sr);
+        if (lane == 0) part[v] += sr;
+      }
+    }
+    cl.gather_sum(part, K, [&](int v, float s) { tot[v] = s; });
   }
   __syncthreads();
-  for (int i = t; i < K * K; i += nt) {
-    int r = row_of(i), c = col_of(i, r);
-    float g = to_f32<T>(Gp[i]) * im;
-    if (wn && i == am) {
-      float a = (rsl && r == c) ? 0.f : Ar[i];
-      if (dn) a = a * (dsq[r] * dsq[c]);
-      g += (a < 0.f ? -argterm : argterm);
+  for (int i = t * V; i < cnt; i += nt * V) {
+    float av[V], gv[V], ov[V];
+    ldv<V, float>(Ar + i, av);
+    gpv(i, gv);
+    const int r = row_of(i), c0 = col_of(i, r);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int c = c0 + j;
+      float g = gv[j] * im;
+      if (wn && i + j == am) {
+        float a = (rsl && r == c) ? 0.f : av[j];
+        if (dn) a = a * (dsq[r] * dsq[c]);
+        g += (a < 0.f ? -argterm : argterm);
+      }
+      float out = g;
+      if (dn) {
+        out = g * (dsq[r] * dsq[c]);
+        int v = tr ? c : r;  // s_v is a column sum (transpose) or a row sum
+        float sv = dvec[(int64_t)b * K + v];
+        // dL/d d_v = -(rdot + cdot) / d_v ;  d d_v / d s_v = 1 / (2 d_v)   (clamp passes the gradient for s_v >= eps)
+        if (sv >= eps) out += -0.5f * tot[v] * dsq[v] * dsq[v];
+      }
+      if (rsl && r == c) out = 0.f;
+      if (r == c) out += c_num;
+      ov[j] = out;
     }
-    float out = g;
-    if (dn) {
-      out = g * (dsq[r] * dsq[c]);
-      int v = tr ? c : r;  // s_v is a column sum (transpose) or a row sum
-      float sv = dvec[(int64_t)b * K + v];
-      // dL/d d_v = -(rdot + cdot) / d_v ;  d d_v / d s_v = 1 / (2 d_v)   (clamp passes the gradient for s_v >= eps)
-      if (sv >= eps) out += -0.5f * (rdot[v] + cdot[v]) * dsq[v] * dsq[v];
-    }
-    if (rsl && r == c) out = 0.f;
-    if (r == c) out += c_num;
-    if (Gt) Gt[(int64_t)b * K * K + i] = from_f32<T>(out); else Gr[i] = out;
+    outv(Gt ? Gt + o0 : nullptr, Graw + o0, i, ov);
   }
+  cl.sync();  // no CTA may retire while a peer can still read its shared memory
 }
 
 // dS += element-wise terms:  c_den * 2 d_i S_ik  +  c_ent * (-log(S+eps) - S/(S+eps)).
@@ -591,6 +869,33 @@ static int mm1(int batch, int M, int N, int kd, Mat A, Mat Bm, TC* out, int64_t 
   return mm<T, TC>(batch, M, N, 1, &kd, &A, &Bm, out, obs, ors, ocs, st);
 }
 
+// How a per-graph kernel splits a [K, K] matrix over a cluster: R CTAs of `threads` threads, `rows_per` rows each;
+// the strips are staged in shared memory when `nvec` K-vectors plus `nstrips` strips fit.
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+struct StripPlan {
+  int R, rows_per, threads, stage, rowp_floats;
+  size_t smem;
+};
+static StripPlan strip_plan(int K, int nvec, int nstrips) {
+  // tuning knobs (read per call; benchmarks/per_graph_kernels.py sweeps them)
+  const char* e = getenv("TGPB200_STRIP_ELEMS");
+  const int ev = e ? atoi(e) : 0;
+  const int target = ev > 0 ? ev : 32768;  // measured best on B200 (K = 256: two CTAs per graph)
+  const char* es = getenv("TGPB200_STRIP_STAGE");
+  const bool allow_stage = es && es[0] == '1';  // staging measured no faster than L2-served re-reads
+  StripPlan p;
+  p.R = 1;
+  while (p.R < 8 && ceil_div(K, p.R) * (int64_t)K > target) p.R *= 2;
+  p.rows_per = (int)ceil_div(K, p.R);
+  p.rowp_floats = (int)(ceil_div((int64_t)p.rows_per * (K >= 128 ? K / 128 : 1), 4) * 4);
+  const size_t vec = ((size_t)nvec * K + p.rowp_floats) * sizeof(float);
+  const size_t strips = (size_t)nstrips * p.rows_per * K * sizeof(float);
+  p.stage = allow_stage && vec + strips <= 160 * 1024;
+  p.smem = vec + (p.stage ? strips : 0);
+  p.threads = (int64_t)p.rows_per * K >= 2048 ? 512 : 256;
+  return p;
+}
+
 template <typename T>
 struct DensePlan {
   T* Tt;  // T = S^T A  [B, K, N]
@@ -668,16 +973,14 @@ static int dense_fwd(const T* A, const T* S, const T* X, int B, int N, int K, in
     if (rc) return rc;
   }
   if (B > 0) {
-    const int stage_e = (size_t)(K + 2 * K * K) * sizeof(float) <= 160 * 1024;
-    const size_t smem_e = (size_t)(K + (stage_e ? 2 * K * K : 0)) * sizeof(float);
-    static bool attr_e = false;
-    if (!attr_e) {
-      attr_e = true;
-      cudaFuncSetAttribute(k_graph_epilogue<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024);
-    }
-    launch("k_graph_epilogue", k_graph_epilogue<T>, B, K * K >= 2048 ? 1024 : 256, smem_e, st,
-           A ? pl.Araw : (float*)nullptr, loss_kind != 0 ? pl.M : (float*)nullptr, pl.d, pl.ss, pl.a2, pl.ent, N, K,
-           flags, eps, Apool, pl.dvec, pl.stats, pl.argmax, stage_e);
+    const StripPlan sp = strip_plan(K, 2, 2);
+    const bool v4 = K % 4 == 0 && aligned16(Apool);
+    auto kern = sp.stage ? (v4 ? k_graph_epilogue<T, 4, true> : k_graph_epilogue<T, 1, true>)
+                         : (v4 ? k_graph_epilogue<T, 4, false> : k_graph_epilogue<T, 1, false>);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024);
+    launch_cluster("k_graph_epilogue", kern, (unsigned)B * sp.R, sp.threads, sp.R, sp.smem, st,
+                   A ? pl.Araw : (float*)nullptr, loss_kind != 0 ? pl.M : (float*)nullptr, pl.d, pl.ss, pl.a2, pl.ent,
+                   N, K, flags, eps, Apool, pl.dvec, pl.stats, pl.argmax, sp.rows_per, sp.rowp_floats);
     launch("k_finalize_losses", k_finalize_losses, 1, 256, 0, st, pl.stats, B, eps, link_div, ent_div, pl.losses);
     if (losses_out) cudaMemcpyAsync(losses_out, pl.losses, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st);
   }
@@ -704,17 +1007,15 @@ static int dense_bwd(const T* A, const T* S, const T* X, const T* gXpool, const 
   const bool have_a = A != nullptr;
   const bool f32 = std::is_same<T, float>::value;
   if (have_a) {
-    const int stage_b = (size_t)(3 * K + 2 * K * K) * sizeof(float) <= 160 * 1024;
-    const size_t smem_b = (size_t)(3 * K + (stage_b ? 2 * K * K : 0)) * sizeof(float);
-    static bool attr_b = false;
-    if (!attr_b) {
-      attr_b = true;
-      cudaFuncSetAttribute(k_graph_bwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024);
-    }
-    launch("k_graph_bwd", k_graph_bwd<T>, B, K * K >= 2048 ? 1024 : 256, smem_b, st, pl.Araw,
-           loss_kind != 0 ? pl.M : (float*)nullptr, gApool, pl.dvec, pl.stats, pl.argmax, gl, pl.losses, B, K, flags,
-           loss_kind, eps, link_div, ent_div, Graw, loss_kind != 0 ? P : (float*)nullptr, coef, stage_b,
-           f32 ? (T*)nullptr : Gt, (f32 || loss_kind == 0) ? (T*)nullptr : Pt);
+    const StripPlan sp = strip_plan(K, 4, 3);
+    const bool v4 = K % 4 == 0 && aligned16(gApool);
+    auto kern = sp.stage ? (v4 ? k_graph_bwd<T, 4, true> : k_graph_bwd<T, 1, true>)
+                         : (v4 ? k_graph_bwd<T, 4, false> : k_graph_bwd<T, 1, false>);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024);
+    launch_cluster("k_graph_bwd", kern, (unsigned)B * sp.R, sp.threads, sp.R, sp.smem, st, pl.Araw,
+                   loss_kind != 0 ? pl.M : (float*)nullptr, gApool, pl.dvec, pl.stats, pl.argmax, gl, pl.losses, B, K,
+                   flags, loss_kind, eps, link_div, ent_div, Graw, loss_kind != 0 ? P : (float*)nullptr, coef,
+                   sp.rows_per, sp.rowp_floats, f32 ? (T*)nullptr : Gt, (f32 || loss_kind == 0) ? (T*)nullptr : Pt);
     if (f32) {
       Gt = reinterpret_cast<T*>(Graw);
       Pt = reinterpret_cast<T*>(P);
