@@ -103,38 +103,15 @@ int bgemm(const TA* A, const TB* B, TC* C, int batch, int M, int N, int Kd, int6
 // Row statistics of one pass over A and S:  d[b,i] = sum_j A[b,i,j];  ss[b,i] = sum_k S^2;
 // a2[b,i] = sum_j A^2;  ent[b,i] = -sum_k S log(S + eps).   One warp per (b, i).
 // ------------------------------------------------------------------------------------------
-template <typename T>
-static __global__ void k_row_stats(const T* __restrict__ A, const T* __restrict__ S, int64_t rows, int N, int K,
-                                   float eps, float* __restrict__ d, float* __restrict__ ss, float* __restrict__ a2,
-                                   float* __restrict__ ent) {
-  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (r >= rows) return;
-  float sd = 0.f, sa2 = 0.f, s2 = 0.f, se = 0.f;
-  if (A) {
-    const T* a = A + r * N;
-    for (int j = lane; j < N; j += 32) {
-      float v = to_f32<T>(a[j]);
-      sd += v;
-      sa2 += v * v;
-    }
-  }
-  const T* s = S + r * K;
-  for (int k = lane; k < K; k += 32) {
-    float v = to_f32<T>(s[k]);
-    s2 += v * v;
-    se -= v * logf(v + eps);
-  }
-  sd = warp_sum(sd), sa2 = warp_sum(sa2), s2 = warp_sum(s2), se = warp_sum(se);
-  if (lane == 0) {
-    d[r] = sd, ss[r] = s2, a2[r] = sa2, ent[r] = se;
-  }
-}
-
 // V consecutive elements <-> registers (V = 4: one 128-bit fp32 / 64-bit bf16 access; V = 1: scalar)
 template <int V, typename T>
 __device__ __forceinline__ void ldv(const T* p, float (&a)[V]) {
-  if constexpr (V == 4 && sizeof(T) == 4) {
+  if constexpr (V == 8 && sizeof(T) == 2) {
+    const uint4 x = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a[2 * q] = __uint_as_float(w[q] << 16), a[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+  } else if constexpr (V == 4 && sizeof(T) == 4) {
     const float4 x = *reinterpret_cast<const float4*>(p);
     a[0] = x.x, a[1] = x.y, a[2] = x.z, a[3] = x.w;
   } else if constexpr (V == 4) {
@@ -166,6 +143,45 @@ __device__ __forceinline__ void stage_strip(float* dst, const T* src, int cnt) {
     float a[V];
     ldv<V, T>(src + i, a);
     stv<V, float>(dst + i, a);
+  }
+}
+
+template <typename T, int V>
+static __global__ void k_row_stats(const T* __restrict__ A, const T* __restrict__ S, int64_t rows, int N, int K,
+                                   float eps, float* __restrict__ d, float* __restrict__ ss, float* __restrict__ a2,
+                                   float* __restrict__ ent) {
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float sd = 0.f, sa2 = 0.f, s2 = 0.f, se = 0.f;
+  if (A) {
+    const T* a = A + r * N;
+#pragma unroll 4
+    for (int j = lane * V; j < N; j += 32 * V) {
+      float v[V];
+      ldv<V, T>(a + j, v);
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        sd += v[q];
+        sa2 += v[q] * v[q];
+      }
+    }
+  }
+  const T* s = S + r * K;
+#pragma unroll 2
+  for (int k = lane * V; k < K; k += 32 * V) {
+    float v[V];
+    ldv<V, T>(s + k, v);
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      s2 += v[q] * v[q];
+      // bf16 inputs carry 8 significant bits: the MUFU-based log is exact enough and frees the issue slots
+      se -= v[q] * (sizeof(T) == 2 ? __logf(v[q] + eps) : logf(v[q] + eps));
+    }
+  }
+  sd = warp_sum(sd), sa2 = warp_sum(sa2), s2 = warp_sum(s2), se = warp_sum(se);
+  if (lane == 0) {
+    d[r] = sd, ss[r] = s2, a2[r] = sa2, ent[r] = se;
   }
 }
 
@@ -964,9 +980,12 @@ static int dense_fwd(const T* A, const T* S, const T* X, int B, int N, int K, in
       if (rc) return rc;
     }
     int64_t rows = (int64_t)B * N;
-    if (rows > 0)
-      launch("k_row_stats", k_row_stats<T>, (unsigned)ceil_div(rows * 32, 256), 256, 0, st, A, S, rows, N, K, eps, pl.d,
-             pl.ss, pl.a2, pl.ent);
+    if (rows > 0) {
+      constexpr int kVec = sizeof(T) == 2 ? 8 : 4;  // 128-bit loads
+      launch("k_row_stats",
+             (N % kVec == 0 && K % kVec == 0 && aligned16(A) && aligned16(S)) ? k_row_stats<T, kVec> : k_row_stats<T, 1>,
+             (unsigned)ceil_div(rows * 32, 256), 256, 0, st, A, S, rows, N, K, eps, pl.d, pl.ss, pl.a2, pl.ent);
+    }
   }
   if (A) {  // A_raw = T S  [K, K]   ((S^T A) S, dense_conn.py:120-121)
     rc = mm1<T, float>(B, K, K, N, Mat{pl.Tt, NK, N, 0}, Smn, pl.Araw, KK, K, 1, st);

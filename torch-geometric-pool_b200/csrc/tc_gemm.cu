@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull(i), 1);
-      mbar_init(bar_tempty(i), 128);
+      mbar_init(bar_tempty(i), kF32 ? 128 : 256);
     }
     fence_barrier_init();
   }
@@ -169,9 +169,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
         umma_commit(bar_tfull(ab));
       }
     }
-  } else if (warp < 6) {
+  } else if (kF32 && warp < 6) {
     // ===================== operand split (fp32 only): lo = x - trunc_tf32(x) =====================
-    if (kF32) {
+    {
       const int t = threadIdx.x - 64;  // 0..127
       int s = 0;
       uint32_t ph = 0;
@@ -207,7 +207,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
+    // fp32: warps 6-9.  bf16 needs no split warps, so warps 2-5 join: each quadrant's two warps take alternate
+    // 32-column chunks (the fused element-wise epilogue of the backward is instruction-bound with four warps).
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int c_first = (!kF32 && warp < 6) ? 32 : 0, c_step = kF32 ? 32 : 64;
     int it = 0;
     for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
       int nt = item % P.n_tiles, mt = (item / P.n_tiles) % P.m_tiles, b = item / (P.n_tiles * P.m_tiles);
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
       const int m_base = mt * BM + quad * 32;
       const int m = m_base + lane;
       const int64_t obase = (int64_t)b * P.out_bs + (int64_t)m * P.out_rs;
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = c_first; c0 < BN; c0 += c_step) {
         float v[32];
         uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN + c0);
         tmem_ld32(taddr, v);
