@@ -437,22 +437,37 @@ def main():
     fwd_ms = statistics.mean(p[0].elapsed_time(p[1]) for p in ev["tgpb200_dense_pool_fwd"])
     bwd_ms = statistics.mean(p[0].elapsed_time(p[1]) for p in ev["tgpb200_dense_pool_bwd"])
 
-    # --- timed region 2: end to end through the public API from pinned host buffers
-    def e2e_step():
-        a_d = a_h.to(dev, non_blocking=True)
-        s_d = s_h.to(dev, non_blocking=True).requires_grad_(True)
-        x_d = x_h.to(dev, non_blocking=True).requires_grad_(True)
-        losses = step(a_d, s_d, x_d)
-        return losses.cpu()  # device -> host read of the step's result
+    # --- timed region 2: end to end through the public API from pinned host buffers.  Every step copies its own
+    # inputs host -> device and reads its result back; the copy of step i+1 runs on a side stream while step i
+    # computes (an ordinary double-buffered input pipeline), so the step time is max(copy, compute), not the sum.
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
 
-    for _ in range(2):
-        e2e_step()
+    def stage_inputs():
+        with torch.cuda.stream(copy_stream):
+            bufs = (a_h.to(dev, non_blocking=True), s_h.to(dev, non_blocking=True), x_h.to(dev, non_blocking=True))
+            done = torch.cuda.Event()
+            done.record(copy_stream)
+        return bufs, done
+
+    def e2e_loop(n):
+        nxt = stage_inputs()
+        for i in range(n):
+            (a_d, s_d, x_d), ready = nxt
+            main_stream.wait_event(ready)
+            if i + 1 < n:
+                nxt = stage_inputs()
+            for t in (a_d, s_d, x_d):
+                t.record_stream(main_stream)
+            losses = step(a_d, s_d.requires_grad_(True), x_d.requires_grad_(True))
+            losses.cpu()  # device -> host read of the step's result
+
+    e2e_loop(2)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_steps = max(3, min(args.steps, 10))
     e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
+    e2e_loop(e2e_steps)
     e1.record()
     barrier()
     t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -496,7 +511,8 @@ def main():
                        "l2_policy": f"inputs larger than L2 ({h2d / 1e6:.0f} MB per step vs 126 MB L2), no flush",
                        "parallelism": f"graph-batch sharding x{world}, no data-path collective"},
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms},
+                    "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms,
+                    "pipeline": "H2D of step i+1 on a copy stream overlaps compute of step i"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": traffic, "kernel": dom, "kernel_launches_timed": dom_n, "kernel_ms": dom_ms, "algorithmic_bytes": dom_bytes,

@@ -420,6 +420,28 @@ def test_dense_per_graph_kernels_all_strip_plans(monkeypatch, elems, stage, K):
                 close32(g_, e_, f"{kind} {kw} {n_}", rtol=1e-5 if not n_.startswith("grad") else 1e-4)
 
 
+def test_fused_forward_exact_and_inexact_adjacency_blocks():
+    """3xTF32 residuals are zero for adjacency entries that are exact in tf32 (0/1) and non-zero for weighted ones.
+    Mix both inside one graph and across the graphs a CTA visits, so that every pipeline slot of the fused forward
+    sees exact and inexact 16-row blocks in turn (guards any data-dependent shortcut in the split warps)."""
+    B, N, K, F = 150, 256, 64, 128  # 150 graphs > 148 SMs: two CTAs process a second graph
+    g = torch.Generator().manual_seed(77)
+    a01, s_raw, x = _dense_inputs(g, B, N, K, F)
+    wts = torch.rand(B, N, N, generator=g) + 0.5
+    wts = 0.5 * (wts + wts.transpose(1, 2))
+    a = a01.clone()
+    a[1::3] = (a01 * wts)[1::3]                       # fully weighted graphs
+    a[2::3, :128] = (a01 * wts)[2::3, :128]           # first half of the rows weighted, second half 0/1
+    a[0, 200:216] = a01[0, 200:216] * wts[0, 200:216]  # one weighted k-block in an otherwise exact graph
+    s = torch.softmax(s_raw, -1)
+    exp = R.mincut_pool(x.double(), a.double(), s.double(), remove_self_loops=False, degree_norm=False)
+    got = T.mincut_pool(x.to(DEV), a.to(DEV), s.to(DEV), remove_self_loops=False, degree_norm=False)
+    close32(got[0].cpu(), exp[0].float(), "x_pool")
+    close32(got[1].cpu(), exp[1].float(), "adj_pool (raw S^T A S)")
+    for k in exp[2]:
+        close32(got[2][k].cpu(), exp[2][k].float(), k)
+
+
 def test_dense_pool_bf16_vs_oracle():
     g = torch.Generator().manual_seed(21)
     B, N, K, F = 3, 128, 32, 64
