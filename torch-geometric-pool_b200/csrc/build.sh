@@ -2,10 +2,10 @@
 # Build libtgp_b200.so (sm_100a only) in-tree next to the python package.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
-OUT="${HERE}/../tgp_b200/libtgp_b200.so"
+OUT="${TGPB200_OUT:-${HERE}/../tgp_b200/libtgp_b200.so}"  # TGPB200_OUT / TGPB200_OBJ_DIR / TGPB200_EXTRA_FLAGS: tuning variants
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC)
-OBJ="${HERE}/build"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC ${TGPB200_EXTRA_FLAGS:-})
+OBJ="${TGPB200_OBJ_DIR:-${HERE}/build}"
 mkdir -p "${OBJ}"
 pids=()
 for src in "${HERE}"/*.cu; do
