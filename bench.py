@@ -443,23 +443,32 @@ def main():
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
 
-    def stage_inputs():
+    # two resident device buffer sets (no allocator traffic inside the loop); a set is overwritten only after the
+    # step that consumed it has finished (event recorded on the compute stream)
+    bufs = [tuple(torch.empty_like(t, device=dev) for t in (a_h, s_h, x_h)) for _ in range(2)]
+    consumed = [None, None]
+
+    def stage_inputs(j):
         with torch.cuda.stream(copy_stream):
-            bufs = (a_h.to(dev, non_blocking=True), s_h.to(dev, non_blocking=True), x_h.to(dev, non_blocking=True))
+            if consumed[j] is not None:
+                copy_stream.wait_event(consumed[j])
+            for dst, src in zip(bufs[j], (a_h, s_h, x_h)):
+                dst.copy_(src, non_blocking=True)
             done = torch.cuda.Event()
             done.record(copy_stream)
-        return bufs, done
+        return done
 
     def e2e_loop(n):
-        nxt = stage_inputs()
+        ready = stage_inputs(0)
         for i in range(n):
-            (a_d, s_d, x_d), ready = nxt
+            j = i & 1
             main_stream.wait_event(ready)
             if i + 1 < n:
-                nxt = stage_inputs()
-            for t in (a_d, s_d, x_d):
-                t.record_stream(main_stream)
-            losses = step(a_d, s_d.requires_grad_(True), x_d.requires_grad_(True))
+                ready = stage_inputs(j ^ 1)
+            a_d, s_d, x_d = bufs[j]
+            losses = step(a_d, s_d.detach().requires_grad_(True), x_d.detach().requires_grad_(True))
+            consumed[j] = torch.cuda.Event()
+            consumed[j].record(main_stream)
             losses.cpu()  # device -> host read of the step's result
 
     e2e_loop(2)

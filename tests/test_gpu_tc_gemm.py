@@ -59,6 +59,28 @@ def test_tc_gemm_bf16(a_mn, b_mn):
     torch.testing.assert_close(outb.double(), ref, rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("pair", ["1", "0"])
+@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("B,M,N,Kd", [(1, 256, 64, 64), (7, 512, 256, 128), (3, 384, 128, 200), (2, 200, 192, 64),
+                                      (160, 256, 128, 64), (2, 1024, 512, 320)])
+def test_tc_gemm_bf16_cta_pairs(monkeypatch, pair, a_mn, b_mn, B, M, N, Kd):
+    """bf16 products with more than one 128-row tile run on CTA pairs (cta_group::2, 256-row tiles).  Ragged M / N,
+    several n-tiles, more pair tiles than SM pairs, and the single-CTA engine on the same inputs."""
+    if (a_mn and M % 8) or (b_mn and N % 8):
+        pytest.skip("MN-major rows must be 16-byte multiples")
+    monkeypatch.setenv("TGPB200_GEMM_PAIR", pair)
+    g = torch.Generator().manual_seed(M + 3 * N + Kd)
+    a = torch.randn((B, Kd, M) if a_mn else (B, M, Kd), generator=g).bfloat16().to(DEV)
+    b = torch.randn((B, Kd, N) if b_mn else (B, N, Kd), generator=g).bfloat16().to(DEV)
+    out = _run(a, b, a_mn, b_mn, M, N, Kd)
+    ref = _ref(a, b, a_mn, b_mn)
+    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=2e-4)
+    acc = torch.randn(B, M, N, generator=g).to(DEV)
+    out2 = _run(a, b, a_mn, b_mn, M, N, Kd, alpha=0.5, acc=acc)
+    torch.testing.assert_close(out2.double(), 0.5 * ref + acc.double(), rtol=1e-5, atol=2e-4)
+
+
 def test_tc_gemm_alpha_accumulate_and_transposed_output():
     B, M, N, Kd = 2, 128, 64, 64
     g = torch.Generator().manual_seed(9)

@@ -16,6 +16,8 @@
 #include <string.h>
 
 #include "dense.cuh"
+#include <type_traits>
+
 #include "tc_gemm.cuh"
 #include "tc_ptx.cuh"
 
@@ -196,49 +198,62 @@ __global__ void __launch_bounds__(320, 1) k_dense_fwd_fused(const __grid_constan
         const uint32_t st = smem_base + (uint32_t)s * stage_bytes + (uint32_t)t * 16;
         float sd = 0.f, sa2 = 0.f, s2 = 0.f, se = 0.f;
         constexpr int NV = 16 / ES;  // values per 16-byte chunk
-        constexpr int U = 4;         // blocks in flight per thread
-        for (int blk0 = 0; blk0 < nb; blk0 += U) {
-          float v[U][NV];
+        // One batch = UU blocks of one segment with no branch inside, so the compiler interleaves the UU
+        // independent load -> round -> subtract -> store chains (the split warps run one warp per scheduler and are
+        // latency-bound: `ncu` showed fixed-latency waits spread over a loop that was serialised by per-chunk
+        // segment branches).  SEG: 0 = A (d, a2), 1 = X (no statistics), 2 = S (ss, ent).
+        auto batch = [&](auto seg_tag, auto uu_tag, int blk0) {
+          constexpr int SEG = decltype(seg_tag)::value;
+          constexpr int UU = decltype(uu_tag)::value;
+          float v[UU][NV];
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            if (blk0 + u < nb) {
+          for (int u = 0; u < UU; ++u) {
+            const uint32_t a = st + (uint32_t)(blk0 + u) * kBlockBytes;
+            if (kF32) {
+              float4 x4 = lds128(a);
+              v[u][0] = x4.x, v[u][1] = x4.y, v[u][2] = x4.z, v[u][3] = x4.w;
+            } else {
+              uint4 w4 = lds128u(a);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w4);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float2 f = __bfloat1622float2(h2[q]);
+                v[u][2 * q] = f.x, v[u][2 * q + 1] = f.y;
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UU; ++u) {
+            if (kF32) {
               const uint32_t a = st + (uint32_t)(blk0 + u) * kBlockBytes;
-              if (kF32) {
-                float4 x4 = lds128(a);
-                v[u][0] = x4.x, v[u][1] = x4.y, v[u][2] = x4.z, v[u][3] = x4.w;
-              } else {
-                uint4 w4 = lds128u(a);
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w4);
+              float4 h, l;
+              h.x = rna_tf32(v[u][0]), h.y = rna_tf32(v[u][1]), h.z = rna_tf32(v[u][2]), h.w = rna_tf32(v[u][3]);
+              l.x = v[u][0] - h.x, l.y = v[u][1] - h.y, l.z = v[u][2] - h.z, l.w = v[u][3] - h.w;
+              sts128(a, h);
+              sts128(a + raw_bytes, l);
+            }
+            if (SEG == 0) {  // per-chunk partial sums keep the accumulator chains one add deep per chunk
+              float ps = 0.f, pq = 0.f;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  float2 f = __bfloat1622float2(h2[q]);
-                  v[u][2 * q] = f.x, v[u][2 * q + 1] = f.y;
-                }
-              }
+              for (int q = 0; q < NV; ++q) { ps += v[u][q]; pq = fmaf(v[u][q], v[u][q], pq); }
+              sd += ps, sa2 += pq;
+            } else if (SEG == 2) {
+              float pq = 0.f, pe = 0.f;
+#pragma unroll
+              for (int q = 0; q < NV; ++q) { pq = fmaf(v[u][q], v[u][q], pq); pe = fmaf(v[u][q], __logf(v[u][q] + P.eps), pe); }
+              s2 += pq, se -= pe;
             }
           }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int blk = blk0 + u;
-            if (blk < nb) {
-              if (kF32) {
-                const uint32_t a = st + (uint32_t)blk * kBlockBytes;
-                float4 h, l;
-                h.x = rna_tf32(v[u][0]), h.y = rna_tf32(v[u][1]), h.z = rna_tf32(v[u][2]), h.w = rna_tf32(v[u][3]);
-                l.x = v[u][0] - h.x, l.y = v[u][1] - h.y, l.z = v[u][2] - h.z, l.w = v[u][3] - h.w;
-                sts128(a, h);
-                sts128(a + raw_bytes, l);
-              }
-              if (blk < P.nb_a) {
-#pragma unroll
-                for (int q = 0; q < NV; ++q) { sd += v[u][q]; sa2 += v[u][q] * v[u][q]; }
-              } else if (blk >= P.nb_a + P.nb_x) {
-#pragma unroll
-                for (int q = 0; q < NV; ++q) { s2 += v[u][q] * v[u][q]; se -= v[u][q] * __logf(v[u][q] + P.eps); }
-              }
-            }
-          }
-        }
+        };
+        auto segment = [&](auto seg_tag, int b0, int b1) {
+          int blk = b0;
+          for (; blk + 4 <= b1; blk += 4) batch(seg_tag, std::integral_constant<int, 4>{}, blk);
+          if (blk + 2 <= b1) { batch(seg_tag, std::integral_constant<int, 2>{}, blk); blk += 2; }
+          if (blk < b1) batch(seg_tag, std::integral_constant<int, 1>{}, blk);
+        };
+        segment(std::integral_constant<int, 0>{}, 0, P.nb_a);
+        segment(std::integral_constant<int, 1>{}, P.nb_a, P.nb_a + P.nb_x);
+        segment(std::integral_constant<int, 2>{}, P.nb_a + P.nb_x, nb);
         // the 8 lanes of a row (fixed lane group, fixed block order -> deterministic)
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) {

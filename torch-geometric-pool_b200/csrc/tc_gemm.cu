@@ -33,6 +33,129 @@ struct KernelParams {
   float ew_eps;
 };
 
+// Epilogue of one 32-column chunk: thread `lane` of a quadrant holds row m of the tile, v[0..32) = columns n0..n0+31.
+template <bool kF32>
+__device__ __forceinline__ void store_chunk(const KernelParams& P, float (&v)[32], int b, int m_base, int m, int n0,
+                                            int64_t obase) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] *= P.alpha;
+  if (P.out_cs == 1) {
+    // Row-major destination: every thread owns one row and moves its 32 values as 8 x 128-bit accesses
+    // (fewer instructions than a shared-memory transposition, which measured slower).
+    if (m < P.M) {
+      const bool full = n0 + 32 <= P.N;
+      if (P.ew_S != nullptr) {
+        // fused element-wise gradient terms of the dense backward (see GemmProblem::ew_*)
+        const float c_den = P.ew_coef[b * 4 + 0], c_ent = P.ew_coef[b * 4 + 2];
+        if (c_den != 0.f || c_ent != 0.f) {
+          const float dd = 2.f * c_den * P.ew_d[(int64_t)b * P.M + m];
+          const int64_t si = ((int64_t)b * P.M + m) * P.N + n0;
+          float sv[32];
+          if (kF32 && full && ((si & 3) == 0)) {
+            const float4* s4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(P.ew_S) + si);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 t4 = __ldg(s4 + j);
+              sv[4 * j] = t4.x, sv[4 * j + 1] = t4.y, sv[4 * j + 2] = t4.z, sv[4 * j + 3] = t4.w;
+            }
+          } else if (!kF32 && full && ((si & 7) == 0)) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(P.ew_S) + si);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 t4 = __ldg(s4 + j);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t4);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float2 f2 = __bfloat1622float2(h2[q]);
+                sv[8 * j + 2 * q] = f2.x, sv[8 * j + 2 * q + 1] = f2.y;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              sv[j] = (n0 + j < P.N)
+                          ? (kF32 ? reinterpret_cast<const float*>(P.ew_S)[si + j]
+                                  : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.ew_S)[si + j]))
+                          : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float add = dd * sv[j];
+            if (c_ent != 0.f) add += c_ent * (-__logf(sv[j] + P.ew_eps) - __fdividef(sv[j], sv[j] + P.ew_eps));
+            v[j] += add;
+          }
+        }
+      }
+      if (!P.out_bf16 && full && (((obase + n0) & 3) == 0)) {
+        float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + obase + n0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 r4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (P.accumulate) {
+            float4 c4 = o4[j];
+            r4.x += c4.x, r4.y += c4.y, r4.z += c4.z, r4.w += c4.w;
+          }
+          o4[j] = r4;
+        }
+      } else if (P.out_bf16 && full && (((obase + n0) & 7) == 0)) {
+        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + obase + n0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 pk;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+          if (P.accumulate) {
+            uint4 c4 = o4[j];
+            const __nv_bfloat162* c2 = reinterpret_cast<const __nv_bfloat162*>(&c4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float2 f = __bfloat1622float2(c2[q]);
+              v[8 * j + 2 * q] += f.x, v[8 * j + 2 * q + 1] += f.y;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) h2[q] = __floats2bfloat162_rn(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
+          o4[j] = pk;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (n0 + j < P.N) {
+            const int64_t idx = obase + n0 + j;
+            float val = v[j];
+            if (P.out_bf16) {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out);
+              if (P.accumulate) val += __bfloat162float(o[idx]);
+              o[idx] = __float2bfloat16_rn(val);
+            } else {
+              float* o = reinterpret_cast<float*>(P.out);
+              if (P.accumulate) val += o[idx];
+              o[idx] = val;
+            }
+          }
+        }
+      }
+    }
+  } else if (m < P.M) {
+    // strided destination (e.g. transposed output, out_rs == 1): lanes already walk the contiguous index
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (n0 + j < P.N) {
+        const int64_t idx = obase + (int64_t)(n0 + j) * P.out_cs;
+        float val = v[j];
+        if (P.out_bf16) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out);
+          if (P.accumulate) val += __bfloat162float(o[idx]);
+          o[idx] = __float2bfloat16_rn(val);
+        } else {
+          float* o = reinterpret_cast<float*>(P.out);
+          if (P.accumulate) val += o[idx];
+          o[idx] = val;
+        }
+      }
+    }
+  }
+}
+
 constexpr int kThreads = 320;
 
 template <bool kF32>
@@ -227,123 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
         tmem_ld32(taddr, v);
         const int n0 = nt * BN + c0;
         if (n0 >= P.N || m_base >= P.M) continue;  // warp-uniform
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= P.alpha;
-        if (P.out_cs == 1) {
-          // Row-major destination: every thread owns one row and moves its 32 values as 8 x 128-bit accesses
-          // (fewer instructions than a shared-memory transposition, which measured slower).
-          if (m < P.M) {
-            const bool full = n0 + 32 <= P.N;
-            if (P.ew_S != nullptr) {
-              // fused element-wise gradient terms of the dense backward (see GemmProblem::ew_*)
-              const float c_den = P.ew_coef[b * 4 + 0], c_ent = P.ew_coef[b * 4 + 2];
-              if (c_den != 0.f || c_ent != 0.f) {
-                const float dd = 2.f * c_den * P.ew_d[(int64_t)b * P.M + m];
-                const int64_t si = ((int64_t)b * P.M + m) * P.N + n0;
-                float sv[32];
-                if (kF32 && full && ((si & 3) == 0)) {
-                  const float4* s4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(P.ew_S) + si);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    float4 t4 = __ldg(s4 + j);
-                    sv[4 * j] = t4.x, sv[4 * j + 1] = t4.y, sv[4 * j + 2] = t4.z, sv[4 * j + 3] = t4.w;
-                  }
-                } else if (!kF32 && full && ((si & 7) == 0)) {
-                  const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(P.ew_S) + si);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    uint4 t4 = __ldg(s4 + j);
-                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t4);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                      float2 f2 = __bfloat1622float2(h2[q]);
-                      sv[8 * j + 2 * q] = f2.x, sv[8 * j + 2 * q + 1] = f2.y;
-                    }
-                  }
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j)
-                    sv[j] = (n0 + j < P.N)
-                                ? (kF32 ? reinterpret_cast<const float*>(P.ew_S)[si + j]
-                                        : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.ew_S)[si + j]))
-                                : 0.f;
-                }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  float add = dd * sv[j];
-                  if (c_ent != 0.f) add += c_ent * (-__logf(sv[j] + P.ew_eps) - __fdividef(sv[j], sv[j] + P.ew_eps));
-                  v[j] += add;
-                }
-              }
-            }
-            if (!P.out_bf16 && full && (((obase + n0) & 3) == 0)) {
-              float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + obase + n0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 r4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                if (P.accumulate) {
-                  float4 c4 = o4[j];
-                  r4.x += c4.x, r4.y += c4.y, r4.z += c4.z, r4.w += c4.w;
-                }
-                o4[j] = r4;
-              }
-            } else if (P.out_bf16 && full && (((obase + n0) & 7) == 0)) {
-              uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + obase + n0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 pk;
-                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-                if (P.accumulate) {
-                  uint4 c4 = o4[j];
-                  const __nv_bfloat162* c2 = reinterpret_cast<const __nv_bfloat162*>(&c4);
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    float2 f = __bfloat1622float2(c2[q]);
-                    v[8 * j + 2 * q] += f.x, v[8 * j + 2 * q + 1] += f.y;
-                  }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) h2[q] = __floats2bfloat162_rn(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
-                o4[j] = pk;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (n0 + j < P.N) {
-                  const int64_t idx = obase + n0 + j;
-                  float val = v[j];
-                  if (P.out_bf16) {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out);
-                    if (P.accumulate) val += __bfloat162float(o[idx]);
-                    o[idx] = __float2bfloat16_rn(val);
-                  } else {
-                    float* o = reinterpret_cast<float*>(P.out);
-                    if (P.accumulate) val += o[idx];
-                    o[idx] = val;
-                  }
-                }
-              }
-            }
-          }
-        } else if (m < P.M) {
-          // strided destination (e.g. transposed output, out_rs == 1): lanes already walk the contiguous index
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (n0 + j < P.N) {
-              const int64_t idx = obase + (int64_t)(n0 + j) * P.out_cs;
-              float val = v[j];
-              if (P.out_bf16) {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out);
-                if (P.accumulate) val += __bfloat162float(o[idx]);
-                o[idx] = __float2bfloat16_rn(val);
-              } else {
-                float* o = reinterpret_cast<float*>(P.out);
-                if (P.accumulate) val += o[idx];
-                o[idx] = val;
-              }
-            }
-          }
-        }
+        store_chunk<kF32>(P, v, b, m_base, m, n0, obase);
       }
       tc_fence_before();
       mbar_arrive(bar_tempty(ab));
@@ -353,6 +360,170 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------
+// bf16 engine on CTA pairs (tcgen05 cta_group::2): the two CTAs of a cluster compute ONE 256 x BN tile.  Each CTA
+// stages its own 128 rows of A and HALF of the B tile, so a B operand crosses L2 -> SM once per 256 output rows
+// instead of once per 128 (the batched products of the dense path are bound by exactly that traffic).
+//   * both CTAs run a TMA producer; every load signals the LEADER's full barrier (transaction bytes of both CTAs),
+//   * only the leader issues tcgen05.mma.cta_group::2; its commits are multicast to the empty / tmem-full barriers
+//     of both CTAs,
+//   * each CTA's eight epilogue warps drain the CTA's own 128 TMEM lanes and arrive on the leader's tmem-empty
+//     barrier (count 2 x 256).
+// P.m_tiles counts 256-row tiles here.
+// ------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    k_tc_gemm_pair(const __grid_constant__ KernelParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int EPB = kStageRowBytes / 2;  // 64 bf16 per 128-byte line (= BK)
+  constexpr int BK = EPB;
+  constexpr int UMMA_K = 16;
+  constexpr int KSTEPS = BK / UMMA_K;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int BN = P.BN, HN = BN / 2;
+  const uint32_t a_bytes = BM * kStageRowBytes, b_bytes = (uint32_t)HN * kStageRowBytes;  // per CTA
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const int stages = P.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stage_bytes * stages);
+  const uint32_t bar_base = smem_u32(bars);
+  auto bar_full = [&](int s) { return bar_base + 8u * s; };
+  auto bar_empty = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto bar_tfull = [&](int i) { return bar_base + 8u * (2 * stages + i); };
+  auto bar_tempty = [&](int i) { return bar_base + 8u * (2 * stages + 2 + i); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(bar_full(s), 1);   // the leader's producer expects the bytes of BOTH CTAs (used in the leader only)
+      mbar_init(bar_empty(s), 1);  // multicast commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull(i), 1);     // multicast commit
+      mbar_init(bar_tempty(i), 512);  // 2 CTAs x 8 epilogue warps (used in the leader only)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(smem_u32(tmem_slot), P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int kblocks[kMaxPairs];
+  for (int p = 0; p < kMaxPairs; ++p) kblocks[p] = p < P.num_pairs ? (P.kd[p] + BK - 1) / BK : 0;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = pair; item < P.num_items; item += npairs) {
+        int nt = item % P.n_tiles, mt = (item / P.n_tiles) % P.m_tiles, b = item / (P.n_tiles * P.m_tiles);
+        const int m0 = (mt * 2 + (int)rank) * BM, n0 = nt * BN + (int)rank * HN;
+        for (int p = 0; p < P.num_pairs; ++p) {
+          for (int kb = 0; kb < kblocks[p]; ++kb) {
+            mbar_wait(bar_empty(s), ph ^ 1);
+            const uint32_t sa = smem_base + (uint32_t)s * stage_bytes, sb = sa + a_bytes;
+            const uint32_t lf = mapa_shared(bar_full(s), 0);
+            // A remote arrive.expect_tx per stage from the peer measured 2x slower end to end (cluster-scope release
+            // on the producer's critical path); the peer's bytes may land before the leader's expect_tx of the same
+            // phase (the transaction count goes negative transiently), never after the phase: the peer refills a
+            // stage only after the multicast commit that follows the phase's completion.
+            if (rank == 0) mbar_arrive_expect_tx(bar_full(s), 2 * (a_bytes + b_bytes));
+            const int k0 = kb * BK;
+            if (P.a_mn[p]) {
+              for (int blk = 0; blk < BM / EPB; ++blk)
+                tma_load_3d_pair(sa + blk * (BK * kStageRowBytes), &P.map_a[p], lf, m0 + blk * EPB, k0, b);
+            } else {
+              tma_load_3d_pair(sa, &P.map_a[p], lf, k0, m0, b);
+            }
+            if (P.b_mn[p]) {
+              for (int blk = 0; blk < HN / EPB; ++blk)
+                tma_load_3d_pair(sb + blk * (BK * kStageRowBytes), &P.map_b[p], lf, n0 + blk * EPB, k0, b);
+            } else {
+              tma_load_3d_pair(sb, &P.map_b[p], lf, k0, n0, b);  // box rows = BN / 2
+            }
+            if (++s == stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int item = pair; item < P.num_items; item += npairs, ++it) {
+        const int ab = it & 1;
+        const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(bar_tempty(ab), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
+        uint32_t accum = 0;
+        for (int p = 0; p < P.num_pairs; ++p) {
+          // bf16 x bf16 -> f32, M = 256 over the pair, N = BN
+          const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)P.a_mn[p] << 15) |
+                                 ((uint32_t)P.b_mn[p] << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+          const uint32_t a_lbo = P.a_mn[p] ? BK * kStageRowBytes : 16, b_lbo = P.b_mn[p] ? BK * kStageRowBytes : 16;
+          const uint32_t a_step = P.a_mn[p] ? UMMA_K * kStageRowBytes : 32, b_step = P.b_mn[p] ? UMMA_K * kStageRowBytes : 32;
+          const uint64_t desc_a0 = make_desc(smem_base, a_lbo, 1024, 2);
+          const uint64_t desc_b0 = make_desc(smem_base, b_lbo, 1024, 2);
+          for (int kb = 0; kb < kblocks[p]; ++kb) {
+            mbar_wait(bar_full(s), ph);
+            tc_fence_after();
+            const uint32_t so = ((uint32_t)s * stage_bytes) >> 4;
+            const uint64_t da0 = desc_a0 + so, db0 = desc_b0 + so + (a_bytes >> 4);
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+              umma_pair_bf16(d_tmem, da0 + (uint64_t)(kk * (a_step >> 4)), db0 + (uint64_t)(kk * (b_step >> 4)), idesc, accum);
+              accum = 1;
+            }
+            umma_commit_pair(bar_empty(s));  // frees the stage in both CTAs
+            if (++s == stages) { s = 0; ph ^= 1; }
+          }
+        }
+        umma_commit_pair(bar_tfull(ab));  // accumulator halves ready in both CTAs
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs): own 128 TMEM lanes -> global =====================
+    const int quad = warp & 3;
+    const int c_first = warp < 6 ? 32 : 0;
+    int it = 0;
+    for (int item = pair; item < P.num_items; item += npairs, ++it) {
+      int nt = item % P.n_tiles, mt = (item / P.n_tiles) % P.m_tiles, b = item / (P.n_tiles * P.m_tiles);
+      const int ab = it & 1;
+      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(bar_tfull(ab), aph);
+      tc_fence_after();
+      const int m_base = (mt * 2 + (int)rank) * BM + quad * 32;
+      const int m = m_base + lane;
+      const int64_t obase = (int64_t)b * P.out_bs + (int64_t)m * P.out_rs;
+      for (int c0 = c_first; c0 < BN; c0 += 64) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN + c0), v);
+        const int n0 = nt * BN + c0;
+        if (n0 >= P.N || m_base >= P.M) continue;  // warp-uniform
+        store_chunk<false>(P, v, b, m_base, m, n0, obase);
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(mapa_shared(bar_tempty(ab), 0));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs are done with TMEM and with each other's barriers
+  if (warp == 1) tmem_dealloc_pair(tmem_base, P.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -481,25 +652,39 @@ int gemm(const GemmProblem& p, cudaStream_t stream) {
     if (num_sms <= 0) num_sms = 148;
     cudaFuncSetAttribute(k_tc_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(k_tc_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_tc_gemm_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   }
   KernelParams P;
   memset(&P, 0, sizeof(P));
   const bool bf16 = p.in_bf16 != 0;
   P.BN = pick_bn(p);
+  // CTA pairs (cta_group::2, 256-row tiles) for bf16 products with at least two 128-row tiles per batch item.
+  // Opt-in (TGPB200_GEMM_PAIR=1): measured on B200 it is on par with the single-CTA engine for the batched products
+  // of the dense path (they run at ~5.3 TB/s of HBM traffic, i.e. they are HBM-bound, not L2->SM bound) and 8 %
+  // slower on a compute-bound 4096^3 product (1132 vs 1232 TFLOP/s; longer cross-CTA hand-off per stage).
+  bool pair = false;
+  {
+    const char* e = getenv("TGPB200_GEMM_PAIR");
+    pair = e && e[0] == '1' && bf16 && p.M > BM && P.BN >= 64 && num_sms >= 2;
+  }
+  for (int i = 0; i < p.num_pairs && pair; ++i)
+    if (p.b[i].mn_major && P.BN % 128 != 0) pair = false;  // each CTA needs whole 128-byte blocks of its half of B
+  const int tile_m = pair ? 2 * BM : BM;
   P.num_pairs = p.num_pairs;
   P.batch = p.batch, P.M = p.M, P.N = p.N;
-  P.m_tiles = (p.M + BM - 1) / BM, P.n_tiles = (p.N + P.BN - 1) / P.BN;
+  P.m_tiles = (p.M + tile_m - 1) / tile_m, P.n_tiles = (p.N + P.BN - 1) / P.BN;
   P.num_items = p.batch * P.m_tiles * P.n_tiles;
   for (int i = 0; i < p.num_pairs; ++i) {
     P.kd[i] = p.kd[i];
     P.a_mn[i] = p.a[i].mn_major, P.b_mn[i] = p.b[i].mn_major;
     if (!make_map(&P.map_a[i], p.a[i], bf16, p.batch, p.M, p.kd[i], BM)) return TGPB200_ERR_UNSUPPORTED;
-    if (!make_map(&P.map_b[i], p.b[i], bf16, p.batch, p.N, p.kd[i], P.BN)) return TGPB200_ERR_UNSUPPORTED;
+    if (!make_map(&P.map_b[i], p.b[i], bf16, p.batch, p.N, p.kd[i], pair ? P.BN / 2 : P.BN)) return TGPB200_ERR_UNSUPPORTED;
   }
-  const size_t stage_bytes = (size_t)(BM + P.BN) * kStageRowBytes * (bf16 ? 1 : 2);
+  const size_t stage_bytes = pair ? (size_t)(BM + P.BN / 2) * kStageRowBytes
+                                  : (size_t)(BM + P.BN) * kStageRowBytes * (bf16 ? 1 : 2);
   const size_t budget = 200 * 1024;
   int stages = (int)(budget / stage_bytes);
-  if (stages > 6) stages = 6;
+  if (stages > (pair ? 8 : 6)) stages = pair ? 8 : 6;
   if (stages < 2) return TGPB200_ERR_UNSUPPORTED;
   P.stages = stages;
   uint32_t cols = 32;
@@ -510,6 +695,11 @@ int gemm(const GemmProblem& p, cudaStream_t stream) {
   P.skip_lo_b_mask = p.skip_lo_b_mask;
   P.ew_S = p.ew_S, P.ew_d = p.ew_d, P.ew_coef = p.ew_coef, P.ew_eps = p.ew_eps;
   const size_t smem = stage_bytes * stages + (3 * stages + 4) * 8 + 16 + 1024;
+  if (pair) {
+    int npairs = P.num_items < num_sms / 2 ? P.num_items : num_sms / 2;
+    launch("k_tc_gemm_pair_bf16", k_tc_gemm_pair, 2 * npairs, kThreads, smem, stream, P);
+    return launch_status();
+  }
   int grid = P.num_items < num_sms ? P.num_items : num_sms;
   if (bf16)
     launch("k_tc_gemm_bf16", k_tc_gemm<false>, grid, kThreads, smem, stream, P);
