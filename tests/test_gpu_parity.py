@@ -96,6 +96,40 @@ def test_segment_reduce_fp32(op, F):
     assert torch.all(got[K - 5:] == 0)
 
 
+@pytest.mark.parametrize("op", ["sum", "mean"])
+@pytest.mark.parametrize("F", [4, 128, 200])
+@pytest.mark.parametrize("layout", ["hard_all", "hard_subset", "soft_multi"])
+def test_segment_reduce_backward_without_weight_grad(op, F, layout):
+    """sum / mean backward when only x needs a gradient (the multi-node-per-warp fast path): every node selected
+    once, a subset selected (zero rows for the rest), and nodes assigned to several clusters."""
+    g = torch.Generator().manual_seed(17 * F + len(layout))
+    N, K = 1003, 257
+    if layout == "hard_all":
+        node = torch.arange(N)
+    elif layout == "hard_subset":
+        node = torch.sort(torch.randperm(N, generator=g)[:611]).values
+    else:
+        node = torch.sort(torch.randint(0, N, (2500,), generator=g)).values
+    cluster = torch.randint(0, K - 3, (node.numel(),), generator=g)
+    if layout == "soft_multi":  # coalesced COO: unique (node, cluster) pairs
+        key = torch.unique(node * K + cluster)
+        node, cluster = key // K, key % K
+    w = torch.rand(node.numel(), generator=g) + 0.5
+    x = torch.randn(N, F, generator=g)
+    gout = torch.randn(K, F, generator=g)
+    so_c = R.OracleSelectOutput(node_index=node, num_nodes=N, cluster_index=cluster, num_supernodes=K, weight=w)
+    xc = x.clone().requires_grad_(True)
+    exp, _ = (R.base_reduce(xc, so_c) if op == "sum" else R.aggr_reduce(xc, so_c, op))
+    (exp * gout).sum().backward()
+    so_g = T.SelectOutput(node_index=node.to(DEV), num_nodes=N, cluster_index=cluster.to(DEV), num_supernodes=K,
+                          weight=w.to(DEV))
+    xg = x.to(DEV).requires_grad_(True)
+    got, _ = T.B200Reduce(op)(xg, so_g)
+    (got * gout.to(DEV)).sum().backward()
+    torch.testing.assert_close(got.detach().cpu(), exp.detach(), **FP32)
+    torch.testing.assert_close(xg.grad.cpu(), xc.grad, **FP32)
+
+
 def test_segment_reduce_bf16():
     g = torch.Generator().manual_seed(3)
     N, K, F = 300, 90, 128

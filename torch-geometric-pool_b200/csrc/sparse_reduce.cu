@@ -143,6 +143,104 @@ static __global__ void __launch_bounds__(256)
   }
 }
 
+// Vector-row fast path of the forward: a warp takes NPW clusters at once.  Lanes 0..2*NPW-1 resolve the first two
+// members of each cluster side by side (ptr -> order -> node_index / weight are dependent loads), then all lanes
+// gather up to 2*NPW member rows with every load in flight; members beyond the second follow in the generic
+// two-at-a-time loop.  Members are combined in CSR order exactly as in k_segment_reduce_fwd (bit-identical sums).
+template <typename XT, typename OT, int NPW>
+static __global__ void __launch_bounds__(256)
+    k_segment_reduce_fwd_rows(const XT* __restrict__ x, const int64_t* __restrict__ node_index,
+                              const float* __restrict__ weight, const int32_t* __restrict__ order,
+                              const int32_t* __restrict__ ptr, int64_t N, int64_t K, int64_t F, int op,
+                              OT* __restrict__ out) {
+  constexpr int W = Vec<XT>::N;
+  const int lane = threadIdx.x & 31;
+  const int64_t c0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * NPW;
+  if (c0 >= K) return;
+  int beg = 0, end = 0;
+  int64_t node = -1;
+  float wt = 0.f;
+  if (lane < 2 * NPW && c0 + (lane >> 1) < K) {
+    const int64_t c = c0 + (lane >> 1);
+    beg = ptr[c], end = ptr[c + 1];
+    const int m = beg + (lane & 1);
+    if (m < end) {
+      const int i = order[m];
+      node = node_index[i];
+      wt = weight ? weight[i] : 1.f;
+      if (node < 0 || node >= N) node = -1;
+    }
+  }
+  int beg_j[NPW], end_j[NPW];
+  int64_t n_j[NPW][2];
+  float w_j[NPW][2];
+#pragma unroll
+  for (int j = 0; j < NPW; ++j) {
+    beg_j[j] = __shfl_sync(kFull, beg, 2 * j), end_j[j] = __shfl_sync(kFull, end, 2 * j);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      n_j[j][k] = __shfl_sync(kFull, node, 2 * j + k);
+      w_j[j][k] = __shfl_sync(kFull, wt, 2 * j + k);
+    }
+  }
+  for (int64_t f = (int64_t)lane * W; f < F; f += 32 * W) {
+    float v[NPW][2][W];
+#pragma unroll
+    for (int j = 0; j < NPW; ++j)
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (n_j[j][k] >= 0) load_chunk<XT, W, true>(x + n_j[j][k] * F, f, F, v[j][k]);
+#pragma unroll
+    for (int j = 0; j < NPW; ++j) {
+      const int64_t c = c0 + j;
+      if (c >= K) break;
+      const int b = beg_j[j], e = end_j[j];
+      float acc[W];
+#pragma unroll
+      for (int k = 0; k < W; ++k) acc[k] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (b + k < e) {
+#pragma unroll
+          for (int q = 0; q < W; ++q)
+            acc[q] = combine(op, acc[q], n_j[j][k] >= 0 ? __fmul_rn(v[j][k][q], w_j[j][k]) : 0.f, k == 0);
+        }
+      }
+      int m = b + 2;
+      for (; m + 1 < e; m += 2) {  // larger clusters: two members in flight
+        int i0 = order[m], i1 = order[m + 1];
+        int64_t n0 = node_index[i0], n1 = node_index[i1];
+        float w0 = weight ? weight[i0] : 1.f, w1 = weight ? weight[i1] : 1.f;
+        float v0[W], v1[W];
+        bool ok0 = n0 >= 0 && n0 < N, ok1 = n1 >= 0 && n1 < N;
+        if (ok0) load_chunk<XT, W, true>(x + n0 * F, f, F, v0);
+        if (ok1) load_chunk<XT, W, true>(x + n1 * F, f, F, v1);
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+          acc[q] = combine(op, acc[q], ok0 ? __fmul_rn(v0[q], w0) : 0.f, false);
+          acc[q] = combine(op, acc[q], ok1 ? __fmul_rn(v1[q], w1) : 0.f, false);
+        }
+      }
+      if (m < e) {
+        int i0 = order[m];
+        int64_t n0 = node_index[i0];
+        float w0 = weight ? weight[i0] : 1.f;
+        float v0[W];
+        bool ok0 = n0 >= 0 && n0 < N;
+        if (ok0) load_chunk<XT, W, true>(x + n0 * F, f, F, v0);
+#pragma unroll
+        for (int q = 0; q < W; ++q) acc[q] = combine(op, acc[q], ok0 ? __fmul_rn(v0[q], w0) : 0.f, false);
+      }
+      if (op == TGPB200_MEAN) {
+        float cnt = (float)(e - b > 1 ? e - b : 1);
+#pragma unroll
+        for (int q = 0; q < W; ++q) acc[q] = __fdiv_rn(acc[q], cnt);
+      }
+      store_chunk<OT, W, true>(out + c * F, f, F, acc);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // MAX / MIN backward pre-pass: inv_ties[c, f] = 1 / #members whose product equals x_pool[c, f].
 // ------------------------------------------------------------------------------------------
@@ -273,6 +371,95 @@ static __global__ void __launch_bounds__(256)
   }
 }
 
+// Fast path of the backward (sum / mean, no weight gradient, vector rows): a warp takes NPW nodes at once.  Lanes
+// 0..NPW-1 run the dependent lookup chains (node -> entry -> cluster -> cluster size) side by side, then all lanes
+// copy the NPW gradient rows with the loads of all rows in flight together.  (One node per warp left the kernel
+// latency-bound: four dependent global loads per 512-byte row.)  Same arithmetic as k_segment_reduce_bwd.
+template <typename XT, typename OT, int NPW>
+static __global__ void __launch_bounds__(256)
+    k_segment_reduce_bwd_rows(const int64_t* __restrict__ node_index, const int64_t* __restrict__ cluster_index,
+                              const float* __restrict__ weight, const int32_t* __restrict__ ptr,
+                              const OT* __restrict__ gpool, int64_t N, int64_t nnz, int64_t K, int64_t F, int op,
+                              XT* __restrict__ gx) {
+  constexpr int W = Vec<XT>::N;
+  const int lane = threadIdx.x & 31;
+  const int64_t n0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * NPW;
+  if (n0 >= N) return;
+  int64_t lo = 0, hi = 0, c = -1;
+  float coef = 0.f;
+  if (lane < NPW && n0 + lane < N) {
+    const int64_t n = n0 + lane;
+    const int64_t a = n < nnz ? node_index[n] : -1;
+    const int64_t pa = (n > 0 && n - 1 < nnz) ? node_index[n - 1] : -1;
+    const int64_t na = n + 1 < nnz ? node_index[n + 1] : -2;
+    if (a == n && pa != n) {
+      lo = n;
+      hi = n + 1;
+      if (na == n)
+        while (hi < nnz && node_index[hi] == n) ++hi;
+    } else {
+      int64_t x0 = 0, x1 = nnz;
+      while (x0 < x1) {
+        int64_t mid = (x0 + x1) >> 1;
+        if (node_index[mid] < n) x0 = mid + 1; else x1 = mid;
+      }
+      lo = x0;
+      hi = lo;
+      while (hi < nnz && node_index[hi] == n) ++hi;
+    }
+    if (hi == lo + 1) {
+      c = cluster_index[lo];
+      if (c < 0 || c >= K) {
+        c = -1;
+      } else {
+        const float wi = weight ? weight[lo] : 1.f;
+        coef = wi;
+        if (op == TGPB200_MEAN) { int cnt = ptr[c + 1] - ptr[c]; coef = wi / (float)(cnt > 1 ? cnt : 1); }
+      }
+    }
+  }
+  int64_t lo_j[NPW], hi_j[NPW], c_j[NPW];
+  float coef_j[NPW];
+#pragma unroll
+  for (int j = 0; j < NPW; ++j) {
+    lo_j[j] = __shfl_sync(kFull, lo, j), hi_j[j] = __shfl_sync(kFull, hi, j), c_j[j] = __shfl_sync(kFull, c, j);
+    coef_j[j] = __shfl_sync(kFull, coef, j);
+  }
+  for (int64_t f = (int64_t)lane * W; f < F; f += 32 * W) {
+    float g[NPW][W];
+#pragma unroll
+    for (int j = 0; j < NPW; ++j)
+      if (c_j[j] >= 0) load_chunk<OT, W, true>(gpool + c_j[j] * F, f, F, g[j]);
+#pragma unroll
+    for (int j = 0; j < NPW; ++j) {
+      const int64_t n = n0 + j;
+      if (n >= N) break;
+      float acc[W];
+      if (c_j[j] >= 0) {
+#pragma unroll
+        for (int k = 0; k < W; ++k) acc[k] = __fadd_rn(0.f, __fmul_rn(g[j][k], coef_j[j]));
+      } else {
+#pragma unroll
+        for (int k = 0; k < W; ++k) acc[k] = 0.f;
+        if (hi_j[j] > lo_j[j] + 1) {
+          for (int64_t i = lo_j[j]; i < hi_j[j]; ++i) {  // a node assigned to several clusters (soft sparse S)
+            const int64_t ci = cluster_index[i];
+            if (ci < 0 || ci >= K) continue;
+            const float wi = weight ? weight[i] : 1.f;
+            float cf = wi;
+            if (op == TGPB200_MEAN) { int cnt = ptr[ci + 1] - ptr[ci]; cf = wi / (float)(cnt > 1 ? cnt : 1); }
+            float gv[W];
+            load_chunk<OT, W, true>(gpool + ci * F, f, F, gv);
+#pragma unroll
+            for (int k = 0; k < W; ++k) acc[k] = __fadd_rn(acc[k], __fmul_rn(gv[k], cf));
+          }
+        }
+      }
+      store_chunk<XT, W, true>(gx + n * F, f, F, acc);
+    }
+  }
+}
+
 // out[c] = batch[node of the LAST member of c in position order] (CPU scatter_ semantics: the
 // last writer wins), or c for an empty cluster (the arange initial value survives).
 static __global__ void k_reduce_batch(const int64_t* __restrict__ batch, const int64_t* __restrict__ node_index,
@@ -295,6 +482,12 @@ static int launch_fwd(const void* x, const int64_t* node_index, const float* wei
   int64_t threads = K * lpr;
   if (threads == 0) return TGPB200_OK;
   dim3 grid((unsigned)ceil_div(threads, 256));
+  if (vec && lpr == 32) {  // rows of at least 32 vector chunks: several clusters per warp (latency-bound otherwise)
+    constexpr int NPW = 4;
+    launch("k_segment_reduce_fwd", k_segment_reduce_fwd_rows<XT, OT, NPW>, (unsigned)ceil_div(ceil_div(K, NPW) * 32, 256), 256, 0,
+           st, (const XT*)x, node_index, weight, order, ptr, N, K, F, op, (OT*)out);
+    return launch_status();
+  }
   if (vec)
     launch("k_segment_reduce_fwd", k_segment_reduce_fwd<XT, OT, true>, grid, 256, 0, st, (const XT*)x, node_index, weight, order, ptr, N, K, F, op,
                                                              lpr, (OT*)out);
@@ -324,6 +517,13 @@ static int launch_bwd(const void* x, const int64_t* node_index, const int64_t* c
   int64_t threads = N * lpr;
   if (threads == 0) return TGPB200_OK;
   dim3 grid((unsigned)ceil_div(threads, 256));
+  if (vec && gw == nullptr && (op == TGPB200_SUM || op == TGPB200_MEAN)) {
+    constexpr int NPW = 4;
+    const int64_t warps = ceil_div(N, NPW);
+    launch("k_segment_reduce_bwd", k_segment_reduce_bwd_rows<XT, OT, NPW>, (unsigned)ceil_div(warps * 32, 256), 256, 0, st,
+           node_index, cluster_index, weight, ptr, (const OT*)gpool, N, nnz, K, F, op, (XT*)gx);
+    return launch_status();
+  }
   if (vec)
     launch("k_segment_reduce_bwd", k_segment_reduce_bwd<XT, OT, true>, grid, 256, 0, st, (const XT*)x, node_index, cluster_index, weight, ptr,
                                                              (const OT*)pool, (const OT*)gpool, inv_ties, N, nnz, K, F,
