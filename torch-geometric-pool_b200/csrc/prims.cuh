@@ -362,16 +362,24 @@ static __global__ void __launch_bounds__(kSortThreads)
   const int64_t tile0 = (int64_t)blockIdx.x * kSortTile;
   const int64_t base = tile0 + (int64_t)w * (32 * kSortItems);
   KeyT key[kSortItems];
+  uint32_t val[kSortItems];
   int rank[kSortItems];
+  // all loads of the tile first (the ranking rounds below are separated by warp-synchronous operations, which keep
+  // the compiler from hoisting a load above the previous round: one exposed memory latency per round)
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    int64_t i = base + j * 32 + lane;
+    key[j] = i < n ? keys_in[i] : (KeyT)0;
+    val[j] = kIota ? (uint32_t)i : (i < n ? vals_in[i] : 0u);
+  }
 #pragma unroll
   for (int j = 0; j < kSortItems; ++j) {
     int64_t i = base + j * 32 + lane;
     bool valid = i < n;
     unsigned vmask = __ballot_sync(kFull, valid);
     rank[j] = 0;
-    key[j] = 0;
     if (valid) {
-      key[j] = keys_in[i];
+      // (issuing the match of every round before the counter chain measured slower: 2.97 vs 2.81 ms on C4)
       int d = (int)((key[j] >> shift) & (BINS - 1));
       unsigned peers = __match_any_sync(vmask, d);
       int leader = __ffs(peers) - 1;
@@ -420,7 +428,7 @@ static __global__ void __launch_bounds__(kSortThreads)
       int d = (int)((key[j] >> shift) & (BINS - 1));
       int lp = dig_base[d] + warp_cnt[w][d] + rank[j];
       s_keys[lp] = key[j];
-      s_vals[lp] = kIota ? (uint32_t)i : vals_in[i];
+      s_vals[lp] = val[j];
     }
   }
   __syncthreads();
