@@ -69,7 +69,7 @@ struct KeptEmit {
 // ------------------------------------------------------------------------------------------
 template <typename KeyT>
 static __global__ void k_remap_keys(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
-                                    const int64_t* __restrict__ cluster, int64_t E, int64_t N, int64_t K,
+                                    const int64_t* __restrict__ cluster, int64_t E, int64_t N, int64_t K, int cb,
                                     KeyT* __restrict__ keys) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= E) return;
@@ -78,7 +78,8 @@ static __global__ void k_remap_keys(const int64_t* __restrict__ row, const int64
   int64_t cc = (c >= 0 && c < N) ? cluster[c] : 0;
   if (cr < 0 || cr >= K) cr = 0;
   if (cc < 0 || cc >= K) cc = 0;
-  keys[i] = (KeyT)((uint64_t)cr * (uint64_t)K + (uint64_t)cc);
+  // (row << cb) | col sorts exactly like row * K + col (cb = bits of K - 1) and decomposes without a 64-bit division
+  keys[i] = (KeyT)(((uint64_t)cr << cb) | (uint64_t)cc);
 }
 
 
@@ -95,6 +96,8 @@ static int key_bits_for_u64(uint64_t max_value) {
   return b < 1 ? 1 : b;
 }
 
+static int coarse_col_bits(int64_t K) { return key_bits_for_u64(K > 1 ? (uint64_t)K - 1 : 1); }
+
 // Fused run handling on the sorted keys: a run head (first position of a key) walks its run, combining the member
 // weights in sorted (= original, the sort is stable) order; the same pass decides whether the coarse edge survives
 // the self-loop / tiny-weight filters.  The count phase stores the combined weight at the head position so that
@@ -106,7 +109,8 @@ struct RunCountPred {
   const uint32_t* perm;
   const float* w;  // null when unweighted
   float* comb;     // [E] combined weight at head positions
-  int64_t E, K;
+  int64_t E;
+  int cb;          // column bits of the key
   int op;
   bool rsl;
   float eps;
@@ -114,7 +118,7 @@ struct RunCountPred {
     const KeyT key = ks[i];
     if (i > 0 && ks[i - 1] == key) return false;
     const uint64_t k64 = (uint64_t)key;
-    const bool self = (int64_t)(k64 / (uint64_t)K) == (int64_t)(k64 % (uint64_t)K);
+    const bool self = (k64 >> cb) == (k64 & ((1ull << cb) - 1ull));
     if (w == nullptr) return !(rsl && self);
     float acc = w[perm[i]];
     int64_t j = i + 1;
@@ -139,15 +143,15 @@ struct RunEmitPred {
   };
   const KeyT* ks;
   const float* comb;  // null when unweighted
-  int64_t K;
+  int cb;
   bool rsl;
   float eps;
   __device__ bool operator()(int64_t i, Payload& p) const {
     const KeyT key = ks[i];
     if (i > 0 && ks[i - 1] == key) return false;
     const uint64_t k64 = (uint64_t)key;
-    p.cr = (int64_t)(k64 / (uint64_t)K);
-    p.cc = (int64_t)(k64 % (uint64_t)K);
+    p.cr = (int64_t)(k64 >> cb);
+    p.cc = (int64_t)(k64 & ((1ull << cb) - 1ull));
     if (rsl && p.cr == p.cc) return false;
     if (comb) {
       p.w = comb[i];
@@ -207,12 +211,13 @@ static int remap_coalesce_count_impl(const int64_t* row, const int64_t* col, con
   CoalescePlan<KeyT> pl(ws, E);
   if (!pl.ok) return TGPB200_ERR_WORKSPACE;
   unsigned grid = (unsigned)ceil_div(E, 256);
-  launch("k_remap_keys", k_remap_keys<KeyT>, grid, 256, 0, st, row, col, cluster, E, N, K, pl.keys0);
-  int bits = key_bits_for_u64((uint64_t)K * (uint64_t)K - 1);
+  const int cb = coarse_col_bits(K);
+  launch("k_remap_keys", k_remap_keys<KeyT>, grid, 256, 0, st, row, col, cluster, E, N, K, cb, pl.keys0);
+  int bits = 2 * cb;
   bool in1 = false;
   int rc = radix_sort_pairs<KeyT>(pl.keys0, nullptr, pl.vals0, pl.keys1, pl.vals1, E, bits, &in1, ws, st);
   if (rc != TGPB200_OK) return rc;
-  RunCountPred<KeyT> pred{in1 ? pl.keys1 : pl.keys0, in1 ? pl.vals1 : pl.vals0, w, pl.comb, E, K, op,
+  RunCountPred<KeyT> pred{in1 ? pl.keys1 : pl.keys0, in1 ? pl.vals1 : pl.vals0, w, pl.comb, E, cb, op,
                           (flags & TGPB200_REMOVE_SELF_LOOPS) != 0, eps};
   return compact_count(pred, E, pl.tile_counts, nullptr, count_out, st);
 }
@@ -223,12 +228,13 @@ static int remap_coalesce_emit_impl(int64_t E, int64_t K, bool weighted, uint32_
                                     Workspace& ws, cudaStream_t st) {
   CoalescePlan<KeyT> pl(ws, E);
   if (!pl.ok) return TGPB200_ERR_WORKSPACE;
-  int bits = key_bits_for_u64((uint64_t)K * (uint64_t)K - 1);
+  const int cb = coarse_col_bits(K);
+  int bits = 2 * cb;
   bool in1 = (radix_passes(bits) & 1) != 0;
   const KeyT* ks = in1 ? pl.keys1 : pl.keys0;
   const uint32_t* perm = in1 ? pl.vals1 : pl.vals0;
   if (edge_slot) cudaMemsetAsync(edge_slot, 0xff, (size_t)E * sizeof(int32_t), st);
-  RunEmitPred<KeyT> pred{ks, weighted ? pl.comb : nullptr, K, (flags & TGPB200_REMOVE_SELF_LOOPS) != 0, eps};
+  RunEmitPred<KeyT> pred{ks, weighted ? pl.comb : nullptr, cb, (flags & TGPB200_REMOVE_SELF_LOOPS) != 0, eps};
   RunEmit2<KeyT> emit{ks, perm, E, out_row, out_col, weighted ? out_w : nullptr, run_len, edge_slot};
   return compact_emit(pred, emit, E, pl.tile_counts, st);
 }
@@ -428,7 +434,7 @@ int tgpb200_remap_coalesce_count(const int64_t* row, const int64_t* col, const f
   }
   if (!row || !col || !cluster_index || K == 0) return TGPB200_ERR_INVALID;
   Workspace ws(workspace, workspace_bytes);
-  if ((uint64_t)K * (uint64_t)K <= 0xffffffffull)
+  if (2 * coarse_col_bits(K) <= 32)
     return remap_coalesce_count_impl<uint32_t>(row, col, edge_weight, E, cluster_index, N, K, op, flags, eps,
                                                count_out, ws, st);
   return remap_coalesce_count_impl<uint64_t>(row, col, edge_weight, E, cluster_index, N, K, op, flags, eps, count_out,
@@ -443,7 +449,7 @@ int tgpb200_remap_coalesce_emit(int64_t E, int64_t K, int weighted, uint32_t fla
   if (!out_row || !out_col || K == 0 || (weighted && !out_weight)) return TGPB200_ERR_INVALID;
   Workspace ws(workspace, workspace_bytes);
   cudaStream_t st = (cudaStream_t)stream;
-  if ((uint64_t)K * (uint64_t)K <= 0xffffffffull)
+  if (2 * coarse_col_bits(K) <= 32)
     return remap_coalesce_emit_impl<uint32_t>(E, K, weighted != 0, flags, eps, out_row, out_col, out_weight,
                                               edge_slot, run_len, ws, st);
   return remap_coalesce_emit_impl<uint64_t>(E, K, weighted != 0, flags, eps, out_row, out_col, out_weight, edge_slot,
