@@ -4,8 +4,8 @@
 // call order from tgp/poolers/mincut.py:219-237 and tgp/poolers/diffpool.py:208-218.
 //
 // This translation unit holds the shape-general path: a strided batched GEMM on the FP32 pipe plus the
-// fused statistics / post-processing / gradient-assembly kernels.  dense_tc.cu provides the tcgen05 GEMMs
-// that replace `bgemm` for the tile-aligned shapes.
+// fused statistics / post-processing / gradient-assembly kernels.  tc_gemm.cu (engine) and dense_fused.cu (fused
+// forward) provide the tcgen05 paths that replace `bgemm` for the supported shapes.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include <string.h>
