@@ -952,8 +952,15 @@ static int dense_fwd(const T* A, const T* S, const T* X, int B, int N, int K, in
   bool fused = false;
   if (A && X && Xpool && B > 0) {
     // one pass over A, X, S: Tt, X_pool, M and the row statistics (dense_fused.cu)
-    rc = tc::dense_fwd_fused(A, S, X, B, N, K, F, std::is_same<T, __nv_bfloat16>::value, eps, pl.Tt, Xpool, pl.M, pl.d,
-                             pl.ss, pl.a2, pl.ent, st);
+    rc = TGPB200_ERR_UNSUPPORTED;
+    if constexpr (std::is_same<T, float>::value) {
+      const char* e = getenv("TGPB200_FUSED_TS");
+      if (!(e && e[0] == '0'))
+        rc = tc::dense_fwd_fused_ts(A, S, X, B, N, K, F, eps, pl.Tt, Xpool, pl.M, pl.d, pl.ss, pl.a2, pl.ent, st);
+    }
+    if (rc == TGPB200_ERR_UNSUPPORTED)
+      rc = tc::dense_fwd_fused(A, S, X, B, N, K, F, std::is_same<T, __nv_bfloat16>::value, eps, pl.Tt, Xpool, pl.M,
+                               pl.d, pl.ss, pl.a2, pl.ent, st);
     if (rc == TGPB200_OK) fused = true;
     else if (rc != TGPB200_ERR_UNSUPPORTED) return rc;
   }

@@ -253,14 +253,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
         uint32_t aph = (uint32_t)(it >> 1) & 1u;
         mbar_wait(bar_tempty(ab), aph ^ 1);
         tc_fence_after();
-        uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
+        // fp32: the accumulator is 2 BN columns wide: [hi_a hi_b + lo_a hi_b | hi_a lo_b] (summed by the epilogue)
+        uint32_t d_tmem = tmem_base + (uint32_t)(ab * (kF32 ? 2 * BN : BN));
         uint32_t accum = 0;
         for (int p = 0; p < P.num_pairs; ++p) {
           const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)P.a_mn[p] << 15) |
                                  ((uint32_t)P.b_mn[p] << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+          // same with N = 2 BN: one instruction multiplies hi_a by [hi_b | lo_b] (the lo tile sits right behind the
+          // hi tile of B in shared memory).  tcgen05.mma has a per-instruction floor of ~120 cycles for N <= 128
+          // (benchmarks/mma_rate.cu), so 3xTF32 as two instructions per k-step instead of three is a third faster.
+          const uint32_t idesc2 = (idesc & ~(0x3fu << 17)) | ((uint32_t)((2 * BN) >> 3) << 17);
           const uint32_t a_lbo = P.a_mn[p] ? BK * kStageRowBytes : 16, b_lbo = P.b_mn[p] ? BK * kStageRowBytes : 16;
           const uint32_t a_step = P.a_mn[p] ? UMMA_K * kStageRowBytes : 32, b_step = P.b_mn[p] ? UMMA_K * kStageRowBytes : 32;
-          const bool skip_lo_b = kF32 && ((P.skip_lo_b_mask >> p) & 1);
           // fp32 MN-major tiles use 4-row (512 B) swizzle atoms, everything else 8-row (1024 B) atoms
           const uint64_t desc_a0 = make_desc(smem_base, a_lbo, (kF32 && P.a_mn[p]) ? 512 : 1024, (kF32 && P.a_mn[p]) ? 1 : 2);
           const uint64_t desc_b0 = make_desc(smem_base, b_lbo, (kF32 && P.b_mn[p]) ? 512 : 1024, (kF32 && P.b_mn[p]) ? 1 : 2);
@@ -271,15 +275,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
             // descriptors differ only in the 14-bit start-address field: build once per pair, then add offsets
             const uint32_t so = ((uint32_t)s * stage_bytes) >> 4;
             const uint64_t da0 = desc_a0 + so, db0 = desc_b0 + so + (a_bytes >> 4);
-            const uint32_t lo_off = (a_bytes + b_bytes) >> 4;
+            const uint32_t a_lo_off = (a_bytes + 2 * b_bytes) >> 4;  // stage = [A | B | B lo | A lo]
 #pragma unroll
             for (int kk = 0; kk < KSTEPS; ++kk) {
               const uint64_t da = da0 + (uint64_t)(kk * (a_step >> 4)), db = db0 + (uint64_t)(kk * (b_step >> 4));
               if (kF32) {
-                umma<true>(d_tmem, da + lo_off, db, idesc, accum);
+                umma<true>(d_tmem, da, db, idesc2, accum);         // hi_a x [hi_b | lo_b]
+                umma<true>(d_tmem, da + a_lo_off, db, idesc, 1u);              // lo_a x hi_b
                 accum = 1;
-                if (!skip_lo_b) umma<true>(d_tmem, da, db + lo_off, idesc, accum);
-                umma<true>(d_tmem, da, db, idesc, accum);
               } else {
                 umma<false>(d_tmem, da, db, idesc, accum);
                 accum = 1;
@@ -306,9 +309,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
             // round-to-nearest split: hi = rna_tf32(x) overwrites the TMA tile in place, lo = x - hi goes next
             // to it.  (The tensor core truncates its fp32 inputs to tf32; with a truncated hi the residual error
             // is one-sided and adds up coherently over long sums, with a rounded hi it is ~2^-23 and zero-mean.)
-            const uint32_t raw = smem_base + (uint32_t)s * stage_bytes, lo = raw + raw_bytes;
+            // stage layout [A | B | B lo | A lo]: the lo tile of B directly follows its hi tile (N-concatenated operand)
+            const uint32_t raw = smem_base + (uint32_t)s * stage_bytes;
             const uint32_t nvec = raw_bytes / 16;  // multiple of 512 (BM and BN are multiples of 64 rows)
+            const uint32_t a_vec = a_bytes / 16;   // multiple of 512 as well: a batch never straddles A and B
             for (uint32_t i0 = t; i0 < nvec; i0 += 128 * 4) {
+              const uint32_t lo_delta = i0 < a_vec ? a_bytes + 2 * b_bytes : b_bytes;
               float4 v[4];
 #pragma unroll
               for (int u = 0; u < 4; ++u) v[u] = lds128(raw + (i0 + u * 128) * 16);
@@ -318,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
                 h.x = rna_tf32(v[u].x), h.y = rna_tf32(v[u].y), h.z = rna_tf32(v[u].z), h.w = rna_tf32(v[u].w);
                 r.x = v[u].x - h.x, r.y = v[u].y - h.y, r.z = v[u].z - h.z, r.w = v[u].w - h.w;
                 sts128(raw + (i0 + u * 128) * 16, h);
-                sts128(lo + (i0 + u * 128) * 16, r);
+                sts128(raw + lo_delta + (i0 + u * 128) * 16, r);
               }
             }
             fence_proxy_async();
@@ -346,8 +352,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
       const int64_t obase = (int64_t)b * P.out_bs + (int64_t)m * P.out_rs;
       for (int c0 = c_first; c0 < BN; c0 += c_step) {
         float v[32];
-        uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN + c0);
+        uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * (kF32 ? 2 * BN : BN) + c0);
         tmem_ld32(taddr, v);
+        if (kF32) {  // + hi_a x lo_b
+          float v2[32];
+          tmem_ld32(taddr + (uint32_t)BN, v2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += v2[j];
+        }
         const int n0 = nt * BN + c0;
         if (n0 >= P.N || m_base >= P.M) continue;  // warp-uniform
         store_chunk<kF32>(P, v, b, m_base, m, n0, obase);
@@ -688,7 +700,7 @@ int gemm(const GemmProblem& p, cudaStream_t stream) {
   if (stages < 2) return TGPB200_ERR_UNSUPPORTED;
   P.stages = stages;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * P.BN)) cols <<= 1;
+  while (cols < (uint32_t)((bf16 ? 2 : 4) * P.BN)) cols <<= 1;  // fp32 accumulators are 2 BN wide ([.. | hi_a lo_b])
   P.tmem_cols = cols;
   P.out = p.out, P.out_bs = p.out_batch_stride, P.out_rs = p.out_row_stride, P.out_cs = p.out_col_stride;
   P.alpha = p.alpha, P.accumulate = p.accumulate, P.out_bf16 = p.out_bf16;
