@@ -34,6 +34,7 @@ struct FusedParams {
   int nb_a, nb_x, nb_s;   // 128-byte column blocks per segment
   int t_a, t_x, t_s;      // 128-row MMA tiles per segment
   int stages, acc_bufs, blocked;
+  int concat;             // fp32: accumulators 2 BN wide, hi_a x [hi_s | lo_s] as ONE MMA (lo of S right behind S)
   uint32_t tmem_cols;
   float eps;
   void* Tt;               // [B, K, N]  operand dtype: T = S^T A
@@ -120,8 +121,9 @@ __global__ void __launch_bounds__(320, 1) k_dense_fwd_fused(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp; tcgen05 instructions on one elected lane) =====================
+    {
+      const uint32_t tm = __shfl_sync(kFull, tmem_base, 0);
       const uint32_t fmt = kF32 ? 2u : 1u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
@@ -139,6 +141,10 @@ __global__ void __launch_bounds__(320, 1) k_dense_fwd_fused(const __grid_constan
       }
       const uint32_t b_off = (uint32_t)(P.nb_a + P.nb_x) * (kBlockBytes >> 4);
       const uint32_t lo_off = raw_bytes >> 4, stage_off = stage_bytes >> 4;
+      // concat mode: stage = [A | X | S | S lo | A lo | X lo]
+      const uint32_t s_lo_off = (uint32_t)P.nb_s * (kBlockBytes >> 4), ax_lo_off = lo_off + s_lo_off;
+      const uint32_t idesc2 = (idesc & ~(0x3fu << 17)) | ((uint32_t)((2 * BN) >> 3) << 17);
+      const int accw = P.concat ? 2 * BN : BN;  // accumulator columns per tile
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -148,14 +154,15 @@ __global__ void __launch_bounds__(320, 1) k_dense_fwd_fused(const __grid_constan
         const uint32_t aph = P.acc_bufs == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
         mbar_wait(bar_tempty(ab), aph ^ 1);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(ab * G * BN);
+        const uint32_t d0 = tm + (uint32_t)(ab * G * accw);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(bar_full(s), ph);
-          if (P.dbg && blockIdx.x == 0 && dbg_m < 96) P.dbg[dbg_m * 8 + 2] = clock64();
+          if (P.dbg && blockIdx.x == 0 && lane == 0 && dbg_m < 96) P.dbg[dbg_m * 8 + 2] = clock64();
           mbar_wait(bar_lo(s), ph);
-          if (P.dbg && blockIdx.x == 0 && dbg_m < 96) P.dbg[dbg_m * 8 + 3] = clock64();
+          if (P.dbg && blockIdx.x == 0 && lane == 0 && dbg_m < 96) P.dbg[dbg_m * 8 + 3] = clock64();
           tc_fence_after();
           const uint64_t dst = desc0 + (uint64_t)((uint32_t)s * stage_off);
+          if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < KSTEPS; ++kk) {
             const uint64_t dk = dst + (uint64_t)(kk * ((UMMA_K * kStageRowBytes) >> 4));
@@ -165,8 +172,12 @@ __global__ void __launch_bounds__(320, 1) k_dense_fwd_fused(const __grid_constan
             for (int g = 0; g < 8; ++g) {
               if (g < G) {
                 const uint64_t da = dk + tile_off[g];
-                const uint32_t dt = d0 + (uint32_t)(g * BN);
-                if (kF32) {
+                const uint32_t dt = d0 + (uint32_t)(g * accw);
+                if (kF32 && P.concat) {
+                  // two instructions per k-step (tcgen05.mma costs ~120 cycles per instruction at these sizes)
+                  umma<true>(dt, da, db, idesc2, acc0);  // hi x [hi_s | lo_s]
+                  umma<true>(dt, da + (g >= P.t_a + P.t_x ? s_lo_off : ax_lo_off), db, idesc, 1u);  // lo x hi_s
+                } else if (kF32) {
                   umma<true>(dt, da + lo_off, db, idesc, acc0);
                   umma<true>(dt, da, db_lo, idesc, 1u);
                   umma<true>(dt, da, db, idesc, 1u);
@@ -177,11 +188,14 @@ __global__ void __launch_bounds__(320, 1) k_dense_fwd_fused(const __grid_constan
             }
           }
           umma_commit(bar_empty(s));
-          if (P.dbg && blockIdx.x == 0 && dbg_m < 96) P.dbg[dbg_m * 8 + 4] = clock64();
+          }
+          __syncwarp();
+          if (P.dbg && blockIdx.x == 0 && lane == 0 && dbg_m < 96) P.dbg[dbg_m * 8 + 4] = clock64();
           ++dbg_m;
           if (++s == stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(bar_tfull(ab));
+        if (elect_one()) umma_commit(bar_tfull(ab));
+        __syncwarp();
       }
     }
   } else if (warp < 6) {
@@ -202,6 +216,9 @@ __global__ void __launch_bounds__(320, 1) k_dense_fwd_fused(const __grid_constan
         // independent load -> round -> subtract -> store chains (the split warps run one warp per scheduler and are
         // latency-bound: `ncu` showed fixed-latency waits spread over a loop that was serialised by per-chunk
         // segment branches).  SEG: 0 = A (d, a2), 1 = X (no statistics), 2 = S (ss, ent).
+        // byte distance from a block to its lo copy: [A/X blocks, S blocks]
+        const uint32_t lo_delta[2] = {P.concat ? raw_bytes + (uint32_t)P.nb_s * kBlockBytes : raw_bytes,
+                                      P.concat ? (uint32_t)P.nb_s * kBlockBytes : raw_bytes};
         auto batch = [&](auto seg_tag, auto uu_tag, int blk0) {
           constexpr int SEG = decltype(seg_tag)::value;
           constexpr int UU = decltype(uu_tag)::value;
@@ -230,7 +247,7 @@ __global__ void __launch_bounds__(320, 1) k_dense_fwd_fused(const __grid_constan
               h.x = rna_tf32(v[u][0]), h.y = rna_tf32(v[u][1]), h.z = rna_tf32(v[u][2]), h.w = rna_tf32(v[u][3]);
               l.x = v[u][0] - h.x, l.y = v[u][1] - h.y, l.z = v[u][2] - h.z, l.w = v[u][3] - h.w;
               sts128(a, h);
-              sts128(a + raw_bytes, l);
+              sts128(a + lo_delta[SEG == 2 ? 1 : 0], l);
             }
             if (SEG == 0) {  // per-chunk partial sums keep the accumulator chains one add deep per chunk
               float ps = 0.f, pq = 0.f;
@@ -290,7 +307,14 @@ __global__ void __launch_bounds__(320, 1) k_dense_fwd_fused(const __grid_constan
         const int m_ext = seg == 0 ? P.N : (seg == 1 ? P.F : P.K);
         for (int c0 = 0; c0 < BN; c0 += 32) {
           float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * G * BN + g * BN + c0), v);
+          const int accw = P.concat ? 2 * BN : BN;
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * G * accw + g * accw + c0), v);
+          if (P.concat) {  // + hi x lo_s
+            float v2[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * G * accw + g * accw + BN + c0), v2);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += v2[j];
+          }
           if (m >= m_ext || c0 >= P.K) continue;
           // All three results are written "transposed": for a fixed accumulator column the 32 lanes of a warp
           // hold 32 consecutive rows, which are made the contiguous index of the destination (128-byte stores).
@@ -340,9 +364,14 @@ int dense_fwd_fused(const void* A, const void* S, const void* X, int B, int N, i
   // every segment must start on an MMA-tile boundary of its own blocks: tiles are 128 columns = BM/epb blocks
   const int G = P.t_a + P.t_x + P.t_s;
   if (G * P.BN > 512 || G > 8) return TGPB200_ERR_UNSUPPORTED;
-  P.acc_bufs = (2 * G * P.BN <= 512) ? 2 : 1;
+  {
+    const char* e = getenv("TGPB200_FUSED_CONCAT");
+    P.concat = (!bf16 && K % 32 == 0 && P.BN == K && 2 * G * P.BN <= 512 && !(e && e[0] == '0')) ? 1 : 0;
+  }
+  const int accw = P.concat ? 2 * P.BN : P.BN;
+  P.acc_bufs = (2 * G * accw <= 512) ? 2 : 1;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(P.acc_bufs * G * P.BN)) cols <<= 1;
+  while (cols < (uint32_t)(P.acc_bufs * G * accw)) cols <<= 1;
   P.tmem_cols = cols;
   const size_t stage_bytes = (size_t)(P.nb_a + P.nb_x + P.nb_s) * kBlockBytes * (bf16 ? 1 : 2);
   int stages = (int)((size_t)(210 * 1024) / stage_bytes);

@@ -38,7 +38,7 @@ struct TsParams {
   int B, N, K, F;
   int BN;                  // MMA N (K rounded up to 16)
   int t_a, t_x, t_s, nb_s;
-  int stages, order;
+  int stages;
   uint32_t tmem_cols, stage_bytes, off_sb;
   float eps;
   float* Tt;               // [B, K, N]
@@ -138,12 +138,13 @@ __global__ void __launch_bounds__(448, 1) k_dense_fwd_fused_ts(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp, tcgen05 instructions on one elected lane) =====================
+    {
       // tf32 x tf32 -> f32, A from TMEM (K-major by construction), B MN-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
       const uint64_t desc0 = make_desc(smem_base, kSBlock, 512, 1);  // 32-byte-atom swizzle, 4-row atoms
+      const uint32_t tm = __shfl_sync(kFull, tmem_base, 0);
       int s = 0;
       uint32_t ph = 0;
       uint32_t kc = 0;
@@ -155,34 +156,29 @@ __global__ void __launch_bounds__(448, 1) k_dense_fwd_fused_ts(const __grid_cons
           mbar_wait(bar_ready(s), ph);
           tc_fence_after();
           const uint32_t ts = kc & 1u;
-          const uint32_t a_stage = tmem_base + a_cols0 + ts * (uint32_t)(G * kACols);
+          const uint32_t a_stage = tm + a_cols0 + ts * (uint32_t)(G * kACols);
           const uint64_t db0 = desc0 + (uint64_t)(((uint32_t)s * stage_bytes + off_sb) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const uint64_t db = db0 + (uint64_t)(kk * ((8 * kStageRowBytes) >> 4)), db_lo = db + (sb_bytes >> 4);
-            const uint32_t acc0 = (kb > 0 || kk > 0) ? 1u : 0u;
-            if (P.order == 1) {  // term-major: consecutive MMAs go to different accumulator tiles
-              for (int g = 0; g < G; ++g)
-                umma_ts_tf32(tmem_base + (uint32_t)(g * BN), a_stage + (uint32_t)(g * kACols + kk * 16 + 8), db, idesc, acc0);
-              for (int g = 0; g < G; ++g)
-                umma_ts_tf32(tmem_base + (uint32_t)(g * BN), a_stage + (uint32_t)(g * kACols + kk * 16), db_lo, idesc, 1u);
-              for (int g = 0; g < G; ++g)
-                umma_ts_tf32(tmem_base + (uint32_t)(g * BN), a_stage + (uint32_t)(g * kACols + kk * 16), db, idesc, 1u);
-            } else {  // tile-major
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint64_t db = db0 + (uint64_t)(kk * ((8 * kStageRowBytes) >> 4)), db_lo = db + (sb_bytes >> 4);
+              const uint32_t acc0 = (kb > 0 || kk > 0) ? 1u : 0u;
               for (int g = 0; g < G; ++g) {
                 const uint32_t a_hi = a_stage + (uint32_t)(g * kACols + kk * 16), a_lo = a_hi + 8;
-                const uint32_t dt = tmem_base + (uint32_t)(g * BN);
+                const uint32_t dt = tm + (uint32_t)(g * BN);
                 umma_ts_tf32(dt, a_lo, db, idesc, acc0);
                 umma_ts_tf32(dt, a_hi, db_lo, idesc, 1u);
                 umma_ts_tf32(dt, a_hi, db, idesc, 1u);
               }
             }
+            umma_commit(bar_empty(s));    // the TMA producer may refill the shared-memory stage
+            umma_commit(bar_tfree(ts));   // the split warps may overwrite the TMEM operand stage
           }
-          umma_commit(bar_empty(s));    // the TMA producer may refill the shared-memory stage
-          umma_commit(bar_tfree(ts));   // the split warps may overwrite the TMEM operand stage
+          __syncwarp();
           if (++s == stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(bar_tfull);
+        if (elect_one()) umma_commit(bar_tfull);
+        __syncwarp();
       }
     }
   } else if (warp < 10) {
@@ -345,10 +341,6 @@ int dense_fwd_fused_ts(const float* A, const float* S, const float* X, int B, in
   if (stages < 2) return TGPB200_ERR_UNSUPPORTED;
   P.stages = stages;
   P.eps = eps;
-  {
-    const char* e = getenv("TGPB200_TS_ORDER");
-    P.order = e ? atoi(e) : 0;
-  }
   P.Tt = Tt, P.Xp = Xp, P.Mm = Mm, P.d = d, P.ss = ss, P.a2 = a2, P.ent = ent;
   if (!make_map_rows(&P.map_a, A, B, N, N) || !make_map_rows(&P.map_x, X, B, N, F) || !make_map_rows(&P.map_s, S, B, N, K))
     return TGPB200_ERR_UNSUPPORTED;

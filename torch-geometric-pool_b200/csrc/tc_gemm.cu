@@ -241,10 +241,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp; tcgen05 instructions on one elected lane) =====================
+    {
       // instruction descriptor: c=F32 (1<<4), a/b format, a/b major, N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t fmt = kF32 ? 2u : 1u;  // TF32 : BF16
+      const uint32_t tm = __shfl_sync(kFull, tmem_base, 0);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
         mbar_wait(bar_tempty(ab), aph ^ 1);
         tc_fence_after();
         // fp32: the accumulator is 2 BN columns wide: [hi_a hi_b + lo_a hi_b | hi_a lo_b] (summed by the epilogue)
-        uint32_t d_tmem = tmem_base + (uint32_t)(ab * (kF32 ? 2 * BN : BN));
+        uint32_t d_tmem = tm + (uint32_t)(ab * (kF32 ? 2 * BN : BN));
         uint32_t accum = 0;
         for (int p = 0; p < P.num_pairs; ++p) {
           const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)P.a_mn[p] << 15) |
@@ -276,23 +277,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
             const uint32_t so = ((uint32_t)s * stage_bytes) >> 4;
             const uint64_t da0 = desc_a0 + so, db0 = desc_b0 + so + (a_bytes >> 4);
             const uint32_t a_lo_off = (a_bytes + 2 * b_bytes) >> 4;  // stage = [A | B | B lo | A lo]
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < KSTEPS; ++kk) {
-              const uint64_t da = da0 + (uint64_t)(kk * (a_step >> 4)), db = db0 + (uint64_t)(kk * (b_step >> 4));
-              if (kF32) {
-                umma<true>(d_tmem, da, db, idesc2, accum);         // hi_a x [hi_b | lo_b]
-                umma<true>(d_tmem, da + a_lo_off, db, idesc, 1u);              // lo_a x hi_b
-                accum = 1;
-              } else {
-                umma<false>(d_tmem, da, db, idesc, accum);
-                accum = 1;
+              for (int kk = 0; kk < KSTEPS; ++kk) {
+                const uint64_t da = da0 + (uint64_t)(kk * (a_step >> 4)), db = db0 + (uint64_t)(kk * (b_step >> 4));
+                if (kF32) {
+                  umma<true>(d_tmem, da, db, idesc2, kk == 0 ? accum : 1u);  // hi_a x [hi_b | lo_b]
+                  umma<true>(d_tmem, da + a_lo_off, db, idesc, 1u);          // lo_a x hi_b
+                } else {
+                  umma<false>(d_tmem, da, db, idesc, kk == 0 ? accum : 1u);
+                }
               }
+              umma_commit(bar_empty(s));
             }
-            umma_commit(bar_empty(s));
+            __syncwarp();
+            accum = 1;
             if (++s == stages) { s = 0; ph ^= 1; }
           }
         }
-        umma_commit(bar_tfull(ab));
+        if (elect_one()) umma_commit(bar_tfull(ab));
+        __syncwarp();
       }
     }
   } else if (kF32 && warp < 6) {
@@ -469,8 +473,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && rank == 0) {
+    // ===================== MMA issuer (leader CTA only; whole warp, one elected lane issues) =====================
+    if (rank == 0) {
+      const uint32_t tm = __shfl_sync(kFull, tmem_base, 0);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -479,7 +484,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const uint32_t aph = (uint32_t)(it >> 1) & 1u;
         mbar_wait(bar_tempty(ab), aph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
+        const uint32_t d_tmem = tm + (uint32_t)(ab * BN);
         uint32_t accum = 0;
         for (int p = 0; p < P.num_pairs; ++p) {
           // bf16 x bf16 -> f32, M = 256 over the pair, N = BN
@@ -494,16 +499,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             tc_fence_after();
             const uint32_t so = ((uint32_t)s * stage_bytes) >> 4;
             const uint64_t da0 = desc_a0 + so, db0 = desc_b0 + so + (a_bytes >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < KSTEPS; ++kk) {
-              umma_pair_bf16(d_tmem, da0 + (uint64_t)(kk * (a_step >> 4)), db0 + (uint64_t)(kk * (b_step >> 4)), idesc, accum);
-              accum = 1;
+              for (int kk = 0; kk < KSTEPS; ++kk)
+                umma_pair_bf16(d_tmem, da0 + (uint64_t)(kk * (a_step >> 4)), db0 + (uint64_t)(kk * (b_step >> 4)), idesc,
+                               kk == 0 ? accum : 1u);
+              umma_commit_pair(bar_empty(s));  // frees the stage in both CTAs
             }
-            umma_commit_pair(bar_empty(s));  // frees the stage in both CTAs
+            __syncwarp();
+            accum = 1;
             if (++s == stages) { s = 0; ph ^= 1; }
           }
         }
-        umma_commit_pair(bar_tfull(ab));  // accumulator halves ready in both CTAs
+        if (elect_one()) umma_commit_pair(bar_tfull(ab));  // accumulator halves ready in both CTAs
+        __syncwarp();
       }
     }
   } else {
