@@ -1,5 +1,7 @@
-// Issue-rate probe for tcgen05.mma on sm_100a: one CTA per SM, one thread issues `iters` back-to-back MMAs of one
-// shape into the same accumulator (operands are whatever the memory holds), clock64 around issue + commit + wait.
+// Rate probe for tcgen05.mma on sm_100a: one CTA per SM, one elected lane of a converged warp issues `iters`
+// back-to-back MMAs of one shape (operands are whatever the memory holds), clock64 around issue + commit + wait.
+// (Issued from inside `if (threadIdx.x == 32)` instead, every shape costs ~120 cycles: the compiler wraps each
+// instruction in an ELECT / R2UR / branch waterfall because the operands are not provably warp-uniform.)
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I../torch-geometric-pool_b200/csrc -I../include \
 //        mma_rate.cu -o mma_rate.bin && ./mma_rate.bin
 #include <cstdio>
@@ -38,26 +40,30 @@ __global__ void __launch_bounds__(128, 1) k_rate(int iters, int N, int tf32, int
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = slot;
-  if (threadIdx.x == 32) {
+  if (warp == 1) {  // whole warp runs the loop; one elected lane issues (uniform operands, no waterfall)
     const uint32_t fmt = tf32 ? 2u : 1u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
                            ((uint32_t)(128 >> 4) << 24);
     const uint64_t da = make_desc(smem_u32(smem), 16, 1024, 2);
     const uint64_t db = b_mn ? make_desc(smem_u32(smem) + 16384, 2048, tf32 ? 512 : 1024, tf32 ? 1 : 2)
                              : make_desc(smem_u32(smem) + 16384, 16, 1024, 2);
+    const uint32_t tmu = __shfl_sync(0xffffffffu, tm, 0);
+    const uint32_t amask = (uint32_t)(n_acc - 1), nn = (uint32_t)N, ta = tmu + 448;
     long long t0 = clock64();
-    const uint32_t amask = (uint32_t)(n_acc - 1), nn = (uint32_t)N, ta = tm + 448;
+    if (elect_one()) {
 #pragma unroll 16
-    for (int i = 0; i < iters; ++i) {
-      const uint32_t d = tm + ((uint32_t)i & amask) * nn;  // n_acc is a power of two
-      if (mode == 1) mma_ts(d, ta, db, idesc, tf32 != 0);
-      else if (tf32) umma<true>(d, da, db, idesc, 1u);
-      else umma<false>(d, da, db, idesc, 1u);
+      for (int i = 0; i < iters; ++i) {
+        const uint32_t d = tmu + ((uint32_t)i & amask) * nn;  // n_acc is a power of two
+        if (mode == 1) mma_ts(d, ta, db, idesc, tf32 != 0);
+        else if (tf32) umma<true>(d, da, db, idesc, 1u);
+        else umma<false>(d, da, db, idesc, 1u);
+      }
+      umma_commit(smem_u32(&bar));
     }
-    umma_commit(smem_u32(&bar));
+    __syncwarp();
     mbar_wait(smem_u32(&bar), 0);
     long long t1 = clock64();
-    if (blockIdx.x == 0) out[0] = t1 - t0;
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) out[0] = t1 - t0;
   }
   tc_fence_before();
   __syncthreads();

@@ -11,8 +11,9 @@
 // * either operand may be K-major or MN-major in global memory (no transposes are materialised),
 // * the epilogue reads TMEM with tcgen05.ld and writes fp32 or bf16 with arbitrary output strides.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator,
-// warps 2-5 = operand split (fp32 only), warps 6-9 = epilogue.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator (the whole warp runs the
+// loop, one elected lane issues), warps 2-5 = operand split (fp32) / extra epilogue warps (bf16), warps 6-9 = epilogue.
+// (Eight split warps for fp32 measured no faster: 53.7 us vs 53.6 us on the C2-shaped products.)
 #pragma once
 #include <cuda.h>
 
