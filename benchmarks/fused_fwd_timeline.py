@@ -13,7 +13,7 @@ T.mincut_pool(x, a, s); torch.cuda.synchronize()
 lib.tgpb200_debug_fused_timeline(None)
 d = dbg.cpu().view(96, 8)
 t0 = int(d[0, 0])
-print("kb   tma_start tma_done | mma_full mma_lo mma_done | split_start split_done   (cycles since first TMA)")
+print("kb   tma_start tma_done | mma_ready ring_wait_done mma_done | split_start split_done pass1_done   (cycles since first TMA; TMEM-operand kernel)")
 for i in list(range(0, 24)) + list(range(40, 52)):
-    r = [int(v) - t0 for v in d[i, :7]]
-    print(f"{i:3d} {r[0]:9d} {r[1]:8d} | {r[2]:8d} {r[3]:7d} {r[4]:8d} | {r[5]:9d} {r[6]:9d}")
+    r = [int(v) - t0 for v in d[i, :8]]
+    print(f"{i:3d} {r[0]:9d} {r[1]:8d} | {r[2]:8d} {r[3]:7d} {r[4]:8d} | {r[5]:9d} {r[6]:9d} {r[7]:9d}")

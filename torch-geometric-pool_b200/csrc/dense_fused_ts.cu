@@ -13,9 +13,9 @@
 //   tensor memory: [0, G*BN) accumulators of the G = t_a + t_x + t_s M-tiles (single buffered),
 //     then 2 stages x G tiles x 2 k-steps x (8 hi + 8 lo) columns of A operand (lane = M row, column = k)
 //
-// Roles (448 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-9 split / statistics /
-// TMEM staging (warp w owns TMEM lanes 32 (w & 3) .., the two warps of a quadrant take alternate M-tiles),
-// warps 10-13 epilogue.
+// Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, then kSplitWarps split / statistics / TMEM staging
+// warps (warp w owns TMEM lanes 32 (w & 3) .., the warps of a quadrant take the M-tiles round robin), then four
+// epilogue warps.
 #include <stdlib.h>
 #include <string.h>
 
@@ -26,10 +26,26 @@
 namespace tgp {
 namespace tc {
 
+extern long long* g_fused_dbg;  // optional clock64 timeline of block 0 (dense_fused.cu, benchmarks/fused_fwd_timeline.py)
+
 namespace {
 
 constexpr int TBK = 16;                              // nodes per k-block
 constexpr int kSBlock = TBK * kStageRowBytes;        // one swizzled 128-byte column block of S: 2 KB
+#ifndef TGPB200_TS_SPLIT_WARPS
+#define TGPB200_TS_SPLIT_WARPS 8
+#endif
+#ifndef TGPB200_TS_SPLIT_GROUPS
+#define TGPB200_TS_SPLIT_GROUPS 2
+#endif
+// The split of one k-block is a latency chain (barrier wait, shared-memory reads, shuffles, proxy fence, TMEM stores
+// and their wait): kSplitGroups groups of kSplitWarps warps each take every kSplitGroups-th k-block, so consecutive
+// k-blocks are split concurrently (group g always fills TMEM operand stage g).
+constexpr int kSplitGroups = TGPB200_TS_SPLIT_GROUPS;   // 1 or 2 (= TMEM operand stages)
+constexpr int kSplitWarps = TGPB200_TS_SPLIT_WARPS;     // per group; multiple of 4: kSplitWarps / 4 warps per lane quadrant
+constexpr int kSplitThreads = kSplitWarps * 32;         // per group
+constexpr int kTsThreads = 64 + kSplitGroups * kSplitThreads + 128;  // TMA, MMA, split groups, epilogue
+constexpr int kTpr = kSplitThreads / 16;                // statistics: threads per node row
 constexpr int kACols = 32;                           // TMEM columns per (tile, k-block): 2 k-steps x (8 hi + 8 lo)
 
 struct TsParams {
@@ -45,6 +61,8 @@ struct TsParams {
   float* Xp;               // [B, K, F]
   float* Mm;               // [B, K, K]
   float *d, *ss, *a2, *ent;
+  long long* dbg;  // [96][8]: 0 tma issue, 1 tma issued, 2 mma ready-wait done, 3 -, 4 mma issued, 5 split start,
+                   //          6 split done, 7 split pass 1 done (TMEM ring wait starts), 3 TMEM ring wait done
 };
 
 __device__ __forceinline__ float lds32(uint32_t addr) {
@@ -74,7 +92,7 @@ __device__ __forceinline__ void umma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
-__global__ void __launch_bounds__(448, 1) k_dense_fwd_fused_ts(const __grid_constant__ TsParams P) {
+__global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __grid_constant__ TsParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int stages = P.stages;
@@ -102,7 +120,7 @@ __global__ void __launch_bounds__(448, 1) k_dense_fwd_fused_ts(const __grid_cons
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_ready(s), 256);
+      mbar_init(bar_ready(s), kSplitThreads);
       mbar_init(bar_empty(s), 1);
     }
     mbar_init(bar_tfree(0), 1);
@@ -123,9 +141,11 @@ __global__ void __launch_bounds__(448, 1) k_dense_fwd_fused_ts(const __grid_cons
       int s = 0;
       uint32_t ph = 0;
       const uint32_t tx = (uint32_t)TBK * (P.N + P.F + P.K) * 4 + sb_bytes;
+      int dbg_n = 0;
       for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(bar_empty(s), ph ^ 1);
+          if (P.dbg && blockIdx.x == 0 && dbg_n < 96) P.dbg[dbg_n * 8 + 0] = clock64();
           const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
           mbar_arrive_expect_tx(bar_full(s), tx);
           const int k0 = kb * TBK;
@@ -133,6 +153,8 @@ __global__ void __launch_bounds__(448, 1) k_dense_fwd_fused_ts(const __grid_cons
           tma_load_3d(dst + off_x, &P.map_x, bar_full(s), 0, k0, b);
           tma_load_3d(dst + off_s, &P.map_s, bar_full(s), 0, k0, b);
           for (int j = 0; j < P.nb_s; ++j) tma_load_3d(dst + off_sb + j * kSBlock, &P.map_sb, bar_full(s), j * 32, k0, b);
+          if (P.dbg && blockIdx.x == 0 && dbg_n < 96) P.dbg[dbg_n * 8 + 1] = clock64();
+          ++dbg_n;
           if (++s == stages) { s = 0; ph ^= 1; }
         }
       }
@@ -154,6 +176,7 @@ __global__ void __launch_bounds__(448, 1) k_dense_fwd_fused_ts(const __grid_cons
         tc_fence_after();
         for (int kb = 0; kb < kblocks; ++kb, ++kc) {
           mbar_wait(bar_ready(s), ph);
+          if (P.dbg && blockIdx.x == 0 && lane == 0 && kc < 96) P.dbg[kc * 8 + 2] = clock64();
           tc_fence_after();
           const uint32_t ts = kc & 1u;
           const uint32_t a_stage = tm + a_cols0 + ts * (uint32_t)(G * kACols);
@@ -175,35 +198,42 @@ __global__ void __launch_bounds__(448, 1) k_dense_fwd_fused_ts(const __grid_cons
             umma_commit(bar_tfree(ts));   // the split warps may overwrite the TMEM operand stage
           }
           __syncwarp();
+          if (P.dbg && blockIdx.x == 0 && lane == 0 && kc < 96) P.dbg[kc * 8 + 4] = clock64();
           if (++s == stages) { s = 0; ph ^= 1; }
         }
         if (elect_one()) umma_commit(bar_tfull);
         __syncwarp();
       }
     }
-  } else if (warp < 10) {
+  } else if (warp < 2 + kSplitGroups * kSplitWarps) {
     // ===================== split: statistics, B operand (smem), A operand (TMEM) =====================
-    const int t = threadIdx.x - 64;  // 0..255
-    const int q = warp & 3;          // TMEM lane quadrant of this warp
-    const int half = (warp - 2) >> 2;  // which of the quadrant's two warps
-    const int r = t >> 4, c16 = t & 15;
+    const int grp = (warp - 2) / kSplitWarps;              // which k-blocks this warp's group takes
+    const int t = (threadIdx.x - 64) % kSplitThreads;      // thread index inside the group
+    const int q = warp & 3;                                // TMEM lane quadrant of this warp
+    const int half = ((warp - 2) % kSplitWarps) >> 2;      // which of the quadrant's warps inside the group
+    const int r = t / kTpr, c16 = t % kTpr;
     int s = 0;
     uint32_t ph = 0, kc = 0;
     for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
       for (int kb = 0; kb < kblocks; ++kb, ++kc) {
+        if (kSplitGroups > 1 && (int)(kc % kSplitGroups) != grp) {  // another group's k-block
+          if (++s == stages) { s = 0; ph ^= 1; }
+          continue;
+        }
         mbar_wait(bar_full(s), ph);
+        if (P.dbg && blockIdx.x == 0 && t == 0 && kc < 96) P.dbg[kc * 8 + 5] = clock64();
         const uint32_t base = smem_base + (uint32_t)s * stage_bytes;
         // ---- pass 1a: row statistics (16 rows x 8 threads, 128-bit reads of the row-major tiles)
         float sd = 0.f, sa2 = 0.f, s2 = 0.f, se = 0.f;
         {
           const uint32_t ra = base + (uint32_t)r * P.N * 4;
-          for (int col = c16 * 4; col < P.N; col += 64) {
+          for (int col = c16 * 4; col < P.N; col += 4 * kTpr) {
             const float4 v = lds128(ra + col * 4);
             sd += (v.x + v.y) + (v.z + v.w);
             sa2 += fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
           }
           const uint32_t rs = base + off_s + (uint32_t)r * P.K * 4;
-          for (int col = c16 * 4; col < P.K; col += 64) {
+          for (int col = c16 * 4; col < P.K; col += 4 * kTpr) {
             const float4 v = lds128(rs + col * 4);
             s2 += fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
             se -= fmaf(v.x, __logf(v.x + P.eps),
@@ -211,7 +241,7 @@ __global__ void __launch_bounds__(448, 1) k_dense_fwd_fused_ts(const __grid_cons
           }
         }
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
+        for (int o = 1; o < kTpr; o <<= 1) {
           sd += __shfl_xor_sync(kFull, sd, o);
           sa2 += __shfl_xor_sync(kFull, sa2, o);
           s2 += __shfl_xor_sync(kFull, s2, o);
@@ -223,7 +253,7 @@ __global__ void __launch_bounds__(448, 1) k_dense_fwd_fused_ts(const __grid_cons
           P.d[o] = sd, P.a2[o] = sa2, P.ss[o] = s2, P.ent[o] = se;
         }
         // ---- pass 1b: hi / lo of the B operand (swizzled S blocks), in place + next to it
-        for (uint32_t ch = t; ch < (uint32_t)P.nb_s * 128; ch += 256) {
+        for (uint32_t ch = t; ch < (uint32_t)P.nb_s * 128; ch += kSplitThreads) {
           const uint32_t a = base + off_sb + ch * 16;
           const float4 v = lds128(a);
           float4 h, l;
@@ -235,10 +265,12 @@ __global__ void __launch_bounds__(448, 1) k_dense_fwd_fused_ts(const __grid_cons
         fence_proxy_async();
         // ---- pass 2: hi / lo of the M-side operand into the TMEM ring (lane = M row, 8 columns = 8 nodes)
         const uint32_t ts = kc & 1u;
+        if (P.dbg && blockIdx.x == 0 && t == 0 && kc < 96) P.dbg[kc * 8 + 7] = clock64();
         mbar_wait(bar_tfree(ts), ((kc >> 1) & 1u) ^ 1u);
+        if (P.dbg && blockIdx.x == 0 && t == 0 && kc < 96) P.dbg[kc * 8 + 3] = clock64();
         tc_fence_after();
         const uint32_t a_stage = tmem_base + ((uint32_t)(q * 32) << 16) + a_cols0 + ts * (uint32_t)(G * kACols);
-        for (int g = half; g < G; g += 2) {
+        for (int g = half; g < G; g += kSplitWarps / 4) {
           const int seg = g < P.t_a ? 0 : (g < P.t_a + P.t_x ? 1 : 2);
           const int m = (seg == 0 ? g : (seg == 1 ? g - P.t_a : g - P.t_a - P.t_x)) * BM + q * 32 + lane;
           const int ext = seg == 0 ? P.N : (seg == 1 ? P.F : P.K);
@@ -261,6 +293,7 @@ __global__ void __launch_bounds__(448, 1) k_dense_fwd_fused_ts(const __grid_cons
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar_ready(s));
+        if (P.dbg && blockIdx.x == 0 && t == 0 && kc < 96) P.dbg[kc * 8 + 6] = clock64();
         if (++s == stages) { s = 0; ph ^= 1; }
       }
     }
@@ -342,6 +375,7 @@ int dense_fwd_fused_ts(const float* A, const float* S, const float* X, int B, in
   P.stages = stages;
   P.eps = eps;
   P.Tt = Tt, P.Xp = Xp, P.Mm = Mm, P.d = d, P.ss = ss, P.a2 = a2, P.ent = ent;
+  P.dbg = g_fused_dbg;
   if (!make_map_rows(&P.map_a, A, B, N, N) || !make_map_rows(&P.map_x, X, B, N, F) || !make_map_rows(&P.map_s, S, B, N, K))
     return TGPB200_ERR_UNSUPPORTED;
   if (!make_map_3d(&P.map_sb, S, false, B, N, K, K, (int64_t)N * K, TBK, true)) return TGPB200_ERR_UNSUPPORTED;
@@ -354,7 +388,7 @@ int dense_fwd_fused_ts(const float* A, const float* S, const float* X, int B, in
   if (smem > 227 * 1024) return TGPB200_ERR_UNSUPPORTED;
   const int sms = device_sm_count();
   const int grid = B < sms ? B : sms;
-  launch("k_dense_fwd_fused_ts", k_dense_fwd_fused_ts, grid, 448, smem, stream, P);
+  launch("k_dense_fwd_fused_ts", k_dense_fwd_fused_ts, grid, kTsThreads, smem, stream, P);
   return launch_status();
 }
 
