@@ -44,7 +44,8 @@ constexpr int kSBlock = TBK * kStageRowBytes;        // one swizzled 128-byte co
 constexpr int kSplitGroups = TGPB200_TS_SPLIT_GROUPS;   // 1 or 2 (= TMEM operand stages)
 constexpr int kSplitWarps = TGPB200_TS_SPLIT_WARPS;     // per group; multiple of 4: kSplitWarps / 4 warps per lane quadrant
 constexpr int kSplitThreads = kSplitWarps * 32;         // per group
-constexpr int kTsThreads = 64 + kSplitGroups * kSplitThreads + 128;  // TMA, MMA, split groups, epilogue
+constexpr int kEpiWarps = 8;                            // two per TMEM lane quadrant, alternate 32-column chunks
+constexpr int kTsThreads = 64 + kSplitGroups * kSplitThreads + kEpiWarps * 32;  // TMA, MMA, split groups, epilogue
 constexpr int kTpr = kSplitThreads / 16;                // statistics: threads per node row
 constexpr int kACols = 32;                           // TMEM columns per (tile, k-block): 2 k-steps x (8 hi + 8 lo)
 
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
     mbar_init(bar_tfree(0), 1);
     mbar_init(bar_tfree(1), 1);
     mbar_init(bar_tfull, 1);
-    mbar_init(bar_tempty, 128);
+    mbar_init(bar_tempty, kEpiWarps * 32);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
@@ -300,16 +301,19 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
   } else {
     // ===================== epilogue (accumulators single-buffered) =====================
     const int quad = warp & 3;
+    const int e2 = ((warp - 2 - kSplitGroups * kSplitWarps) >> 2) & 1;  // which of the quadrant's two epilogue warps
     int it = 0;
     for (int b = blockIdx.x; b < P.B; b += gridDim.x, ++it) {
       mbar_wait(bar_tfull, (uint32_t)it & 1u);
       tc_fence_after();
       const int row = quad * 32 + lane;
+      int chunk = 0;
       for (int g = 0; g < G; ++g) {
         const int seg = g < P.t_a ? 0 : (g < P.t_a + P.t_x ? 1 : 2);
         const int m = (seg == 0 ? g : (seg == 1 ? g - P.t_a : g - P.t_a - P.t_x)) * BM + row;
         const int m_ext = seg == 0 ? P.N : (seg == 1 ? P.F : P.K);
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < BN; c0 += 32, ++chunk) {
+          if ((chunk & 1) != e2) continue;
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * BN + c0), v);
           if (m >= m_ext || c0 >= P.K) continue;
