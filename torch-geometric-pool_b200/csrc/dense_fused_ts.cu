@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp; one elected lane issues) =====================
+    {
       int s = 0;
       uint32_t ph = 0;
       const uint32_t tx = (uint32_t)TBK * (P.N + P.F + P.K) * 4 + sb_bytes;
@@ -146,15 +146,18 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
       for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(bar_empty(s), ph ^ 1);
-          if (P.dbg && blockIdx.x == 0 && dbg_n < 96) P.dbg[dbg_n * 8 + 0] = clock64();
+          if (P.dbg && blockIdx.x == 0 && lane == 0 && dbg_n < 96) P.dbg[dbg_n * 8 + 0] = clock64();
           const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
-          mbar_arrive_expect_tx(bar_full(s), tx);
           const int k0 = kb * TBK;
-          tma_load_3d(dst, &P.map_a, bar_full(s), 0, k0, b);
-          tma_load_3d(dst + off_x, &P.map_x, bar_full(s), 0, k0, b);
-          tma_load_3d(dst + off_s, &P.map_s, bar_full(s), 0, k0, b);
-          for (int j = 0; j < P.nb_s; ++j) tma_load_3d(dst + off_sb + j * kSBlock, &P.map_sb, bar_full(s), j * 32, k0, b);
-          if (P.dbg && blockIdx.x == 0 && dbg_n < 96) P.dbg[dbg_n * 8 + 1] = clock64();
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_full(s), tx);
+            tma_load_3d(dst, &P.map_a, bar_full(s), 0, k0, b);
+            tma_load_3d(dst + off_x, &P.map_x, bar_full(s), 0, k0, b);
+            tma_load_3d(dst + off_s, &P.map_s, bar_full(s), 0, k0, b);
+            for (int j = 0; j < P.nb_s; ++j) tma_load_3d(dst + off_sb + j * kSBlock, &P.map_sb, bar_full(s), j * 32, k0, b);
+          }
+          __syncwarp();
+          if (P.dbg && blockIdx.x == 0 && lane == 0 && dbg_n < 96) P.dbg[dbg_n * 8 + 1] = clock64();
           ++dbg_n;
           if (++s == stages) { s = 0; ph ^= 1; }
         }

@@ -208,8 +208,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
   for (int p = 0; p < kMaxPairs; ++p) kblocks[p] = p < P.num_pairs ? (P.kd[p] + BK - 1) / BK : 0;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp; one elected lane issues) =====================
+    {
       int s = 0;
       uint32_t ph = 0;
       for (int item = blockIdx.x; item < P.num_items; item += gridDim.x) {
@@ -219,8 +219,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
           for (int kb = 0; kb < kblocks[p]; ++kb) {
             mbar_wait(bar_empty(s), ph ^ 1);
             uint32_t sa = smem_base + (uint32_t)s * stage_bytes, sb = sa + a_bytes;
-            mbar_arrive_expect_tx(bar_full(s), a_bytes + b_bytes);
             int k0 = kb * BK;
+            if (elect_one()) {
+            mbar_arrive_expect_tx(bar_full(s), a_bytes + b_bytes);
             // K-major: one box [rows x 128 B].  MN-major: one box [BK k-rows x 128 B] per 128-byte block of
             // the MN extent, laid out block after block (the canonical UMMA MN-major SW128 layout, LBO = BK*128 B).
             if (P.a_mn[p]) {
@@ -235,6 +236,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
             } else {
               tma_load_3d(sb, &P.map_b[p], bar_full(s), k0, n0, b);
             }
+            }
+            __syncwarp();
             if (++s == stages) { s = 0; ph ^= 1; }
           }
         }
