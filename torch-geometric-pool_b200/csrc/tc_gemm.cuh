@@ -13,7 +13,8 @@
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator (the whole warp runs the
 // loop, one elected lane issues), warps 2-5 = operand split (fp32) / extra epilogue warps (bf16), warps 6-9 = epilogue.
-// (Eight split warps for fp32 measured no faster: 53.7 us vs 53.6 us on the C2-shaped products.)
+// (Eight split warps for fp32, data-parallel or as two groups on alternate stages, measured no faster: 53 us on the
+// C2-shaped products either way -- with operands in shared memory the engine sits on the shared-memory pipe.)
 #pragma once
 #include <cuda.h>
 
