@@ -551,6 +551,228 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------
+// fp32 engine with the A operand in TENSOR MEMORY (3xTF32).  With both operands in shared memory the fp32 engine sits
+// on the shared-memory pipe (TMA write + split read + hi/lo write back + three operand fetches per k-step); here
+// the split warps read the A tile once, round / subtract in registers and tcgen05.st hi and lo into a two-stage
+// ring of TMEM columns (lane = output row, 8 columns = 8 k); only B (hi, lo) stays in shared memory.
+//   * two groups of four split warps take alternate k-blocks (the split of a stage is a latency chain); group g
+//     fills TMEM operand stage g,
+//   * K-major A tiles are read row-wise (128-bit, un-doing the 128B swizzle: conflict-free), MN-major A tiles are
+//     loaded UNswizzled ([k][128 m]) and read column-wise (32-bit, conflict-free),
+//   * three MMAs per k-step (lo_a hi_b, hi_a lo_b, hi_a hi_b), accumulators BN wide, double-buffered.
+// Warp roles (448 threads): 0 TMA, 1 MMA, 2-5 split group 0, 6-9 epilogue, 10-13 split group 1.
+// ------------------------------------------------------------------------------------------
+constexpr int kThreadsTs = 448;
+constexpr int kRingCols = 64;  // TMEM columns per operand stage: 4 k-steps x (8 hi + 8 lo)
+
+__global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_constant__ KernelParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int BK = 32, KSTEPS = 4;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int BN = P.BN;
+  const uint32_t a_bytes = BM * kStageRowBytes, b_bytes = (uint32_t)BN * kStageRowBytes;
+  const uint32_t stage_bytes = a_bytes + 2 * b_bytes;  // [A raw | B hi | B lo]
+  const int stages = P.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stage_bytes * stages);
+  const uint32_t bar_base = smem_u32(bars);
+  auto bar_full = [&](int s) { return bar_base + 8u * s; };
+  auto bar_lo = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto bar_empty = [&](int s) { return bar_base + 8u * (2 * stages + s); };
+  auto bar_tfull = [&](int i) { return bar_base + 8u * (3 * stages + i); };
+  auto bar_tempty = [&](int i) { return bar_base + 8u * (3 * stages + 2 + i); };
+  auto bar_tfree = [&](int i) { return bar_base + 8u * (3 * stages + 4 + i); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t ring0 = (uint32_t)(2 * BN);  // first TMEM column of the operand ring
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_lo(s), 128);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull(i), 1);
+      mbar_init(bar_tempty(i), 128);
+      mbar_init(bar_tfree(i), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int kblocks[kMaxPairs];
+  for (int p = 0; p < kMaxPairs; ++p) kblocks[p] = p < P.num_pairs ? (P.kd[p] + BK - 1) / BK : 0;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int item = blockIdx.x; item < P.num_items; item += gridDim.x) {
+      int nt = item % P.n_tiles, mt = (item / P.n_tiles) % P.m_tiles, b = item / (P.n_tiles * P.m_tiles);
+      int m0 = mt * BM, n0 = nt * BN;
+      for (int p = 0; p < P.num_pairs; ++p) {
+        for (int kb = 0; kb < kblocks[p]; ++kb) {
+          mbar_wait(bar_empty(s), ph ^ 1);
+          const uint32_t sa = smem_base + (uint32_t)s * stage_bytes, sb = sa + a_bytes;
+          const int k0 = kb * BK;
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_full(s), a_bytes + b_bytes);
+            if (P.a_mn[p]) tma_load_3d(sa, &P.map_a[p], bar_full(s), m0, k0, b);  // [32 k][128 m], no swizzle
+            else tma_load_3d(sa, &P.map_a[p], bar_full(s), k0, m0, b);            // [128 m][32 k], 128B swizzle
+            if (P.b_mn[p]) {
+              for (int blk = 0; blk < BN / 32; ++blk)
+                tma_load_3d(sb + blk * (BK * kStageRowBytes), &P.map_b[p], bar_full(s), n0 + blk * 32, k0, b);
+            } else {
+              tma_load_3d(sb, &P.map_b[p], bar_full(s), k0, n0, b);
+            }
+          }
+          __syncwarp();
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    const uint32_t tm = __shfl_sync(kFull, tmem_base, 0);
+    int s = 0;
+    uint32_t ph = 0, kc = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
+      const int ab = it & 1;
+      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(bar_tempty(ab), aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tm + (uint32_t)(ab * BN);
+      uint32_t accum = 0;
+      for (int p = 0; p < P.num_pairs; ++p) {
+        // tf32 x tf32 -> f32; A from TMEM (K-major by construction), B as stored
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)P.b_mn[p] << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint32_t b_lbo = P.b_mn[p] ? BK * kStageRowBytes : 16;
+        const uint32_t b_step = P.b_mn[p] ? 8 * kStageRowBytes : 32;
+        const uint64_t desc_b0 = make_desc(smem_base, b_lbo, P.b_mn[p] ? 512 : 1024, P.b_mn[p] ? 1 : 2);
+        for (int kb = 0; kb < kblocks[p]; ++kb, ++kc) {
+          mbar_wait(bar_lo(s), ph);
+          tc_fence_after();
+          const uint32_t ts = kc & 1u;
+          const uint32_t a_stage = tm + ring0 + ts * kRingCols;
+          const uint64_t db0 = desc_b0 + (uint64_t)(((uint32_t)s * stage_bytes + a_bytes) >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+              const uint64_t db = db0 + (uint64_t)(kk * (b_step >> 4)), db_lo = db + (b_bytes >> 4);
+              const uint32_t a_hi = a_stage + (uint32_t)(kk * 16), a_lo = a_hi + 8;
+              umma_ts_tf32(d_tmem, a_lo, db, idesc, kk == 0 ? accum : 1u);
+              umma_ts_tf32(d_tmem, a_hi, db_lo, idesc, 1u);
+              umma_ts_tf32(d_tmem, a_hi, db, idesc, 1u);
+            }
+            umma_commit(bar_empty(s));
+            umma_commit(bar_tfree(ts));
+          }
+          __syncwarp();
+          accum = 1;
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+      }
+      if (elect_one()) umma_commit(bar_tfull(ab));
+      __syncwarp();
+    }
+  } else if (warp < 6 || warp >= 10) {
+    // ===================== split: B hi/lo in shared memory, A hi/lo into the TMEM ring =====================
+    const int grp = warp >= 10 ? 1 : 0;
+    const int t = (threadIdx.x - 64) & 127;
+    const int q = warp & 3;            // TMEM lane quadrant of this warp
+    const int m_local = q * 32 + lane; // output row of the tile this thread stages
+    int s = 0;
+    uint32_t ph = 0, kc = 0;
+    for (int item = blockIdx.x; item < P.num_items; item += gridDim.x) {
+      for (int p = 0; p < P.num_pairs; ++p) {
+        for (int kb = 0; kb < kblocks[p]; ++kb, ++kc) {
+          if ((int)(kc & 1u) != grp) {  // the other group's k-block
+            if (++s == stages) { s = 0; ph ^= 1; }
+            continue;
+          }
+          mbar_wait(bar_full(s), ph);
+          const uint32_t sa = smem_base + (uint32_t)s * stage_bytes, sb = sa + a_bytes;
+          // B: hi in place, lo behind it
+          for (uint32_t ch = t; ch < b_bytes / 16; ch += 128) {
+            const float4 v = lds128(sb + ch * 16);
+            float4 h, l;
+            h.x = rna_tf32(v.x), h.y = rna_tf32(v.y), h.z = rna_tf32(v.z), h.w = rna_tf32(v.w);
+            l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
+            sts128(sb + ch * 16, h);
+            sts128(sb + b_bytes + ch * 16, l);
+          }
+          fence_proxy_async();
+          // A: this thread's row, 32 k values
+          float x[32];
+          if (P.a_mn[p]) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) x[k] = lds32(sa + (uint32_t)k * (BM * 4) + (uint32_t)m_local * 4);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 v = lds128(sa + (uint32_t)m_local * kStageRowBytes + (uint32_t)((c ^ (m_local & 7)) << 4));
+              x[4 * c] = v.x, x[4 * c + 1] = v.y, x[4 * c + 2] = v.z, x[4 * c + 3] = v.w;
+            }
+          }
+          mbar_wait(bar_tfree(grp), ((kc >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t a_stage = tmem_base + ((uint32_t)(q * 32) << 16) + ring0 + (uint32_t)grp * kRingCols;
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS; ++kk) {
+            float hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              hi[i] = rna_tf32(x[kk * 8 + i]);
+              lo[i] = x[kk * 8 + i] - hi[i];
+            }
+            tmem_st16(a_stage + (uint32_t)(kk * 16), hi, lo);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(bar_lo(s));
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 6-9) =====================
+    const int quad = warp & 3;
+    int it = 0;
+    for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
+      int nt = item % P.n_tiles, mt = (item / P.n_tiles) % P.m_tiles, b = item / (P.n_tiles * P.m_tiles);
+      const int ab = it & 1;
+      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(bar_tfull(ab), aph);
+      tc_fence_after();
+      const int m_base = mt * BM + quad * 32;
+      const int m = m_base + lane;
+      const int64_t obase = (int64_t)b * P.out_bs + (int64_t)m * P.out_rs;
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN + c0), v);
+        const int n0 = nt * BN + c0;
+        if (n0 >= P.N || m_base >= P.M) continue;  // warp-uniform
+        store_chunk<true>(P, v, b, m_base, m, n0, obase);
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty(ab));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------
 // Host side: tensor maps and launch
 // ------------------------------------------------------------------------------------------
 EncodeTiledFn encode_fn() {
@@ -642,6 +864,20 @@ static bool make_map(CUtensorMap* map, const OperandDesc& op, bool bf16, int bat
   return r == CUDA_SUCCESS;
 }
 
+// MN-major operand as ONE unswizzled box [BK k-rows][128 MN columns] (TMEM-operand engine: only the split warps read it)
+static bool make_map_mn_plain(CUtensorMap* map, const OperandDesc& op, int batch, int mn_extent, int k_extent) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)mn_extent, (cuuint64_t)k_extent, (cuuint64_t)batch};
+  cuuint64_t bstride = (cuuint64_t)(op.batch_stride > 0 ? op.batch_stride : (int64_t)op.row_stride * k_extent) * 4;
+  cuuint64_t strides[2] = {(cuuint64_t)op.row_stride * 4, bstride};
+  cuuint32_t box[3] = {(cuuint32_t)BM, 32, 1}, estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(op.ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 static int pick_bn(const GemmProblem& p) {
   int cap = p.in_bf16 ? 256 : 128;
   int bn = 64;
@@ -677,6 +913,7 @@ int gemm(const GemmProblem& p, cudaStream_t stream) {
     cudaFuncSetAttribute(k_tc_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(k_tc_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(k_tc_gemm_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_tc_gemm_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   }
   KernelParams P;
   memset(&P, 0, sizeof(P));
@@ -693,6 +930,11 @@ int gemm(const GemmProblem& p, cudaStream_t stream) {
   }
   for (int i = 0; i < p.num_pairs && pair; ++i)
     if (p.b[i].mn_major && P.BN % 128 != 0) pair = false;  // each CTA needs whole 128-byte blocks of its half of B
+  bool ts = !bf16;  // fp32: A operand staged in tensor memory
+  {
+    const char* e = getenv("TGPB200_GEMM_TS");
+    if (e && e[0] == '0') ts = false;
+  }
   const int tile_m = pair ? 2 * BM : BM;
   P.num_pairs = p.num_pairs;
   P.batch = p.batch, P.M = p.M, P.N = p.N;
@@ -701,10 +943,15 @@ int gemm(const GemmProblem& p, cudaStream_t stream) {
   for (int i = 0; i < p.num_pairs; ++i) {
     P.kd[i] = p.kd[i];
     P.a_mn[i] = p.a[i].mn_major, P.b_mn[i] = p.b[i].mn_major;
-    if (!make_map(&P.map_a[i], p.a[i], bf16, p.batch, p.M, p.kd[i], BM)) return TGPB200_ERR_UNSUPPORTED;
+    if (ts && p.a[i].mn_major) {
+      if (!make_map_mn_plain(&P.map_a[i], p.a[i], p.batch, p.M, p.kd[i])) return TGPB200_ERR_UNSUPPORTED;
+    } else if (!make_map(&P.map_a[i], p.a[i], bf16, p.batch, p.M, p.kd[i], BM)) {
+      return TGPB200_ERR_UNSUPPORTED;
+    }
     if (!make_map(&P.map_b[i], p.b[i], bf16, p.batch, p.N, p.kd[i], pair ? P.BN / 2 : P.BN)) return TGPB200_ERR_UNSUPPORTED;
   }
   const size_t stage_bytes = pair ? (size_t)(BM + P.BN / 2) * kStageRowBytes
+                             : ts ? (size_t)(BM + 2 * P.BN) * kStageRowBytes
                                   : (size_t)(BM + P.BN) * kStageRowBytes * (bf16 ? 1 : 2);
   const size_t budget = 200 * 1024;
   int stages = (int)(budget / stage_bytes);
@@ -712,7 +959,8 @@ int gemm(const GemmProblem& p, cudaStream_t stream) {
   if (stages < 2) return TGPB200_ERR_UNSUPPORTED;
   P.stages = stages;
   uint32_t cols = 32;
-  while (cols < (uint32_t)((bf16 ? 2 : 4) * P.BN)) cols <<= 1;  // fp32 accumulators are 2 BN wide ([.. | hi_a lo_b])
+  // shared-memory fp32 accumulators are 2 BN wide ([.. | hi_a lo_b]); the TMEM-operand form adds a 2 x 64 column ring
+  while (cols < (uint32_t)(ts ? 2 * P.BN + 2 * kRingCols : (bf16 ? 2 : 4) * P.BN)) cols <<= 1;
   P.tmem_cols = cols;
   P.out = p.out, P.out_bs = p.out_batch_stride, P.out_rs = p.out_row_stride, P.out_cs = p.out_col_stride;
   P.alpha = p.alpha, P.accumulate = p.accumulate, P.out_bf16 = p.out_bf16;
@@ -725,6 +973,10 @@ int gemm(const GemmProblem& p, cudaStream_t stream) {
     return launch_status();
   }
   int grid = P.num_items < num_sms ? P.num_items : num_sms;
+  if (ts) {
+    launch("k_tc_gemm_ts_3xtf32", k_tc_gemm_ts, grid, kThreadsTs, smem + 64, stream, P);
+    return launch_status();
+  }
   if (bf16)
     launch("k_tc_gemm_bf16", k_tc_gemm<false>, grid, kThreads, smem, stream, P);
   else
