@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(320, 1) k_dense_fwd_fused(const __grid_constan
                 const uint64_t da = dk + tile_off[g];
                 const uint32_t dt = d0 + (uint32_t)(g * accw);
                 if (kF32 && P.concat) {
-                  // two instructions per k-step (tcgen05.mma costs ~120 cycles per instruction at these sizes)
+                  // two instructions per k-step: an MMA costs ~43 + N/2 cycles (benchmarks/mma_rate.cu), so one
+                  // N = 2 BN instruction is cheaper than two N = BN ones
                   umma<true>(dt, da, db, idesc2, acc0);  // hi x [hi_s | lo_s]
                   umma<true>(dt, da + (g >= P.t_a + P.t_x ? s_lo_off : ax_lo_off), db, idesc, 1u);  // lo x hi_s
                 } else if (kF32) {

@@ -264,8 +264,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
           const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)P.a_mn[p] << 15) |
                                  ((uint32_t)P.b_mn[p] << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
           // same with N = 2 BN: one instruction multiplies hi_a by [hi_b | lo_b] (the lo tile sits right behind the
-          // hi tile of B in shared memory).  tcgen05.mma has a per-instruction floor of ~120 cycles for N <= 128
-          // (benchmarks/mma_rate.cu), so 3xTF32 as two instructions per k-step instead of three is a third faster.
+          // hi tile of B in shared memory).  An MMA costs ~43 + N/2 cycles (benchmarks/mma_rate.cu), so 3xTF32 as two
+          // instructions per k-step (N = 2 BN, N = BN) is cheaper than three N = BN ones.
           const uint32_t idesc2 = (idesc & ~(0x3fu << 17)) | ((uint32_t)((2 * BN) >> 3) << 17);
           const uint32_t a_lbo = P.a_mn[p] ? BK * kStageRowBytes : 16, b_lbo = P.b_mn[p] ? BK * kStageRowBytes : 16;
           const uint32_t a_step = P.a_mn[p] ? UMMA_K * kStageRowBytes : 32, b_step = P.b_mn[p] ? UMMA_K * kStageRowBytes : 32;
