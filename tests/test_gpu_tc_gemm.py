@@ -45,6 +45,23 @@ def test_tc_gemm_fp32_3xtf32(a_mn, b_mn, B, M, N, Kd):
     assert err <= 2e-6 * scale * max(1.0, (Kd / 64) ** 0.5), f"3xTF32 error {err} vs scale {scale}"
 
 
+@pytest.mark.parametrize("ts", ["1", "0"])
+@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("B,M,N,Kd", [(2, 200, 40, 100), (3, 132, 72, 36), (1, 640, 320, 260), (300, 128, 64, 64)])
+def test_tc_gemm_fp32_ragged_shapes_both_engines(monkeypatch, ts, a_mn, b_mn, B, M, N, Kd):
+    """fp32 products with ragged M / N / K (partial tiles, zero-filled TMA tails, several n-tiles, more tiles than
+    SMs) on the TMEM-operand engine and on the shared-memory engine."""
+    monkeypatch.setenv("TGPB200_GEMM_TS", ts)
+    g = torch.Generator().manual_seed(5 * M + N + Kd)
+    a = torch.randn((B, Kd, M) if a_mn else (B, M, Kd), generator=g).to(DEV)
+    b = torch.randn((B, Kd, N) if b_mn else (B, N, Kd), generator=g).to(DEV)
+    out = _run(a, b, a_mn, b_mn, M, N, Kd)
+    ref = _ref(a, b, a_mn, b_mn)
+    scale = ref.abs().max().item()
+    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5 * scale)
+
+
 @pytest.mark.parametrize("a_mn", [False, True])
 @pytest.mark.parametrize("b_mn", [False, True])
 def test_tc_gemm_bf16(a_mn, b_mn):
