@@ -476,6 +476,33 @@ def test_fused_forward_exact_and_inexact_adjacency_blocks():
         close32(got[2][k].cpu(), exp[2][k].float(), k)
 
 
+@pytest.mark.parametrize("B,N,K,F", [(5, 200, 48, 100), (3, 72, 20, 36), (2, 256, 256, 64), (150, 64, 8, 16)])
+@pytest.mark.parametrize("fused_ts", ["1", "0"])
+def test_dense_pool_fp32_ragged_shapes(monkeypatch, fused_ts, B, N, K, F):
+    """Shapes off the tile grid (partial last k-block, K not a multiple of 16 / 32, more graphs than SMs, a K too
+    wide for any fused forward) through the TMEM-operand fused forward and through its shared-memory sibling."""
+    monkeypatch.setenv("TGPB200_FUSED_TS", fused_ts)
+    g = torch.Generator().manual_seed(B + 7 * N + K)
+    a, s_raw, x = _dense_inputs(g, B, N, K, F)
+    a = a * (torch.rand(B, N, N, generator=g) + 0.5)
+    a = 0.5 * (a + a.transpose(1, 2))
+    gx = torch.randn(B, K, F, generator=g)
+    ga = torch.randn(B, K, K, generator=g)
+
+    def run(mod, dev, dt):
+        sr = s_raw.detach().clone().to(dev, dt).requires_grad_(True)
+        xx = x.detach().clone().to(dev, dt).requires_grad_(True)
+        aa = a.detach().clone().to(dev, dt).requires_grad_(True)
+        xp, ap, loss = mod.mincut_pool(xx, aa, torch.softmax(sr, -1))
+        ((xp * gx.to(dev, dt)).sum() + (ap * ga.to(dev, dt)).sum() + sum(loss.values())).backward()
+        return [t.detach().cpu().float() for t in (xp, ap, *loss.values(), sr.grad, xx.grad, aa.grad)]
+
+    exp = run(R, "cpu", torch.float64)
+    got = run(T, DEV, torch.float32)
+    for n_, e_, g_ in zip(["x_pool", "adj_pool", "cut", "ortho", "grad_s", "grad_x", "grad_adj"], exp, got):
+        close32(g_, e_, n_, rtol=1e-5 if not n_.startswith("grad") else 1e-4)
+
+
 def test_dense_pool_bf16_vs_oracle():
     g = torch.Generator().manual_seed(21)
     B, N, K, F = 3, 128, 32, 64
