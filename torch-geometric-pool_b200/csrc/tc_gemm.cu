@@ -887,7 +887,7 @@ static int pick_bn(const GemmProblem& p) {
 
 bool gemm_supported(const GemmProblem& p) {
   if (p.batch <= 0 || p.M <= 0 || p.N <= 0 || p.num_pairs < 1 || p.num_pairs > kMaxPairs) return false;
-  const int es = p.in_bf16 ? 2 : 4, epb = kStageRowBytes / es;
+  const int es = p.in_bf16 ? 2 : 4;
   for (int i = 0; i < p.num_pairs; ++i) {
     if (p.kd[i] <= 0) return false;
     const OperandDesc* ops[2] = {&p.a[i], &p.b[i]};
