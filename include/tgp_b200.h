@@ -57,6 +57,9 @@ long long tgpb200_debug_launch_count(void);
  * stream (NULL stops and resets); tgpb200_debug_kernel_time_ms returns the mean duration of the recorded launches. */
 void tgpb200_debug_time_kernel(const char* filter);
 double tgpb200_debug_kernel_time_ms(int* count);
+/* Trace of the recorded launches ("*" as the filter records every kernel), in launch order: one
+ * "name<TAB>ms" line per launch; returns the bytes written into host `buf`. */
+size_t tgpb200_debug_kernel_times(char* host_buf, size_t cap);
 
 /* ------------------------------------------------------------------------------------------
  * CSR-by-cluster of a sparse assignment (replaces the stable torch.sort in
@@ -126,9 +129,10 @@ int tgpb200_filter_relabel_onepass(const int64_t* row, const int64_t* col, const
                                    float eps, int64_t* out_row, int64_t* out_col, float* out_weight, int32_t* src_edge,
                                    int64_t* count_out, void* workspace, size_t workspace_bytes,
                                    tgpb200_stream_t stream);
-/* Backward: grad_in[src_edge[j]] = grad_out[j], zero elsewhere. */
-int tgpb200_filter_relabel_bwd(const float* grad_out, const int32_t* src_edge, int64_t num_out, int64_t num_edges,
-                               float* grad_in, tgpb200_stream_t stream);
+/* Backward: grad_in[src_edge[j]] = grad_out[j], zero elsewhere.  num_out_dev (may be NULL) is a device-side
+ * count <= num_out for callers that never read the survivor count back (grad_out then has capacity num_out). */
+int tgpb200_filter_relabel_bwd(const float* grad_out, const int32_t* src_edge, int64_t num_out,
+                               const int64_t* num_out_dev, int64_t num_edges, float* grad_in, tgpb200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Sparse connect, cluster branch  tgp/connect/base_conn.py:83-89:
@@ -161,28 +165,54 @@ size_t tgpb200_coalesce_bwd_workspace_bytes(int64_t num_edges, int64_t num_out, 
  *               (w == NULL means ones, ops.py:384-385).  deg_out [K] fp32 is kept for backward.
  * weight_norm:  mx[g] = max |w| over edges with batch_pooled[row] == g (0 -> 1); w'' = w / mx[g];
  *               arg_out[g] (int32) = first edge attaining the max, -1 if none (torch_scatter CPU rule).
+ * All sums are DETERMINISTIC (no floating-point atomics): per-key segmented sums with a fixed combination shape.
+ * rows_sorted != 0 asserts that `row` is non-decreasing (true for every cluster-path output and for the kept-node
+ * output of a row-sorted input; tgpb200_rows_sorted checks it) and takes the sort-free path; otherwise the edges are
+ * first grouped by key with the stable radix sort.  num_edges_dev (may be NULL) is a device-side edge count
+ * <= num_edges (the launch capacity), for pipelines that never read the filtered edge count back to the host.
+ * `workspace`: tgpb200_edge_norm_workspace_bytes(num_edges, num_clusters).
  * ------------------------------------------------------------------------------------------ */
+size_t tgpb200_edge_norm_workspace_bytes(int64_t num_edges, int64_t num_clusters);
+/* *sorted_out (device int32) = 1 if row[0..E) is non-decreasing else 0. */
+int tgpb200_rows_sorted(const int64_t* row, int64_t num_edges, int32_t* sorted_out, tgpb200_stream_t stream);
 int tgpb200_degree_norm_fwd(const int64_t* row, const int64_t* col, const float* w, int64_t num_edges,
-                            int64_t num_clusters, float eps, float* deg_out, float* w_out, tgpb200_stream_t stream);
-int tgpb200_degree_norm_bwd(const int64_t* row, const int64_t* col, const float* w, const float* deg,
-                            const float* grad_out, int64_t num_edges, int64_t num_clusters, float eps,
-                            float* grad_dinv /* [K] scratch, overwritten */, float* grad_w, tgpb200_stream_t stream);
-/* Split forms for the edge-sharded multi-GPU path: accumulate the [K] degree / [G] max partials on
- * the local edge shard, combine them across ranks (all-reduce sum / max), then apply. */
-int tgpb200_degree_accumulate(const int64_t* row, const float* w, int64_t num_edges, int64_t num_clusters, float* deg,
-                              tgpb200_stream_t stream);
-int tgpb200_degree_apply(const int64_t* row, const int64_t* col, const float* w, const float* deg, int64_t num_edges,
-                         int64_t num_clusters, float eps, float* w_out, tgpb200_stream_t stream);
-int tgpb200_weight_max_accumulate(const int64_t* row, const float* w, const int64_t* batch_pooled, int64_t num_edges,
-                                  int64_t num_graphs, float* max_out, tgpb200_stream_t stream);
-int tgpb200_weight_max_apply(const int64_t* row, const float* w, const int64_t* batch_pooled, const float* max_in,
-                             int64_t num_edges, int64_t num_graphs, float* w_out, tgpb200_stream_t stream);
-int tgpb200_weight_norm_fwd(const int64_t* row, const float* w, const int64_t* batch_pooled, int64_t num_edges,
-                            int64_t num_graphs, float* max_out, int32_t* arg_out, float* w_out,
+                            const int64_t* num_edges_dev, int64_t num_clusters, float eps, int rows_sorted,
+                            float* deg_out, float* w_out, void* workspace, size_t workspace_bytes,
                             tgpb200_stream_t stream);
+int tgpb200_degree_norm_bwd(const int64_t* row, const int64_t* col, const float* w, const float* deg,
+                            const float* grad_out, int64_t num_edges, const int64_t* num_edges_dev,
+                            int64_t num_clusters, float eps, int rows_sorted,
+                            float* grad_dinv /* [K] scratch, overwritten */, float* grad_w, void* workspace,
+                            size_t workspace_bytes, tgpb200_stream_t stream);
+/* Split forms for the edge-sharded multi-GPU path: accumulate the [K] degree / [K] grad-dinv / [G] max
+ * partials on the local edge shard, combine them across ranks (all-reduce sum / max), then apply. */
+int tgpb200_degree_accumulate(const int64_t* row, const float* w, int64_t num_edges, const int64_t* num_edges_dev,
+                              int64_t num_clusters, int rows_sorted, float* deg, void* workspace,
+                              size_t workspace_bytes, tgpb200_stream_t stream);
+int tgpb200_degree_apply(const int64_t* row, const int64_t* col, const float* w, const float* deg, int64_t num_edges,
+                         const int64_t* num_edges_dev, int64_t num_clusters, float eps, float* w_out,
+                         tgpb200_stream_t stream);
+int tgpb200_degree_bwd_accumulate(const int64_t* row, const int64_t* col, const float* w, const float* deg,
+                                  const float* grad_out, int64_t num_edges, const int64_t* num_edges_dev,
+                                  int64_t num_clusters, float eps, int rows_sorted, float* grad_dinv, void* workspace,
+                                  size_t workspace_bytes, tgpb200_stream_t stream);
+int tgpb200_degree_bwd_apply(const int64_t* row, const int64_t* col, const float* deg, const float* grad_out,
+                             const float* grad_dinv, int64_t num_edges, const int64_t* num_edges_dev,
+                             int64_t num_clusters, float eps, float* grad_w, tgpb200_stream_t stream);
+int tgpb200_weight_max_accumulate(const int64_t* row, const float* w, const int64_t* batch_pooled, int64_t num_edges,
+                                  const int64_t* num_edges_dev, int64_t num_graphs, float* max_out,
+                                  tgpb200_stream_t stream);
+int tgpb200_weight_max_apply(const int64_t* row, const float* w, const int64_t* batch_pooled, const float* max_in,
+                             int64_t num_edges, const int64_t* num_edges_dev, int64_t num_graphs, float* w_out,
+                             tgpb200_stream_t stream);
+int tgpb200_weight_norm_fwd(const int64_t* row, const float* w, const int64_t* batch_pooled, int64_t num_edges,
+                            const int64_t* num_edges_dev, int64_t num_graphs, float* max_out, int32_t* arg_out,
+                            float* w_out, tgpb200_stream_t stream);
 int tgpb200_weight_norm_bwd(const int64_t* row, const float* w, const int64_t* batch_pooled, const float* max_in,
-                            const int32_t* arg_in, const float* grad_out, int64_t num_edges, int64_t num_graphs,
-                            float* graph_acc /* [num_graphs] scratch */, float* grad_w, tgpb200_stream_t stream);
+                            const int32_t* arg_in, const float* grad_out, int64_t num_edges,
+                            const int64_t* num_edges_dev, int64_t num_clusters, int64_t num_graphs, int rows_sorted,
+                            float* graph_acc /* [num_graphs] scratch */, float* grad_w, void* workspace,
+                            size_t workspace_bytes, tgpb200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dense Reduce + Connect + auxiliary losses, one fused call per direction.

@@ -1,6 +1,7 @@
 """CPU, world_size 2, gloo: the sharding / routing logic of tgp_b200.distributed with the oracle's CPU operators
 as the local kernels.  The sharded result (rank-order concatenation) must equal the single-process oracle:
 bit-exact indices and edge order, rtol 1e-6 weights."""
+import io
 import os
 import socket
 
@@ -34,9 +35,27 @@ class OracleOps:
         return ei, w
 
     @staticmethod
-    def degree_accumulate(row, w, K):
+    def degree_accumulate(row, w, K, rows_sorted=False):
         w = torch.ones(row.numel()) if w is None else w
         return torch.zeros(max(K, 1)).scatter_add_(0, row, w)
+
+    @staticmethod
+    def degree_bwd_accumulate(edge_index, w, deg, grad_out, K, rows_sorted=False):
+        # d loss / d dinv[v] = sum_{row = v} g w dinv[col] + sum_{col = v} g w dinv[row]   
+        dinv = deg.clamp(min=EPS).pow(-0.5)
+        t = grad_out * w
+        return (torch.zeros(max(K, 1)).scatter_add_(0, edge_index[0], t * dinv[edge_index[1]])
+                + torch.zeros(max(K, 1)).scatter_add_(0, edge_index[1], t * dinv[edge_index[0]]))
+
+    @staticmethod
+    def degree_bwd_apply(edge_index, deg, grad_out, grad_dinv, K):
+        dinv = deg.clamp(min=EPS).pow(-0.5)
+        gdeg = torch.where(deg >= EPS, -0.5 * grad_dinv * dinv ** 3, torch.zeros_like(deg))
+        return grad_out * dinv[edge_index[0]] * dinv[edge_index[1]] + gdeg[edge_index[0]]
+
+    @staticmethod
+    def segment_sum(x, cluster_index, K):
+        return torch.zeros(K, x.size(1)).index_add_(0, cluster_index, x)
 
     @staticmethod
     def degree_apply(edge_index, w, deg, K):
@@ -95,8 +114,27 @@ def _worker(rank, world, port, q):
         dist.all_gather_object(outs3, (ec2, wc2))
         losses = D.combine_losses({"cut_loss": torch.tensor(float(rank + 1)), "link_loss": torch.tensor(3.0 + rank)},
                                   local_graphs=2 + rank)
+        # ---- mean coalesce, node-sharded feature reduce (reduce_scatter of [K, F] partials), gradients
+        ec4, wc4, _ = D.sharded_cluster_connect(ei_l, ew_l, cluster, 97, reduce_op="mean", ops=OracleOps)
+        outs4 = [None] * world
+        dist.all_gather_object(outs4, (ec4, wc4))
+        x = torch.randn(n, 6, generator=g)
+        lo, hi = D.even_ranges(n, world)[rank]
+        outs5 = [None] * world
+        for op in ("sum", "mean"):
+            xp, rows = D.sharded_cluster_reduce(x[lo:hi], cluster[lo:hi], 97, reduce_op=op, ops=OracleOps)
+            got = [None] * world
+            dist.all_gather_object(got, (xp, rows))
+            outs5[0 if op == "sum" else 1] = got
+        ew_g = ew_l.clone().requires_grad_(True)
+        _, wg, _, _ = D.sharded_kept_node_connect(ei_l, ew_g, so.node_index, n, degree_norm=True, ops=OracleOps)
+        (wg * torch.arange(1, wg.numel() + 1)).sum().backward()
+        outs6 = [None] * world
+        dist.all_gather_object(outs6, (ew_g.grad, wg.numel()))
         if rank == 0:
-            q.put((outs, outs2, outs3, losses))
+            buf = io.BytesIO()  # plain bytes: tensors in a SimpleQueue travel by fd passing, which dies with the worker
+            torch.save((outs, outs2, outs3, losses, outs4, outs5, outs6), buf)
+            q.put(buf.getvalue())
     finally:
         dist.destroy_process_group()
 
@@ -109,7 +147,7 @@ def test_edge_sharded_connect_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    outs, outs2, outs3, losses = q.get()
+    outs, outs2, outs3, losses, outs4, outs5, outs6 = torch.load(io.BytesIO(q.get()), weights_only=False)
     for p in procs:
         p.join(600)
         assert p.exitcode == 0, f"worker exit code {p.exitcode}"
@@ -138,6 +176,29 @@ def test_edge_sharded_connect_matches_single_process():
     e_ref2, w_ref2 = R.sparse_connect_so(ei, so_c)
     assert w_ref2 is None and all(o[1] is None for o in outs3)
     assert torch.equal(torch.cat([o[0] for o in outs3], 1), e_ref2)
+
+    e_ref4, w_ref4 = R.sparse_connect_so(ei, so_c, edge_weight=ew, reduce_op="mean")
+    assert torch.equal(torch.cat([o[0] for o in outs4], 1), e_ref4)
+    torch.testing.assert_close(torch.cat([o[1] for o in outs4]), w_ref4, rtol=1e-6, atol=1e-7)
+    x = torch.randn(n, 6, generator=g)
+    ones = R.OracleSelectOutput(cluster_index=cluster, num_supernodes=97)
+    for j, op in enumerate(("sum", "mean")):
+        ref = R.base_reduce(x, ones)[0] if op == "sum" else R.aggr_reduce(x, ones, op="mean")[0]
+        got = torch.cat([o[0] for o in outs5[j]])
+        torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-6)
+        assert outs5[j][0][1][0] == 0 and outs5[j][-1][1][1] == 97
+    # gradient of the sharded degree normalisation (all-reduce of the [K] partials in the backward)
+    ew_full = ew.clone().requires_grad_(True)
+    _, w_full = R.sparse_connect_so(ei, so, edge_weight=ew_full, degree_norm=True)
+    off = 0
+    coef = torch.zeros(w_full.numel())
+    for gr, cnt in outs6:  # every rank weighted ITS output slice with 1..cnt
+        coef[off:off + cnt] = torch.arange(1, cnt + 1).float()
+        off += cnt
+    (w_full * coef).sum().backward()
+    # (fp32 sums of terms weighted up to ~700 with cancellation: the bound is relative to the largest gradient)
+    torch.testing.assert_close(torch.cat([o[0] for o in outs6]), ew_full.grad, rtol=1e-4,
+                               atol=1e-5 * float(ew_full.grad.abs().max()))
 
     # losses: weighted batch mean, and sqrt of the summed squares for the global Frobenius norm
     torch.testing.assert_close(losses["cut_loss"], torch.tensor((1.0 * 2 + 2.0 * 3) / 5))

@@ -845,9 +845,10 @@ struct EwHook {  // fused element-wise terms of dS (tc::GemmProblem::ew_*); *app
 
 template <typename T, typename TC>
 static int mm(int batch, int M, int N, int npairs, const int* kd, const Mat* A, const Mat* Bm, TC* out, int64_t obs,
-              int64_t ors, int64_t ocs, cudaStream_t st, EwHook hook = EwHook()) {
+              int64_t ors, int64_t ocs, cudaStream_t st, EwHook hook = EwHook(), const char* tag = nullptr) {
   tc::GemmProblem p;
   memset(&p, 0, sizeof(p));
+  p.tag = tag;
   p.batch = batch, p.M = M, p.N = N, p.num_pairs = npairs;
   for (int i = 0; i < npairs; ++i) {
     p.kd[i] = kd[i];
@@ -867,7 +868,7 @@ static int mm(int batch, int M, int N, int npairs, const int* kd, const Mat* A, 
   }
   if (ocs != 1) {  // transposed output: D^T = B^T A^T has unit column stride
     if (ors != 1) return TGPB200_ERR_UNSUPPORTED;
-    return mm<T, TC>(batch, N, M, npairs, kd, Bm, A, out, obs, ocs, ors, st);
+    return mm<T, TC>(batch, N, M, npairs, kd, Bm, A, out, obs, ocs, ors, st, EwHook(), tag);
   }
   for (int i = 0; i < npairs; ++i) {
     int64_t sAm = A[i].mn ? 1 : A[i].rs, sAk = A[i].mn ? A[i].rs : 1;
@@ -881,8 +882,8 @@ static int mm(int batch, int M, int N, int npairs, const int* kd, const Mat* A, 
 
 template <typename T, typename TC>
 static int mm1(int batch, int M, int N, int kd, Mat A, Mat Bm, TC* out, int64_t obs, int64_t ors, int64_t ocs,
-               cudaStream_t st) {
-  return mm<T, TC>(batch, M, N, 1, &kd, &A, &Bm, out, obs, ors, ocs, st);
+               cudaStream_t st, const char* tag = nullptr) {
+  return mm<T, TC>(batch, M, N, 1, &kd, &A, &Bm, out, obs, ors, ocs, st, EwHook(), tag);
 }
 
 // How a per-graph kernel splits a [K, K] matrix over a cluster: R CTAs of `threads` threads, `rows_per` rows each;
@@ -974,20 +975,20 @@ static int dense_fwd(const T* A, const T* S, const T* X, int B, int N, int K, in
       // (transposed stores are scalar per element; when K already fills the 128-row tile the natural orientation
       //  with vectorised row stores is the faster one)
       if (F >= K && K % 128 != 0)  // D[f, k] = sum_i X[i, f] S[i, k], written transposed into X_pool[k, f]
-        rc = mm1<T, T>(B, F, K, N, Mat{X, NF, F, 1}, Smn, Xpool, KF, 1, F, st);
+        rc = mm1<T, T>(B, F, K, N, Mat{X, NF, F, 1}, Smn, Xpool, KF, 1, F, st, "k_tc_gemm:Xpool=StX");
       else
-        rc = mm1<T, T>(B, K, F, N, Smn, Mat{X, NF, F, 1}, Xpool, KF, F, 1, st);
+        rc = mm1<T, T>(B, K, F, N, Smn, Mat{X, NF, F, 1}, Xpool, KF, F, 1, st, "k_tc_gemm:Xpool=StX");
       if (rc) return rc;
     }
     if (A) {  // T = S^T A  [K, N]
       if (K % 128 == 0)  // natural orientation: D[k, j] = sum_i S[i, k] A[i, j]
-        rc = mm1<T, T>(B, K, N, N, Smn, Mat{A, NN, N, 1}, pl.Tt, NK, N, 1, st);
+        rc = mm1<T, T>(B, K, N, N, Smn, Mat{A, NN, N, 1}, pl.Tt, NK, N, 1, st, "k_tc_gemm:T=StA");
       else  // D[j, k] = sum_i A[i, j] S[i, k], written transposed (no padding of K up to the 128-row tile)
-        rc = mm1<T, T>(B, N, K, N, Mat{A, NN, N, 1}, Smn, pl.Tt, NK, 1, N, st);
+        rc = mm1<T, T>(B, N, K, N, Mat{A, NN, N, 1}, Smn, pl.Tt, NK, 1, N, st, "k_tc_gemm:T=StA");
       if (rc) return rc;
     }
     if (loss_kind != 0) {  // M = S^T S
-      rc = mm1<T, float>(B, K, K, N, Smn, Smn, pl.M, KK, K, 1, st);
+      rc = mm1<T, float>(B, K, K, N, Smn, Smn, pl.M, KK, K, 1, st, "k_tc_gemm:M=StS");
       if (rc) return rc;
     }
     int64_t rows = (int64_t)B * N;
@@ -999,7 +1000,7 @@ static int dense_fwd(const T* A, const T* S, const T* X, int B, int N, int K, in
     }
   }
   if (A) {  // A_raw = T S  [K, K]   ((S^T A) S, dense_conn.py:120-121)
-    rc = mm1<T, float>(B, K, K, N, Mat{pl.Tt, NK, N, 0}, Smn, pl.Araw, KK, K, 1, st);
+    rc = mm1<T, float>(B, K, K, N, Mat{pl.Tt, NK, N, 0}, Smn, pl.Araw, KK, K, 1, st, "k_tc_gemm:Araw=TS");
     if (rc) return rc;
   }
   if (B > 0) {
@@ -1054,11 +1055,11 @@ static int dense_bwd(const T* A, const T* S, const T* X, const T* gXpool, const 
   }
   const bool have_x = X && gXpool;
   if (have_x && dX_out) {  // dX = S Gx  [N, F]
-    rc = mm1<T, T>(B, N, F, K, Mat{S, NK, K, 0}, Mat{gXpool, KF, F, 1}, dX_out, NF, F, 1, st);
+    rc = mm1<T, T>(B, N, F, K, Mat{S, NK, K, 0}, Mat{gXpool, KF, F, 1}, dX_out, NF, F, 1, st, "k_tc_gemm:dX=SGx");
     if (rc) return rc;
   }
   if (have_a) {  // W = A S  [N, K]
-    rc = mm1<T, T>(B, N, K, N, Mat{A, NN, N, 0}, Mat{S, NK, K, 1}, W, NK, K, 1, st);
+    rc = mm1<T, T>(B, N, K, N, Mat{A, NN, N, 0}, Mat{S, NK, K, 1}, W, NK, K, 1, st, "k_tc_gemm:W=AS");
     if (rc) return rc;
   }
   // dS = X Gx^T + W Graw^T + T^T Graw + S P   (one accumulation chain in TMEM; the element-wise loss terms
@@ -1079,7 +1080,7 @@ static int dense_bwd(const T* A, const T* S, const T* X, const T* gXpool, const 
       if (have_a && loss_kind != 0) {
         hook.S = S, hook.d = pl.d, hook.coef = coef, hook.eps = eps, hook.applied = &ew_done;
       }
-      rc = mm<T, T>(B, N, K, n, kd, a, b, dS_out, NK, K, 1, st, hook);
+      rc = mm<T, T>(B, N, K, n, kd, a, b, dS_out, NK, K, 1, st, hook, "k_tc_gemm:dS");
       if (rc) return rc;
     } else {
       cudaMemsetAsync(dS_out, 0, (size_t)B * NK * sizeof(T), st);
@@ -1089,9 +1090,9 @@ static int dense_bwd(const T* A, const T* S, const T* X, const T* gXpool, const 
     launch("k_ds_elementwise", k_ds_elementwise<T>, (unsigned)ceil_div((int64_t)B * NK, 256), 256, 0, st, S, pl.d, coef,
            (int64_t)B * NK, N, K, eps, dS_out);
   if (have_a && dA_out) {  // dA = (S Graw) S^T + element-wise terms
-    rc = mm1<T, T>(B, N, K, K, Mat{S, NK, K, 0}, Mat{Gt, KK, K, 1}, U, NK, K, 1, st);
+    rc = mm1<T, T>(B, N, K, K, Mat{S, NK, K, 0}, Mat{Gt, KK, K, 1}, U, NK, K, 1, st, "k_tc_gemm:U=SG");
     if (rc) return rc;
-    rc = mm1<T, T>(B, N, N, K, Mat{U, NK, K, 0}, Mat{S, NK, K, 0}, dA_out, NN, N, 1, st);
+    rc = mm1<T, T>(B, N, N, K, Mat{U, NK, K, 0}, Mat{S, NK, K, 0}, dA_out, NN, N, 1, st, "k_tc_gemm:dA=USt");
     if (rc) return rc;
     if (loss_kind != 0)
       launch("k_da_elementwise", k_da_elementwise<T>, (unsigned)ceil_div((int64_t)B * NN, 256), 256, 0, st, A, pl.ss,

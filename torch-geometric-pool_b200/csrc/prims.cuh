@@ -320,10 +320,11 @@ inline RadixPlan radix_plan(int key_bits) {
 inline int radix_passes(int key_bits) { return radix_plan(key_bits).passes; }
 
 template <typename KeyT, int BITS>
-static __global__ void k_radix_hist(const KeyT* __restrict__ keys, int64_t n, int shift, int* __restrict__ tile_hist,
-                                    int nt) {
+static __global__ void k_radix_hist(const KeyT* __restrict__ keys, int64_t n, const int64_t* __restrict__ n_dev,
+                                    int shift, int* __restrict__ tile_hist, int nt) {
   constexpr int BINS = 1 << BITS;
   __shared__ int h[BINS];
+  if (n_dev) n = min(n, *n_dev);  // device-side count (capacity launch): tiles past it publish empty histograms
   for (int d = threadIdx.x; d < BINS; d += kSortThreads) h[d] = 0;
   __syncthreads();
   int64_t base = (int64_t)blockIdx.x * kSortTile;
@@ -343,9 +344,11 @@ static __global__ void k_radix_hist(const KeyT* __restrict__ keys, int64_t n, in
 template <typename KeyT, int BITS, bool kIota>
 static __global__ void __launch_bounds__(kSortThreads)
     k_radix_scatter(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                    KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
-                    const int* __restrict__ tile_off, int nt) {
+                    KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n,
+                    const int64_t* __restrict__ n_dev, int shift, const int* __restrict__ tile_off, int nt) {
   constexpr int NW = kSortThreads / 32;
+  if (n_dev) n = min(n, *n_dev);
+  if ((int64_t)blockIdx.x * kSortTile >= n) return;
   constexpr int BINS = 1 << BITS;
   constexpr int DPT = BINS / kSortThreads;  // digits owned by one thread (consecutive)
   extern __shared__ __align__(16) unsigned char radix_smem[];
@@ -455,8 +458,8 @@ inline size_t radix_sort_workspace_bytes(int64_t n) {
 // "attribute already set" flag below must be per translation unit too; an `inline` function would share one flag
 // across units and leave the other units' kernel copies without the > 48 KB shared-memory opt-in.
 template <typename KeyT, int BITS>
-static int radix_pass(const KeyT* kin, const uint32_t* vin, KeyT* kout, uint32_t* vout, int64_t n, int shift, int* hist,
-                      int nt, Workspace& ws, cudaStream_t stream) {
+static int radix_pass(const KeyT* kin, const uint32_t* vin, KeyT* kout, uint32_t* vout, int64_t n,
+                      const int64_t* n_dev, int shift, int* hist, int nt, Workspace& ws, cudaStream_t stream) {
   constexpr int BINS = 1 << BITS;
   static bool smem_attr_set = false;  // per instantiation: > 48 KB dynamic shared memory needs the opt-in
   if (!smem_attr_set) {
@@ -466,24 +469,26 @@ static int radix_pass(const KeyT* kin, const uint32_t* vin, KeyT* kout, uint32_t
     cudaFuncSetAttribute(k_radix_scatter<KeyT, BITS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)radix_scatter_smem<KeyT, BITS>());
   }
-  launch("k_radix_hist", k_radix_hist<KeyT, BITS>, nt, kSortThreads, 0, stream, kin, n, shift, hist, nt);
+  launch("k_radix_hist", k_radix_hist<KeyT, BITS>, nt, kSortThreads, 0, stream, kin, n, n_dev, shift, hist, nt);
   int rc = exclusive_scan_i32(hist, hist, (int64_t)nt * BINS, nullptr, nullptr, ws, stream);
   if (rc != TGPB200_OK) return rc;
   if (vin == nullptr)
     launch("k_radix_scatter", k_radix_scatter<KeyT, BITS, true>, nt, kSortThreads, radix_scatter_smem<KeyT, BITS>(),
-           stream, kin, (const uint32_t*)nullptr, kout, vout, n, shift, hist, nt);
+           stream, kin, (const uint32_t*)nullptr, kout, vout, n, n_dev, shift, hist, nt);
   else
     launch("k_radix_scatter", k_radix_scatter<KeyT, BITS, false>, nt, kSortThreads, radix_scatter_smem<KeyT, BITS>(),
-           stream, kin, vin, kout, vout, n, shift, hist, nt);
+           stream, kin, vin, kout, vout, n, n_dev, shift, hist, nt);
   return TGPB200_OK;
 }
 
-// Sorts n pairs by the low `key_bits` bits of the key.  The first pass takes the payload as
+// Sorts n pairs by the low `key_bits` bits of the key (n_dev, when given, is a device-side count <= n: the launch
+// covers the capacity n and tiles past the count do nothing).  The first pass takes the payload as
 // iota when vals0 == nullptr.  Buffers (keys0, vals0) and (keys1, vals1) ping-pong; returns
 // (via *result_in_1) which pair holds the result.  keys0 is overwritten.
 template <typename KeyT>
 static int radix_sort_pairs(KeyT* keys0, uint32_t* vals0_or_null, uint32_t* vals0_buf, KeyT* keys1, uint32_t* vals1,
-                            int64_t n, int key_bits, bool* result_in_1, Workspace& ws, cudaStream_t stream) {
+                            int64_t n, int key_bits, bool* result_in_1, Workspace& ws, cudaStream_t stream,
+                            const int64_t* n_dev = nullptr) {
   int nt = (int)ceil_div(n > 0 ? n : 1, kSortTile);
   const RadixPlan plan = radix_plan(key_bits);
   int* hist = ws.take<int>((size_t)nt * (1 << plan.bits));
@@ -498,9 +503,9 @@ static int radix_sort_pairs(KeyT* keys0, uint32_t* vals0_or_null, uint32_t* vals
     int shift = plan.bits * p;
     ws.off = mark2;
     int rc;
-    if (plan.bits == 8) rc = radix_pass<KeyT, 8>(kin, vin, kout, vout, n, shift, hist, nt, ws, stream);
-    else if (plan.bits == 10) rc = radix_pass<KeyT, 10>(kin, vin, kout, vout, n, shift, hist, nt, ws, stream);
-    else rc = radix_pass<KeyT, 11>(kin, vin, kout, vout, n, shift, hist, nt, ws, stream);
+    if (plan.bits == 8) rc = radix_pass<KeyT, 8>(kin, vin, kout, vout, n, n_dev, shift, hist, nt, ws, stream);
+    else if (plan.bits == 10) rc = radix_pass<KeyT, 10>(kin, vin, kout, vout, n, n_dev, shift, hist, nt, ws, stream);
+    else rc = radix_pass<KeyT, 11>(kin, vin, kout, vout, n, n_dev, shift, hist, nt, ws, stream);
     if (rc != TGPB200_OK) return rc;
     in1 = !in1;
     KeyT* tk = kin;

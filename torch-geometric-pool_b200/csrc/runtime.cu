@@ -26,19 +26,29 @@ void report_launch_failure(const char* name, cudaError_t e) {
   fflush(stderr);
 }
 
+// Diagnostics only (bench.py): event pairs around the kernels whose name matches the filter ("*" = every kernel).
+// Off unless tgpb200_debug_time_kernel() was called; never active during a CUDA-graph capture (bench.py times its
+// kernels in a separate eager pass).
+constexpr int kMaxEv = 8192;
 static char g_filter[128] = {0};
-static cudaEvent_t g_ev[2][512];
+static cudaEvent_t g_ev[2][kMaxEv];
+static const char* g_ev_name[kMaxEv];
 static int g_ev_n = 0;
-static bool g_ev_init = false;
+static int g_ev_made = 0;
 
-bool timing_match(const char* name) { return g_filter[0] != 0 && strstr(name, g_filter) != nullptr && g_ev_n < 512; }
+bool timing_match(const char* name) {
+  if (g_filter[0] == 0 || g_ev_n >= kMaxEv) return false;
+  if (g_filter[0] == '*' || strstr(name, g_filter) != nullptr) {
+    g_ev_name[g_ev_n] = name;  // kernel names are string literals
+    return true;
+  }
+  return false;
+}
 void timing_begin(cudaStream_t st) {
-  if (!g_ev_init) {
-    for (int i = 0; i < 512; ++i) {
-      cudaEventCreate(&g_ev[0][i]);
-      cudaEventCreate(&g_ev[1][i]);
-    }
-    g_ev_init = true;
+  while (g_ev_made <= g_ev_n) {
+    cudaEventCreate(&g_ev[0][g_ev_made]);
+    cudaEventCreate(&g_ev[1][g_ev_made]);
+    ++g_ev_made;
   }
   cudaEventRecord(g_ev[0][g_ev_n], st);
 }
@@ -73,5 +83,22 @@ double tgpb200_debug_kernel_time_ms(int* count) {
   }
   if (count) *count = n;
   return n > 0 ? tot / n : 0.0;
+}
+// Trace of the recorded launches in launch order: one "name<TAB>ms" line per launch.  Returns the number of bytes
+// written (0-terminated, truncated to `cap`).
+size_t tgpb200_debug_kernel_times(char* buf, size_t cap) {
+  const int n = tgp::g_ev_n;
+  if (!buf || cap == 0) return 0;
+  size_t off = 0;
+  buf[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaEventSynchronize(tgp::g_ev[1][i]);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, tgp::g_ev[0][i], tgp::g_ev[1][i]);
+    int w = snprintf(buf + off, cap - off, "%s\t%.6f\n", tgp::g_ev_name[i], ms);
+    if (w < 0 || (size_t)w >= cap - off) break;
+    off += (size_t)w;
+  }
+  return off;
 }
 }

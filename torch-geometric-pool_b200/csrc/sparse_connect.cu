@@ -267,20 +267,191 @@ static __global__ void k_coalesce_bwd(const float* __restrict__ w, const float* 
 }
 
 // ------------------------------------------------------------------------------------------
+// Deterministic segmented sums (degree / normalisation partials): no floating-point atomics.
+//   out[k] = sum of val(i) over the positions i with key(i) == k, k in [0, K)
+// Non-decreasing keys (coarse edge lists are row-sorted: the cluster path sorts them, the kept-node path keeps the
+// order of a row-sorted input) take the direct path: a span pass marks [first, last) of every key, then one warp per
+// key adds its span lane-strided and combines the 32 partials in a fixed butterfly (bitwise reproducible).  Other key
+// sequences are first grouped with the stable radix sort (positions stay ascending inside a key).  Spans longer than
+// kLongSpan go to a block-per-span kernel through a small work list (its order does not matter: every span's sum
+// has a fixed shape).  `n_dev`, when given, is the device-side element count (<= the launch capacity n).
+// ------------------------------------------------------------------------------------------
+constexpr int kLongSpan = 8192;
+
+struct KeyOfArray64 {
+  const int64_t* k;
+  __device__ int64_t operator()(int64_t i) const { return k[i]; }
+};
+struct KeyOfArray32 {
+  const uint32_t* k;
+  __device__ int64_t operator()(int64_t i) const { return (int64_t)k[i]; }
+};
+
+template <typename KeyF>
+static __global__ void k_key_spans(KeyF key, int64_t n, const int64_t* __restrict__ n_dev, int64_t K,
+                                   int2* __restrict__ span) {
+  if (n_dev) n = min(n, *n_dev);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t k = key(i);
+  if (k < 0 || k >= K) return;
+  if (i == 0 || key(i - 1) != k) span[k].x = (int)i;
+  if (i + 1 == n || key(i + 1) != k) span[k].y = (int)(i + 1);
+}
+
+template <typename KeyF>
+static __global__ void k_fill_keys32(KeyF key, int64_t n, const int64_t* __restrict__ n_dev, int64_t K,
+                                     uint32_t* __restrict__ keys) {
+  if (n_dev) n = min(n, *n_dev);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t k = key(i);
+  keys[i] = (k < 0 || k >= K) ? (uint32_t)K : (uint32_t)k;  // out-of-range keys sort last and match no span
+}
+
+template <typename ValF>
+static __global__ void __launch_bounds__(256)
+    k_span_sum(const int2* __restrict__ span, int64_t K, ValF val, float* __restrict__ out,
+               int* __restrict__ long_list, int* __restrict__ long_cnt) {
+  const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= K) return;
+  const int2 s = span[k];
+  if (s.x < 0 || s.y <= s.x) {
+    if (lane == 0) out[k] = 0.f;
+    return;
+  }
+  if (s.y - s.x > kLongSpan) {
+    if (lane == 0) long_list[atomicAdd(long_cnt, 1)] = (int)k;
+    return;
+  }
+  float acc = 0.f;
+  for (int i = s.x + lane; i < s.y; i += 32) acc = __fadd_rn(acc, val(i));
+  acc = warp_sum(acc);
+  if (lane == 0) out[k] = acc;
+}
+
+template <typename ValF>
+static __global__ void __launch_bounds__(256)
+    k_span_sum_long(const int2* __restrict__ span, ValF val, float* __restrict__ out,
+                    const int* __restrict__ long_list, const int* __restrict__ long_cnt) {
+  __shared__ float red[32];
+  const int n_long = *long_cnt;
+  for (int j = blockIdx.x; j < n_long; j += gridDim.x) {
+    const int k = long_list[j];
+    const int2 s = span[k];
+    float acc = 0.f;
+    for (int i = s.x + threadIdx.x; i < s.y; i += 256) acc = __fadd_rn(acc, val(i));
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[k] = acc;
+    __syncthreads();
+  }
+}
+
+template <typename ValF>
+struct ValThroughOrder {
+  ValF v;
+  const uint32_t* order;
+  __device__ float operator()(int64_t i) const { return v((int64_t)order[i]); }
+};
+
+static size_t det_segment_sum_workspace_bytes(int64_t n, int64_t K) {
+  size_t m = (size_t)(n > 0 ? n : 1);
+  return 4 * align_up(m * sizeof(uint32_t)) + radix_sort_workspace_bytes(n) + align_up((size_t)(K + 1) * sizeof(int2)) +
+         align_up((m / kLongSpan + 2) * sizeof(int)) + 1024;
+}
+
+template <typename ValF>
+static void span_sums(const int2* span, int64_t n, int64_t K, ValF val, float* out, int* long_list, cudaStream_t st) {
+  int* long_cnt = long_list;  // slot 0 = counter, entries follow
+  cudaMemsetAsync(long_cnt, 0, sizeof(int), st);
+  launch("k_span_sum", k_span_sum<ValF>, (unsigned)ceil_div(K * 32, 256), 256, 0, st, span, K, val, out, long_list + 1,
+         long_cnt);
+  if (n > kLongSpan) {
+    const int64_t cap = n / kLongSpan + 1;
+    launch("k_span_sum_long", k_span_sum_long<ValF>, (unsigned)(cap < 1184 ? cap : 1184), 256, 0, st, span, val, out,
+           long_list + 1, long_cnt);
+  }
+}
+
+template <typename KeyF, typename ValF>
+static int det_segment_sum(KeyF key, ValF val, int64_t n, const int64_t* n_dev, int64_t K, bool keys_sorted, float* out,
+                           Workspace& ws, cudaStream_t st) {
+  if (K <= 0) return TGPB200_OK;
+  const size_t m = (size_t)(n > 0 ? n : 1);
+  int2* span = ws.take<int2>((size_t)K + 1);
+  int* long_list = ws.take<int>(m / kLongSpan + 2);
+  if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+  cudaMemsetAsync(span, 0xff, (size_t)K * sizeof(int2), st);
+  const unsigned grid = (unsigned)ceil_div(n > 0 ? n : 1, 256);
+  if (n <= 0) {
+    cudaMemsetAsync(out, 0, (size_t)K * sizeof(float), st);
+    return launch_status();
+  }
+  if (keys_sorted) {
+    launch("k_key_spans", k_key_spans<KeyF>, grid, 256, 0, st, key, n, n_dev, K, span);
+    span_sums(span, n, K, val, out, long_list, st);
+    return launch_status();
+  }
+  uint32_t* keys0 = ws.take<uint32_t>(m);
+  uint32_t* keys1 = ws.take<uint32_t>(m);
+  uint32_t* vals0 = ws.take<uint32_t>(m);
+  uint32_t* vals1 = ws.take<uint32_t>(m);
+  if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+  launch("k_fill_keys32", k_fill_keys32<KeyF>, grid, 256, 0, st, key, n, n_dev, K, keys0);
+  bool in1 = false;
+  int rc = radix_sort_pairs<uint32_t>(keys0, nullptr, vals0, keys1, vals1, n, key_bits_for_u64((uint64_t)K), &in1, ws, st,
+                                      n_dev);
+  if (rc != TGPB200_OK) return rc;
+  KeyOfArray32 skey{in1 ? keys1 : keys0};
+  launch("k_key_spans", k_key_spans<KeyOfArray32>, grid, 256, 0, st, skey, n, n_dev, K, span);
+  ValThroughOrder<ValF> ival{val, in1 ? vals1 : vals0};
+  span_sums(span, n, K, ival, out, long_list, st);
+  return launch_status();
+}
+
+static __global__ void k_rows_sorted(const int64_t* __restrict__ row, int64_t E, int32_t* __restrict__ sorted_out) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e + 1 < E && row[e + 1] < row[e]) *sorted_out = 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // degree / max-weight normalisation
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float dinv_of(float deg, float eps) { return 1.0f / sqrtf(fmaxf(deg, eps)); }
 
-static __global__ void k_deg_accum(const int64_t* __restrict__ row, const float* __restrict__ w, int64_t E, int64_t K,
-                                   float* __restrict__ deg) {
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  int64_t r = row[e];
-  if (r >= 0 && r < K) atomicAdd(&deg[r], w ? w[e] : 1.f);
-}
+struct DegVal {
+  const float* w;
+  __device__ float operator()(int64_t e) const { return w ? w[e] : 1.f; }
+};
+// gradient w.r.t. dinv: row side sum_{e: row = v} g w dinv[col], column side sum_{e: col = v} g w dinv[row]
+struct DegBwdVal {
+  const int64_t* other;  // the opposite endpoint of the key
+  const float* w;
+  const float* deg;
+  const float* gout;
+  int64_t K;
+  float eps;
+  __device__ float operator()(int64_t e) const {
+    const int64_t o = other[e];
+    if (o < 0 || o >= K) return 0.f;
+    return gout[e] * (w ? w[e] : 1.f) * dinv_of(deg[o], eps);
+  }
+};
+struct ProdVal {
+  const float* a;
+  const float* b;
+  __device__ float operator()(int64_t e) const { return a[e] * b[e]; }
+};
+struct ArrVal {
+  const float* a;
+  __device__ float operator()(int64_t i) const { return a[i]; }
+};
+
 static __global__ void k_deg_apply(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
-                                   const float* __restrict__ w, const float* __restrict__ deg, int64_t E, int64_t K,
-                                   float eps, float* __restrict__ w_out) {
+                                   const float* __restrict__ w, const float* __restrict__ deg, int64_t E,
+                                   const int64_t* __restrict__ E_dev, int64_t K, float eps, float* __restrict__ w_out) {
+  if (E_dev) E = min(E, *E_dev);
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   int64_t r = row[e], c = col[e];
@@ -288,22 +459,16 @@ static __global__ void k_deg_apply(const int64_t* __restrict__ row, const int64_
   float v = w ? w[e] : 1.f;
   w_out[e] = __fmul_rn(__fmul_rn(v, dinv_of(deg[r], eps)), dinv_of(deg[c], eps));
 }
-static __global__ void k_deg_bwd_accum(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
-                                       const float* __restrict__ w, const float* __restrict__ deg,
-                                       const float* __restrict__ gout, int64_t E, int64_t K, float eps,
-                                       float* __restrict__ gdinv) {
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  int64_t r = row[e], c = col[e];
-  if (r < 0 || r >= K || c < 0 || c >= K) return;
-  float t = gout[e] * (w ? w[e] : 1.f);
-  atomicAdd(&gdinv[r], t * dinv_of(deg[c], eps));
-  atomicAdd(&gdinv[c], t * dinv_of(deg[r], eps));
+static __global__ void k_add_vec(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                                 float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __fadd_rn(a[i], b[i]);
 }
 static __global__ void k_deg_bwd_apply(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
                                        const float* __restrict__ deg, const float* __restrict__ gout,
-                                       const float* __restrict__ gdinv, int64_t E, int64_t K, float eps,
-                                       float* __restrict__ gw) {
+                                       const float* __restrict__ gdinv, int64_t E, const int64_t* __restrict__ E_dev,
+                                       int64_t K, float eps, float* __restrict__ gw) {
+  if (E_dev) E = min(E, *E_dev);
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   int64_t r = row[e], c = col[e];
@@ -314,7 +479,9 @@ static __global__ void k_deg_bwd_apply(const int64_t* __restrict__ row, const in
 }
 
 static __global__ void k_wn_max(const int64_t* __restrict__ row, const float* __restrict__ w,
-                                const int64_t* __restrict__ batch, int64_t E, int64_t G, float* __restrict__ mx) {
+                                const int64_t* __restrict__ batch, int64_t E, const int64_t* __restrict__ E_dev,
+                                int64_t G, float* __restrict__ mx) {
+  if (E_dev) E = min(E, *E_dev);
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   int64_t g = batch[row[e]];
@@ -324,7 +491,9 @@ static __global__ void k_wn_max(const int64_t* __restrict__ row, const float* __
 }
 static __global__ void k_wn_apply(const int64_t* __restrict__ row, const float* __restrict__ w,
                                   const int64_t* __restrict__ batch, const float* __restrict__ mx, int64_t E,
-                                  int64_t G, int32_t* __restrict__ arg, float* __restrict__ w_out) {
+                                  const int64_t* __restrict__ E_dev, int64_t G, int32_t* __restrict__ arg,
+                                  float* __restrict__ w_out) {
+  if (E_dev) E = min(E, *E_dev);
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   int64_t g = batch[row[e]];
@@ -333,18 +502,12 @@ static __global__ void k_wn_apply(const int64_t* __restrict__ row, const float* 
   if (arg && fabsf(w[e]) == m) atomicMin(&arg[g], (int)e);
   w_out[e] = __fdiv_rn(w[e], m == 0.f ? 1.f : m);
 }
-static __global__ void k_wn_bwd_accum(const int64_t* __restrict__ row, const float* __restrict__ w,
-                                      const int64_t* __restrict__ batch, const float* __restrict__ gout, int64_t E,
-                                      int64_t G, float* __restrict__ acc) {
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  int64_t g = batch[row[e]];
-  if (g >= 0 && g < G) atomicAdd(&acc[g], gout[e] * w[e]);
-}
 static __global__ void k_wn_bwd_apply(const int64_t* __restrict__ row, const float* __restrict__ w,
                                       const int64_t* __restrict__ batch, const float* __restrict__ mx,
                                       const int32_t* __restrict__ arg, const float* __restrict__ gout,
-                                      const float* __restrict__ acc, int64_t E, int64_t G, float* __restrict__ gw) {
+                                      const float* __restrict__ acc, int64_t E, const int64_t* __restrict__ E_dev,
+                                      int64_t G, float* __restrict__ gw) {
+  if (E_dev) E = min(E, *E_dev);
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   int64_t g = batch[row[e]];
@@ -487,19 +650,20 @@ int tgpb200_filter_relabel_onepass(const int64_t* row, const int64_t* col, const
 
 // grad_in[e] = grad_out[j] for the surviving edges (src_edge[j] == e), 0 elsewhere.
 static __global__ void k_unfilter(const float* __restrict__ gout, const int32_t* __restrict__ src, int64_t cnt,
-                                  float* __restrict__ gin) {
+                                  const int64_t* __restrict__ cnt_dev, float* __restrict__ gin) {
+  if (cnt_dev) cnt = min(cnt, *cnt_dev);
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j < cnt) gin[src[j]] = gout[j];
 }
 
-int tgpb200_filter_relabel_bwd(const float* grad_out, const int32_t* src_edge, int64_t num_out, int64_t E,
-                               float* grad_in, tgpb200_stream_t stream) {
+int tgpb200_filter_relabel_bwd(const float* grad_out, const int32_t* src_edge, int64_t num_out,
+                               const int64_t* num_out_dev, int64_t E, float* grad_in, tgpb200_stream_t stream) {
   if (num_out < 0 || E < 0) return TGPB200_ERR_INVALID;
   if (E == 0) return TGPB200_OK;
   if (!grad_in || (num_out > 0 && (!grad_out || !src_edge))) return TGPB200_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(grad_in, 0, (size_t)E * sizeof(float), st);
-  if (num_out > 0) launch("k_unfilter", k_unfilter, (unsigned)ceil_div(num_out, 256), 256, 0, st, grad_out, src_edge, num_out, grad_in);
+  if (num_out > 0) launch("k_unfilter", k_unfilter, (unsigned)ceil_div(num_out, 256), 256, 0, st, grad_out, src_edge, num_out, num_out_dev, grad_in);
   return launch_status();
 }
 
@@ -531,51 +695,98 @@ int tgpb200_coalesce_bwd(const float* edge_weight, const float* out_weight, cons
   return launch_status();
 }
 
-int tgpb200_degree_norm_fwd(const int64_t* row, const int64_t* col, const float* w, int64_t E, int64_t K, float eps,
-                            float* deg_out, float* w_out, tgpb200_stream_t stream) {
-  if (E < 0 || K < 0) return TGPB200_ERR_INVALID;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (K > 0) {
-    if (!deg_out) return TGPB200_ERR_INVALID;
-    cudaMemsetAsync(deg_out, 0, (size_t)K * sizeof(float), st);
-  }
-  if (E == 0) return launch_status();
-  if (!row || !col || !w_out) return TGPB200_ERR_INVALID;
-  unsigned grid = (unsigned)ceil_div(E, 256);
-  launch("k_deg_accum", k_deg_accum, grid, 256, 0, st, row, w, E, K, deg_out);
-  launch("k_deg_apply", k_deg_apply, grid, 256, 0, st, row, col, w, deg_out, E, K, eps, w_out);
-  return launch_status();
+size_t tgpb200_edge_norm_workspace_bytes(int64_t E, int64_t K) {
+  // two segmented sums (row side, column side) + two [K] partial vectors
+  return 2 * det_segment_sum_workspace_bytes(E, K) + 3 * align_up((size_t)(K > 0 ? K : 1) * sizeof(float)) +
+         det_segment_sum_workspace_bytes(K, K) + 1024;
 }
 
-// Split form of the two normalisations, for the edge-sharded multi-GPU path: accumulate locally, combine the
-// [K] / [G] partials across ranks (NCCL all-reduce, sum / max), then apply.
-int tgpb200_degree_accumulate(const int64_t* row, const float* w, int64_t E, int64_t K, float* deg,
-                              tgpb200_stream_t stream) {
-  if (E < 0 || K < 0) return TGPB200_ERR_INVALID;
+int tgpb200_rows_sorted(const int64_t* row, int64_t E, int32_t* sorted_out, tgpb200_stream_t stream) {
+  if (E < 0 || !sorted_out) return TGPB200_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
-  if (K > 0) {
-    if (!deg) return TGPB200_ERR_INVALID;
-    cudaMemsetAsync(deg, 0, (size_t)K * sizeof(float), st);
-  }
-  if (E > 0) {
+  const int32_t one = 1;
+  cudaMemcpyAsync(sorted_out, &one, sizeof(one), cudaMemcpyHostToDevice, st);
+  if (E > 1) {
     if (!row) return TGPB200_ERR_INVALID;
-    launch("k_deg_accum", k_deg_accum, (unsigned)ceil_div(E, 256), 256, 0, st, row, w, E, K, deg);
+    launch("k_rows_sorted", k_rows_sorted, (unsigned)ceil_div(E, 256), 256, 0, st, row, E, sorted_out);
   }
   return launch_status();
 }
 
-int tgpb200_degree_apply(const int64_t* row, const int64_t* col, const float* w, const float* deg, int64_t E, int64_t K,
-                         float eps, float* w_out, tgpb200_stream_t stream) {
+int tgpb200_degree_accumulate(const int64_t* row, const float* w, int64_t E, const int64_t* E_dev, int64_t K,
+                              int rows_sorted, float* deg, void* workspace, size_t workspace_bytes,
+                              tgpb200_stream_t stream) {
+  if (E < 0 || K < 0 || E >= INT32_MAX) return TGPB200_ERR_INVALID;
+  if (K == 0) return TGPB200_OK;
+  if (!deg || (E > 0 && !row)) return TGPB200_ERR_INVALID;
+  Workspace ws(workspace, workspace_bytes);
+  return det_segment_sum(KeyOfArray64{row}, DegVal{w}, E, E_dev, K, rows_sorted != 0, deg, ws, (cudaStream_t)stream);
+}
+
+int tgpb200_degree_apply(const int64_t* row, const int64_t* col, const float* w, const float* deg, int64_t E,
+                         const int64_t* E_dev, int64_t K, float eps, float* w_out, tgpb200_stream_t stream) {
   if (E < 0 || K < 0) return TGPB200_ERR_INVALID;
   if (E == 0) return TGPB200_OK;
   if (!row || !col || !deg || !w_out) return TGPB200_ERR_INVALID;
-  launch("k_deg_apply", k_deg_apply, (unsigned)ceil_div(E, 256), 256, 0, (cudaStream_t)stream, row, col, w, deg, E, K, eps,
-         w_out);
+  launch("k_deg_apply", k_deg_apply, (unsigned)ceil_div(E, 256), 256, 0, (cudaStream_t)stream, row, col, w, deg, E, E_dev,
+         K, eps, w_out);
   return launch_status();
 }
 
-int tgpb200_weight_max_accumulate(const int64_t* row, const float* w, const int64_t* batch_pooled, int64_t E, int64_t G,
-                                  float* max_out, tgpb200_stream_t stream) {
+int tgpb200_degree_norm_fwd(const int64_t* row, const int64_t* col, const float* w, int64_t E, const int64_t* E_dev,
+                            int64_t K, float eps, int rows_sorted, float* deg_out, float* w_out, void* workspace,
+                            size_t workspace_bytes, tgpb200_stream_t stream) {
+  int rc = tgpb200_degree_accumulate(row, w, E, E_dev, K, rows_sorted, deg_out, workspace, workspace_bytes, stream);
+  if (rc != TGPB200_OK) return rc;
+  return tgpb200_degree_apply(row, col, w, deg_out, E, E_dev, K, eps, w_out, stream);
+}
+
+int tgpb200_degree_bwd_accumulate(const int64_t* row, const int64_t* col, const float* w, const float* deg,
+                                  const float* grad_out, int64_t E, const int64_t* E_dev, int64_t K, float eps,
+                                  int rows_sorted, float* grad_dinv, void* workspace, size_t workspace_bytes,
+                                  tgpb200_stream_t stream) {
+  if (E < 0 || K < 0 || E >= INT32_MAX) return TGPB200_ERR_INVALID;
+  if (K == 0) return TGPB200_OK;
+  if (!grad_dinv || (E > 0 && (!row || !col || !deg || !grad_out))) return TGPB200_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  float* part_row = ws.take<float>((size_t)K);
+  float* part_col = ws.take<float>((size_t)K);
+  if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+  int rc = det_segment_sum(KeyOfArray64{row}, DegBwdVal{col, w, deg, grad_out, K, eps}, E, E_dev, K, rows_sorted != 0,
+                           part_row, ws, st);
+  if (rc != TGPB200_OK) return rc;
+  // the column side is a scatter by `col`: always grouped through the stable sort
+  rc = det_segment_sum(KeyOfArray64{col}, DegBwdVal{row, w, deg, grad_out, K, eps}, E, E_dev, K, false, part_col, ws, st);
+  if (rc != TGPB200_OK) return rc;
+  launch("k_add_vec", k_add_vec, (unsigned)ceil_div(K, 256), 256, 0, st, part_row, part_col, K, grad_dinv);
+  return launch_status();
+}
+
+int tgpb200_degree_bwd_apply(const int64_t* row, const int64_t* col, const float* deg, const float* grad_out,
+                             const float* grad_dinv, int64_t E, const int64_t* E_dev, int64_t K, float eps,
+                             float* grad_w, tgpb200_stream_t stream) {
+  if (E < 0 || K < 0) return TGPB200_ERR_INVALID;
+  if (E == 0) return TGPB200_OK;
+  if (!row || !col || !deg || !grad_out || !grad_dinv || !grad_w) return TGPB200_ERR_INVALID;
+  launch("k_deg_bwd_apply", k_deg_bwd_apply, (unsigned)ceil_div(E, 256), 256, 0, (cudaStream_t)stream, row, col, deg,
+         grad_out, grad_dinv, E, E_dev, K, eps, grad_w);
+  return launch_status();
+}
+
+int tgpb200_degree_norm_bwd(const int64_t* row, const int64_t* col, const float* w, const float* deg,
+                            const float* grad_out, int64_t E, const int64_t* E_dev, int64_t K, float eps,
+                            int rows_sorted, float* grad_dinv, float* grad_w, void* workspace, size_t workspace_bytes,
+                            tgpb200_stream_t stream) {
+  if (E == 0) return TGPB200_OK;
+  int rc = tgpb200_degree_bwd_accumulate(row, col, w, deg, grad_out, E, E_dev, K, eps, rows_sorted, grad_dinv, workspace,
+                                         workspace_bytes, stream);
+  if (rc != TGPB200_OK) return rc;
+  return tgpb200_degree_bwd_apply(row, col, deg, grad_out, grad_dinv, E, E_dev, K, eps, grad_w, stream);
+}
+
+int tgpb200_weight_max_accumulate(const int64_t* row, const float* w, const int64_t* batch_pooled, int64_t E,
+                                  const int64_t* E_dev, int64_t G, float* max_out, tgpb200_stream_t stream) {
   if (E < 0 || G < 0) return TGPB200_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   if (G > 0) {
@@ -584,37 +795,24 @@ int tgpb200_weight_max_accumulate(const int64_t* row, const float* w, const int6
   }
   if (E > 0) {
     if (!row || !w || !batch_pooled) return TGPB200_ERR_INVALID;
-    launch("k_wn_max", k_wn_max, (unsigned)ceil_div(E, 256), 256, 0, st, row, w, batch_pooled, E, G, max_out);
+    launch("k_wn_max", k_wn_max, (unsigned)ceil_div(E, 256), 256, 0, st, row, w, batch_pooled, E, E_dev, G, max_out);
   }
   return launch_status();
 }
 
 int tgpb200_weight_max_apply(const int64_t* row, const float* w, const int64_t* batch_pooled, const float* max_in,
-                             int64_t E, int64_t G, float* w_out, tgpb200_stream_t stream) {
+                             int64_t E, const int64_t* E_dev, int64_t G, float* w_out, tgpb200_stream_t stream) {
   if (E < 0 || G < 0) return TGPB200_ERR_INVALID;
   if (E == 0) return TGPB200_OK;
   if (!row || !w || !batch_pooled || !max_in || !w_out) return TGPB200_ERR_INVALID;
   launch("k_wn_apply", k_wn_apply, (unsigned)ceil_div(E, 256), 256, 0, (cudaStream_t)stream, row, w, batch_pooled, max_in,
-         E, G, (int32_t*)nullptr, w_out);
+         E, E_dev, G, (int32_t*)nullptr, w_out);
   return launch_status();
 }
 
-int tgpb200_degree_norm_bwd(const int64_t* row, const int64_t* col, const float* w, const float* deg,
-                            const float* grad_out, int64_t E, int64_t K, float eps, float* grad_dinv, float* grad_w,
+int tgpb200_weight_norm_fwd(const int64_t* row, const float* w, const int64_t* batch_pooled, int64_t E,
+                            const int64_t* E_dev, int64_t G, float* max_out, int32_t* arg_out, float* w_out,
                             tgpb200_stream_t stream) {
-  if (E < 0 || K < 0) return TGPB200_ERR_INVALID;
-  if (E == 0) return TGPB200_OK;
-  if (!row || !col || !deg || !grad_out || !grad_dinv || !grad_w) return TGPB200_ERR_INVALID;
-  cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(grad_dinv, 0, (size_t)K * sizeof(float), st);
-  unsigned grid = (unsigned)ceil_div(E, 256);
-  launch("k_deg_bwd_accum", k_deg_bwd_accum, grid, 256, 0, st, row, col, w, deg, grad_out, E, K, eps, grad_dinv);
-  launch("k_deg_bwd_apply", k_deg_bwd_apply, grid, 256, 0, st, row, col, deg, grad_out, grad_dinv, E, K, eps, grad_w);
-  return launch_status();
-}
-
-int tgpb200_weight_norm_fwd(const int64_t* row, const float* w, const int64_t* batch_pooled, int64_t E, int64_t G,
-                            float* max_out, int32_t* arg_out, float* w_out, tgpb200_stream_t stream) {
   if (E < 0 || G < 0) return TGPB200_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   if (G > 0) {
@@ -625,23 +823,31 @@ int tgpb200_weight_norm_fwd(const int64_t* row, const float* w, const int64_t* b
   if (E == 0) return launch_status();
   if (!row || !w || !batch_pooled || !w_out) return TGPB200_ERR_INVALID;
   unsigned grid = (unsigned)ceil_div(E, 256);
-  launch("k_wn_max", k_wn_max, grid, 256, 0, st, row, w, batch_pooled, E, G, max_out);
-  launch("k_wn_apply", k_wn_apply, grid, 256, 0, st, row, w, batch_pooled, max_out, E, G, arg_out, w_out);
+  launch("k_wn_max", k_wn_max, grid, 256, 0, st, row, w, batch_pooled, E, E_dev, G, max_out);
+  launch("k_wn_apply", k_wn_apply, grid, 256, 0, st, row, w, batch_pooled, max_out, E, E_dev, G, arg_out, w_out);
   return launch_status();
 }
 
+// graph_acc[g] = sum over the graph's edges of grad_out * w, deterministically: per pooled node first (segmented by
+// row), then per graph (pooled nodes grouped by batch_pooled with the stable sort).
 int tgpb200_weight_norm_bwd(const int64_t* row, const float* w, const int64_t* batch_pooled, const float* max_in,
-                            const int32_t* arg_in, const float* grad_out, int64_t E, int64_t G, float* graph_acc,
-                            float* grad_w, tgpb200_stream_t stream) {
-  if (E < 0 || G < 0) return TGPB200_ERR_INVALID;
+                            const int32_t* arg_in, const float* grad_out, int64_t E, const int64_t* E_dev, int64_t K,
+                            int64_t G, int rows_sorted, float* graph_acc, float* grad_w, void* workspace,
+                            size_t workspace_bytes, tgpb200_stream_t stream) {
+  if (E < 0 || G < 0 || K < 0 || E >= INT32_MAX) return TGPB200_ERR_INVALID;
   if (E == 0) return TGPB200_OK;
   if (!row || !w || !batch_pooled || !max_in || !arg_in || !grad_out || !graph_acc || !grad_w)
     return TGPB200_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(graph_acc, 0, (size_t)G * sizeof(float), st);
-  unsigned grid = (unsigned)ceil_div(E, 256);
-  launch("k_wn_bwd_accum", k_wn_bwd_accum, grid, 256, 0, st, row, w, batch_pooled, grad_out, E, G, graph_acc);
-  launch("k_wn_bwd_apply", k_wn_bwd_apply, grid, 256, 0, st, row, w, batch_pooled, max_in, arg_in, grad_out, graph_acc, E, G, grad_w);
+  Workspace ws(workspace, workspace_bytes);
+  float* node_acc = ws.take<float>((size_t)(K > 0 ? K : 1));
+  if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+  int rc = det_segment_sum(KeyOfArray64{row}, ProdVal{grad_out, w}, E, E_dev, K, rows_sorted != 0, node_acc, ws, st);
+  if (rc != TGPB200_OK) return rc;
+  rc = det_segment_sum(KeyOfArray64{batch_pooled}, ArrVal{node_acc}, K, nullptr, G, false, graph_acc, ws, st);
+  if (rc != TGPB200_OK) return rc;
+  launch("k_wn_bwd_apply", k_wn_bwd_apply, (unsigned)ceil_div(E, 256), 256, 0, st, row, w, batch_pooled, max_in, arg_in,
+         grad_out, graph_acc, E, E_dev, G, grad_w);
   return launch_status();
 }
 

@@ -969,18 +969,18 @@ int gemm(const GemmProblem& p, cudaStream_t stream) {
   const size_t smem = stage_bytes * stages + (3 * stages + 4) * 8 + 16 + 1024;
   if (pair) {
     int npairs = P.num_items < num_sms / 2 ? P.num_items : num_sms / 2;
-    launch("k_tc_gemm_pair_bf16", k_tc_gemm_pair, 2 * npairs, kThreads, smem, stream, P);
+    launch(p.tag ? p.tag : "k_tc_gemm_pair_bf16", k_tc_gemm_pair, 2 * npairs, kThreads, smem, stream, P);
     return launch_status();
   }
   int grid = P.num_items < num_sms ? P.num_items : num_sms;
   if (ts) {
-    launch("k_tc_gemm_ts_3xtf32", k_tc_gemm_ts, grid, kThreadsTs, smem + 64, stream, P);
+    launch(p.tag ? p.tag : "k_tc_gemm_ts_3xtf32", k_tc_gemm_ts, grid, kThreadsTs, smem + 64, stream, P);
     return launch_status();
   }
   if (bf16)
-    launch("k_tc_gemm_bf16", k_tc_gemm<false>, grid, kThreads, smem, stream, P);
+    launch(p.tag ? p.tag : "k_tc_gemm_bf16", k_tc_gemm<false>, grid, kThreads, smem, stream, P);
   else
-    launch("k_tc_gemm_3xtf32", k_tc_gemm<true>, grid, kThreads, smem, stream, P);
+    launch(p.tag ? p.tag : "k_tc_gemm_3xtf32", k_tc_gemm<true>, grid, kThreads, smem, stream, P);
   return launch_status();
 }
 

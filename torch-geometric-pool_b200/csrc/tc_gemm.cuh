@@ -56,6 +56,7 @@ struct GemmProblem {
   const float* ew_d;     // [batch, M]
   const float* ew_coef;  // [batch, 4]
   float ew_eps;
+  const char* tag;       // optional launch name (string literal) shown by the per-kernel timing of bench.py
 };
 
 // Enqueue on `stream`.  Returns TGPB200_ERR_UNSUPPORTED when the shape violates the TMA / UMMA constraints

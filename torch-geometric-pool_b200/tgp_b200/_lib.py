@@ -30,6 +30,7 @@ SIGNATURES = {
     "tgpb200_debug_launch_count": (ctypes.c_longlong, []),
     "tgpb200_debug_time_kernel": (None, [ctypes.c_char_p]),
     "tgpb200_debug_kernel_time_ms": (ctypes.c_double, [ctypes.POINTER(ctypes.c_int)]),
+    "tgpb200_debug_kernel_times": (_SZ, [ctypes.c_char_p, _SZ]),
     "tgpb200_build_csr_workspace_bytes": (_SZ, [_I64, _I64]),
     "tgpb200_build_csr": (_INT, [_P, _I64, _I64, _P, _P, _P, _SZ, _P]),
     "tgpb200_segment_reduce_fwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _INT, _INT, _INT, _P, _P]),
@@ -44,20 +45,24 @@ SIGNATURES = {
     "tgpb200_filter_relabel_emit": (_INT, [_P, _P, _P, _I64, _I64, _U32, _F, _P, _P, _P, _P, _P, _SZ, _P]),
     "tgpb200_filter_relabel_onepass_workspace_bytes": (_SZ, [_I64, _I64]),
     "tgpb200_filter_relabel_onepass": (_INT, [_P, _P, _P, _I64, _P, _I64, _I64, _U32, _F, _P, _P, _P, _P, _P, _P, _SZ, _P]),
-    "tgpb200_filter_relabel_bwd": (_INT, [_P, _P, _I64, _I64, _P, _P]),
+    "tgpb200_filter_relabel_bwd": (_INT, [_P, _P, _I64, _P, _I64, _P, _P]),
     "tgpb200_remap_coalesce_workspace_bytes": (_SZ, [_I64, _I64]),
     "tgpb200_remap_coalesce_count": (_INT, [_P, _P, _P, _I64, _P, _I64, _I64, _INT, _U32, _F, _P, _P, _SZ, _P]),
     "tgpb200_remap_coalesce_emit": (_INT, [_I64, _I64, _INT, _U32, _F, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "tgpb200_coalesce_bwd_workspace_bytes": (_SZ, [_I64, _I64, _INT]),
     "tgpb200_coalesce_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _INT, _P, _P, _SZ, _P]),
-    "tgpb200_degree_norm_fwd": (_INT, [_P, _P, _P, _I64, _I64, _F, _P, _P, _P]),
-    "tgpb200_degree_norm_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _F, _P, _P, _P]),
-    "tgpb200_degree_accumulate": (_INT, [_P, _P, _I64, _I64, _P, _P]),
-    "tgpb200_degree_apply": (_INT, [_P, _P, _P, _P, _I64, _I64, _F, _P, _P]),
-    "tgpb200_weight_max_accumulate": (_INT, [_P, _P, _P, _I64, _I64, _P, _P]),
-    "tgpb200_weight_max_apply": (_INT, [_P, _P, _P, _P, _I64, _I64, _P, _P]),
-    "tgpb200_weight_norm_fwd": (_INT, [_P, _P, _P, _I64, _I64, _P, _P, _P, _P]),
-    "tgpb200_weight_norm_bwd": (_INT, [_P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P]),
+    "tgpb200_edge_norm_workspace_bytes": (_SZ, [_I64, _I64]),
+    "tgpb200_rows_sorted": (_INT, [_P, _I64, _P, _P]),
+    "tgpb200_degree_norm_fwd": (_INT, [_P, _P, _P, _I64, _P, _I64, _F, _INT, _P, _P, _P, _SZ, _P]),
+    "tgpb200_degree_norm_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _P, _I64, _F, _INT, _P, _P, _P, _SZ, _P]),
+    "tgpb200_degree_accumulate": (_INT, [_P, _P, _I64, _P, _I64, _INT, _P, _P, _SZ, _P]),
+    "tgpb200_degree_apply": (_INT, [_P, _P, _P, _P, _I64, _P, _I64, _F, _P, _P]),
+    "tgpb200_degree_bwd_accumulate": (_INT, [_P, _P, _P, _P, _P, _I64, _P, _I64, _F, _INT, _P, _P, _SZ, _P]),
+    "tgpb200_degree_bwd_apply": (_INT, [_P, _P, _P, _P, _P, _I64, _P, _I64, _F, _P, _P]),
+    "tgpb200_weight_max_accumulate": (_INT, [_P, _P, _P, _I64, _P, _I64, _P, _P]),
+    "tgpb200_weight_max_apply": (_INT, [_P, _P, _P, _P, _I64, _P, _I64, _P, _P]),
+    "tgpb200_weight_norm_fwd": (_INT, [_P, _P, _P, _I64, _P, _I64, _P, _P, _P, _P]),
+    "tgpb200_weight_norm_bwd": (_INT, [_P, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _INT, _P, _P, _P, _SZ, _P]),
     "tgpb200_tc_gemm": (
         _INT,
         [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _INT, _I64, _I64, _INT, _I64, _I64, _I64, _INT, _INT, _F, _INT, _P],
@@ -154,6 +159,17 @@ def kernel_time_ms():
     n = ctypes.c_int(0)
     ms = load().tgpb200_debug_kernel_time_ms(ctypes.byref(n))
     return float(ms), int(n.value)
+
+
+def kernel_trace() -> list:
+    """[(kernel name, ms)] in launch order for the launches recorded since ``time_kernel("*")``."""
+    buf = ctypes.create_string_buffer(1 << 20)
+    load().tgpb200_debug_kernel_times(buf, len(buf))
+    out = []
+    for line in buf.value.decode().splitlines():
+        name, ms = line.split("\t")
+        out.append((name, float(ms)))
+    return out
 
 
 def call(name: str, *args) -> None:

@@ -216,9 +216,10 @@ class B200DenseConnect(Connect):
         n_super = B * K
         flags = F_.L.REMOVE_SELF_LOOPS if self.remove_self_loops else 0
         ident = torch.arange(n_super, device=s.device)
-        ei, ew = F_._FilterRelabel.apply(ew.to(torch.float32), ei[0].contiguous(), ei[1].contiguous(), ident, n_super,
-                                         flags, F_.EPS)
-        ew = F_.edge_postprocess(ei, ew, n_super, self.degree_norm, self.edge_weight_norm, batch_pooled)
+        ei, ew, _ = F_._FilterRelabel.apply(ew.to(torch.float32), ei[0].contiguous(), ei[1].contiguous(), ident, n_super,
+                                            flags, F_.EPS)
+        ew = F_.edge_postprocess(ei, ew, n_super, self.degree_norm, self.edge_weight_norm, batch_pooled,
+                                 sorted_rows=True)  # block-diagonal order is row-major
         if to_coo:
             return torch.sparse_coo_tensor(ei, ew, (n_super, n_super)).coalesce(), None
         return ei, ew

@@ -125,57 +125,81 @@ def _read_count(count: Tensor) -> int:
     return int(count.item())  # the one device->host word per data-dependent output size
 
 
+_SORTED_CACHE: dict = {}
+
+
+def rows_sorted(edge_index: Tensor) -> bool:
+    """Is ``edge_index[0]`` non-decreasing (PyG datasets and every coalesced list are)?  Checked on the device once
+    per tensor (one host read) and cached by storage / version, so a static graph pays it on the first call only.
+    Row-sorted lists take the sort-free deterministic normalisation sums and the row-bucketed coalesce."""
+    key = (edge_index.data_ptr(), edge_index.size(-1), edge_index._version, edge_index.device.index)
+    hit = _SORTED_CACHE.get(key)
+    if hit is None:
+        row = edge_index[0].contiguous()
+        flag = torch.empty(1, dtype=torch.int32, device=row.device)
+        L.call("tgpb200_rows_sorted", L.ptr(row), row.numel(), L.ptr(flag), L.stream())
+        hit = bool(flag.item())
+        if len(_SORTED_CACHE) > 256:
+            _SORTED_CACHE.clear()
+        _SORTED_CACHE[key] = hit
+    return hit
+
+
 class _FilterRelabel(torch.autograd.Function):
-    """Kept-node branch + self-loop / tiny-weight filters (one order-preserving compaction)."""
+    """Kept-node branch + self-loop / tiny-weight filters (one order-preserving compaction).
+
+    ``padded=False``: exact-size outputs (one host read of the survivor count).  ``padded=True``: capacity-``E``
+    outputs plus the device-side count, no host read (CUDA-graph capturable)."""
 
     @staticmethod
-    def forward(ctx, edge_weight, row, col, node_index, num_nodes, flags, eps):
+    def forward(ctx, edge_weight, row, col, node_index, num_nodes, flags, eps, padded=False):
         E = row.numel()
         dev = row.device
         lib = L.load()
         need_grad = edge_weight is not None and ctx.needs_input_grad[0]
-        # single pass over the edge list (decoupled look-back compaction) into capacity-E buffers, then the survivor
-        # count (the one device->host word) sizes the exact, contiguous outputs
+        # single pass over the edge list (decoupled look-back compaction) into capacity-E buffers
         ws = L.workspace(lib.tgpb200_filter_relabel_onepass_workspace_bytes(E, num_nodes), dev)
         count = torch.empty(1, dtype=torch.long, device=dev)
         cap = max(E, 1)
-        row_c = torch.empty(cap, dtype=torch.long, device=dev)
-        col_c = torch.empty(cap, dtype=torch.long, device=dev)
+        ei_c = torch.empty((2, cap), dtype=torch.long, device=dev)
         w_c = None if edge_weight is None else torch.empty(cap, dtype=torch.float32, device=dev)
         src_c = torch.empty(cap, dtype=torch.int32, device=dev) if need_grad else None
         L.call("tgpb200_filter_relabel_onepass", L.ptr(row), L.ptr(col), L.ptr(edge_weight), E, L.ptr(node_index),
-               node_index.numel(), num_nodes, flags, eps, L.ptr(row_c), L.ptr(col_c), L.ptr(w_c), L.ptr(src_c),
+               node_index.numel(), num_nodes, flags, eps, L.ptr(ei_c[0]), L.ptr(ei_c[1]), L.ptr(w_c), L.ptr(src_c),
                L.ptr(count), L.ptr(ws), ws.numel(), L.stream())
-        n_out = _read_count(count)
-        ei = torch.empty((2, n_out), dtype=torch.long, device=dev)
-        ei[0].copy_(row_c[:n_out])
-        ei[1].copy_(col_c[:n_out])
+        ctx.E, ctx.padded = E, padded
+        if padded:
+            ctx.mark_non_differentiable(ei_c, count)
+            if need_grad:
+                ctx.save_for_backward(src_c, count)
+            ctx.n_out = E
+            return ei_c[:, :E], (None if w_c is None else w_c[:E]), count
+        n_out = _read_count(count)  # sizes the exact, contiguous outputs
+        ei = ei_c[:, :n_out].contiguous()
         w_out = None if edge_weight is None else w_c[:n_out].clone()
         src = src_c[:max(n_out, 1)].clone() if need_grad else None
-        ctx.mark_non_differentiable(ei)
+        ctx.mark_non_differentiable(ei, count)
         if need_grad:
-            ctx.save_for_backward(src)
-        ctx.E, ctx.n_out = E, n_out
-        if w_out is None:
-            return ei, None
-        return ei, w_out
+            ctx.save_for_backward(src, None)
+        ctx.n_out = n_out
+        return ei, w_out, count
 
     @staticmethod
-    def backward(ctx, _gei, gw):
+    def backward(ctx, _gei, gw, _gc):
         if gw is None:
-            return (None,) * 7
-        (src,) = ctx.saved_tensors
+            return (None,) * 8
+        src, count = ctx.saved_tensors
         gin = torch.empty(ctx.E, dtype=torch.float32, device=gw.device)
-        L.call("tgpb200_filter_relabel_bwd", L.ptr(gw.contiguous()), L.ptr(src), ctx.n_out, ctx.E, L.ptr(gin),
-               L.stream())
-        return gin, None, None, None, None, None, None
+        L.call("tgpb200_filter_relabel_bwd", L.ptr(gw.contiguous()), L.ptr(src), ctx.n_out, L.ptr(count), ctx.E,
+               L.ptr(gin), L.stream())
+        return gin, None, None, None, None, None, None, None
 
 
 class _RemapCoalesce(torch.autograd.Function):
     """Cluster branch: remap -> stable radix sort -> in-order combine -> filters -> compaction."""
 
     @staticmethod
-    def forward(ctx, edge_weight, row, col, cluster_index, num_nodes, num_clusters, op, flags, eps):
+    def forward(ctx, edge_weight, row, col, cluster_index, num_nodes, num_clusters, op, flags, eps, padded=False):
         E = row.numel()
         dev = row.device
         lib = L.load()
@@ -183,7 +207,7 @@ class _RemapCoalesce(torch.autograd.Function):
         count = torch.empty(1, dtype=torch.long, device=dev)
         L.call("tgpb200_remap_coalesce_count", L.ptr(row), L.ptr(col), L.ptr(edge_weight), E, L.ptr(cluster_index),
                num_nodes, num_clusters, op, flags, eps, L.ptr(count), L.ptr(ws), ws.numel(), L.stream())
-        n_out = _read_count(count)
+        n_out = E if padded else _read_count(count)
         ei = torch.empty((2, n_out), dtype=torch.long, device=dev)
         weighted = edge_weight is not None
         w_out = torch.empty(n_out, dtype=torch.float32, device=dev) if weighted else None
@@ -195,76 +219,86 @@ class _RemapCoalesce(torch.autograd.Function):
                    L.ptr(ei[1]), L.ptr(w_out), L.ptr(slot), L.ptr(run_len), L.ptr(ws), ws.numel(), L.stream())
         elif slot is not None:
             slot.fill_(-1)
-        ctx.mark_non_differentiable(ei)
+        ctx.mark_non_differentiable(ei, count)
         if need_grad:
             ctx.save_for_backward(edge_weight, w_out, slot, run_len)
         ctx.E, ctx.n_out, ctx.op = E, n_out, op
-        if w_out is None:
-            return ei, None
-        return ei, w_out
+        return ei, w_out, count
 
     @staticmethod
-    def backward(ctx, _gei, gw):
+    def backward(ctx, _gei, gw, _gc):
         if gw is None:
-            return (None,) * 9
+            return (None,) * 10
         w, w_out, slot, run_len = ctx.saved_tensors
         gin = torch.empty(ctx.E, dtype=torch.float32, device=gw.device)
         lib = L.load()
         ws = L.workspace(lib.tgpb200_coalesce_bwd_workspace_bytes(ctx.E, ctx.n_out, ctx.op), gw.device)
         L.call("tgpb200_coalesce_bwd", L.ptr(w), L.ptr(w_out), L.ptr(gw.contiguous()), L.ptr(slot), L.ptr(run_len),
                ctx.E, ctx.n_out, ctx.op, L.ptr(gin), L.ptr(ws), ws.numel(), L.stream())
-        return gin, None, None, None, None, None, None, None, None
+        return gin, None, None, None, None, None, None, None, None, None
+
+
+def _norm_workspace(E: int, K: int, dev) -> Tensor:
+    return L.workspace(L.load().tgpb200_edge_norm_workspace_bytes(E, K), dev)
 
 
 class _DegreeNorm(torch.autograd.Function):
+    """``w * dinv[row] * dinv[col]`` with ``deg = scatter_sum(w, row)`` as a deterministic segmented sum.
+    ``count`` (optional device int64) bounds the edges of a padded list."""
+
     @staticmethod
-    def forward(ctx, w, row, col, num_clusters, eps):
+    def forward(ctx, w, row, col, num_clusters, eps, sorted_rows, count):
         E = row.numel()
         dev = row.device
         deg = torch.empty(max(num_clusters, 1), dtype=torch.float32, device=dev)
         out = torch.empty(E, dtype=torch.float32, device=dev)
-        L.call("tgpb200_degree_norm_fwd", L.ptr(row), L.ptr(col), L.ptr(w), E, num_clusters, eps, L.ptr(deg),
-               L.ptr(out), L.stream())
-        ctx.save_for_backward(w, row, col, deg)
-        ctx.K, ctx.eps = num_clusters, eps
+        ws = _norm_workspace(E, num_clusters, dev)
+        L.call("tgpb200_degree_norm_fwd", L.ptr(row), L.ptr(col), L.ptr(w), E, L.ptr(count), num_clusters, eps,
+               int(sorted_rows), L.ptr(deg), L.ptr(out), L.ptr(ws), ws.numel(), L.stream())
+        ctx.save_for_backward(w, row, col, deg, count)
+        ctx.K, ctx.eps, ctx.sorted_rows = num_clusters, eps, sorted_rows
         return out
 
     @staticmethod
     def backward(ctx, g):
-        w, row, col, deg = ctx.saved_tensors
+        w, row, col, deg, count = ctx.saved_tensors
         if w is None:
-            return None, None, None, None, None
+            return (None,) * 7
         E = row.numel()
         gd = torch.empty(max(ctx.K, 1), dtype=torch.float32, device=g.device)
         gw = torch.empty(E, dtype=torch.float32, device=g.device)
+        ws = _norm_workspace(E, ctx.K, g.device)
         L.call("tgpb200_degree_norm_bwd", L.ptr(row), L.ptr(col), L.ptr(w), L.ptr(deg), L.ptr(g.contiguous()), E,
-               ctx.K, ctx.eps, L.ptr(gd), L.ptr(gw), L.stream())
-        return gw, None, None, None, None
+               L.ptr(count), ctx.K, ctx.eps, int(ctx.sorted_rows), L.ptr(gd), L.ptr(gw), L.ptr(ws), ws.numel(),
+               L.stream())
+        return gw, None, None, None, None, None, None
 
 
 class _WeightNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, w, row, batch_pooled, num_graphs):
+    def forward(ctx, w, row, batch_pooled, num_clusters, num_graphs, sorted_rows, count):
         E = row.numel()
         dev = row.device
         mx = torch.empty(max(num_graphs, 1), dtype=torch.float32, device=dev)
         arg = torch.empty(max(num_graphs, 1), dtype=torch.int32, device=dev)
         out = torch.empty(E, dtype=torch.float32, device=dev)
-        L.call("tgpb200_weight_norm_fwd", L.ptr(row), L.ptr(w), L.ptr(batch_pooled), E, num_graphs, L.ptr(mx),
-               L.ptr(arg), L.ptr(out), L.stream())
-        ctx.save_for_backward(w, row, batch_pooled, mx, arg)
-        ctx.G = num_graphs
+        L.call("tgpb200_weight_norm_fwd", L.ptr(row), L.ptr(w), L.ptr(batch_pooled), E, L.ptr(count), num_graphs,
+               L.ptr(mx), L.ptr(arg), L.ptr(out), L.stream())
+        ctx.save_for_backward(w, row, batch_pooled, mx, arg, count)
+        ctx.G, ctx.K, ctx.sorted_rows = num_graphs, num_clusters, sorted_rows
         return out
 
     @staticmethod
     def backward(ctx, g):
-        w, row, batch_pooled, mx, arg = ctx.saved_tensors
+        w, row, batch_pooled, mx, arg, count = ctx.saved_tensors
         E = row.numel()
         acc = torch.empty(max(ctx.G, 1), dtype=torch.float32, device=g.device)
         gw = torch.empty(E, dtype=torch.float32, device=g.device)
+        ws = _norm_workspace(E, max(ctx.K, ctx.G), g.device)
         L.call("tgpb200_weight_norm_bwd", L.ptr(row), L.ptr(w), L.ptr(batch_pooled), L.ptr(mx), L.ptr(arg),
-               L.ptr(g.contiguous()), E, ctx.G, L.ptr(acc), L.ptr(gw), L.stream())
-        return gw, None, None, None
+               L.ptr(g.contiguous()), E, L.ptr(count), ctx.K, ctx.G, int(ctx.sorted_rows), L.ptr(acc), L.ptr(gw),
+               L.ptr(ws), ws.numel(), L.stream())
+        return gw, None, None, None, None, None, None
 
 
 def _as_f32_weight(edge_weight: Optional[Tensor]) -> Optional[Tensor]:
@@ -306,16 +340,56 @@ def edge_postprocess(
     edge_weight_norm: bool = False,
     batch_pooled: Optional[Tensor] = None,
     num_graphs: Optional[int] = None,
+    sorted_rows: Optional[bool] = None,
+    count: Optional[Tensor] = None,
 ) -> Optional[Tensor]:
-    """Degree / max-weight normalisation of tgp/utils/ops.py:383-417 on already-filtered edges."""
+    """Degree / max-weight normalisation of tgp/utils/ops.py:383-417 on already-filtered edges.
+
+    ``sorted_rows``: whether ``edge_index[0]`` is non-decreasing (``None`` = check, cached per tensor);
+    ``count``: device-side number of valid edges of a padded list (``None`` = all)."""
     row, col = edge_index[0], edge_index[1]
+    if not (degree_norm or (edge_weight_norm and edge_weight is not None)):
+        return edge_weight
+    if not row.is_contiguous():
+        row, col = row.contiguous(), col.contiguous()
+    if sorted_rows is None:
+        sorted_rows = rows_sorted(edge_index)
     if degree_norm:
-        edge_weight = _DegreeNorm.apply(edge_weight, row, col, num_nodes, EPS)
+        edge_weight = _DegreeNorm.apply(edge_weight, row, col, num_nodes, EPS, sorted_rows, count)
     if edge_weight_norm and edge_weight is not None:
-        if num_graphs is None:
+        if num_graphs is None:  # costs a device sync: pass num_graphs to avoid it
             num_graphs = int(batch_pooled.max().item()) + 1 if batch_pooled.numel() > 0 else 0
-        edge_weight = _WeightNorm.apply(edge_weight, row, batch_pooled.contiguous(), num_graphs)
+        edge_weight = _WeightNorm.apply(edge_weight, row, batch_pooled.contiguous(), num_nodes, num_graphs, sorted_rows,
+                                        count)
     return edge_weight
+
+
+def _sparse_connect_core(edge_index, edge_weight, node_index, cluster_index, num_nodes, num_supernodes,
+                         remove_self_loops, reduce_op, edge_weight_norm, batch_pooled, degree_norm, num_graphs,
+                         padded):
+    w = _as_f32_weight(edge_weight)
+    if reduce_op not in L.OPS:
+        raise ValueError(f"unknown reduce_op '{reduce_op}'")
+    edge_index = edge_index.contiguous()
+    row, col = edge_index[0], edge_index[1]
+    if num_nodes is None:  # maybe_num_nodes (base_conn.py:78) -- costs a device sync
+        num_nodes = int(edge_index.max().item()) + 1 if edge_index.numel() > 0 else 0
+    flags = L.REMOVE_SELF_LOOPS if remove_self_loops else 0
+    need_norm = degree_norm or (edge_weight_norm and w is not None)
+
+    if node_index is not None and len(node_index) < num_nodes:
+        # the relabelling is monotone (node_index ascending), so the output keeps the row order of the input
+        out_sorted = rows_sorted(edge_index) if need_norm else None
+        ei, w, count = _FilterRelabel.apply(w, row, col, node_index.contiguous(), num_nodes, flags, EPS, padded)
+    elif cluster_index is not None and len(cluster_index) == num_nodes:
+        out_sorted = True  # coalesced output is lexicographic
+        ei, w, count = _RemapCoalesce.apply(w, row, col, cluster_index.contiguous(), num_nodes, num_supernodes,
+                                            L.OPS[reduce_op], flags, EPS, padded)
+    else:
+        raise RuntimeError
+    w = edge_postprocess(ei, w, num_supernodes, degree_norm, edge_weight_norm, batch_pooled, num_graphs,
+                         sorted_rows=out_sorted, count=count if padded else None)
+    return ei, w, count
 
 
 def sparse_connect(
@@ -338,6 +412,8 @@ def sparse_connect(
     ``len(node_index) < num_nodes`` (input order kept, endpoints relabelled to their position in
     ``node_index``), cluster path when ``len(cluster_index) == num_nodes`` (lexicographic order,
     duplicates combined with ``reduce_op`` in original order), else ``RuntimeError``.
+    One host read per call (the output edge count; ``num_graphs`` avoids a second one with
+    ``edge_weight_norm``).
     """
     _require_cuda(edge_index)
     to_coo = edge_index.is_sparse
@@ -346,30 +422,41 @@ def sparse_connect(
         edge_index, edge_weight = coo.indices().contiguous(), coo.values()
     else:
         _validate_edge_index(edge_index)
-    w = _as_f32_weight(edge_weight)
-    if reduce_op not in L.OPS:
-        raise ValueError(f"unknown reduce_op '{reduce_op}'")
-    edge_index = edge_index.contiguous()
-    row, col = edge_index[0], edge_index[1]
-    if num_nodes is None:  # maybe_num_nodes (base_conn.py:78) -- costs a device sync
-        num_nodes = int(edge_index.max().item()) + 1 if edge_index.numel() > 0 else 0
-    flags = L.REMOVE_SELF_LOOPS if remove_self_loops else 0
-
-    if node_index is not None and len(node_index) < num_nodes:
-        ei, w = _FilterRelabel.apply(w, row, col, node_index.contiguous(), num_nodes, flags, EPS)
-    elif cluster_index is not None and len(cluster_index) == num_nodes:
-        ei, w = _RemapCoalesce.apply(w, row, col, cluster_index.contiguous(), num_nodes, num_supernodes,
-                                     L.OPS[reduce_op], flags, EPS)
-    else:
-        raise RuntimeError
-
-    w = edge_postprocess(ei, w, num_supernodes, degree_norm, edge_weight_norm, batch_pooled, num_graphs)
-
+    ei, w, _ = _sparse_connect_core(edge_index, edge_weight, node_index, cluster_index, num_nodes, num_supernodes,
+                                    remove_self_loops, reduce_op, edge_weight_norm, batch_pooled, degree_norm,
+                                    num_graphs, False)
     if to_coo:  # tgp/connect/base_conn.py:107-110 -> connectivity_to_torch_coo
         if w is None:
             w = torch.ones(ei.size(1), device=ei.device)
         return torch.sparse_coo_tensor(ei, w, (num_supernodes, num_supernodes)).coalesce(), None
     return ei, w
+
+
+def sparse_connect_padded(
+    edge_index: Tensor,
+    edge_weight: Optional[Tensor] = None,
+    node_index: Optional[Tensor] = None,
+    cluster_index: Optional[Tensor] = None,
+    num_nodes: Optional[int] = None,
+    num_supernodes: Optional[int] = None,
+    remove_self_loops: bool = True,
+    reduce_op: str = "sum",
+    edge_weight_norm: bool = False,
+    batch_pooled: Optional[Tensor] = None,
+    degree_norm: bool = False,
+    num_graphs: Optional[int] = None,
+) -> Tuple[Tensor, Optional[Tensor], Tensor]:
+    """``sparse_connect`` without any host read: returns ``(edge_index [2, E], edge_weight [E], count)`` where only
+    the first ``count`` (a device int64) columns are valid.  Every kernel bounds itself by the device-side count, so
+    the whole call can be captured in a CUDA graph (``tgp_b200.GraphedStep``) -- the form for small, launch-bound
+    batches; ``num_nodes`` and (with ``edge_weight_norm``) ``num_graphs`` must be given."""
+    _require_cuda(edge_index)
+    _validate_edge_index(edge_index)
+    if num_nodes is None or (edge_weight_norm and num_graphs is None):
+        raise ValueError("sparse_connect_padded needs num_nodes (and num_graphs with edge_weight_norm): no host reads")
+    return _sparse_connect_core(edge_index, edge_weight, node_index, cluster_index, num_nodes, num_supernodes,
+                                remove_self_loops, reduce_op, edge_weight_norm, batch_pooled, degree_norm, num_graphs,
+                                True)
 
 
 # --------------------------------------------------------------------------- #
