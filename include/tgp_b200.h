@@ -256,6 +256,13 @@ int tgpb200_tc_gemm(const void* a, const void* b, void* out, int64_t batch, int6
                     int64_t out_col_stride, int in_dtype, int out_dtype, float alpha, int accumulate,
                     tgpb200_stream_t stream);
 
+/* Batched product with shape-general fallback (the engine above when the layout satisfies its TMA constraints,
+ * FP32-pipe tiles otherwise): out[b] (M x N, row-major, contiguous) = A[b] B[b].  Used by the dense lift
+ * (tgp/lift/base_lift.py:125-160: S x_pool) for cluster / feature counts off the 16-byte stride grid. */
+int tgpb200_bmm(const void* a, const void* b, void* out, int64_t batch, int64_t M, int64_t N, int64_t Kd,
+                int64_t a_batch_stride, int64_t a_row_stride, int a_mn_major, int64_t b_batch_stride,
+                int64_t b_row_stride, int b_mn_major, int dtype, tgpb200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * TopK selection (producer of the kept-node SelectOutput):
  * TopkSelect.forward  tgp/select/topk_select.py:194-203 (PyG topk, ratio mode) + the ascending node sort of

@@ -67,6 +67,7 @@ SIGNATURES = {
         _INT,
         [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _INT, _I64, _I64, _INT, _I64, _I64, _I64, _INT, _INT, _F, _INT, _P],
     ),
+    "tgpb200_bmm": (_INT, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _INT, _I64, _I64, _INT, _INT, _P]),
     "tgpb200_topk_select_workspace_bytes": (_SZ, [_I64, _I64]),
     "tgpb200_topk_select": (_INT, [_P, _P, _I64, _I64, _F, _P, _P, _P, _P, _SZ, _P]),
     "tgpb200_block_diag_workspace_bytes": (_SZ, [_I64, _I64]),

@@ -93,9 +93,16 @@ def postprocess_adj_pool_dense(
     adj_transpose: bool = False,
     edge_weight_norm: bool = False,
 ) -> Tensor:
-    """tgp/utils/ops.py:282-335 as a stand-alone call (returns a new tensor; the reference
-    zeroes the diagonal in place).  Implemented as the fused op with S = I."""
-    raise NotImplementedError("use tgp_b200.functional.dense_pool (fused post-processing)")
+    """tgp/utils/ops.py:282-335 as a stand-alone call (returns a new tensor; the reference zeroes the diagonal in
+    place): the post-processing epilogue of the fused op, reached with S = I (``I^T A I = A``; differentiable)."""
+    squeeze = adj_pool.dim() == 2
+    a = adj_pool.unsqueeze(0) if squeeze else adj_pool
+    if a.dim() != 3 or a.size(-1) != a.size(-2):
+        raise ValueError("adj_pool must have shape [B, K, K] or [K, K].")
+    eye = torch.eye(a.size(-1), dtype=a.dtype, device=a.device).expand(a.size(0), -1, -1).contiguous()
+    _, out, _ = F_.dense_pool(None, a, eye, remove_self_loops=remove_self_loops, degree_norm=degree_norm,
+                              adj_transpose=adj_transpose, edge_weight_norm=edge_weight_norm)
+    return out.squeeze(0) if squeeze else out
 
 
 class B200DenseConnect(Connect):

@@ -91,8 +91,14 @@ def segment_reduce(
     op: str = "sum",
     csr: Optional[Tuple[Tensor, Tensor]] = None,
 ) -> Tensor:
-    """``x_pool[c] = op_{i in c} weight[i] * x[node_index[i]]`` (deterministic member order)."""
+    """``x_pool[c] = op_{i in c} weight[i] * x[node_index[i]]`` (deterministic member order).
+
+    ``node_index`` must be sorted ascending (the SelectOutput invariant, tgp/select/base_select.py:56-60): the
+    backward locates a node's entries by binary search.  A ``csr`` taken from a ``SelectOutput`` vouches for it;
+    a bare call is checked (once per tensor) and raises ``ValueError`` otherwise."""
     _require_cuda(x, node_index, cluster_index, weight)
+    if csr is None and node_index.numel() > 1 and not is_sorted(node_index):
+        raise ValueError("segment_reduce: node_index must be sorted ascending (SelectOutput invariant)")
     if op not in ("sum", "add", "mean", "max", "min"):
         raise ValueError(f"unsupported reduce op '{op}'")
     if x.dim() != 2:
@@ -128,21 +134,26 @@ def _read_count(count: Tensor) -> int:
 _SORTED_CACHE: dict = {}
 
 
-def rows_sorted(edge_index: Tensor) -> bool:
-    """Is ``edge_index[0]`` non-decreasing (PyG datasets and every coalesced list are)?  Checked on the device once
-    per tensor (one host read) and cached by storage / version, so a static graph pays it on the first call only.
-    Row-sorted lists take the sort-free deterministic normalisation sums and the row-bucketed coalesce."""
-    key = (edge_index.data_ptr(), edge_index.size(-1), edge_index._version, edge_index.device.index)
+def is_sorted(index: Tensor) -> bool:
+    """Is the 1-D int64 tensor non-decreasing?  Checked on the device once per tensor (one host read) and cached by
+    storage / version, so a static graph pays it on the first call only."""
+    key = (index.data_ptr(), index.numel(), index._version, index.device.index)
     hit = _SORTED_CACHE.get(key)
     if hit is None:
-        row = edge_index[0].contiguous()
-        flag = torch.empty(1, dtype=torch.int32, device=row.device)
-        L.call("tgpb200_rows_sorted", L.ptr(row), row.numel(), L.ptr(flag), L.stream())
+        idx = index.contiguous()
+        flag = torch.empty(1, dtype=torch.int32, device=idx.device)
+        L.call("tgpb200_rows_sorted", L.ptr(idx), idx.numel(), L.ptr(flag), L.stream())
         hit = bool(flag.item())
         if len(_SORTED_CACHE) > 256:
             _SORTED_CACHE.clear()
         _SORTED_CACHE[key] = hit
     return hit
+
+
+def rows_sorted(edge_index: Tensor) -> bool:
+    """Is ``edge_index[0]`` non-decreasing (PyG datasets and every coalesced list are)?  Row-sorted lists take the
+    sort-free deterministic normalisation sums and the row-bucketed coalesce."""
+    return is_sorted(edge_index[0])
 
 
 class _FilterRelabel(torch.autograd.Function):

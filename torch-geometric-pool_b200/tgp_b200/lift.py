@@ -60,8 +60,7 @@ class _LiftDense(torch.autograd.Function):
         F = x_pool.size(-1)
         out = torch.empty((B, N, F), dtype=s.dtype, device=s.device)
         dt = L.dtype_code(s.dtype)
-        L.call("tgpb200_tc_gemm", L.ptr(s), L.ptr(x_pool), L.ptr(out), B, N, F, K, N * K, K, 0, K * F, F, 1, N * F, F, 1,
-               dt, dt, 1.0, 0, L.stream())
+        L.call("tgpb200_bmm", L.ptr(s), L.ptr(x_pool), L.ptr(out), B, N, F, K, N * K, K, 0, K * F, F, 1, dt, L.stream())
         ctx.save_for_backward(s, x_pool)
         return out
 
@@ -73,11 +72,9 @@ class _LiftDense(torch.autograd.Function):
         g = g.contiguous()
         dt = L.dtype_code(s.dtype)
         gs = torch.empty_like(s)      # g x_pool^T  [N, K]
-        L.call("tgpb200_tc_gemm", L.ptr(g), L.ptr(x_pool), L.ptr(gs), B, N, K, F, N * F, F, 0, K * F, F, 0, N * K, K, 1,
-               dt, dt, 1.0, 0, L.stream())
+        L.call("tgpb200_bmm", L.ptr(g), L.ptr(x_pool), L.ptr(gs), B, N, K, F, N * F, F, 0, K * F, F, 0, dt, L.stream())
         gx = torch.empty_like(x_pool)  # S^T g  [K, F]
-        L.call("tgpb200_tc_gemm", L.ptr(s), L.ptr(g), L.ptr(gx), B, K, F, N, N * K, K, 1, N * F, F, 1, K * F, F, 1,
-               dt, dt, 1.0, 0, L.stream())
+        L.call("tgpb200_bmm", L.ptr(s), L.ptr(g), L.ptr(gx), B, K, F, N, N * K, K, 1, N * F, F, 1, dt, L.stream())
         return gs, gx
 
 
@@ -86,6 +83,9 @@ class B200Lift(nn.Module):
         super().__init__()
         if matrix_op not in ("precomputed", "transpose"):
             raise RuntimeError(f"'matrix_op' must be 'precomputed' or 'transpose' on this backend ({matrix_op} given)")
+        if reduce_op not in ("sum", "add"):
+            # BaseLift's default; the other scatter reductions would need their own backward
+            raise ValueError(f"tgp_b200 lift supports reduce_op='sum' only ({reduce_op} given)")
         self.matrix_op = matrix_op
         self.reduce_op = reduce_op
 
@@ -109,7 +109,15 @@ class B200Lift(nn.Module):
             return _LiftDense.apply(s.contiguous(), x_pool.reshape(B, K, -1).contiguous())
         if s.dim() == 2 and x_pool.dim() == 2 and x_pool.size(0) == s.size(-1):
             return _LiftDense.apply(s.unsqueeze(0).contiguous(), x_pool.unsqueeze(0).contiguous()).squeeze(0)
-        raise NotImplementedError("tgp_b200 lift: dense [N, K] assignments over multi-graph batches are not covered")
+        if s.dim() == 2 and x_pool.dim() == 2 and batch is not None:
+            # dense [N, K] assignment over a multi-graph batch (base_lift.py:170-190): pad to [B, Nmax, K], one
+            # batched product, gather the valid rows back
+            K = s.size(-1)
+            B = x_pool.size(0) // K
+            s3, mask = F_.to_dense_batch(s, batch, B)
+            out = _LiftDense.apply(s3.contiguous(), x_pool.reshape(B, K, -1).contiguous())
+            return out[mask]
+        raise ValueError("tgp_b200 lift: dense [N, K] assignment with x_pool [B*K, F] needs `batch`")
 
     def __repr__(self) -> str:
         return f"{self.__class__.__name__}(matrix_op={self.matrix_op}, reduce_op={self.reduce_op})"

@@ -59,4 +59,4 @@ def topk_select(
     node_index, cluster_index = topk(score, ratio, batch, num_graphs)
     s = torch.sparse_coo_tensor(torch.stack([node_index, cluster_index]), score[node_index],
                                 (x.size(0), node_index.numel()), is_coalesced=True, check_invariants=False)
-    return SelectOutput(s=s)
+    return SelectOutput(s=s, _trusted=True)  # node_index ascending by construction

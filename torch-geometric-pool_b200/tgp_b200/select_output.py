@@ -49,12 +49,28 @@ class SelectOutput:
         weight: Optional[Tensor] = None,
         batch: Optional[Tensor] = None,
         in_mask: Optional[Tensor] = None,
+        s_inv_op: str = "transpose",
+        _trusted: bool = False,
         **extra_args,
     ):
+        if s_inv_op != "transpose":
+            raise ValueError(f"tgp_b200.SelectOutput supports s_inv_op='transpose' only, got '{s_inv_op}'")
         if isinstance(s, Tensor):
             if s.is_sparse:
                 assert cluster_index is None and node_index is None
                 s = s.coalesce()
+                if weight is not None or num_nodes is not None or num_supernodes is not None:
+                    # rebuild with the new values / size (tgp/select/base_select.py:122-141)
+                    size = (num_nodes if num_nodes is not None else s.size(0),
+                            num_supernodes if num_supernodes is not None else s.size(1))
+                    s = torch.sparse_coo_tensor(s.indices(), weight if weight is not None else s.values(), size,
+                                                is_coalesced=True, check_invariants=False)
+                if s.is_cuda and not _trusted and s.indices().size(1) > 1:
+                    # a tensor flagged coalesced is taken at its word by torch; the kernels rely on ascending node ids
+                    from .functional import is_sorted
+
+                    if not is_sorted(s.indices()[0]):
+                        s = cluster_to_s(s.indices()[1], s.indices()[0], s.values(), s.size(0), s.size(1))
             else:
                 assert cluster_index is None and node_index is None and weight is None
         elif s is None:
@@ -113,8 +129,13 @@ class SelectOutput:
         return None
 
     def to(self, device) -> "SelectOutput":
-        out = SelectOutput(s=self.s.to(device), batch=None if self.batch is None else self.batch.to(device),
-                           in_mask=None if self.in_mask is None else self.in_mask.to(device))
+        out = SelectOutput(s=self.s.to(device), s_inv=None if self.s_inv is None else self.s_inv.to(device),
+                           batch=None if self.batch is None else self.batch.to(device),
+                           in_mask=None if self.in_mask is None else self.in_mask.to(device), _trusted=True)
+        skip = ("s", "s_inv", "batch", "in_mask")
+        for k, v in self.__dict__.items():  # extra attributes travel along (tgp/select/base_select.py:226-244)
+            if k not in skip and not k.startswith("_"):
+                setattr(out, k, v.to(device) if isinstance(v, Tensor) else v)
         return out
 
     def __repr__(self) -> str:
