@@ -153,10 +153,36 @@ int tgpb200_remap_coalesce_emit(int64_t num_edges, int64_t num_clusters, int wei
                                 int32_t* run_len, void* workspace, size_t workspace_bytes, tgpb200_stream_t stream);
 
 /* Backward of the coalesce: grad_in[e] = d out_weight[slot(e)] / d w[e] * grad_out[slot(e)]  (0 if dropped).
- * SUM: 1; MEAN: 1/len; MAX/MIN: even split among ties; MUL: out/w[e]. */
+ * SUM: 1; MEAN: 1/len; MAX/MIN: even split among ties; MUL: out/w[e] -- or, when run_aux is given (row-bucketed
+ * path: run_len = number of zero members, run_aux = product of the non-zero members), the exact product rule. */
 int tgpb200_coalesce_bwd(const float* edge_weight, const float* out_weight, const float* grad_out,
-                         const int32_t* edge_slot, const int32_t* run_len, int64_t num_edges, int64_t num_out, int op,
-                         float* grad_in, void* workspace, size_t workspace_bytes, tgpb200_stream_t stream);
+                         const int32_t* edge_slot, const int32_t* run_len, const float* run_aux, int64_t num_edges,
+                         int64_t num_out, int op, float* grad_in, void* workspace, size_t workspace_bytes,
+                         tgpb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row-bucketed form of the cluster branch for ROW-SORTED edge lists (csrc/sparse_coalesce.cu): same results as
+ * tgpb200_remap_coalesce_*, ~2 passes over the edges instead of ~12.  `order` / `ptr` = tgpb200_build_csr of
+ * cluster_index (one entry per fine node: node_index = arange(N)).  Three calls sharing one workspace:
+ *   plan   virtual layout; plan_out (device int64[4]) = {virtual entries, edges of hub rows, hub rows, 0};
+ *   count  tiles + hub rows + survivor count.  virt_cap / hub_cap bound the launches: the values read back from
+ *          plan_out (large inputs, one host read) or -1 = capacity (E + N, E) for callers that never synchronise;
+ *   emit   writes the lexicographic coarse edge list; edge_slot / run_len / run_aux need need_slots != 0 in count.
+ * Returns TGPB200_ERR_UNSUPPORTED when E + N >= 2^31 (use the generic path).
+ * ------------------------------------------------------------------------------------------ */
+size_t tgpb200_bucket_coalesce_workspace_bytes(int64_t num_edges, int64_t num_nodes, int64_t num_clusters);
+int tgpb200_bucket_coalesce_plan(const int64_t* row, int64_t num_edges, const int64_t* cluster_index,
+                                 const int32_t* order, const int32_t* ptr, int64_t num_nodes, int64_t num_clusters,
+                                 int64_t* plan_out, void* workspace, size_t workspace_bytes, tgpb200_stream_t stream);
+int tgpb200_bucket_coalesce_count(const int64_t* row, const int64_t* col, const float* edge_weight, int64_t num_edges,
+                                  const int64_t* cluster_index, const int32_t* order, const int32_t* ptr,
+                                  int64_t num_nodes, int64_t num_clusters, int op, uint32_t flags, float eps,
+                                  int64_t virt_cap, int64_t hub_cap, int need_slots, int64_t* count_out,
+                                  void* workspace, size_t workspace_bytes, tgpb200_stream_t stream);
+int tgpb200_bucket_coalesce_emit(int64_t num_edges, int64_t num_nodes, int64_t num_clusters, int weighted,
+                                 int64_t virt_cap, int64_t* out_row, int64_t* out_col, float* out_weight,
+                                 int32_t* edge_slot, int32_t* run_len, float* run_aux, void* workspace,
+                                 size_t workspace_bytes, tgpb200_stream_t stream);
 size_t tgpb200_coalesce_bwd_workspace_bytes(int64_t num_edges, int64_t num_out, int op);
 
 /* ------------------------------------------------------------------------------------------

@@ -291,7 +291,9 @@ def test_c1_batch_topk_pool_parity_padded_and_graph_replay():
         assert n_out == eo.size(1) and torch.equal(e2[:, :n_out], eo) and torch.equal(bp2, bp)
         assert torch.equal(w2[:n_out].detach(), wo.detach()) and torch.equal(xp2.detach(), xp.detach())
         assert torch.equal(wg2.grad, wg.grad) and torch.equal(xg2.grad, xg.grad)
-        # ... and replayed as one CUDA graph
+        # ... and replayed as one CUDA graph (the eager outputs must be released first: they keep the autograd
+        # graph, and with it AccumulateGrad nodes bound to the default stream, alive across the capture)
+        del xp2, e2, w2, bp2, cnt
         graphed = T.GraphedStep(step)
         wg2.grad.zero_()
         xp3, e3, w3, bp3, cnt3 = graphed.replay()
@@ -320,11 +322,13 @@ def test_dense_step_graph_replay_matches_eager():
 
     eager = [t.detach().clone() for t in step()] + [x.grad.clone(), s.grad.clone()]
     graphed = T.GraphedStep(step)
+    x0 = x.detach().clone()
     with torch.no_grad():
-        x.add_(1.0)  # new data in the static input buffer ...
+        x.copy_(torch.randn_like(x0))  # new data in the static input buffer ...
     graphed.replay()
+    assert not torch.equal(graphed.outputs[0].detach(), eager[0])
     with torch.no_grad():
-        x.sub_(1.0)  # ... and the original data again: the replay must reproduce the eager step bit for bit
+        x.copy_(x0)  # ... and the original data again: the replay must reproduce the eager step bit for bit
     out = graphed.replay()
     torch.cuda.synchronize()
     for got, exp in zip([*out, x.grad, s.grad], eager):
@@ -435,3 +439,60 @@ def test_lift_dense_off_grid_shapes_and_multigraph():
     torch.testing.assert_close(got.cpu(), exp, rtol=1e-5, atol=1e-5)
     with pytest.raises(ValueError):
         T.B200Lift(reduce_op="max")
+
+
+# --------------------------------------------------------------------------- #
+# row-bucketed coalesce (row-sorted inputs): tiles, hub rows, long runs, isolated nodes, empty clusters
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("n,e,K", [(5000, 200_000, 3), (5000, 200_000, 40), (60_000, 900_000, 25_000),
+                                   (300_000, 700_000, 290_000), (2_000, 30, 1_500), (70_000, 2_000_000, 70_000)])
+@pytest.mark.parametrize("weighted", [True, False])
+def test_bucketed_coalesce_matches_oracle(n, e, K, weighted):
+    g = torch.Generator().manual_seed(n + e + K)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    ei[:, : e // 50] = ei[:, e // 50: 2 * (e // 50)]                     # exact duplicate edges
+    ei = ei[:, torch.argsort(ei[0] * n + ei[1], stable=True)]
+    cluster = torch.randint(0, max(K - K // 10, 1), (n,), generator=g)    # the last 10 % of the clusters are empty
+    ew = (torch.rand(e, generator=g) + 0.5) if weighted else None
+    so_c = R.OracleSelectOutput(cluster_index=cluster, num_supernodes=K)
+    so_g = T.SelectOutput(cluster_index=cluster.to(DEV), num_supernodes=K)
+    for op in (("sum", "mean", "max", "mul") if weighted else ("sum",)):
+        w64 = None if ew is None else (ew.double() if op != "mul" else (0.98 + 0.04 * ew.double()))
+        eo, wo = R.sparse_connect_so(ei, so_c, edge_weight=w64, reduce_op=op)
+        wg_in = None if w64 is None else w64.float().to(DEV).requires_grad_(True)
+        eg, wg = T.B200SparseConnect(op)(ei.to(DEV), so_g, edge_weight=wg_in)
+        assert torch.equal(eg.cpu(), eo), op
+        if weighted:
+            # long runs are sequential fp32 sums (like the reference's own CPU path): 2e-5 against the exact value
+            torch.testing.assert_close(wg.detach().cpu().double(), wo, rtol=2e-5 if op != "mul" else 2e-4, atol=1e-6,
+                                       msg=op)
+            if op in ("sum", "mean"):
+                wc = w64.clone().requires_grad_(True)
+                _, wo2 = R.sparse_connect_so(ei, so_c, edge_weight=wc, reduce_op=op)
+                coef = torch.randn(wo2.numel(), generator=g).double()
+                (wo2 * coef).sum().backward()
+                (wg * coef.float().to(DEV)).sum().backward()
+                torch.testing.assert_close(wg_in.grad.cpu().double(), wc.grad, rtol=1e-5, atol=1e-7, msg=f"{op} grad")
+        else:
+            assert wg is None and wo is None
+
+
+def test_bucketed_coalesce_mul_gradient_with_zero_weights():
+    g = torch.Generator().manual_seed(31)
+    n, e, K = 400, 6000, 30
+    ei = torch.randint(0, n, (2, e), generator=g)
+    ei = ei[:, torch.argsort(ei[0] * n + ei[1], stable=True)]
+    cluster = torch.randint(0, K, (n,), generator=g)
+    ew = 0.9 + 0.2 * torch.rand(e, generator=g)
+    ew[torch.randint(0, e, (40,), generator=g)] = 0.0       # runs with one zero, with several zeros
+    wc = ew.clone().double().requires_grad_(True)
+    eo, wo = R.sparse_connect_so(ei, R.OracleSelectOutput(cluster_index=cluster, num_supernodes=K), edge_weight=wc,
+                                 reduce_op="mul", remove_self_loops=False)
+    coef = torch.randn(wo.numel(), generator=g).double()
+    (wo * coef).sum().backward()
+    wg = ew.to(DEV).requires_grad_(True)
+    eg, wgo = T.B200SparseConnect("mul", remove_self_loops=False)(
+        ei.to(DEV), T.SelectOutput(cluster_index=cluster.to(DEV), num_supernodes=K), edge_weight=wg)
+    assert torch.equal(eg.cpu(), eo)
+    (wgo * coef.float().to(DEV)).sum().backward()
+    torch.testing.assert_close(wg.grad.cpu().double(), wc.grad, rtol=1e-4, atol=1e-9)

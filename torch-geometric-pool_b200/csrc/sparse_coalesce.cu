@@ -1,0 +1,624 @@
+// Row-bucketed cluster connect (tgp/connect/base_conn.py:83-89: edge_index = cluster[edge_index], PyG coalesce).
+//
+// The generic path (sparse_connect.cu) remaps every edge to a 2 x bits(K) bit key and runs a global LSD radix sort:
+// 5 passes over 20 M edges for the 1 M-node workload, ~12 passes over the edge list in total.  When the input edge
+// list is sorted by row (PyG datasets, every coalesced list), the expensive half of that sort is already there: the
+// edges of a fine node are contiguous, so the edges of a COARSE row are the union of its members' ranges, and the
+// cluster CSR (members per coarse row, ascending node id) enumerates them in original edge order.  What is left is
+// to order each coarse row's short neighbour list by coarse column, which fits in shared memory:
+//
+//   plan   fine row spans -> per-member entry counts -> exclusive scan ("virtual" positions: coarse row c owns
+//          [rowoff[c], rowoff[c+1]), rows in ascending order) -> hub rows (more than kBkHub entries) flagged
+//   tiles  one CTA per window of kBkTile virtual positions: gather the member ranges of the rows that start in the
+//          window, map columns through the cluster map, bitonic-sort (row, col, arrival) keys in shared memory,
+//          combine each run in arrival (= original edge) order, apply the self-loop / tiny-weight filters and write
+//          the surviving coarse edges at their virtual positions
+//   hubs   coarse rows too long for a tile (power-law hubs) go through the radix sort restricted to their edges and
+//          land in their own virtual ranges
+//   emit   one order-preserving compaction of the virtual array into the int64 output (lexicographic by construction)
+//
+// The edge list is read twice (row spans, gather) and the output written once; everything in between moves 32-bit
+// entries.  Exact same results as the generic path: stable order, in-order combination, same filters.
+#include <limits.h>
+
+#include "prims.cuh"
+
+namespace tgp {
+
+constexpr int kBkThreads = 256;
+constexpr int kBkTile = 1536;  // virtual positions per tile window
+constexpr int kBkHub = 2560;   // coarse rows with more entries than this take the radix path
+constexpr int kBkCap = 4096;   // >= kBkTile + kBkHub, power of two (largest bitonic network)
+constexpr int kBkLongRun = 4096;  // hub runs longer than this are combined by a whole block
+
+__device__ __forceinline__ int64_t clamp_cluster(int64_t c, int64_t K) { return (c < 0 || c >= K) ? K - 1 : c; }
+
+__device__ __forceinline__ float combine_w(int op, float acc, float v) {
+  if (op == TGPB200_SUM || op == TGPB200_MEAN) return __fadd_rn(acc, v);
+  if (op == TGPB200_MAX) return fmaxf(acc, v);
+  if (op == TGPB200_MIN) return fminf(acc, v);
+  return __fmul_rn(acc, v);
+}
+
+// rs[v] / re[v] = first / one-past-last edge of fine row v in the row-sorted edge list (0 / 0 when absent)
+static __global__ void k_fine_row_spans(const int64_t* __restrict__ row, int64_t E, int64_t N, int32_t* __restrict__ rs,
+                                        int32_t* __restrict__ re) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int64_t r = row[e];
+  if (r < 0 || r >= N) return;
+  if (e == 0 || row[e - 1] != r) rs[r] = (int32_t)e;
+  if (e + 1 == E || row[e + 1] != r) re[r] = (int32_t)(e + 1);
+}
+
+// cost[m] = entries of CSR member m: its degree, or one placeholder for an isolated node (so that the number of
+// members of a tile is bounded by its number of entries); cost[N] = 0 closes the scan
+static __global__ void k_member_cost(const int32_t* __restrict__ order, const int32_t* __restrict__ rs,
+                                     const int32_t* __restrict__ re, int64_t N, int* __restrict__ cost) {
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m > N) return;
+  if (m == N) {
+    cost[N] = 0;
+    return;
+  }
+  const int v = order[m];
+  const int d = re[v] - rs[v];
+  cost[m] = d > 1 ? d : 1;
+}
+
+// per member: start of its coarse row in the virtual array, its coarse row; hub rows flagged and counted
+// plan[0] = total virtual entries (written by the scan), plan[1] = edges of hub rows, plan[2] = hub rows
+static __global__ void k_member_rows(const int32_t* __restrict__ order, const int32_t* __restrict__ ptr,
+                                     const int64_t* __restrict__ cluster, const int* __restrict__ voff,
+                                     const int32_t* __restrict__ rs, const int32_t* __restrict__ re, int64_t N,
+                                     int64_t K, int32_t* __restrict__ mrowoff, int32_t* __restrict__ mcrow,
+                                     uint32_t* __restrict__ hubbits, unsigned long long* __restrict__ plan) {
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= N) return;
+  const int v = order[m];
+  const int64_t c = clamp_cluster(cluster[v], K);
+  const int p0 = ptr[c], p1 = ptr[c + 1];
+  const int ro = voff[p0];
+  mrowoff[m] = ro;
+  mcrow[m] = (int32_t)c;
+  if (voff[p1] - ro > kBkHub) {
+    atomicAdd(&plan[1], (unsigned long long)(re[v] - rs[v]));
+    if (m == p0) {
+      atomicOr(&hubbits[c >> 5], 1u << (c & 31));
+      atomicAdd(&plan[2], 1ull);
+    }
+  }
+}
+
+static __global__ void k_fill_i32(int32_t* __restrict__ p, int64_t n, int32_t v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// tile_mlo[t] = first member whose coarse row starts in window t or later (tile_mlo is pre-filled with N)
+static __global__ void k_tile_bounds(const int32_t* __restrict__ mrowoff, int64_t N, int ntiles,
+                                     int32_t* __restrict__ tile_mlo) {
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= N) return;
+  const int t = mrowoff[m] / kBkTile;
+  const int tp = m > 0 ? mrowoff[m - 1] / kBkTile : -1;
+  for (int u = tp + 1; u <= t && u <= ntiles; ++u) tile_mlo[u] = (int32_t)m;
+}
+
+struct BucketArgs {
+  const int64_t* col;
+  const float* w;  // null when unweighted
+  const int64_t* cluster;
+  const int32_t *order, *ptr, *rs, *re, *mrowoff, *mcrow, *tile_mlo;
+  const int* voff;
+  const uint32_t* hubbits;
+  int64_t N, K;
+  int op;
+  bool rsl;
+  float eps;
+  int32_t *t_row, *t_col, *t_len;  // virtual array (t_len optional)
+  float *t_w, *t_aux;              // (t_aux optional: product of the non-zero members, MUL backward)
+  int32_t* slot_tmp;               // optional: virtual position of the run every input edge joined
+};
+
+// largest i in [0, n) with a[i] <= x   (a ascending, a[0] <= x)
+__device__ __forceinline__ int upper_slot(const int32_t* a, int n, int x) {
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] <= x) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+static __global__ void __launch_bounds__(kBkThreads) k_bucket_tiles(BucketArgs A) {
+  extern __shared__ __align__(16) unsigned char bk_smem[];
+  unsigned long long* s_key = reinterpret_cast<unsigned long long*>(bk_smem);          // [kBkCap]
+  int32_t* m_voff = reinterpret_cast<int32_t*>(s_key + kBkCap);                          // [kBkCap + 1] tile-relative
+  int32_t* m_es = m_voff + kBkCap + 1;                                                   // [kBkCap] first edge or -1
+  int32_t* m_c = m_es + kBkCap;                                                          // [kBkCap] coarse row
+  uint16_t* m_rk = reinterpret_cast<uint16_t*>(m_c + kBkCap);                            // [kBkCap] row rank key
+  const int tile = blockIdx.x;
+  const int m_lo = A.tile_mlo[tile];
+  int m_hi = A.tile_mlo[tile + 1];
+  if (m_lo >= m_hi) return;
+  {
+    const int64_t cl = A.mcrow[m_hi - 1];  // at most one hub row starts in a window, and it is the last one
+    if ((A.hubbits[cl >> 5] >> (cl & 31)) & 1u) m_hi = A.ptr[cl];
+    if (m_lo >= m_hi) return;
+  }
+  const int tile_base = A.voff[m_lo];
+  const int n_ent = A.voff[m_hi] - tile_base;
+  const int n_mem = m_hi - m_lo;
+  for (int i = threadIdx.x; i < n_mem; i += kBkThreads) {
+    const int m = m_lo + i;
+    const int v = A.order[m];
+    const int s = A.rs[v], e = A.re[v];
+    m_voff[i] = A.voff[m] - tile_base;
+    m_es[i] = e > s ? s : -1;
+    const int c = A.mcrow[m];
+    m_c[i] = c;
+    m_rk[i] = (uint16_t)(A.ptr[c] - m_lo);  // first member of the row: ascending with the row, < n_mem
+  }
+  if (threadIdx.x == 0) m_voff[n_mem] = n_ent;
+  int P = 64;
+  while (P < n_ent) P <<= 1;
+  __syncthreads();
+  // gather: entry j = (member, edge); key = (row rank | coarse column | arrival index)
+  for (int j = threadIdx.x; j < P; j += kBkThreads) {
+    unsigned long long key = ~0ull;
+    if (j < n_ent) {
+      const int mi = upper_slot(m_voff, n_mem, j);
+      const int es = m_es[mi];
+      if (es >= 0) {
+        const int64_t e = (int64_t)es + (j - m_voff[mi]);
+        int64_t q = __ldg(A.col + e);
+        if (q < 0 || q >= A.N) q = 0;
+        const int64_t cc = clamp_cluster(A.cluster[q], A.K);
+        key = ((unsigned long long)m_rk[mi] << 43) | ((unsigned long long)cc << 12) | (unsigned)j;
+      }
+    }
+    s_key[j] = key;
+  }
+  __syncthreads();
+  // bitonic sort of P keys (keys are unique: no stability question)
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+      for (int i = threadIdx.x; i < (P >> 1); i += kBkThreads) {
+        const int ix = 2 * i - (i & (jj - 1));
+        const int iy = ix + jj;
+        const unsigned long long a = s_key[ix], b = s_key[iy];
+        const bool asc = (ix & k) == 0;
+        if ((a > b) == asc) {
+          s_key[ix] = b;
+          s_key[iy] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // run heads combine their members in arrival order
+  for (int i = threadIdx.x; i < n_ent; i += kBkThreads) {
+    const unsigned long long key = s_key[i];
+    if (key == ~0ull) continue;
+    if (i > 0 && (s_key[i - 1] >> 12) == (key >> 12)) continue;
+    const int64_t cc = (int64_t)((key >> 12) & 0x7fffffffull);
+    int mi = upper_slot(m_voff, n_mem, (int)(key & 0xfffu));
+    const int64_t cr = m_c[mi];
+    const int tpos = tile_base + i;
+    float acc = 0.f, prod_nz = 1.f;
+    int len = 0, zeros = 0;
+    for (int q = i; q < n_ent; ++q) {
+      const unsigned long long kq = s_key[q];
+      if ((kq >> 12) != (key >> 12)) break;
+      const int j = (int)(kq & 0xfffu);
+      mi = upper_slot(m_voff, n_mem, j);
+      const int64_t e = (int64_t)m_es[mi] + (j - m_voff[mi]);
+      if (A.w) {
+        const float v = A.w[e];
+        acc = len == 0 ? v : combine_w(A.op, acc, v);
+        if (A.t_aux) {
+          if (v == 0.f) ++zeros; else prod_nz = __fmul_rn(prod_nz, v);
+        }
+      }
+      if (A.slot_tmp) A.slot_tmp[e] = tpos;
+      ++len;
+    }
+    if (A.w && A.op == TGPB200_MEAN) acc = __fdiv_rn(acc, (float)len);
+    if (A.rsl && cr == cc) continue;
+    if (A.w && !(fabsf(acc) > A.eps)) continue;
+    A.t_row[tpos] = (int32_t)cr;
+    A.t_col[tpos] = (int32_t)cc;
+    if (A.w) A.t_w[tpos] = acc;
+    if (A.t_len) A.t_len[tpos] = (A.t_aux && A.op == TGPB200_MUL) ? zeros : len;
+    if (A.t_aux) A.t_aux[tpos] = prod_nz;
+  }
+}
+
+constexpr size_t kBkSmem = (size_t)kBkCap * 8 + (size_t)(kBkCap + 1) * 4 + (size_t)kBkCap * 4 * 2 + (size_t)kBkCap * 2 + 16;
+
+// ---- hub rows: radix sort of their edges only ------------------------------------------------------------------
+struct HubPred {
+  struct Payload {
+    unsigned long long key;
+  };
+  const int64_t* row;
+  const int64_t* col;
+  const int64_t* cluster;
+  const uint32_t* hubbits;
+  int64_t N, K;
+  int cb;
+  __device__ bool operator()(int64_t e, Payload& p) const {
+    const int64_t r = row[e];
+    if (r < 0 || r >= N) return false;
+    const int64_t c = clamp_cluster(cluster[r], K);
+    if (!((hubbits[c >> 5] >> (c & 31)) & 1u)) return false;
+    const int64_t q = col[e];
+    const int64_t cc = clamp_cluster(cluster[(q < 0 || q >= N) ? 0 : q], K);
+    p.key = ((unsigned long long)c << cb) | (unsigned long long)cc;
+    return true;
+  }
+};
+struct HubEmit {
+  unsigned long long* keys;
+  uint32_t* vals;
+  __device__ void operator()(int64_t e, int pos, const HubPred::Payload& p) const {
+    keys[pos] = p.key;
+    vals[pos] = (uint32_t)e;
+  }
+};
+
+static __global__ void k_hub_first(const unsigned long long* __restrict__ ks, const int64_t* __restrict__ n_dev, int cb,
+                                   int32_t* __restrict__ hubfirst) {
+  const int64_t n = *n_dev;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long c = ks[i] >> cb;
+  if (i == 0 || (ks[i - 1] >> cb) != c) hubfirst[c] = (int32_t)i;
+}
+
+struct HubRunArgs {
+  const unsigned long long* ks;
+  const uint32_t* perm;
+  const int64_t* n_dev;
+  const float* w;
+  const int32_t* hubfirst;
+  const int32_t* ptr;
+  const int* voff;
+  int cb, op;
+  bool rsl;
+  float eps;
+  int32_t *t_row, *t_col, *t_len;
+  float *t_w, *t_aux;
+  int32_t* slot_tmp;
+  int* long_list;  // [0] = count, entries follow
+};
+
+__device__ __forceinline__ void hub_write(const HubRunArgs& A, unsigned long long key, int64_t i, float acc, int len,
+                                          int zeros, float prod_nz) {
+  const int64_t cr = (int64_t)(key >> A.cb), cc = (int64_t)(key & ((1ull << A.cb) - 1ull));
+  if (A.w && A.op == TGPB200_MEAN) acc = __fdiv_rn(acc, (float)len);
+  if (A.rsl && cr == cc) return;
+  if (A.w && !(fabsf(acc) > A.eps)) return;
+  const int tpos = A.voff[A.ptr[cr]] + (int)(i - A.hubfirst[cr]);
+  A.t_row[tpos] = (int32_t)cr;
+  A.t_col[tpos] = (int32_t)cc;
+  if (A.w) A.t_w[tpos] = acc;
+  if (A.t_len) A.t_len[tpos] = (A.t_aux && A.op == TGPB200_MUL) ? zeros : len;
+  if (A.t_aux) A.t_aux[tpos] = prod_nz;
+}
+
+static __global__ void k_hub_runs(HubRunArgs A) {
+  const int64_t n = *A.n_dev;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = A.ks[i];
+  if (i > 0 && A.ks[i - 1] == key) return;
+  const int64_t cr = (int64_t)(key >> A.cb);
+  const int tpos = A.voff[A.ptr[cr]] + (int)(i - A.hubfirst[cr]);
+  float acc = 0.f, prod_nz = 1.f;
+  int len = 0, zeros = 0;
+  for (int64_t q = i; q < n && A.ks[q] == key; ++q) {
+    if (len >= kBkLongRun) {  // hand the whole run to a block (fixed-shape reduction, see k_hub_long_runs)
+      A.long_list[1 + atomicAdd(&A.long_list[0], 1)] = (int)i;
+      return;
+    }
+    const uint32_t e = A.perm[q];
+    if (A.w) {
+      const float v = A.w[e];
+      acc = len == 0 ? v : combine_w(A.op, acc, v);
+      if (A.t_aux) {
+        if (v == 0.f) ++zeros; else prod_nz = __fmul_rn(prod_nz, v);
+      }
+    }
+    if (A.slot_tmp) A.slot_tmp[e] = tpos;
+    ++len;
+  }
+  hub_write(A, key, i, acc, len, zeros, prod_nz);
+}
+
+// Runs longer than kBkLongRun (a few coarse columns taking most of a hub row): one block per run, thread-strided
+// partials in double (sum / mean) or in the op itself, combined over the block in a fixed order.
+static __global__ void __launch_bounds__(256) k_hub_long_runs(HubRunArgs A) {
+  __shared__ double redd[256];
+  __shared__ float redf[256];
+  __shared__ int redi[256];
+  __shared__ int s_len;
+  const int64_t n = *A.n_dev;
+  const int n_long = A.long_list[0];
+  for (int r = blockIdx.x; r < n_long; r += gridDim.x) {
+    const int64_t i = A.long_list[1 + r];
+    const unsigned long long key = A.ks[i];
+    const int64_t cr = (int64_t)(key >> A.cb);
+    const int tpos = A.voff[A.ptr[cr]] + (int)(i - A.hubfirst[cr]);
+    double sd = 0.0;
+    float acc = 0.f, prod_nz = 1.f;
+    int cnt = 0, zeros = 0;
+    for (int64_t q = i + threadIdx.x; q < n && A.ks[q] == key; q += 256) {
+      const uint32_t e = A.perm[q];
+      if (A.w) {
+        const float v = A.w[e];
+        sd += (double)v;
+        acc = cnt == 0 ? v : combine_w(A.op == TGPB200_MEAN ? TGPB200_SUM : A.op, acc, v);
+        if (A.t_aux) {
+          if (v == 0.f) ++zeros; else prod_nz = __fmul_rn(prod_nz, v);
+        }
+      }
+      if (A.slot_tmp) A.slot_tmp[e] = tpos;
+      ++cnt;
+    }
+    const bool add = A.op == TGPB200_SUM || A.op == TGPB200_MEAN;
+    redd[threadIdx.x] = sd;
+    redf[threadIdx.x] = acc;
+    redi[threadIdx.x] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {  // threads with cnt == 0 hold no member (only past the end of the run)
+      double tot = 0.0;
+      float a = 0.f;
+      int len = 0;
+      for (int t = 0; t < 256; ++t) {
+        if (redi[t] == 0) continue;
+        tot += redd[t];
+        a = len == 0 ? redf[t] : combine_w(add ? TGPB200_SUM : A.op, a, redf[t]);
+        len += redi[t];
+      }
+      redf[0] = add ? (float)tot : a;
+      s_len = len;
+    }
+    __syncthreads();
+    const float total = redf[0];
+    const int len = s_len;
+    __syncthreads();
+    // MUL bookkeeping (zero count, product of the non-zeros) over the block, fixed order
+    redf[threadIdx.x] = prod_nz;
+    redi[threadIdx.x] = zeros;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float p = 1.f;
+      int z = 0;
+      for (int t = 0; t < 256; ++t) p = __fmul_rn(p, redf[t]), z += redi[t];
+      hub_write(A, key, i, total, len, z, p);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- emit: compaction of the virtual array ---------------------------------------------------------------------
+struct VirtPred {
+  struct Payload {};
+  const int32_t* t_row;
+  __device__ bool operator()(int64_t i, Payload&) const { return t_row[i] >= 0; }
+};
+struct VirtEmit {
+  const int32_t *t_row, *t_col, *t_len;
+  const float *t_w, *t_aux;
+  int64_t *out_row, *out_col;
+  float *out_w, *run_aux;
+  int32_t *run_len, *tpos2out;
+  __device__ void operator()(int64_t i, int pos, const VirtPred::Payload&) const {
+    out_row[pos] = t_row[i];
+    out_col[pos] = t_col[i];
+    if (out_w) out_w[pos] = t_w[i];
+    if (run_len) run_len[pos] = t_len[i];
+    if (run_aux) run_aux[pos] = t_aux[i];
+    if (tpos2out) tpos2out[i] = pos;
+  }
+};
+
+static __global__ void k_slot_fixup(const int32_t* __restrict__ slot_tmp, const int32_t* __restrict__ tpos2out, int64_t E,
+                                    int32_t* __restrict__ edge_slot) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int t = slot_tmp[e];
+  edge_slot[e] = t >= 0 ? tpos2out[t] : -1;
+}
+
+static int cb_of(int64_t K) {
+  int b = 0;
+  uint64_t v = K > 1 ? (uint64_t)K - 1 : 1;
+  while (v) ++b, v >>= 1;
+  return b < 1 ? 1 : b;
+}
+
+// Workspace layout shared by plan / count / emit (carved identically in the three calls).
+struct BucketPlan {
+  int32_t *rs, *re, *mrowoff, *mcrow, *tile_mlo, *hubfirst;
+  int* voff;
+  uint32_t* hubbits;
+  unsigned long long* plan;  // [4] device copy of the plan
+  int64_t* hub_count;
+  int32_t *t_row, *t_col, *t_len, *tpos2out, *slot_tmp;
+  float *t_w, *t_aux;
+  unsigned long long *hk0, *hk1;
+  uint32_t *hv0, *hv1;
+  int* long_list;
+  int* tile_counts;
+  int64_t V;  // virtual capacity E + N
+  int ntiles;
+  bool ok;
+  BucketPlan(Workspace& ws, int64_t E, int64_t N, int64_t K) {
+    V = E + N;
+    ntiles = (int)ceil_div(V > 0 ? V : 1, kBkTile);
+    const size_t n = (size_t)(N > 0 ? N : 1), e = (size_t)(E > 0 ? E : 1), v = (size_t)(V > 0 ? V : 1);
+    rs = ws.take<int32_t>(n);
+    re = ws.take<int32_t>(n);
+    voff = ws.take<int>(n + 1);
+    mrowoff = ws.take<int32_t>(n);
+    mcrow = ws.take<int32_t>(n);
+    tile_mlo = ws.take<int32_t>((size_t)ntiles + 2);
+    hubbits = ws.take<uint32_t>((size_t)(K / 32 + 1));
+    hubfirst = ws.take<int32_t>((size_t)(K > 0 ? K : 1));
+    plan = ws.take<unsigned long long>(4);
+    hub_count = ws.take<int64_t>(1);
+    t_row = ws.take<int32_t>(v);
+    t_col = ws.take<int32_t>(v);
+    t_w = ws.take<float>(v);
+    t_len = ws.take<int32_t>(v);
+    t_aux = ws.take<float>(v);
+    tpos2out = ws.take<int32_t>(v);
+    slot_tmp = ws.take<int32_t>(e);
+    hk0 = ws.take<unsigned long long>(e);
+    hk1 = ws.take<unsigned long long>(e);
+    hv0 = ws.take<uint32_t>(e);
+    hv1 = ws.take<uint32_t>(e);
+    long_list = ws.take<int>(e / kBkLongRun + 2);
+    tile_counts = ws.take<int>((size_t)ceil_div(v, kCompactTile) + 1);
+    ok = ws.ok;
+  }
+};
+
+}  // namespace tgp
+
+using namespace tgp;
+
+extern "C" {
+
+size_t tgpb200_bucket_coalesce_workspace_bytes(int64_t E, int64_t N, int64_t K) {
+  const size_t n = (size_t)(N > 0 ? N : 1), e = (size_t)(E > 0 ? E : 1), v = n + e;
+  return 5 * align_up((n + 1) * 4) + align_up((v / kBkTile + 4) * 4) + align_up((size_t)(K / 32 + 1) * 4) +
+         align_up((size_t)(K > 0 ? K : 1) * 4) + 2 * 256 + 6 * align_up(v * 4) + align_up(e * 4) + 2 * align_up(e * 8) +
+         2 * align_up(e * 4) + align_up((e / kBkLongRun + 2) * 4) + align_up((v / kCompactTile + 2) * 4) +
+         scan_workspace_bytes(N + 1) + radix_sort_workspace_bytes(E) + compact_onepass_workspace_bytes(E) + 8192;
+}
+
+// Phase 0: virtual layout of the coarse rows.  plan_out (device int64[4]) = {virtual entries, hub edges, hub rows, 0}.
+// Large inputs read it back once to size the later launches exactly; small / graph-captured ones skip the read and
+// launch at capacity (virt_cap = E + N, hub_cap = E).
+int tgpb200_bucket_coalesce_plan(const int64_t* row, int64_t E, const int64_t* cluster_index, const int32_t* order,
+                                 const int32_t* ptr, int64_t N, int64_t K, int64_t* plan_out, void* workspace,
+                                 size_t workspace_bytes, tgpb200_stream_t stream) {
+  if (E < 0 || N <= 0 || K <= 0 || !plan_out || !cluster_index || !order || !ptr) return TGPB200_ERR_INVALID;
+  if (E + N >= INT32_MAX || K >= INT32_MAX) return TGPB200_ERR_UNSUPPORTED;
+  if (E > 0 && !row) return TGPB200_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  BucketPlan pl(ws, E, N, K);
+  if (!pl.ok) return TGPB200_ERR_WORKSPACE;
+  cudaMemsetAsync(pl.rs, 0, (size_t)N * 4, st);
+  cudaMemsetAsync(pl.re, 0, (size_t)N * 4, st);
+  cudaMemsetAsync(pl.hubbits, 0, (size_t)(K / 32 + 1) * 4, st);
+  cudaMemsetAsync(pl.plan, 0, 4 * sizeof(unsigned long long), st);
+  if (E > 0)
+    launch("k_fine_row_spans", k_fine_row_spans, (unsigned)ceil_div(E, 256), 256, 0, st, row, E, N, pl.rs, pl.re);
+  launch("k_member_cost", k_member_cost, (unsigned)ceil_div(N + 1, 256), 256, 0, st, order, pl.rs, pl.re, N, pl.voff);
+  int rc = exclusive_scan_i32(pl.voff, pl.voff, N + 1, nullptr, reinterpret_cast<int64_t*>(pl.plan), ws, st);
+  if (rc != TGPB200_OK) return rc;
+  launch("k_member_rows", k_member_rows, (unsigned)ceil_div(N, 256), 256, 0, st, order, ptr, cluster_index, pl.voff, pl.rs,
+         pl.re, N, K, pl.mrowoff, pl.mcrow, pl.hubbits, pl.plan);
+  launch("k_fill_i32", k_fill_i32, (unsigned)ceil_div(pl.ntiles + 2, 256), 256, 0, st, pl.tile_mlo,
+         (int64_t)pl.ntiles + 2, (int32_t)N);
+  launch("k_tile_bounds", k_tile_bounds, (unsigned)ceil_div(N, 256), 256, 0, st, pl.mrowoff, N, pl.ntiles + 1, pl.tile_mlo);
+  cudaMemcpyAsync(plan_out, pl.plan, 4 * sizeof(int64_t), cudaMemcpyDeviceToDevice, st);
+  return launch_status();
+}
+
+// Phase 1 + count: tiles, hub rows, survivor count.  virt_cap / hub_cap bound the launches (plan values, or E + N / E).
+// need_slots: record the run of every input edge (backward).  Same workspace as the plan call.
+int tgpb200_bucket_coalesce_count(const int64_t* row, const int64_t* col, const float* edge_weight, int64_t E,
+                                  const int64_t* cluster_index, const int32_t* order, const int32_t* ptr, int64_t N,
+                                  int64_t K, int op, uint32_t flags, float eps, int64_t virt_cap, int64_t hub_cap,
+                                  int need_slots, int64_t* count_out, void* workspace, size_t workspace_bytes,
+                                  tgpb200_stream_t stream) {
+  if (E < 0 || N <= 0 || K <= 0 || !count_out || op < TGPB200_SUM || op > TGPB200_MUL) return TGPB200_ERR_INVALID;
+  if (E + N >= INT32_MAX || K >= INT32_MAX) return TGPB200_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  BucketPlan pl(ws, E, N, K);
+  if (!pl.ok) return TGPB200_ERR_WORKSPACE;
+  if (virt_cap < 0 || virt_cap > pl.V) virt_cap = pl.V;
+  if (hub_cap < 0 || hub_cap > E) hub_cap = E;
+  const bool weighted = edge_weight != nullptr;
+  const bool slots = need_slots != 0;
+  const bool aux = slots && weighted && op == TGPB200_MUL;
+  cudaMemsetAsync(pl.t_row, 0xff, (size_t)(virt_cap > 0 ? virt_cap : 1) * 4, st);
+  if (slots) {
+    cudaMemsetAsync(pl.slot_tmp, 0xff, (size_t)(E > 0 ? E : 1) * 4, st);
+    cudaMemsetAsync(pl.tpos2out, 0xff, (size_t)(virt_cap > 0 ? virt_cap : 1) * 4, st);
+  }
+  const bool rsl = (flags & TGPB200_REMOVE_SELF_LOOPS) != 0;
+  if (E > 0) {
+    BucketArgs A;
+    A.col = col, A.w = edge_weight, A.cluster = cluster_index;
+    A.order = order, A.ptr = ptr, A.rs = pl.rs, A.re = pl.re, A.mrowoff = pl.mrowoff, A.mcrow = pl.mcrow;
+    A.tile_mlo = pl.tile_mlo, A.voff = pl.voff, A.hubbits = pl.hubbits, A.N = N, A.K = K, A.op = op, A.rsl = rsl, A.eps = eps;
+    A.t_row = pl.t_row, A.t_col = pl.t_col, A.t_len = slots ? pl.t_len : nullptr, A.t_w = pl.t_w;
+    A.t_aux = aux ? pl.t_aux : nullptr, A.slot_tmp = slots ? pl.slot_tmp : nullptr;
+    static bool attr_set = false;
+    if (!attr_set) {
+      attr_set = true;
+      cudaFuncSetAttribute(k_bucket_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBkSmem);
+    }
+    const int tiles = (int)ceil_div(virt_cap > 0 ? virt_cap : 1, kBkTile);
+    launch("k_bucket_tiles", k_bucket_tiles, (unsigned)tiles, kBkThreads, kBkSmem, st, A);
+    if (hub_cap > 0) {
+      const int cb = cb_of(K);
+      HubPred pred{row, col, cluster_index, pl.hubbits, N, K, cb};
+      HubEmit emit{pl.hk0, pl.hv0};
+      int rc = compact_onepass(pred, emit, E, pl.hub_count, ws, st);
+      if (rc != TGPB200_OK) return rc;
+      bool in1 = false;
+      rc = radix_sort_pairs<unsigned long long>(pl.hk0, pl.hv0, pl.hv0, pl.hk1, pl.hv1, hub_cap, 2 * cb, &in1, ws, st,
+                                                pl.hub_count);
+      if (rc != TGPB200_OK) return rc;
+      HubRunArgs H;
+      H.ks = in1 ? pl.hk1 : pl.hk0, H.perm = in1 ? pl.hv1 : pl.hv0, H.n_dev = pl.hub_count, H.w = edge_weight;
+      H.hubfirst = pl.hubfirst, H.ptr = ptr, H.voff = pl.voff, H.cb = cb, H.op = op, H.rsl = rsl, H.eps = eps;
+      H.t_row = pl.t_row, H.t_col = pl.t_col, H.t_len = slots ? pl.t_len : nullptr, H.t_w = pl.t_w;
+      H.t_aux = aux ? pl.t_aux : nullptr, H.slot_tmp = slots ? pl.slot_tmp : nullptr, H.long_list = pl.long_list;
+      cudaMemsetAsync(pl.long_list, 0, sizeof(int), st);
+      const unsigned hg = (unsigned)ceil_div(hub_cap, 256);
+      launch("k_hub_first", k_hub_first, hg, 256, 0, st, H.ks, pl.hub_count, cb, pl.hubfirst);
+      launch("k_hub_runs", k_hub_runs, hg, 256, 0, st, H);
+      const int64_t lcap = hub_cap / kBkLongRun + 1;
+      launch("k_hub_long_runs", k_hub_long_runs, (unsigned)(lcap < 592 ? lcap : 592), 256, 0, st, H);
+    }
+  }
+  VirtPred vp{pl.t_row};
+  return compact_count(vp, virt_cap, pl.tile_counts, nullptr, count_out, st);
+}
+
+// Phase 2: write the coarse edge list (int64 at the boundary).  edge_slot / run_len / run_aux as in
+// tgpb200_remap_coalesce_emit (run_len holds the number of zero members and run_aux the product of the non-zero
+// members for op = MUL: exact product-rule gradients with zero weights); they need need_slots != 0 in the count call.
+int tgpb200_bucket_coalesce_emit(int64_t E, int64_t N, int64_t K, int weighted, int64_t virt_cap, int64_t* out_row,
+                                 int64_t* out_col, float* out_weight, int32_t* edge_slot, int32_t* run_len,
+                                 float* run_aux, void* workspace, size_t workspace_bytes, tgpb200_stream_t stream) {
+  if (E < 0 || N <= 0 || K <= 0) return TGPB200_ERR_INVALID;
+  if (E + N >= INT32_MAX || K >= INT32_MAX) return TGPB200_ERR_UNSUPPORTED;
+  if (!out_row || !out_col || (weighted && !out_weight)) return TGPB200_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  BucketPlan pl(ws, E, N, K);
+  if (!pl.ok) return TGPB200_ERR_WORKSPACE;
+  if (virt_cap < 0 || virt_cap > pl.V) virt_cap = pl.V;
+  VirtPred vp{pl.t_row};
+  VirtEmit ve{pl.t_row, pl.t_col, pl.t_len, pl.t_w, pl.t_aux, out_row, out_col, weighted ? out_weight : nullptr,
+              run_aux, run_len, edge_slot ? pl.tpos2out : nullptr};
+  int rc = compact_emit(vp, ve, virt_cap, pl.tile_counts, st);
+  if (rc != TGPB200_OK) return rc;
+  if (edge_slot && E > 0)
+    launch("k_slot_fixup", k_slot_fixup, (unsigned)ceil_div(E, 256), 256, 0, st, pl.slot_tmp, pl.tpos2out, E, edge_slot);
+  return launch_status();
+}
+
+}  // extern "C"

@@ -251,8 +251,8 @@ static __global__ void k_coalesce_ties(const float* __restrict__ w, const float*
 }
 static __global__ void k_coalesce_bwd(const float* __restrict__ w, const float* __restrict__ out_w,
                                       const float* __restrict__ gout, const int32_t* __restrict__ slot,
-                                      const int32_t* __restrict__ run_len, const int* __restrict__ ties, int64_t E,
-                                      int op, float* __restrict__ gin) {
+                                      const int32_t* __restrict__ run_len, const float* __restrict__ run_aux,
+                                      const int* __restrict__ ties, int64_t E, int op, float* __restrict__ gin) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   int s = slot[e];
@@ -261,7 +261,14 @@ static __global__ void k_coalesce_bwd(const float* __restrict__ w, const float* 
     g = gout[s];
     if (op == TGPB200_MEAN) g = g / (float)run_len[s];
     else if (op == TGPB200_MAX || op == TGPB200_MIN) g = (w[e] == out_w[s]) ? g / (float)ties[s] : 0.f;
-    else if (op == TGPB200_MUL) g = (w[e] != 0.f) ? g * out_w[s] / w[e] : 0.f;
+    else if (op == TGPB200_MUL) {
+      if (run_aux) {  // run_len = zero members of the run, run_aux = product of the others: exact product rule
+        const int z = run_len[s];
+        g = z == 0 ? g * out_w[s] / w[e] : ((z == 1 && w[e] == 0.f) ? g * run_aux[s] : 0.f);
+      } else {
+        g = (w[e] != 0.f) ? g * out_w[s] / w[e] : 0.f;
+      }
+    }
   }
   gin[e] = g;
 }
@@ -269,14 +276,17 @@ static __global__ void k_coalesce_bwd(const float* __restrict__ w, const float* 
 // ------------------------------------------------------------------------------------------
 // Deterministic segmented sums (degree / normalisation partials): no floating-point atomics.
 //   out[k] = sum of val(i) over the positions i with key(i) == k, k in [0, K)
-// Non-decreasing keys (coarse edge lists are row-sorted: the cluster path sorts them, the kept-node path keeps the
-// order of a row-sorted input) take the direct path: a span pass marks [first, last) of every key, then one warp per
-// key adds its span lane-strided and combines the 32 partials in a fixed butterfly (bitwise reproducible).  Other key
-// sequences are first grouped with the stable radix sort (positions stay ascending inside a key).  Spans longer than
-// kLongSpan go to a block-per-span kernel through a small work list (its order does not matter: every span's sum
-// has a fixed shape).  `n_dev`, when given, is the device-side element count (<= the launch capacity n).
+// For a non-decreasing key sequence (coarse edge lists are row-sorted: the cluster path sorts them, the kept-node
+// path keeps the order of a row-sorted input) the sum of a key's run is the difference of two values of ONE
+// running prefix sum over all positions, carried in double precision with a fixed reduce-then-scan structure
+// (tile sums -> sequential spine -> tile down-sweep): bitwise reproducible, perfectly load-balanced whatever the
+// run lengths (a power-law hub row is just a long run), and accurate to ~1e-16 of the total, i.e. far below the
+// fp32 rounding of the result.  Other key sequences are first grouped with the stable radix sort.
+// `n_dev`, when given, is the device-side element count (<= the launch capacity n).
 // ------------------------------------------------------------------------------------------
-constexpr int kLongSpan = 8192;
+constexpr int kDsThreads = 256;
+constexpr int kDsItems = 8;
+constexpr int kDsTile = kDsThreads * kDsItems;
 
 struct KeyOfArray64 {
   const int64_t* k;
@@ -287,16 +297,134 @@ struct KeyOfArray32 {
   __device__ int64_t operator()(int64_t i) const { return (int64_t)k[i]; }
 };
 
-template <typename KeyF>
-static __global__ void k_key_spans(KeyF key, int64_t n, const int64_t* __restrict__ n_dev, int64_t K,
-                                   int2* __restrict__ span) {
+// exclusive scan of one double per thread over the block (fixed shape); *total = block sum
+__device__ __forceinline__ double block_exclusive_scan_d(double v, double* smem /* >= 33 */, double* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) smem[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    double s = lane < nw ? smem[lane] : 0.0;
+    double si = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double t = __shfl_up_sync(kFull, si, o);
+      if (lane >= o) si += t;
+    }
+    smem[lane] = si - s;
+    if (lane == 31) smem[32] = si;
+  }
+  __syncthreads();
+  if (total) *total = smem[32];
+  return smem[w] + inc - v;
+}
+
+// Tile layout of both passes: warp w of the block owns the 256 consecutive positions [tile + 256 w, +256) and reads
+// them in 8 rounds of 32 (round r, lane l -> position 256 w + 32 r + l): every load is a full coalesced line.
+template <typename KeyF, typename ValF>
+static __global__ void __launch_bounds__(kDsThreads)
+    k_dsum_reduce(KeyF key, ValF val, int64_t n, const int64_t* __restrict__ n_dev, int64_t K,
+                  double* __restrict__ tile_sums) {
+  __shared__ double red[33];
   if (n_dev) n = min(n, *n_dev);
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int64_t k = key(i);
-  if (k < 0 || k >= K) return;
-  if (i == 0 || key(i - 1) != k) span[k].x = (int)i;
-  if (i + 1 == n || key(i + 1) != k) span[k].y = (int)(i + 1);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t wbase = (int64_t)blockIdx.x * kDsTile + (int64_t)w * (32 * kDsItems);
+  double s = 0.0;
+#pragma unroll
+  for (int r = 0; r < kDsItems; ++r) {
+    const int64_t i = wbase + r * 32 + lane;
+    if (i < n) {
+      const int64_t k = key(i);
+      if (k >= 0 && k < K) s += (double)val(i);
+    }
+  }
+  double tot;
+  block_exclusive_scan_d(s, red, &tot);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+// one block: exclusive scan of the tile sums in place, tile after tile in a fixed order
+static __global__ void k_dsum_spine(double* __restrict__ tile_sums, int nt) {
+  __shared__ double red[33];
+  double carry = 0.0;
+  for (int start = 0; start < nt; start += blockDim.x) {
+    const int i = start + threadIdx.x;
+    const double v = i < nt ? tile_sums[i] : 0.0;
+    double tot;
+    const double ex = block_exclusive_scan_d(v, red, &tot);
+    if (i < nt) tile_sums[i] = carry + ex;
+    carry += tot;
+    __syncthreads();
+  }
+}
+
+// down-sweep: running prefix at every position; a run's first position stores its prefix in pb[key], its last
+// position the prefix after it in pe[key]
+template <typename KeyF, typename ValF>
+static __global__ void __launch_bounds__(kDsThreads)
+    k_dsum_down(KeyF key, ValF val, int64_t n, const int64_t* __restrict__ n_dev, int64_t K,
+                const double* __restrict__ tile_off, double* __restrict__ pb, double* __restrict__ pe) {
+  __shared__ double wsum[kDsThreads / 32];
+  if (n_dev) n = min(n, *n_dev);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t wbase = (int64_t)blockIdx.x * kDsTile + (int64_t)w * (32 * kDsItems);
+  int64_t k[kDsItems];
+  double v[kDsItems], inc[kDsItems];
+#pragma unroll
+  for (int r = 0; r < kDsItems; ++r) {
+    const int64_t i = wbase + r * 32 + lane;
+    k[r] = i < n ? key(i) : -1;
+    if (k[r] < 0 || k[r] >= K) k[r] = -1;
+    v[r] = k[r] >= 0 ? (double)val(i) : 0.0;
+  }
+  // keys just outside the warp's window (raw values: only compared for inequality with valid keys)
+  const int64_t k_before = (lane == 0 && wbase > 0 && wbase - 1 < n) ? key(wbase - 1) : -1;
+  const int64_t k_after = (lane == 31 && wbase + 32 * kDsItems < n) ? key(wbase + 32 * kDsItems) : -1;
+  double wtot = 0.0;
+#pragma unroll
+  for (int r = 0; r < kDsItems; ++r) {  // inclusive prefix over the warp's positions, round after round
+    double x = v[r];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double t = __shfl_up_sync(kFull, x, o);
+      if (lane >= o) x += t;
+    }
+    inc[r] = wtot + x;
+    wtot += __shfl_sync(kFull, x, 31);
+  }
+  if (lane == 0) wsum[w] = wtot;
+  __syncthreads();
+  double off = tile_off[blockIdx.x];
+  for (int q = 0; q < w; ++q) off += wsum[q];
+#pragma unroll
+  for (int r = 0; r < kDsItems; ++r) {
+    int64_t prev = __shfl_up_sync(kFull, k[r], 1);
+    int64_t next = __shfl_down_sync(kFull, k[r], 1);
+    const int64_t last_prev = __shfl_sync(kFull, r > 0 ? k[r > 0 ? r - 1 : 0] : k_before, r > 0 ? 31 : 0);
+    const int64_t first_next =
+        __shfl_sync(kFull, r + 1 < kDsItems ? k[r + 1 < kDsItems ? r + 1 : r] : k_after, r + 1 < kDsItems ? 0 : 31);
+    if (lane == 0) prev = last_prev;
+    if (lane == 31) next = first_next;
+    const int64_t kk = k[r];
+    if (kk >= 0) {
+      if (prev != kk) pb[kk] = off + inc[r] - v[r];
+      if (next != kk) pe[kk] = off + inc[r];
+    }
+  }
+}
+
+static __global__ void k_dsum_finish(const double* __restrict__ pb, const double* __restrict__ pe, int64_t K,
+                                     float* __restrict__ out) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const double b = pb[k];
+  out[k] = (b == b) ? (float)(pe[k] - b) : 0.f;  // pb is NaN-filled: keys without a run sum to 0
 }
 
 template <typename KeyF>
@@ -306,72 +434,43 @@ static __global__ void k_fill_keys32(KeyF key, int64_t n, const int64_t* __restr
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t k = key(i);
-  keys[i] = (k < 0 || k >= K) ? (uint32_t)K : (uint32_t)k;  // out-of-range keys sort last and match no span
+  keys[i] = (k < 0 || k >= K) ? (uint32_t)K : (uint32_t)k;  // out-of-range keys sort last and match no run
 }
 
+// grouped (unsorted-key) path: the values are evaluated once in position order (coalesced operand reads) and then
+// permuted into key order with ONE 4-byte gather per position; the prefix passes read them linearly
 template <typename ValF>
-static __global__ void __launch_bounds__(256)
-    k_span_sum(const int2* __restrict__ span, int64_t K, ValF val, float* __restrict__ out,
-               int* __restrict__ long_list, int* __restrict__ long_cnt) {
-  const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (k >= K) return;
-  const int2 s = span[k];
-  if (s.x < 0 || s.y <= s.x) {
-    if (lane == 0) out[k] = 0.f;
-    return;
-  }
-  if (s.y - s.x > kLongSpan) {
-    if (lane == 0) long_list[atomicAdd(long_cnt, 1)] = (int)k;
-    return;
-  }
-  float acc = 0.f;
-  for (int i = s.x + lane; i < s.y; i += 32) acc = __fadd_rn(acc, val(i));
-  acc = warp_sum(acc);
-  if (lane == 0) out[k] = acc;
+static __global__ void k_eval_vals(ValF val, int64_t n, const int64_t* __restrict__ n_dev, float* __restrict__ out) {
+  if (n_dev) n = min(n, *n_dev);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = val(i);
 }
-
-template <typename ValF>
-static __global__ void __launch_bounds__(256)
-    k_span_sum_long(const int2* __restrict__ span, ValF val, float* __restrict__ out,
-                    const int* __restrict__ long_list, const int* __restrict__ long_cnt) {
-  __shared__ float red[32];
-  const int n_long = *long_cnt;
-  for (int j = blockIdx.x; j < n_long; j += gridDim.x) {
-    const int k = long_list[j];
-    const int2 s = span[k];
-    float acc = 0.f;
-    for (int i = s.x + threadIdx.x; i < s.y; i += 256) acc = __fadd_rn(acc, val(i));
-    acc = block_sum(acc, red);
-    if (threadIdx.x == 0) out[k] = acc;
-    __syncthreads();
-  }
+static __global__ void k_permute_vals(const float* __restrict__ in, const uint32_t* __restrict__ order, int64_t n,
+                                      const int64_t* __restrict__ n_dev, float* __restrict__ out) {
+  if (n_dev) n = min(n, *n_dev);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[order[i]];
 }
-
-template <typename ValF>
-struct ValThroughOrder {
-  ValF v;
-  const uint32_t* order;
-  __device__ float operator()(int64_t i) const { return v((int64_t)order[i]); }
+struct ValOfArray {
+  const float* a;
+  __device__ float operator()(int64_t i) const { return a[i]; }
 };
 
 static size_t det_segment_sum_workspace_bytes(int64_t n, int64_t K) {
   size_t m = (size_t)(n > 0 ? n : 1);
-  return 4 * align_up(m * sizeof(uint32_t)) + radix_sort_workspace_bytes(n) + align_up((size_t)(K + 1) * sizeof(int2)) +
-         align_up((m / kLongSpan + 2) * sizeof(int)) + 1024;
+  return 6 * align_up(m * sizeof(uint32_t)) + radix_sort_workspace_bytes(n) +
+         2 * align_up((size_t)(K + 1) * sizeof(double)) + align_up((m / kDsTile + 2) * sizeof(double)) + 1024;
 }
 
-template <typename ValF>
-static void span_sums(const int2* span, int64_t n, int64_t K, ValF val, float* out, int* long_list, cudaStream_t st) {
-  int* long_cnt = long_list;  // slot 0 = counter, entries follow
-  cudaMemsetAsync(long_cnt, 0, sizeof(int), st);
-  launch("k_span_sum", k_span_sum<ValF>, (unsigned)ceil_div(K * 32, 256), 256, 0, st, span, K, val, out, long_list + 1,
-         long_cnt);
-  if (n > kLongSpan) {
-    const int64_t cap = n / kLongSpan + 1;
-    launch("k_span_sum_long", k_span_sum_long<ValF>, (unsigned)(cap < 1184 ? cap : 1184), 256, 0, st, span, val, out,
-           long_list + 1, long_cnt);
-  }
+template <typename KeyF, typename ValF>
+static void prefix_run_sums(KeyF key, ValF val, int64_t n, const int64_t* n_dev, int64_t K, double* pb, double* pe,
+                            double* tiles, float* out, cudaStream_t st) {
+  const int nt = (int)ceil_div(n, kDsTile);
+  cudaMemsetAsync(pb, 0xff, (size_t)K * sizeof(double), st);
+  launch("k_dsum_reduce", k_dsum_reduce<KeyF, ValF>, nt, kDsThreads, 0, st, key, val, n, n_dev, K, tiles);
+  launch("k_dsum_spine", k_dsum_spine, 1, 1024, 0, st, tiles, nt);
+  launch("k_dsum_down", k_dsum_down<KeyF, ValF>, nt, kDsThreads, 0, st, key, val, n, n_dev, K, tiles, pb, pe);
+  launch("k_dsum_finish", k_dsum_finish, (unsigned)ceil_div(K, 256), 256, 0, st, pb, pe, K, out);
 }
 
 template <typename KeyF, typename ValF>
@@ -379,34 +478,34 @@ static int det_segment_sum(KeyF key, ValF val, int64_t n, const int64_t* n_dev, 
                            Workspace& ws, cudaStream_t st) {
   if (K <= 0) return TGPB200_OK;
   const size_t m = (size_t)(n > 0 ? n : 1);
-  int2* span = ws.take<int2>((size_t)K + 1);
-  int* long_list = ws.take<int>(m / kLongSpan + 2);
+  double* pb = ws.take<double>((size_t)K + 1);
+  double* pe = ws.take<double>((size_t)K + 1);
+  double* tiles = ws.take<double>(m / kDsTile + 2);
   if (!ws.ok) return TGPB200_ERR_WORKSPACE;
-  cudaMemsetAsync(span, 0xff, (size_t)K * sizeof(int2), st);
-  const unsigned grid = (unsigned)ceil_div(n > 0 ? n : 1, 256);
   if (n <= 0) {
     cudaMemsetAsync(out, 0, (size_t)K * sizeof(float), st);
     return launch_status();
   }
   if (keys_sorted) {
-    launch("k_key_spans", k_key_spans<KeyF>, grid, 256, 0, st, key, n, n_dev, K, span);
-    span_sums(span, n, K, val, out, long_list, st);
+    prefix_run_sums(key, val, n, n_dev, K, pb, pe, tiles, out, st);
     return launch_status();
   }
   uint32_t* keys0 = ws.take<uint32_t>(m);
   uint32_t* keys1 = ws.take<uint32_t>(m);
   uint32_t* vals0 = ws.take<uint32_t>(m);
   uint32_t* vals1 = ws.take<uint32_t>(m);
+  float* ev = ws.take<float>(m);
+  float* sv = ws.take<float>(m);
   if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+  const unsigned grid = (unsigned)ceil_div(n, 256);
   launch("k_fill_keys32", k_fill_keys32<KeyF>, grid, 256, 0, st, key, n, n_dev, K, keys0);
+  launch("k_eval_vals", k_eval_vals<ValF>, grid, 256, 0, st, val, n, n_dev, ev);
   bool in1 = false;
   int rc = radix_sort_pairs<uint32_t>(keys0, nullptr, vals0, keys1, vals1, n, key_bits_for_u64((uint64_t)K), &in1, ws, st,
                                       n_dev);
   if (rc != TGPB200_OK) return rc;
-  KeyOfArray32 skey{in1 ? keys1 : keys0};
-  launch("k_key_spans", k_key_spans<KeyOfArray32>, grid, 256, 0, st, skey, n, n_dev, K, span);
-  ValThroughOrder<ValF> ival{val, in1 ? vals1 : vals0};
-  span_sums(span, n, K, ival, out, long_list, st);
+  launch("k_permute_vals", k_permute_vals, grid, 256, 0, st, ev, in1 ? vals1 : vals0, n, n_dev, sv);
+  prefix_run_sums(KeyOfArray32{in1 ? keys1 : keys0}, ValOfArray{sv}, n, n_dev, K, pb, pe, tiles, out, st);
   return launch_status();
 }
 
@@ -674,8 +773,9 @@ size_t tgpb200_coalesce_bwd_workspace_bytes(int64_t E, int64_t num_out, int op) 
 }
 
 int tgpb200_coalesce_bwd(const float* edge_weight, const float* out_weight, const float* grad_out,
-                         const int32_t* edge_slot, const int32_t* run_len, int64_t E, int64_t num_out, int op,
-                         float* grad_in, void* workspace, size_t workspace_bytes, tgpb200_stream_t stream) {
+                         const int32_t* edge_slot, const int32_t* run_len, const float* run_aux, int64_t E,
+                         int64_t num_out, int op, float* grad_in, void* workspace, size_t workspace_bytes,
+                         tgpb200_stream_t stream) {
   if (E < 0 || num_out < 0 || op < TGPB200_SUM || op > TGPB200_MUL) return TGPB200_ERR_INVALID;
   if (E == 0) return TGPB200_OK;
   if (!edge_slot || !grad_in || (num_out > 0 && !grad_out)) return TGPB200_ERR_INVALID;
@@ -691,7 +791,7 @@ int tgpb200_coalesce_bwd(const float* edge_weight, const float* out_weight, cons
     cudaMemsetAsync(ties, 0, (size_t)(num_out > 0 ? num_out : 1) * sizeof(int), st);
     launch("k_coalesce_ties", k_coalesce_ties, grid, 256, 0, st, edge_weight, out_weight, edge_slot, E, ties);
   }
-  launch("k_coalesce_bwd", k_coalesce_bwd, grid, 256, 0, st, edge_weight, out_weight, grad_out, edge_slot, run_len, ties, E, op, grad_in);
+  launch("k_coalesce_bwd", k_coalesce_bwd, grid, 256, 0, st, edge_weight, out_weight, grad_out, edge_slot, run_len, run_aux, ties, E, op, grad_in);
   return launch_status();
 }
 

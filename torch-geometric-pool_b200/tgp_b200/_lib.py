@@ -50,7 +50,12 @@ SIGNATURES = {
     "tgpb200_remap_coalesce_count": (_INT, [_P, _P, _P, _I64, _P, _I64, _I64, _INT, _U32, _F, _P, _P, _SZ, _P]),
     "tgpb200_remap_coalesce_emit": (_INT, [_I64, _I64, _INT, _U32, _F, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "tgpb200_coalesce_bwd_workspace_bytes": (_SZ, [_I64, _I64, _INT]),
-    "tgpb200_coalesce_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _INT, _P, _P, _SZ, _P]),
+    "tgpb200_coalesce_bwd": (_INT, [_P, _P, _P, _P, _P, _P, _I64, _I64, _INT, _P, _P, _SZ, _P]),
+    "tgpb200_bucket_coalesce_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
+    "tgpb200_bucket_coalesce_plan": (_INT, [_P, _I64, _P, _P, _P, _I64, _I64, _P, _P, _SZ, _P]),
+    "tgpb200_bucket_coalesce_count": (
+        _INT, [_P, _P, _P, _I64, _P, _P, _P, _I64, _I64, _INT, _U32, _F, _I64, _I64, _INT, _P, _P, _SZ, _P]),
+    "tgpb200_bucket_coalesce_emit": (_INT, [_I64, _I64, _I64, _INT, _I64, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "tgpb200_edge_norm_workspace_bytes": (_SZ, [_I64, _I64]),
     "tgpb200_rows_sorted": (_INT, [_P, _I64, _P, _P]),
     "tgpb200_degree_norm_fwd": (_INT, [_P, _P, _P, _I64, _P, _I64, _F, _INT, _P, _P, _P, _SZ, _P]),

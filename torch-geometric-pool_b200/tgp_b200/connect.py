@@ -66,6 +66,7 @@ class B200SparseConnect(Connect):
             edge_weight_norm=self.edge_weight_norm,
             batch_pooled=batch_pooled,
             degree_norm=self.degree_norm,
+            csr=F_.csr_of(so) if (so.cluster_index is not None and len(so.cluster_index) == so.num_nodes) else None,
         )
 
     def __repr__(self) -> str:

@@ -131,29 +131,33 @@ def _read_count(count: Tensor) -> int:
     return int(count.item())  # the one device->host word per data-dependent output size
 
 
-_SORTED_CACHE: dict = {}
+def _sorted_check(holder: Tensor, index: Tensor) -> bool:
+    """Device-side "is non-decreasing" of ``index`` (one host read), remembered ON the tensor object ``holder``
+    together with its version counter: a static graph pays the check on the first call only, and the memo can never
+    outlive the data it describes (an address-keyed cache would, once the allocator recycles the block)."""
+    memo = getattr(holder, "_b200_sorted", None)
+    if memo is not None and memo[0] == holder._version:
+        return memo[1]
+    idx = index.contiguous()
+    flag = torch.empty(1, dtype=torch.int32, device=idx.device)
+    L.call("tgpb200_rows_sorted", L.ptr(idx), idx.numel(), L.ptr(flag), L.stream())
+    hit = bool(flag.item())
+    try:
+        holder._b200_sorted = (holder._version, hit)
+    except (AttributeError, RuntimeError):
+        pass
+    return hit
 
 
 def is_sorted(index: Tensor) -> bool:
-    """Is the 1-D int64 tensor non-decreasing?  Checked on the device once per tensor (one host read) and cached by
-    storage / version, so a static graph pays it on the first call only."""
-    key = (index.data_ptr(), index.numel(), index._version, index.device.index)
-    hit = _SORTED_CACHE.get(key)
-    if hit is None:
-        idx = index.contiguous()
-        flag = torch.empty(1, dtype=torch.int32, device=idx.device)
-        L.call("tgpb200_rows_sorted", L.ptr(idx), idx.numel(), L.ptr(flag), L.stream())
-        hit = bool(flag.item())
-        if len(_SORTED_CACHE) > 256:
-            _SORTED_CACHE.clear()
-        _SORTED_CACHE[key] = hit
-    return hit
+    """Is the 1-D int64 tensor non-decreasing?"""
+    return _sorted_check(index, index)
 
 
 def rows_sorted(edge_index: Tensor) -> bool:
     """Is ``edge_index[0]`` non-decreasing (PyG datasets and every coalesced list are)?  Row-sorted lists take the
     sort-free deterministic normalisation sums and the row-bucketed coalesce."""
-    return is_sorted(edge_index[0])
+    return _sorted_check(edge_index, edge_index[0])
 
 
 class _FilterRelabel(torch.autograd.Function):
@@ -206,47 +210,75 @@ class _FilterRelabel(torch.autograd.Function):
         return gin, None, None, None, None, None, None, None
 
 
+PLAN_SYNC_MIN_EDGES = 1 << 20  # larger row-sorted inputs read the bucket plan back to size the launches exactly
+
+
 class _RemapCoalesce(torch.autograd.Function):
-    """Cluster branch: remap -> stable radix sort -> in-order combine -> filters -> compaction."""
+    """Cluster branch.  Row-sorted edge lists take the row-bucketed coalesce (gather the members' edge ranges per
+    coarse row, sort each short neighbour list in shared memory, combine in order; hub rows through the radix
+    sort); other inputs take the generic remap -> global stable radix sort -> in-order combine.  Both: filters and
+    one order-preserving compaction, identical results."""
 
     @staticmethod
-    def forward(ctx, edge_weight, row, col, cluster_index, num_nodes, num_clusters, op, flags, eps, padded=False):
+    def forward(ctx, edge_weight, row, col, cluster_index, num_nodes, num_clusters, op, flags, eps, padded=False,
+                csr=None):
         E = row.numel()
         dev = row.device
         lib = L.load()
-        ws = L.workspace(lib.tgpb200_remap_coalesce_workspace_bytes(E, num_clusters), dev)
+        weighted = edge_weight is not None
+        need_grad = weighted and ctx.needs_input_grad[0]
         count = torch.empty(1, dtype=torch.long, device=dev)
-        L.call("tgpb200_remap_coalesce_count", L.ptr(row), L.ptr(col), L.ptr(edge_weight), E, L.ptr(cluster_index),
-               num_nodes, num_clusters, op, flags, eps, L.ptr(count), L.ptr(ws), ws.numel(), L.stream())
+        run_aux = None
+        bucketed = csr is not None and E > 0 and E + num_nodes < 2 ** 31 - 1
+        if bucketed:
+            order, ptr = csr
+            ws = L.workspace(lib.tgpb200_bucket_coalesce_workspace_bytes(E, num_nodes, num_clusters), dev)
+            plan = torch.empty(4, dtype=torch.long, device=dev)
+            L.call("tgpb200_bucket_coalesce_plan", L.ptr(row), E, L.ptr(cluster_index), L.ptr(order), L.ptr(ptr),
+                   num_nodes, num_clusters, L.ptr(plan), L.ptr(ws), ws.numel(), L.stream())
+            virt_cap, hub_cap = -1, -1
+            if not padded and E >= PLAN_SYNC_MIN_EDGES:
+                virt_cap, hub_cap = plan[:2].tolist()  # one host read: exact launch sizes for large graphs
+            L.call("tgpb200_bucket_coalesce_count", L.ptr(row), L.ptr(col), L.ptr(edge_weight), E,
+                   L.ptr(cluster_index), L.ptr(order), L.ptr(ptr), num_nodes, num_clusters, op, flags, eps, virt_cap,
+                   hub_cap, int(need_grad), L.ptr(count), L.ptr(ws), ws.numel(), L.stream())
+        else:
+            ws = L.workspace(lib.tgpb200_remap_coalesce_workspace_bytes(E, num_clusters), dev)
+            L.call("tgpb200_remap_coalesce_count", L.ptr(row), L.ptr(col), L.ptr(edge_weight), E, L.ptr(cluster_index),
+                   num_nodes, num_clusters, op, flags, eps, L.ptr(count), L.ptr(ws), ws.numel(), L.stream())
         n_out = E if padded else _read_count(count)
         ei = torch.empty((2, n_out), dtype=torch.long, device=dev)
-        weighted = edge_weight is not None
         w_out = torch.empty(n_out, dtype=torch.float32, device=dev) if weighted else None
-        need_grad = weighted and ctx.needs_input_grad[0]
         slot = torch.empty(max(E, 1), dtype=torch.int32, device=dev) if need_grad else None
         run_len = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev) if need_grad else None
-        if n_out > 0:
+        if n_out > 0 and bucketed:
+            if need_grad and op == L.MUL:
+                run_aux = torch.empty(max(n_out, 1), dtype=torch.float32, device=dev)
+            L.call("tgpb200_bucket_coalesce_emit", E, num_nodes, num_clusters, int(weighted), virt_cap, L.ptr(ei[0]),
+                   L.ptr(ei[1]), L.ptr(w_out), L.ptr(slot), L.ptr(run_len), L.ptr(run_aux), L.ptr(ws), ws.numel(),
+                   L.stream())
+        elif n_out > 0:
             L.call("tgpb200_remap_coalesce_emit", E, num_clusters, int(weighted), flags, eps, L.ptr(ei[0]),
                    L.ptr(ei[1]), L.ptr(w_out), L.ptr(slot), L.ptr(run_len), L.ptr(ws), ws.numel(), L.stream())
         elif slot is not None:
             slot.fill_(-1)
         ctx.mark_non_differentiable(ei, count)
         if need_grad:
-            ctx.save_for_backward(edge_weight, w_out, slot, run_len)
+            ctx.save_for_backward(edge_weight, w_out, slot, run_len, run_aux)
         ctx.E, ctx.n_out, ctx.op = E, n_out, op
         return ei, w_out, count
 
     @staticmethod
     def backward(ctx, _gei, gw, _gc):
         if gw is None:
-            return (None,) * 10
-        w, w_out, slot, run_len = ctx.saved_tensors
+            return (None,) * 11
+        w, w_out, slot, run_len, run_aux = ctx.saved_tensors
         gin = torch.empty(ctx.E, dtype=torch.float32, device=gw.device)
         lib = L.load()
         ws = L.workspace(lib.tgpb200_coalesce_bwd_workspace_bytes(ctx.E, ctx.n_out, ctx.op), gw.device)
         L.call("tgpb200_coalesce_bwd", L.ptr(w), L.ptr(w_out), L.ptr(gw.contiguous()), L.ptr(slot), L.ptr(run_len),
-               ctx.E, ctx.n_out, ctx.op, L.ptr(gin), L.ptr(ws), ws.numel(), L.stream())
-        return gin, None, None, None, None, None, None, None, None, None
+               L.ptr(run_aux), ctx.E, ctx.n_out, ctx.op, L.ptr(gin), L.ptr(ws), ws.numel(), L.stream())
+        return gin, None, None, None, None, None, None, None, None, None, None
 
 
 def _norm_workspace(E: int, K: int, dev) -> Tensor:
@@ -377,7 +409,7 @@ def edge_postprocess(
 
 def _sparse_connect_core(edge_index, edge_weight, node_index, cluster_index, num_nodes, num_supernodes,
                          remove_self_loops, reduce_op, edge_weight_norm, batch_pooled, degree_norm, num_graphs,
-                         padded):
+                         padded, csr=None):
     w = _as_f32_weight(edge_weight)
     if reduce_op not in L.OPS:
         raise ValueError(f"unknown reduce_op '{reduce_op}'")
@@ -394,8 +426,13 @@ def _sparse_connect_core(edge_index, edge_weight, node_index, cluster_index, num
         ei, w, count = _FilterRelabel.apply(w, row, col, node_index.contiguous(), num_nodes, flags, EPS, padded)
     elif cluster_index is not None and len(cluster_index) == num_nodes:
         out_sorted = True  # coalesced output is lexicographic
-        ei, w, count = _RemapCoalesce.apply(w, row, col, cluster_index.contiguous(), num_nodes, num_supernodes,
-                                            L.OPS[reduce_op], flags, EPS, padded)
+        cluster_index = cluster_index.contiguous()
+        if rows_sorted(edge_index):  # row-bucketed coalesce over the cluster CSR (cached on the SelectOutput)
+            csr = csr if csr is not None else build_csr(cluster_index, num_supernodes)
+        else:
+            csr = None
+        ei, w, count = _RemapCoalesce.apply(w, row, col, cluster_index, num_nodes, num_supernodes,
+                                            L.OPS[reduce_op], flags, EPS, padded, csr)
     else:
         raise RuntimeError
     w = edge_postprocess(ei, w, num_supernodes, degree_norm, edge_weight_norm, batch_pooled, num_graphs,
@@ -416,6 +453,7 @@ def sparse_connect(
     batch_pooled: Optional[Tensor] = None,
     degree_norm: bool = False,
     num_graphs: Optional[int] = None,
+    csr: Optional[Tuple[Tensor, Tensor]] = None,
 ) -> Tuple[Tensor, Optional[Tensor]]:
     """Drop-in for ``tgp.connect.base_conn.sparse_connect`` (base_conn.py:57-112).
 
@@ -435,7 +473,7 @@ def sparse_connect(
         _validate_edge_index(edge_index)
     ei, w, _ = _sparse_connect_core(edge_index, edge_weight, node_index, cluster_index, num_nodes, num_supernodes,
                                     remove_self_loops, reduce_op, edge_weight_norm, batch_pooled, degree_norm,
-                                    num_graphs, False)
+                                    num_graphs, False, csr)
     if to_coo:  # tgp/connect/base_conn.py:107-110 -> connectivity_to_torch_coo
         if w is None:
             w = torch.ones(ei.size(1), device=ei.device)
@@ -456,6 +494,7 @@ def sparse_connect_padded(
     batch_pooled: Optional[Tensor] = None,
     degree_norm: bool = False,
     num_graphs: Optional[int] = None,
+    csr: Optional[Tuple[Tensor, Tensor]] = None,
 ) -> Tuple[Tensor, Optional[Tensor], Tensor]:
     """``sparse_connect`` without any host read: returns ``(edge_index [2, E], edge_weight [E], count)`` where only
     the first ``count`` (a device int64) columns are valid.  Every kernel bounds itself by the device-side count, so
@@ -467,7 +506,7 @@ def sparse_connect_padded(
         raise ValueError("sparse_connect_padded needs num_nodes (and num_graphs with edge_weight_norm): no host reads")
     return _sparse_connect_core(edge_index, edge_weight, node_index, cluster_index, num_nodes, num_supernodes,
                                 remove_self_loops, reduce_op, edge_weight_norm, batch_pooled, degree_norm, num_graphs,
-                                True)
+                                True, csr)
 
 
 # --------------------------------------------------------------------------- #

@@ -20,7 +20,9 @@ from . import _lib as L
 class GraphedStep:
     """Capture ``fn()`` into one CUDA graph.  ``fn`` must read its inputs from tensors that stay alive (their
     storage is baked into the graph), may call ``torch.autograd.backward`` (set ``.grad = None`` first so the
-    gradient buffers are allocated inside the capture and stay static), and must not synchronise."""
+    gradient buffers are allocated inside the capture and stay static), and must not synchronise.  Outputs of an
+    earlier eager call of the same step must be released before capturing: they keep that call's autograd graph
+    (and its AccumulateGrad nodes, bound to the default stream) alive, which CUDA rejects inside a capture."""
 
     def __init__(self, fn: Callable[[], Any], warmup: int = 3):
         if not torch.cuda.is_available():

@@ -107,7 +107,8 @@ def sparse_pool_padded(
     ei, ew, count = F_.sparse_connect_padded(
         edge_index, edge_weight, node_index=so.node_index, cluster_index=so.cluster_index, num_nodes=so.num_nodes,
         num_supernodes=so.num_supernodes, remove_self_loops=remove_self_loops, reduce_op=connect_op,
-        edge_weight_norm=edge_weight_norm, batch_pooled=batch_pool, degree_norm=degree_norm, num_graphs=num_graphs)
+        edge_weight_norm=edge_weight_norm, batch_pooled=batch_pool, degree_norm=degree_norm, num_graphs=num_graphs,
+        csr=F_.csr_of(so) if len(so.cluster_index) == so.num_nodes else None)
     return x_pool, ei, ew, batch_pool, count
 
 
