@@ -464,7 +464,8 @@ def test_bucketed_coalesce_matches_oracle(n, e, K, weighted):
         assert torch.equal(eg.cpu(), eo), op
         if weighted:
             # long runs are sequential fp32 sums (like the reference's own CPU path): 2e-5 against the exact value
-            torch.testing.assert_close(wg.detach().cpu().double(), wo, rtol=2e-5 if op != "mul" else 2e-4, atol=1e-6,
+            # (a 20 000-term fp32 product accumulates ~1e-3 of rounding: the mul bound scales with the run length)
+            torch.testing.assert_close(wg.detach().cpu().double(), wo, rtol=2e-5 if op != "mul" else 5e-3, atol=1e-6,
                                        msg=op)
             if op in ("sum", "mean"):
                 wc = w64.clone().requires_grad_(True)

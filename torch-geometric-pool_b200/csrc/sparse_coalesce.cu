@@ -10,7 +10,7 @@
 //   plan   fine row spans -> per-member entry counts -> exclusive scan ("virtual" positions: coarse row c owns
 //          [rowoff[c], rowoff[c+1]), rows in ascending order) -> hub rows (more than kBkHub entries) flagged
 //   tiles  one CTA per window of kBkTile virtual positions: gather the member ranges of the rows that start in the
-//          window, map columns through the cluster map, bitonic-sort (row, col, arrival) keys in shared memory,
+//          window, map columns through the cluster map, rank every entry inside its own (short) row by counting,
 //          combine each run in arrival (= original edge) order, apply the self-loop / tiny-weight filters and write
 //          the surviving coarse edges at their virtual positions
 //   hubs   coarse rows too long for a tile (power-law hubs) go through the radix sort restricted to their edges and
@@ -27,8 +27,8 @@ namespace tgp {
 
 constexpr int kBkThreads = 256;
 constexpr int kBkTile = 1536;  // virtual positions per tile window
-constexpr int kBkHub = 2560;   // coarse rows with more entries than this take the radix path
-constexpr int kBkCap = 4096;   // >= kBkTile + kBkHub, power of two (largest bitonic network)
+constexpr int kBkHub = 512;    // coarse rows with more entries than this take the radix path
+constexpr int kBkCap = 2048;   // >= kBkTile + kBkHub: entries (and members) a tile can hold
 constexpr int kBkLongRun = 4096;  // hub runs longer than this are combined by a whole block
 
 __device__ __forceinline__ int64_t clamp_cluster(int64_t c, int64_t K) { return (c < 0 || c >= K) ? K - 1 : c; }
@@ -121,23 +121,20 @@ struct BucketArgs {
   int32_t* slot_tmp;               // optional: virtual position of the run every input edge joined
 };
 
-// largest i in [0, n) with a[i] <= x   (a ascending, a[0] <= x)
-__device__ __forceinline__ int upper_slot(const int32_t* a, int n, int x) {
-  int lo = 0, hi = n;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (a[mid] <= x) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-
+// One CTA per window.  Entries are gathered in arrival order (grouped by coarse row, original edge order inside a
+// row), then every entry finds its rank inside its OWN row by counting (rows are short: 76 % of the entries of the
+// power-law workload sit in rows of <= 64, and nothing longer than kBkHub reaches a tile) -- no sorting network, no
+// block-wide synchronisation between steps, shared-memory reads that are broadcasts within a warp.
 static __global__ void __launch_bounds__(kBkThreads) k_bucket_tiles(BucketArgs A) {
-  extern __shared__ __align__(16) unsigned char bk_smem[];
-  unsigned long long* s_key = reinterpret_cast<unsigned long long*>(bk_smem);          // [kBkCap]
-  int32_t* m_voff = reinterpret_cast<int32_t*>(s_key + kBkCap);                          // [kBkCap + 1] tile-relative
-  int32_t* m_es = m_voff + kBkCap + 1;                                                   // [kBkCap] first edge or -1
-  int32_t* m_c = m_es + kBkCap;                                                          // [kBkCap] coarse row
-  uint16_t* m_rk = reinterpret_cast<uint16_t*>(m_c + kBkCap);                            // [kBkCap] row rank key
+  __shared__ uint32_t s_cc[kBkCap];     // coarse column per entry (arrival order), kDummy for a placeholder
+  __shared__ uint16_t s_mi[kBkCap];     // member of the entry
+  __shared__ uint16_t s_rk[kBkCap];     // first member of the entry's row (= row id inside the tile)
+  __shared__ uint16_t s_sorted[kBkCap];  // arrival index at every (row, column, arrival)-sorted position
+  __shared__ uint16_t m_voff[kBkCap + 1];  // member -> first entry (tile-relative)
+  __shared__ uint16_t m_rk[kBkCap];
+  __shared__ int32_t m_es[kBkCap];      // member -> first edge, -1 for an isolated node
+  __shared__ int32_t m_c[kBkCap];       // member -> coarse row
+  constexpr uint32_t kDummy = 0xffffffffu;
   const int tile = blockIdx.x;
   const int m_lo = A.tile_mlo[tile];
   int m_hi = A.tile_mlo[tile + 1];
@@ -154,66 +151,62 @@ static __global__ void __launch_bounds__(kBkThreads) k_bucket_tiles(BucketArgs A
     const int m = m_lo + i;
     const int v = A.order[m];
     const int s = A.rs[v], e = A.re[v];
-    m_voff[i] = A.voff[m] - tile_base;
+    m_voff[i] = (uint16_t)(A.voff[m] - tile_base);
     m_es[i] = e > s ? s : -1;
     const int c = A.mcrow[m];
     m_c[i] = c;
     m_rk[i] = (uint16_t)(A.ptr[c] - m_lo);  // first member of the row: ascending with the row, < n_mem
   }
-  if (threadIdx.x == 0) m_voff[n_mem] = n_ent;
-  int P = 64;
-  while (P < n_ent) P <<= 1;
+  if (threadIdx.x == 0) m_voff[n_mem] = (uint16_t)n_ent;
   __syncthreads();
-  // gather: entry j = (member, edge); key = (row rank | coarse column | arrival index)
-  for (int j = threadIdx.x; j < P; j += kBkThreads) {
-    unsigned long long key = ~0ull;
-    if (j < n_ent) {
-      const int mi = upper_slot(m_voff, n_mem, j);
-      const int es = m_es[mi];
-      if (es >= 0) {
-        const int64_t e = (int64_t)es + (j - m_voff[mi]);
-        int64_t q = __ldg(A.col + e);
-        if (q < 0 || q >= A.N) q = 0;
-        const int64_t cc = clamp_cluster(A.cluster[q], A.K);
-        key = ((unsigned long long)m_rk[mi] << 43) | ((unsigned long long)cc << 12) | (unsigned)j;
-      }
+  // gather: entry j -> (member, edge) -> coarse column
+  for (int j = threadIdx.x; j < n_ent; j += kBkThreads) {
+    int lo = 0, hi = n_mem;  // largest member with m_voff <= j
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (m_voff[mid] <= j) lo = mid; else hi = mid;
     }
-    s_key[j] = key;
+    const int es = m_es[lo];
+    uint32_t cc = kDummy;
+    if (es >= 0) {
+      int64_t q = __ldg(A.col + es + (j - m_voff[lo]));
+      if (q < 0 || q >= A.N) q = 0;
+      cc = (uint32_t)clamp_cluster(A.cluster[q], A.K);
+    }
+    s_cc[j] = cc;
+    s_mi[j] = (uint16_t)lo;
+    s_rk[j] = m_rk[lo];
   }
   __syncthreads();
-  // bitonic sort of P keys (keys are unique: no stability question)
-  for (int k = 2; k <= P; k <<= 1) {
-    for (int jj = k >> 1; jj > 0; jj >>= 1) {
-      for (int i = threadIdx.x; i < (P >> 1); i += kBkThreads) {
-        const int ix = 2 * i - (i & (jj - 1));
-        const int iy = ix + jj;
-        const unsigned long long a = s_key[ix], b = s_key[iy];
-        const bool asc = (ix & k) == 0;
-        if ((a > b) == asc) {
-          s_key[ix] = b;
-          s_key[iy] = a;
-        }
-      }
-      __syncthreads();
+  // rank inside the row: entries of the row with a smaller column, or the same column and an earlier arrival
+  for (int j = threadIdx.x; j < n_ent; j += kBkThreads) {
+    const uint32_t cc = s_cc[j];
+    const uint16_t rk = s_rk[j];
+    const int start = m_voff[rk];
+    int rank = 0;
+    for (int q = start; q < n_ent && s_rk[q] == rk; ++q) {
+      const uint32_t cq = s_cc[q];
+      rank += (cq < cc) || (cq == cc && q < j);
     }
+    s_sorted[start + rank] = (uint16_t)j;
   }
+  __syncthreads();
   // run heads combine their members in arrival order
-  for (int i = threadIdx.x; i < n_ent; i += kBkThreads) {
-    const unsigned long long key = s_key[i];
-    if (key == ~0ull) continue;
-    if (i > 0 && (s_key[i - 1] >> 12) == (key >> 12)) continue;
-    const int64_t cc = (int64_t)((key >> 12) & 0x7fffffffull);
-    int mi = upper_slot(m_voff, n_mem, (int)(key & 0xfffu));
-    const int64_t cr = m_c[mi];
-    const int tpos = tile_base + i;
+  for (int p = threadIdx.x; p < n_ent; p += kBkThreads) {
+    const int j = s_sorted[p];
+    const uint32_t cc = s_cc[j];
+    if (cc == kDummy) continue;
+    const uint16_t rk = s_rk[j];
+    if (p > (int)m_voff[rk] && s_cc[s_sorted[p - 1]] == cc) continue;  // same row, same column: not a head
+    const int64_t cr = m_c[s_mi[j]];
+    const int tpos = tile_base + p;
     float acc = 0.f, prod_nz = 1.f;
     int len = 0, zeros = 0;
-    for (int q = i; q < n_ent; ++q) {
-      const unsigned long long kq = s_key[q];
-      if ((kq >> 12) != (key >> 12)) break;
-      const int j = (int)(kq & 0xfffu);
-      mi = upper_slot(m_voff, n_mem, j);
-      const int64_t e = (int64_t)m_es[mi] + (j - m_voff[mi]);
+    for (int q = p; q < n_ent; ++q) {
+      const int jq = s_sorted[q];
+      if (s_rk[jq] != rk || s_cc[jq] != cc) break;
+      const int mi = s_mi[jq];
+      const int64_t e = (int64_t)m_es[mi] + (jq - m_voff[mi]);
       if (A.w) {
         const float v = A.w[e];
         acc = len == 0 ? v : combine_w(A.op, acc, v);
@@ -225,7 +218,7 @@ static __global__ void __launch_bounds__(kBkThreads) k_bucket_tiles(BucketArgs A
       ++len;
     }
     if (A.w && A.op == TGPB200_MEAN) acc = __fdiv_rn(acc, (float)len);
-    if (A.rsl && cr == cc) continue;
+    if (A.rsl && cr == (int64_t)cc) continue;
     if (A.w && !(fabsf(acc) > A.eps)) continue;
     A.t_row[tpos] = (int32_t)cr;
     A.t_col[tpos] = (int32_t)cc;
@@ -234,8 +227,6 @@ static __global__ void __launch_bounds__(kBkThreads) k_bucket_tiles(BucketArgs A
     if (A.t_aux) A.t_aux[tpos] = prod_nz;
   }
 }
-
-constexpr size_t kBkSmem = (size_t)kBkCap * 8 + (size_t)(kBkCap + 1) * 4 + (size_t)kBkCap * 4 * 2 + (size_t)kBkCap * 2 + 16;
 
 // ---- hub rows: radix sort of their edges only ------------------------------------------------------------------
 struct HubPred {
@@ -563,13 +554,8 @@ int tgpb200_bucket_coalesce_count(const int64_t* row, const int64_t* col, const 
     A.tile_mlo = pl.tile_mlo, A.voff = pl.voff, A.hubbits = pl.hubbits, A.N = N, A.K = K, A.op = op, A.rsl = rsl, A.eps = eps;
     A.t_row = pl.t_row, A.t_col = pl.t_col, A.t_len = slots ? pl.t_len : nullptr, A.t_w = pl.t_w;
     A.t_aux = aux ? pl.t_aux : nullptr, A.slot_tmp = slots ? pl.slot_tmp : nullptr;
-    static bool attr_set = false;
-    if (!attr_set) {
-      attr_set = true;
-      cudaFuncSetAttribute(k_bucket_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBkSmem);
-    }
     const int tiles = (int)ceil_div(virt_cap > 0 ? virt_cap : 1, kBkTile);
-    launch("k_bucket_tiles", k_bucket_tiles, (unsigned)tiles, kBkThreads, kBkSmem, st, A);
+    launch("k_bucket_tiles", k_bucket_tiles, (unsigned)tiles, kBkThreads, 0, st, A);
     if (hub_cap > 0) {
       const int cb = cb_of(K);
       HubPred pred{row, col, cluster_index, pl.hubbits, N, K, cb};
