@@ -457,7 +457,7 @@ def test_bucketed_coalesce_matches_oracle(n, e, K, weighted):
     so_c = R.OracleSelectOutput(cluster_index=cluster, num_supernodes=K)
     so_g = T.SelectOutput(cluster_index=cluster.to(DEV), num_supernodes=K)
     for op in (("sum", "mean", "max", "mul") if weighted else ("sum",)):
-        w64 = None if ew is None else (ew.double() if op != "mul" else (0.98 + 0.04 * ew.double()))
+        w64 = None if ew is None else (ew.double() if op != "mul" else (0.98 + 0.04 * (ew.double() - 0.5)))
         eo, wo = R.sparse_connect_so(ei, so_c, edge_weight=w64, reduce_op=op)
         wg_in = None if w64 is None else w64.float().to(DEV).requires_grad_(True)
         eg, wg = T.B200SparseConnect(op)(ei.to(DEV), so_g, edge_weight=wg_in)

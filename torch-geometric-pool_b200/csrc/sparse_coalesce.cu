@@ -25,7 +25,7 @@
 
 namespace tgp {
 
-constexpr int kBkThreads = 256;
+constexpr int kBkThreads = 512;
 constexpr int kBkTile = 1536;  // virtual positions per tile window
 constexpr int kBkHub = 512;    // coarse rows with more entries than this take the radix path
 constexpr int kBkCap = 2048;   // >= kBkTile + kBkHub: entries (and members) a tile can hold
@@ -109,7 +109,8 @@ struct BucketArgs {
   const int64_t* col;
   const float* w;  // null when unweighted
   const int64_t* cluster;
-  const int32_t *order, *ptr, *rs, *re, *mrowoff, *mcrow, *tile_mlo;
+  const int32_t *order, *ptr, *rs, *re, *mrowoff, *mcrow;
+  const int4* desc;
   const int* voff;
   const uint32_t* hubbits;
   int64_t N, K;
@@ -121,143 +122,258 @@ struct BucketArgs {
   int32_t* slot_tmp;               // optional: virtual position of the run every input edge joined
 };
 
+// tile descriptor {first member, one past the last member (hub row cut off), first virtual position, entries}
+static __global__ void k_tile_desc(const int32_t* __restrict__ tile_mlo, const int32_t* __restrict__ mcrow,
+                                   const int32_t* __restrict__ ptr, const int* __restrict__ voff,
+                                   const uint32_t* __restrict__ hubbits, int ntiles, int4* __restrict__ desc) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  const int m_lo = tile_mlo[t];
+  int m_hi = tile_mlo[t + 1];
+  if (m_lo < m_hi) {
+    const int cl = mcrow[m_hi - 1];  // at most one hub row starts in a window, and it is the last one
+    if ((hubbits[cl >> 5] >> (cl & 31)) & 1u) m_hi = ptr[cl];
+  }
+  int4 d = make_int4(m_lo, m_hi, 0, 0);
+  if (m_lo < m_hi) {
+    d.z = voff[m_lo];
+    d.w = voff[m_hi] - d.z;
+  }
+  desc[t] = d;
+}
+
 // One CTA per window.  Entries are gathered in arrival order (grouped by coarse row, original edge order inside a
 // row), then every entry finds its rank inside its OWN row by counting (rows are short: 76 % of the entries of the
 // power-law workload sit in rows of <= 64, and nothing longer than kBkHub reaches a tile) -- no sorting network, no
-// block-wide synchronisation between steps, shared-memory reads that are broadcasts within a warp.
+// block-wide synchronisation between steps, shared-memory reads that are broadcasts within a warp.  A thread owns
+// at most kBkPer = kBkCap / kBkThreads entries, so every phase is a fixed, fully unrolled loop whose global loads
+// are all issued before the first one is consumed.  kPacked: coarse column and arrival index share one 32-bit rank
+// key (column < 2^21), so that the counting loop is one compare per element on 128-bit shared-memory reads.
+constexpr int kBkPer = kBkCap / kBkThreads;
+
+template <bool kPacked>
 static __global__ void __launch_bounds__(kBkThreads) k_bucket_tiles(BucketArgs A) {
-  __shared__ uint32_t s_cc[kBkCap];     // coarse column per entry (arrival order), kDummy for a placeholder
-  __shared__ uint16_t s_mi[kBkCap];     // member of the entry
-  __shared__ uint16_t s_rk[kBkCap];     // first member of the entry's row (= row id inside the tile)
-  __shared__ uint16_t s_sorted[kBkCap];  // arrival index at every (row, column, arrival)-sorted position
+  __shared__ __align__(16) uint32_t s_cc[kBkCap + 4];  // rank key per entry (arrival order), kDummy for a placeholder
+  __shared__ uint16_t s_mi[kBkCap];       // member of the entry
+  __shared__ uint16_t s_sorted[kBkCap];   // arrival index at every (row, column, arrival)-sorted position
   __shared__ uint16_t m_voff[kBkCap + 1];  // member -> first entry (tile-relative)
-  __shared__ uint16_t m_rk[kBkCap];
-  __shared__ int32_t m_es[kBkCap];      // member -> first edge, -1 for an isolated node
-  __shared__ int32_t m_c[kBkCap];       // member -> coarse row
+  __shared__ uint16_t m_rk[kBkCap];       // member -> first member of its row (= row id inside the tile)
+  __shared__ uint16_t r_end[kBkCap];      // first member of a row -> one past the row's last entry
+  __shared__ int32_t m_es[kBkCap];        // member -> first edge, -1 for an isolated node
   constexpr uint32_t kDummy = 0xffffffffu;
-  const int tile = blockIdx.x;
-  const int m_lo = A.tile_mlo[tile];
-  int m_hi = A.tile_mlo[tile + 1];
+  const int4 desc = A.desc[blockIdx.x];
+  const int m_lo = desc.x, m_hi = desc.y, tile_base = desc.z, n_ent = desc.w;
   if (m_lo >= m_hi) return;
-  {
-    const int64_t cl = A.mcrow[m_hi - 1];  // at most one hub row starts in a window, and it is the last one
-    if ((A.hubbits[cl >> 5] >> (cl & 31)) & 1u) m_hi = A.ptr[cl];
-    if (m_lo >= m_hi) return;
-  }
-  const int tile_base = A.voff[m_lo];
-  const int n_ent = A.voff[m_hi] - tile_base;
   const int n_mem = m_hi - m_lo;
-  for (int i = threadIdx.x; i < n_mem; i += kBkThreads) {
-    const int m = m_lo + i;
-    const int v = A.order[m];
-    const int s = A.rs[v], e = A.re[v];
-    m_voff[i] = (uint16_t)(A.voff[m] - tile_base);
-    m_es[i] = e > s ? s : -1;
-    const int c = A.mcrow[m];
-    m_c[i] = c;
-    m_rk[i] = (uint16_t)(A.ptr[c] - m_lo);  // first member of the row: ascending with the row, < n_mem
+  {
+    int v[kBkPer], c[kBkPer];
+#pragma unroll
+    for (int k = 0; k < kBkPer; ++k) {
+      const int i = threadIdx.x + k * kBkThreads;
+      v[k] = i < n_mem ? A.order[m_lo + i] : 0;
+      c[k] = i < n_mem ? A.mcrow[m_lo + i] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < kBkPer; ++k) {
+      const int i = threadIdx.x + k * kBkThreads;
+      if (i < n_mem) {
+        const int s = A.rs[v[k]], e = A.re[v[k]];
+        m_voff[i] = (uint16_t)(A.voff[m_lo + i] - tile_base);
+        m_es[i] = e > s ? s : -1;
+        m_rk[i] = (uint16_t)(A.ptr[c[k]] - m_lo);  // first member of the row: ascending with the row, < n_mem
+      }
+    }
   }
   if (threadIdx.x == 0) m_voff[n_mem] = (uint16_t)n_ent;
   __syncthreads();
+  for (int i = threadIdx.x; i < n_mem; i += kBkThreads)
+    if (i + 1 == n_mem || m_rk[i + 1] != m_rk[i]) r_end[m_rk[i]] = m_voff[i + 1];
   // gather: entry j -> (member, edge) -> coarse column
-  for (int j = threadIdx.x; j < n_ent; j += kBkThreads) {
-    int lo = 0, hi = n_mem;  // largest member with m_voff <= j
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (m_voff[mid] <= j) lo = mid; else hi = mid;
+  {
+    int64_t e[kBkPer], q[kBkPer];
+    int mem[kBkPer];
+#pragma unroll
+    for (int k = 0; k < kBkPer; ++k) {
+      const int j = threadIdx.x + k * kBkThreads;
+      e[k] = -1;
+      mem[k] = 0;
+      if (j < n_ent) {
+        int lo = 0, hi = n_mem;  // largest member with m_voff <= j
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (m_voff[mid] <= j) lo = mid; else hi = mid;
+        }
+        mem[k] = lo;
+        const int es = m_es[lo];
+        if (es >= 0) e[k] = (int64_t)es + (j - m_voff[lo]);
+      }
     }
-    const int es = m_es[lo];
-    uint32_t cc = kDummy;
-    if (es >= 0) {
-      int64_t q = __ldg(A.col + es + (j - m_voff[lo]));
-      if (q < 0 || q >= A.N) q = 0;
-      cc = (uint32_t)clamp_cluster(A.cluster[q], A.K);
+#pragma unroll
+    for (int k = 0; k < kBkPer; ++k) q[k] = e[k] >= 0 ? __ldg(A.col + e[k]) : 0;
+#pragma unroll
+    for (int k = 0; k < kBkPer; ++k) {
+      if (q[k] < 0 || q[k] >= A.N) q[k] = 0;
+      q[k] = e[k] >= 0 ? __ldg(A.cluster + q[k]) : 0;
     }
-    s_cc[j] = cc;
-    s_mi[j] = (uint16_t)lo;
-    s_rk[j] = m_rk[lo];
+#pragma unroll
+    for (int k = 0; k < kBkPer; ++k) {
+      const int j = threadIdx.x + k * kBkThreads;
+      if (j < n_ent) {
+        const uint32_t cc = (uint32_t)clamp_cluster(q[k], A.K);
+        s_cc[j] = e[k] >= 0 ? (kPacked ? ((cc << 11) | (uint32_t)j) : cc) : kDummy;
+        s_mi[j] = (uint16_t)mem[k];
+      }
+    }
   }
   __syncthreads();
   // rank inside the row: entries of the row with a smaller column, or the same column and an earlier arrival
-  for (int j = threadIdx.x; j < n_ent; j += kBkThreads) {
+#pragma unroll 1
+  for (int k = 0; k < kBkPer; ++k) {
+    const int j = threadIdx.x + k * kBkThreads;
+    if (j >= n_ent) break;
     const uint32_t cc = s_cc[j];
-    const uint16_t rk = s_rk[j];
-    const int start = m_voff[rk];
+    const uint16_t rk = m_rk[s_mi[j]];
+    const int start = m_voff[rk], end = r_end[rk];
     int rank = 0;
-    for (int q = start; q < n_ent && s_rk[q] == rk; ++q) {
-      const uint32_t cq = s_cc[q];
-      rank += (cq < cc) || (cq == cc && q < j);
+    int q = start;
+    if (kPacked) {  // keys are unique (arrival index in the low bits); dummies (all ones) rank last, ties impossible
+      for (; (q & 3) && q < end; ++q) rank += s_cc[q] < cc;
+      for (; q + 4 <= end; q += 4) {
+        const uint4 c4 = *reinterpret_cast<const uint4*>(s_cc + q);
+        rank += (c4.x < cc) + (c4.y < cc) + (c4.z < cc) + (c4.w < cc);
+      }
+      for (; q < end; ++q) rank += s_cc[q] < cc;
+      if (cc == kDummy) {  // several placeholders of one row: order them by arrival
+        rank = 0;
+        for (q = start; q < end; ++q) rank += (s_cc[q] != kDummy) || q < j;
+      }
+    } else {
+      for (; q < end; ++q) {
+        const uint32_t cq = s_cc[q];
+        rank += (cq < cc) || (cq == cc && q < j);
+      }
     }
     s_sorted[start + rank] = (uint16_t)j;
   }
   __syncthreads();
-  // run heads combine their members in arrival order
-  for (int p = threadIdx.x; p < n_ent; p += kBkThreads) {
-    const int j = s_sorted[p];
-    const uint32_t cc = s_cc[j];
-    if (cc == kDummy) continue;
-    const uint16_t rk = s_rk[j];
-    if (p > (int)m_voff[rk] && s_cc[s_sorted[p - 1]] == cc) continue;  // same row, same column: not a head
-    const int64_t cr = m_c[s_mi[j]];
-    const int tpos = tile_base + p;
-    float acc = 0.f, prod_nz = 1.f;
-    int len = 0, zeros = 0;
-    for (int q = p; q < n_ent; ++q) {
-      const int jq = s_sorted[q];
-      if (s_rk[jq] != rk || s_cc[jq] != cc) break;
-      const int mi = s_mi[jq];
-      const int64_t e = (int64_t)m_es[mi] + (jq - m_voff[mi]);
-      if (A.w) {
-        const float v = A.w[e];
-        acc = len == 0 ? v : combine_w(A.op, acc, v);
-        if (A.t_aux) {
-          if (v == 0.f) ++zeros; else prod_nz = __fmul_rn(prod_nz, v);
+  // run heads combine their members in arrival order; the first member's weight of every head is loaded up front
+  {
+    constexpr uint32_t kColMask = kPacked ? ~0x7ffu : ~0u;
+    int64_t e0[kBkPer];
+    float w0[kBkPer];
+    int cr[kBkPer];
+    bool head[kBkPer];
+#pragma unroll
+    for (int k = 0; k < kBkPer; ++k) {
+      const int p = threadIdx.x + k * kBkThreads;
+      head[k] = false;
+      e0[k] = 0;
+      cr[k] = 0;
+      if (p < n_ent) {
+        const int j = s_sorted[p];
+        const uint32_t cc = s_cc[j];
+        const int mi = s_mi[j];
+        if (cc != kDummy && !(p > (int)m_voff[m_rk[mi]] && ((s_cc[s_sorted[p - 1]] ^ cc) & kColMask) == 0)) {
+          head[k] = true;
+          e0[k] = (int64_t)m_es[mi] + (j - m_voff[mi]);
+          cr[k] = m_lo + mi;
         }
       }
-      if (A.slot_tmp) A.slot_tmp[e] = tpos;
-      ++len;
     }
-    if (A.w && A.op == TGPB200_MEAN) acc = __fdiv_rn(acc, (float)len);
-    if (A.rsl && cr == (int64_t)cc) continue;
-    if (A.w && !(fabsf(acc) > A.eps)) continue;
-    A.t_row[tpos] = (int32_t)cr;
-    A.t_col[tpos] = (int32_t)cc;
-    if (A.w) A.t_w[tpos] = acc;
-    if (A.t_len) A.t_len[tpos] = (A.t_aux && A.op == TGPB200_MUL) ? zeros : len;
-    if (A.t_aux) A.t_aux[tpos] = prod_nz;
+#pragma unroll
+    for (int k = 0; k < kBkPer; ++k) {
+      w0[k] = (head[k] && A.w) ? __ldg(A.w + e0[k]) : 1.f;
+      cr[k] = head[k] ? __ldg(A.mcrow + cr[k]) : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < kBkPer; ++k) {
+      if (!head[k]) continue;
+      const int p = threadIdx.x + k * kBkThreads;
+      const int j = s_sorted[p];
+      const uint32_t cc = s_cc[j];
+      const int end = r_end[m_rk[s_mi[j]]];
+      const int tpos = tile_base + p;
+      float acc = w0[k], prod_nz = 1.f;
+      int len = 1, zeros = 0;
+      if (A.t_aux) {
+        if (acc == 0.f) zeros = 1; else prod_nz = acc;
+      }
+      if (A.slot_tmp) A.slot_tmp[e0[k]] = tpos;
+      for (int q = p + 1; q < end; ++q) {  // duplicates of the coarse edge (rare, short)
+        const int jq = s_sorted[q];
+        if (((s_cc[jq] ^ cc) & kColMask) != 0) break;
+        const int mi = s_mi[jq];
+        const int64_t e = (int64_t)m_es[mi] + (jq - m_voff[mi]);
+        if (A.w) {
+          const float v = A.w[e];
+          acc = combine_w(A.op, acc, v);
+          if (A.t_aux) {
+            if (v == 0.f) ++zeros; else prod_nz = __fmul_rn(prod_nz, v);
+          }
+        }
+        if (A.slot_tmp) A.slot_tmp[e] = tpos;
+        ++len;
+      }
+      const uint32_t col = kPacked ? (cc >> 11) : cc;
+      if (A.w && A.op == TGPB200_MEAN) acc = __fdiv_rn(acc, (float)len);
+      if (A.rsl && (uint32_t)cr[k] == col) continue;
+      if (A.w && !(fabsf(acc) > A.eps)) continue;
+      A.t_row[tpos] = cr[k];
+      A.t_col[tpos] = (int32_t)col;
+      if (A.w) A.t_w[tpos] = acc;
+      if (A.t_len) A.t_len[tpos] = (A.t_aux && A.op == TGPB200_MUL) ? zeros : len;
+      if (A.t_aux) A.t_aux[tpos] = prod_nz;
+    }
   }
 }
 
-// ---- hub rows: radix sort of their edges only ------------------------------------------------------------------
-struct HubPred {
+// The edges of the hub rows are enumerated through the hub MEMBERS (a compaction over the N members, not a scan of
+// all E edges): member list + degree prefix, then one thread per hub edge.  Order = (coarse row, node, edge) =
+// ascending original edge id inside a coarse row, so the stable sort keeps duplicates in arrival order.
+struct HubMemPred {
   struct Payload {
-    unsigned long long key;
+    int v, c, deg;
   };
-  const int64_t* row;
-  const int64_t* col;
-  const int64_t* cluster;
+  const int32_t *order, *mcrow, *rs, *re;
   const uint32_t* hubbits;
-  int64_t N, K;
-  int cb;
-  __device__ bool operator()(int64_t e, Payload& p) const {
-    const int64_t r = row[e];
-    if (r < 0 || r >= N) return false;
-    const int64_t c = clamp_cluster(cluster[r], K);
-    if (!((hubbits[c >> 5] >> (c & 31)) & 1u)) return false;
-    const int64_t q = col[e];
-    const int64_t cc = clamp_cluster(cluster[(q < 0 || q >= N) ? 0 : q], K);
-    p.key = ((unsigned long long)c << cb) | (unsigned long long)cc;
-    return true;
+  __device__ bool operator()(int64_t m, Payload& p) const {
+    p.c = mcrow[m];
+    if (!((hubbits[p.c >> 5] >> (p.c & 31)) & 1u)) return false;
+    p.v = order[m];
+    p.deg = re[p.v] - rs[p.v];
+    return p.deg > 0;
   }
 };
-struct HubEmit {
-  unsigned long long* keys;
-  uint32_t* vals;
-  __device__ void operator()(int64_t e, int pos, const HubPred::Payload& p) const {
-    keys[pos] = p.key;
-    vals[pos] = (uint32_t)e;
+struct HubMemEmit {
+  int32_t *hm_v, *hm_c;
+  int* hoff;
+  __device__ void operator()(int64_t, int pos, const HubMemPred::Payload& p) const {
+    hm_v[pos] = p.v;
+    hm_c[pos] = p.c;
+    hoff[pos] = p.deg;
   }
 };
+static __global__ void k_hub_edges(const int64_t* __restrict__ col, const int64_t* __restrict__ cluster,
+                                   const int32_t* __restrict__ rs, const int32_t* __restrict__ hm_v,
+                                   const int32_t* __restrict__ hm_c, const int* __restrict__ hoff,
+                                   const int64_t* __restrict__ n_mem_dev, const int64_t* __restrict__ n_edges_dev,
+                                   int64_t N, int64_t K, int cb, unsigned long long* __restrict__ keys,
+                                   uint32_t* __restrict__ vals) {
+  const int64_t n = *n_edges_dev;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lo = 0, hi = (int)*n_mem_dev;  // largest hub member with hoff <= i
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (hoff[mid] <= i) lo = mid; else hi = mid;
+  }
+  const int64_t e = (int64_t)rs[hm_v[lo]] + (i - hoff[lo]);
+  int64_t q = col[e];
+  if (q < 0 || q >= N) q = 0;
+  const int64_t cc = clamp_cluster(cluster[q], K);
+  keys[i] = ((unsigned long long)hm_c[lo] << cb) | (unsigned long long)cc;
+  vals[i] = (uint32_t)e;
+}
 
 static __global__ void k_hub_first(const unsigned long long* __restrict__ ks, const int64_t* __restrict__ n_dev, int cb,
                                    int32_t* __restrict__ hubfirst) {
@@ -434,6 +550,7 @@ static int cb_of(int64_t K) {
 // Workspace layout shared by plan / count / emit (carved identically in the three calls).
 struct BucketPlan {
   int32_t *rs, *re, *mrowoff, *mcrow, *tile_mlo, *hubfirst;
+  int4* desc;
   int* voff;
   uint32_t* hubbits;
   unsigned long long* plan;  // [4] device copy of the plan
@@ -442,6 +559,9 @@ struct BucketPlan {
   float *t_w, *t_aux;
   unsigned long long *hk0, *hk1;
   uint32_t *hv0, *hv1;
+  int32_t *hm_v, *hm_c;
+  int* hoff;
+  int64_t* hub_members;
   int* long_list;
   int* tile_counts;
   int64_t V;  // virtual capacity E + N
@@ -457,6 +577,7 @@ struct BucketPlan {
     mrowoff = ws.take<int32_t>(n);
     mcrow = ws.take<int32_t>(n);
     tile_mlo = ws.take<int32_t>((size_t)ntiles + 2);
+    desc = ws.take<int4>((size_t)ntiles + 1);
     hubbits = ws.take<uint32_t>((size_t)(K / 32 + 1));
     hubfirst = ws.take<int32_t>((size_t)(K > 0 ? K : 1));
     plan = ws.take<unsigned long long>(4);
@@ -472,6 +593,10 @@ struct BucketPlan {
     hk1 = ws.take<unsigned long long>(e);
     hv0 = ws.take<uint32_t>(e);
     hv1 = ws.take<uint32_t>(e);
+    hm_v = ws.take<int32_t>(n);
+    hm_c = ws.take<int32_t>(n);
+    hoff = ws.take<int>(n + 1);
+    hub_members = ws.take<int64_t>(1);
     long_list = ws.take<int>(e / kBkLongRun + 2);
     tile_counts = ws.take<int>((size_t)ceil_div(v, kCompactTile) + 1);
     ok = ws.ok;
@@ -486,10 +611,10 @@ extern "C" {
 
 size_t tgpb200_bucket_coalesce_workspace_bytes(int64_t E, int64_t N, int64_t K) {
   const size_t n = (size_t)(N > 0 ? N : 1), e = (size_t)(E > 0 ? E : 1), v = n + e;
-  return 5 * align_up((n + 1) * 4) + align_up((v / kBkTile + 4) * 4) + align_up((size_t)(K / 32 + 1) * 4) +
+  return 8 * align_up((n + 1) * 4) + 256 + 5 * align_up((v / kBkTile + 4) * 4) + align_up((size_t)(K / 32 + 1) * 4) +
          align_up((size_t)(K > 0 ? K : 1) * 4) + 2 * 256 + 6 * align_up(v * 4) + align_up(e * 4) + 2 * align_up(e * 8) +
          2 * align_up(e * 4) + align_up((e / kBkLongRun + 2) * 4) + align_up((v / kCompactTile + 2) * 4) +
-         scan_workspace_bytes(N + 1) + radix_sort_workspace_bytes(E) + compact_onepass_workspace_bytes(E) + 8192;
+         2 * scan_workspace_bytes(N + 1) + radix_sort_workspace_bytes(E) + compact_onepass_workspace_bytes(N) + 8192;
 }
 
 // Phase 0: virtual layout of the coarse rows.  plan_out (device int64[4]) = {virtual entries, hub edges, hub rows, 0}.
@@ -519,6 +644,8 @@ int tgpb200_bucket_coalesce_plan(const int64_t* row, int64_t E, const int64_t* c
   launch("k_fill_i32", k_fill_i32, (unsigned)ceil_div(pl.ntiles + 2, 256), 256, 0, st, pl.tile_mlo,
          (int64_t)pl.ntiles + 2, (int32_t)N);
   launch("k_tile_bounds", k_tile_bounds, (unsigned)ceil_div(N, 256), 256, 0, st, pl.mrowoff, N, pl.ntiles + 1, pl.tile_mlo);
+  launch("k_tile_desc", k_tile_desc, (unsigned)ceil_div(pl.ntiles, 256), 256, 0, st, pl.tile_mlo, pl.mcrow, ptr, pl.voff,
+         pl.hubbits, pl.ntiles, pl.desc);
   cudaMemcpyAsync(plan_out, pl.plan, 4 * sizeof(int64_t), cudaMemcpyDeviceToDevice, st);
   return launch_status();
 }
@@ -551,17 +678,25 @@ int tgpb200_bucket_coalesce_count(const int64_t* row, const int64_t* col, const 
     BucketArgs A;
     A.col = col, A.w = edge_weight, A.cluster = cluster_index;
     A.order = order, A.ptr = ptr, A.rs = pl.rs, A.re = pl.re, A.mrowoff = pl.mrowoff, A.mcrow = pl.mcrow;
-    A.tile_mlo = pl.tile_mlo, A.voff = pl.voff, A.hubbits = pl.hubbits, A.N = N, A.K = K, A.op = op, A.rsl = rsl, A.eps = eps;
+    A.desc = pl.desc, A.voff = pl.voff, A.hubbits = pl.hubbits, A.N = N, A.K = K, A.op = op, A.rsl = rsl, A.eps = eps;
     A.t_row = pl.t_row, A.t_col = pl.t_col, A.t_len = slots ? pl.t_len : nullptr, A.t_w = pl.t_w;
     A.t_aux = aux ? pl.t_aux : nullptr, A.slot_tmp = slots ? pl.slot_tmp : nullptr;
     const int tiles = (int)ceil_div(virt_cap > 0 ? virt_cap : 1, kBkTile);
-    launch("k_bucket_tiles", k_bucket_tiles, (unsigned)tiles, kBkThreads, 0, st, A);
+    if (K < (1 << 21))
+      launch("k_bucket_tiles", k_bucket_tiles<true>, (unsigned)tiles, kBkThreads, 0, st, A);
+    else
+      launch("k_bucket_tiles", k_bucket_tiles<false>, (unsigned)tiles, kBkThreads, 0, st, A);
     if (hub_cap > 0) {
       const int cb = cb_of(K);
-      HubPred pred{row, col, cluster_index, pl.hubbits, N, K, cb};
-      HubEmit emit{pl.hk0, pl.hv0};
-      int rc = compact_onepass(pred, emit, E, pl.hub_count, ws, st);
+      HubMemPred pred{order, pl.mcrow, pl.rs, pl.re, pl.hubbits};
+      HubMemEmit emit{pl.hm_v, pl.hm_c, pl.hoff};
+      cudaMemsetAsync(pl.hoff, 0, (size_t)(N + 1) * sizeof(int), st);
+      int rc = compact_onepass(pred, emit, N, pl.hub_members, ws, st);
       if (rc != TGPB200_OK) return rc;
+      rc = exclusive_scan_i32(pl.hoff, pl.hoff, N + 1, nullptr, pl.hub_count, ws, st);
+      if (rc != TGPB200_OK) return rc;
+      launch("k_hub_edges", k_hub_edges, (unsigned)ceil_div(hub_cap, 256), 256, 0, st, col, cluster_index, pl.rs, pl.hm_v,
+             pl.hm_c, pl.hoff, pl.hub_members, pl.hub_count, N, K, cb, pl.hk0, pl.hv0);
       bool in1 = false;
       rc = radix_sort_pairs<unsigned long long>(pl.hk0, pl.hv0, pl.hv0, pl.hk1, pl.hv1, hub_cap, 2 * cb, &in1, ws, st,
                                                 pl.hub_count);
