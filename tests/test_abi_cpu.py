@@ -78,3 +78,37 @@ def test_select_output_mirror_matches_oracle():
     assert torch.equal(a.node_index, b.node_index) and torch.equal(a.cluster_index, b.cluster_index)
     assert torch.equal(a.weight, b.weight) and a.num_nodes == 12 and a.num_supernodes == 4
     assert repr(T.B200Reduce()) == "B200Reduce(reduce_op=sum)"
+
+
+def test_torch_custom_ops_registered_with_fake_kernels():
+    """the path's operators are torch custom ops (dispatcher schemas, fake kernels, autograd)."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    from tgp_b200 import ops
+
+    for name in ops.OP_NAMES:
+        assert hasattr(torch.ops.tgp_b200, name), name
+    schema = str(torch.ops.tgp_b200.stas_fused.default._schema)
+    assert "Tensor? x" in schema and "Tensor? adj" in schema and "int loss_kind" in schema
+    with FakeTensorMode():  # shape propagation without a device (what torch.compile / export trace through)
+        s = torch.empty(4, 32, 8, device="cuda")
+        x = torch.empty(4, 32, 16, device="cuda")
+        a = torch.empty(4, 32, 32, device="cuda")
+        xp, ap, losses, saved = torch.ops.tgp_b200.stas_fused(x, a, s, 3, 1, 1.0, 1.0)
+        assert xp.shape == (4, 8, 16) and ap.shape == (4, 8, 8) and losses.shape == (4,) and saved.dtype == torch.uint8
+        xp, ap, _, _ = torch.ops.tgp_b200.stas_fused(None, a, s, 0, 0, 1.0, 1.0)
+        assert xp.numel() == 0 and ap.shape == (4, 8, 8)
+        idx = torch.empty(100, dtype=torch.long, device="cuda")
+        order, ptr = torch.ops.tgp_b200.build_csr(idx, 7)
+        assert order.dtype == torch.int32 and ptr.shape == (8,)
+        feats = torch.empty(100, 12, device="cuda")
+        assert torch.ops.tgp_b200.segment_reduce(feats, idx, idx, None, order, ptr, 7, 0).shape == (7, 12)
+        ei, w, src, cnt = torch.ops.tgp_b200.filter_relabel_edges(idx, idx, None, idx, 50, 1, 1e-8, True, False)
+        assert ei.shape == (2, 100) and w.numel() == 0 and cnt.shape == (1,)
+        wts = torch.empty(100, device="cuda")
+        out = torch.ops.tgp_b200.remap_coalesce(idx, idx, wts, idx, None, None, 100, 7, 0, 1, 1e-8, True, True)
+        assert out[0].shape == (2, 100) and out[1].shape == (100,) and out[2].shape == (100,)
+        assert torch.ops.tgp_b200.degree_norm(wts, idx, idx, 7, 1e-8, True, None)[0].shape == (100,)
+    with pytest.raises(NotImplementedError):  # no CPU kernel by design
+        torch.ops.tgp_b200.stas_fused(None, None, torch.zeros(1, 2, 2), 0, 0, 1.0, 1.0)

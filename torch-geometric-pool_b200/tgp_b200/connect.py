@@ -224,8 +224,9 @@ class B200DenseConnect(Connect):
         n_super = B * K
         flags = F_.L.REMOVE_SELF_LOOPS if self.remove_self_loops else 0
         ident = torch.arange(n_super, device=s.device)
-        ei, ew, _ = F_._FilterRelabel.apply(ew.to(torch.float32), ei[0].contiguous(), ei[1].contiguous(), ident, n_super,
-                                            flags, F_.EPS)
+        ew32 = ew.to(torch.float32)
+        ei, ew, _, _ = F_.O.filter_relabel_edges(ei[0].contiguous(), ei[1].contiguous(), ew32, ident, n_super, flags,
+                                                 F_.EPS, False, ew32.requires_grad)
         ew = F_.edge_postprocess(ei, ew, n_super, self.degree_norm, self.edge_weight_norm, batch_pooled,
                                  sorted_rows=True)  # block-diagonal order is row-major
         if to_coo:

@@ -1,7 +1,10 @@
-"""Functional layer: autograd wiring around the C-ABI kernels.
+"""Functional layer: the reference's functional API on top of the ``torch.ops.tgp_b200.*`` custom ops.
 
-Every function here launches kernels from ``libtgp_b200.so`` through ``_lib.call`` on the
-current CUDA stream.  There is no eager / CPU fallback: CPU tensors raise ``RuntimeError``.
+The differentiable operators of the path are torch custom ops (``tgp_b200/ops.py``: C++ dispatcher ops for the
+dense path and the segment reduce, ``torch.library.custom_op`` for the sparse connect), each with a fake kernel and
+a registered autograd formula; the helpers here (dense pre-processing, block-diagonal output) call the C ABI of
+``libtgp_b200.so`` through ``_lib.call`` directly.  Everything runs on the current CUDA stream.  There is no eager /
+CPU fallback: CPU tensors raise ``RuntimeError``.
 """
 from __future__ import annotations
 
@@ -11,8 +14,10 @@ import torch
 from torch import Tensor
 
 from . import _lib as L
+from . import ops as O
 
 EPS = 1e-8  # tgp/__init__.py:6
+_T = torch.ops.tgp_b200
 
 
 def _require_cuda(*tensors) -> None:
@@ -26,15 +31,7 @@ def _require_cuda(*tensors) -> None:
 # --------------------------------------------------------------------------- #
 def build_csr(cluster_index: Tensor, num_clusters: int) -> Tuple[Tensor, Tensor]:
     _require_cuda(cluster_index)
-    cluster_index = cluster_index.contiguous()
-    nnz = cluster_index.numel()
-    dev = cluster_index.device
-    order = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-    ptr = torch.empty(num_clusters + 1, dtype=torch.int32, device=dev)
-    ws = L.workspace(L.load().tgpb200_build_csr_workspace_bytes(nnz, num_clusters), dev)
-    L.call("tgpb200_build_csr", L.ptr(cluster_index), nnz, num_clusters, L.ptr(order), L.ptr(ptr), L.ptr(ws),
-           ws.numel(), L.stream())
-    return order, ptr
+    return _T.build_csr(cluster_index.contiguous(), num_clusters)
 
 
 def csr_of(so) -> Tuple[Tensor, Tensor]:
@@ -51,37 +48,6 @@ def csr_of(so) -> Tuple[Tensor, Tensor]:
 # --------------------------------------------------------------------------- #
 # Sparse reduce
 # --------------------------------------------------------------------------- #
-class _SegmentReduce(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, weight, node_index, cluster_index, order, ptr, num_clusters, op, out_dtype):
-        N, F = x.shape
-        nnz = node_index.numel()
-        out = torch.empty((num_clusters, F), dtype=out_dtype, device=x.device)
-        L.call("tgpb200_segment_reduce_fwd", L.ptr(x), L.ptr(node_index), L.ptr(weight), L.ptr(order), L.ptr(ptr), N,
-               nnz, num_clusters, F, op, L.dtype_code(x.dtype), L.dtype_code(out_dtype), L.ptr(out), L.stream())
-        ctx.save_for_backward(x, weight, node_index, cluster_index, order, ptr, out)
-        ctx.op, ctx.K = op, num_clusters
-        return out
-
-    @staticmethod
-    def backward(ctx, g):
-        x, weight, node_index, cluster_index, order, ptr, out = ctx.saved_tensors
-        N, F = x.shape
-        nnz = node_index.numel()
-        g = g.contiguous()
-        if g.dtype != x.dtype:
-            raise RuntimeError("tgp_b200 segment_reduce backward: mixed x / output dtypes are not supported")
-        gx = torch.empty_like(x)
-        need_w = weight is not None and ctx.needs_input_grad[1]
-        gw = torch.empty(nnz, dtype=torch.float32, device=x.device) if need_w else None
-        lib = L.load()
-        ws = L.workspace(lib.tgpb200_segment_reduce_bwd_workspace_bytes(nnz, ctx.K, F, ctx.op), x.device)
-        L.call("tgpb200_segment_reduce_bwd", L.ptr(x), L.ptr(node_index), L.ptr(cluster_index), L.ptr(weight),
-               L.ptr(order), L.ptr(ptr), L.ptr(out), L.ptr(g), N, nnz, ctx.K, F, ctx.op, L.dtype_code(x.dtype),
-               L.dtype_code(g.dtype), L.ptr(gx), L.ptr(gw), L.ptr(ws), ws.numel(), L.stream())
-        return gx, gw, None, None, None, None, None, None, None
-
-
 def segment_reduce(
     x: Tensor,
     node_index: Tensor,
@@ -109,8 +75,8 @@ def segment_reduce(
     x = x.contiguous()
     w32 = None if weight is None else weight.to(torch.float32).contiguous()
     order, ptr = csr if csr is not None else build_csr(cluster_index, num_clusters)
-    return _SegmentReduce.apply(x, w32, node_index.contiguous(), cluster_index.contiguous(), order, ptr, num_clusters,
-                                L.OPS[op], out_dtype)
+    return _T.segment_reduce(x, node_index.contiguous(), cluster_index.contiguous(), w32, order, ptr, num_clusters,
+                             L.OPS[op])
 
 
 def reduce_batch_sparse(so, batch: Tensor) -> Tensor:
@@ -158,190 +124,6 @@ def rows_sorted(edge_index: Tensor) -> bool:
     """Is ``edge_index[0]`` non-decreasing (PyG datasets and every coalesced list are)?  Row-sorted lists take the
     sort-free deterministic normalisation sums and the row-bucketed coalesce."""
     return _sorted_check(edge_index, edge_index[0])
-
-
-class _FilterRelabel(torch.autograd.Function):
-    """Kept-node branch + self-loop / tiny-weight filters (one order-preserving compaction).
-
-    ``padded=False``: exact-size outputs (one host read of the survivor count).  ``padded=True``: capacity-``E``
-    outputs plus the device-side count, no host read (CUDA-graph capturable)."""
-
-    @staticmethod
-    def forward(ctx, edge_weight, row, col, node_index, num_nodes, flags, eps, padded=False):
-        E = row.numel()
-        dev = row.device
-        lib = L.load()
-        need_grad = edge_weight is not None and ctx.needs_input_grad[0]
-        # single pass over the edge list (decoupled look-back compaction) into capacity-E buffers
-        ws = L.workspace(lib.tgpb200_filter_relabel_onepass_workspace_bytes(E, num_nodes), dev)
-        count = torch.empty(1, dtype=torch.long, device=dev)
-        cap = max(E, 1)
-        ei_c = torch.empty((2, cap), dtype=torch.long, device=dev)
-        w_c = None if edge_weight is None else torch.empty(cap, dtype=torch.float32, device=dev)
-        src_c = torch.empty(cap, dtype=torch.int32, device=dev) if need_grad else None
-        L.call("tgpb200_filter_relabel_onepass", L.ptr(row), L.ptr(col), L.ptr(edge_weight), E, L.ptr(node_index),
-               node_index.numel(), num_nodes, flags, eps, L.ptr(ei_c[0]), L.ptr(ei_c[1]), L.ptr(w_c), L.ptr(src_c),
-               L.ptr(count), L.ptr(ws), ws.numel(), L.stream())
-        ctx.E, ctx.padded = E, padded
-        if padded:
-            ctx.mark_non_differentiable(ei_c, count)
-            if need_grad:
-                ctx.save_for_backward(src_c, count)
-            ctx.n_out = E
-            return ei_c[:, :E], (None if w_c is None else w_c[:E]), count
-        n_out = _read_count(count)  # sizes the exact, contiguous outputs
-        ei = ei_c[:, :n_out].contiguous()
-        w_out = None if edge_weight is None else w_c[:n_out].clone()
-        src = src_c[:max(n_out, 1)].clone() if need_grad else None
-        ctx.mark_non_differentiable(ei, count)
-        if need_grad:
-            ctx.save_for_backward(src, None)
-        ctx.n_out = n_out
-        return ei, w_out, count
-
-    @staticmethod
-    def backward(ctx, _gei, gw, _gc):
-        if gw is None:
-            return (None,) * 8
-        src, count = ctx.saved_tensors
-        gin = torch.empty(ctx.E, dtype=torch.float32, device=gw.device)
-        L.call("tgpb200_filter_relabel_bwd", L.ptr(gw.contiguous()), L.ptr(src), ctx.n_out, L.ptr(count), ctx.E,
-               L.ptr(gin), L.stream())
-        return gin, None, None, None, None, None, None, None
-
-
-PLAN_SYNC_MIN_EDGES = 1 << 20  # larger row-sorted inputs read the bucket plan back to size the launches exactly
-
-
-class _RemapCoalesce(torch.autograd.Function):
-    """Cluster branch.  Row-sorted edge lists take the row-bucketed coalesce (gather the members' edge ranges per
-    coarse row, sort each short neighbour list in shared memory, combine in order; hub rows through the radix
-    sort); other inputs take the generic remap -> global stable radix sort -> in-order combine.  Both: filters and
-    one order-preserving compaction, identical results."""
-
-    @staticmethod
-    def forward(ctx, edge_weight, row, col, cluster_index, num_nodes, num_clusters, op, flags, eps, padded=False,
-                csr=None):
-        E = row.numel()
-        dev = row.device
-        lib = L.load()
-        weighted = edge_weight is not None
-        need_grad = weighted and ctx.needs_input_grad[0]
-        count = torch.empty(1, dtype=torch.long, device=dev)
-        run_aux = None
-        bucketed = csr is not None and E > 0 and E + num_nodes < 2 ** 31 - 1
-        if bucketed:
-            order, ptr = csr
-            ws = L.workspace(lib.tgpb200_bucket_coalesce_workspace_bytes(E, num_nodes, num_clusters), dev)
-            plan = torch.empty(4, dtype=torch.long, device=dev)
-            L.call("tgpb200_bucket_coalesce_plan", L.ptr(row), E, L.ptr(cluster_index), L.ptr(order), L.ptr(ptr),
-                   num_nodes, num_clusters, L.ptr(plan), L.ptr(ws), ws.numel(), L.stream())
-            virt_cap, hub_cap = -1, -1
-            if not padded and E >= PLAN_SYNC_MIN_EDGES:
-                virt_cap, hub_cap = plan[:2].tolist()  # one host read: exact launch sizes for large graphs
-            L.call("tgpb200_bucket_coalesce_count", L.ptr(row), L.ptr(col), L.ptr(edge_weight), E,
-                   L.ptr(cluster_index), L.ptr(order), L.ptr(ptr), num_nodes, num_clusters, op, flags, eps, virt_cap,
-                   hub_cap, int(need_grad), L.ptr(count), L.ptr(ws), ws.numel(), L.stream())
-        else:
-            ws = L.workspace(lib.tgpb200_remap_coalesce_workspace_bytes(E, num_clusters), dev)
-            L.call("tgpb200_remap_coalesce_count", L.ptr(row), L.ptr(col), L.ptr(edge_weight), E, L.ptr(cluster_index),
-                   num_nodes, num_clusters, op, flags, eps, L.ptr(count), L.ptr(ws), ws.numel(), L.stream())
-        n_out = E if padded else _read_count(count)
-        ei = torch.empty((2, n_out), dtype=torch.long, device=dev)
-        w_out = torch.empty(n_out, dtype=torch.float32, device=dev) if weighted else None
-        slot = torch.empty(max(E, 1), dtype=torch.int32, device=dev) if need_grad else None
-        run_len = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev) if need_grad else None
-        if n_out > 0 and bucketed:
-            if need_grad and op == L.MUL:
-                run_aux = torch.empty(max(n_out, 1), dtype=torch.float32, device=dev)
-            L.call("tgpb200_bucket_coalesce_emit", E, num_nodes, num_clusters, int(weighted), virt_cap, L.ptr(ei[0]),
-                   L.ptr(ei[1]), L.ptr(w_out), L.ptr(slot), L.ptr(run_len), L.ptr(run_aux), L.ptr(ws), ws.numel(),
-                   L.stream())
-        elif n_out > 0:
-            L.call("tgpb200_remap_coalesce_emit", E, num_clusters, int(weighted), flags, eps, L.ptr(ei[0]),
-                   L.ptr(ei[1]), L.ptr(w_out), L.ptr(slot), L.ptr(run_len), L.ptr(ws), ws.numel(), L.stream())
-        elif slot is not None:
-            slot.fill_(-1)
-        ctx.mark_non_differentiable(ei, count)
-        if need_grad:
-            ctx.save_for_backward(edge_weight, w_out, slot, run_len, run_aux)
-        ctx.E, ctx.n_out, ctx.op = E, n_out, op
-        return ei, w_out, count
-
-    @staticmethod
-    def backward(ctx, _gei, gw, _gc):
-        if gw is None:
-            return (None,) * 11
-        w, w_out, slot, run_len, run_aux = ctx.saved_tensors
-        gin = torch.empty(ctx.E, dtype=torch.float32, device=gw.device)
-        lib = L.load()
-        ws = L.workspace(lib.tgpb200_coalesce_bwd_workspace_bytes(ctx.E, ctx.n_out, ctx.op), gw.device)
-        L.call("tgpb200_coalesce_bwd", L.ptr(w), L.ptr(w_out), L.ptr(gw.contiguous()), L.ptr(slot), L.ptr(run_len),
-               L.ptr(run_aux), ctx.E, ctx.n_out, ctx.op, L.ptr(gin), L.ptr(ws), ws.numel(), L.stream())
-        return gin, None, None, None, None, None, None, None, None, None, None
-
-
-def _norm_workspace(E: int, K: int, dev) -> Tensor:
-    return L.workspace(L.load().tgpb200_edge_norm_workspace_bytes(E, K), dev)
-
-
-class _DegreeNorm(torch.autograd.Function):
-    """``w * dinv[row] * dinv[col]`` with ``deg = scatter_sum(w, row)`` as a deterministic segmented sum.
-    ``count`` (optional device int64) bounds the edges of a padded list."""
-
-    @staticmethod
-    def forward(ctx, w, row, col, num_clusters, eps, sorted_rows, count):
-        E = row.numel()
-        dev = row.device
-        deg = torch.empty(max(num_clusters, 1), dtype=torch.float32, device=dev)
-        out = torch.empty(E, dtype=torch.float32, device=dev)
-        ws = _norm_workspace(E, num_clusters, dev)
-        L.call("tgpb200_degree_norm_fwd", L.ptr(row), L.ptr(col), L.ptr(w), E, L.ptr(count), num_clusters, eps,
-               int(sorted_rows), L.ptr(deg), L.ptr(out), L.ptr(ws), ws.numel(), L.stream())
-        ctx.save_for_backward(w, row, col, deg, count)
-        ctx.K, ctx.eps, ctx.sorted_rows = num_clusters, eps, sorted_rows
-        return out
-
-    @staticmethod
-    def backward(ctx, g):
-        w, row, col, deg, count = ctx.saved_tensors
-        if w is None:
-            return (None,) * 7
-        E = row.numel()
-        gd = torch.empty(max(ctx.K, 1), dtype=torch.float32, device=g.device)
-        gw = torch.empty(E, dtype=torch.float32, device=g.device)
-        ws = _norm_workspace(E, ctx.K, g.device)
-        L.call("tgpb200_degree_norm_bwd", L.ptr(row), L.ptr(col), L.ptr(w), L.ptr(deg), L.ptr(g.contiguous()), E,
-               L.ptr(count), ctx.K, ctx.eps, int(ctx.sorted_rows), L.ptr(gd), L.ptr(gw), L.ptr(ws), ws.numel(),
-               L.stream())
-        return gw, None, None, None, None, None, None
-
-
-class _WeightNorm(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, w, row, batch_pooled, num_clusters, num_graphs, sorted_rows, count):
-        E = row.numel()
-        dev = row.device
-        mx = torch.empty(max(num_graphs, 1), dtype=torch.float32, device=dev)
-        arg = torch.empty(max(num_graphs, 1), dtype=torch.int32, device=dev)
-        out = torch.empty(E, dtype=torch.float32, device=dev)
-        L.call("tgpb200_weight_norm_fwd", L.ptr(row), L.ptr(w), L.ptr(batch_pooled), E, L.ptr(count), num_graphs,
-               L.ptr(mx), L.ptr(arg), L.ptr(out), L.stream())
-        ctx.save_for_backward(w, row, batch_pooled, mx, arg, count)
-        ctx.G, ctx.K, ctx.sorted_rows = num_graphs, num_clusters, sorted_rows
-        return out
-
-    @staticmethod
-    def backward(ctx, g):
-        w, row, batch_pooled, mx, arg, count = ctx.saved_tensors
-        E = row.numel()
-        acc = torch.empty(max(ctx.G, 1), dtype=torch.float32, device=g.device)
-        gw = torch.empty(E, dtype=torch.float32, device=g.device)
-        ws = _norm_workspace(E, max(ctx.K, ctx.G), g.device)
-        L.call("tgpb200_weight_norm_bwd", L.ptr(row), L.ptr(w), L.ptr(batch_pooled), L.ptr(mx), L.ptr(arg),
-               L.ptr(g.contiguous()), E, L.ptr(count), ctx.K, ctx.G, int(ctx.sorted_rows), L.ptr(acc), L.ptr(gw),
-               L.ptr(ws), ws.numel(), L.stream())
-        return gw, None, None, None, None, None, None
 
 
 def _as_f32_weight(edge_weight: Optional[Tensor]) -> Optional[Tensor]:
@@ -398,12 +180,12 @@ def edge_postprocess(
     if sorted_rows is None:
         sorted_rows = rows_sorted(edge_index)
     if degree_norm:
-        edge_weight = _DegreeNorm.apply(edge_weight, row, col, num_nodes, EPS, sorted_rows, count)
+        edge_weight, _ = O.degree_norm(edge_weight, row, col, num_nodes, EPS, sorted_rows, count)
     if edge_weight_norm and edge_weight is not None:
         if num_graphs is None:  # costs a device sync: pass num_graphs to avoid it
             num_graphs = int(batch_pooled.max().item()) + 1 if batch_pooled.numel() > 0 else 0
-        edge_weight = _WeightNorm.apply(edge_weight, row, batch_pooled.contiguous(), num_nodes, num_graphs, sorted_rows,
-                                        count)
+        edge_weight, _, _ = O.weight_norm(edge_weight, row, batch_pooled.contiguous(), num_nodes, num_graphs,
+                                          sorted_rows, count)
     return edge_weight
 
 
@@ -419,22 +201,25 @@ def _sparse_connect_core(edge_index, edge_weight, node_index, cluster_index, num
         num_nodes = int(edge_index.max().item()) + 1 if edge_index.numel() > 0 else 0
     flags = L.REMOVE_SELF_LOOPS if remove_self_loops else 0
     need_norm = degree_norm or (edge_weight_norm and w is not None)
+    need_grad = w is not None and w.requires_grad and torch.is_grad_enabled()
 
     if node_index is not None and len(node_index) < num_nodes:
         # the relabelling is monotone (node_index ascending), so the output keeps the row order of the input
         out_sorted = rows_sorted(edge_index) if need_norm else None
-        ei, w, count = _FilterRelabel.apply(w, row, col, node_index.contiguous(), num_nodes, flags, EPS, padded)
+        ei, w_out, _, count = O.filter_relabel_edges(row, col, w, node_index.contiguous(), num_nodes, flags, EPS,
+                                                     padded, need_grad)
     elif cluster_index is not None and len(cluster_index) == num_nodes:
         out_sorted = True  # coalesced output is lexicographic
         cluster_index = cluster_index.contiguous()
         if rows_sorted(edge_index):  # row-bucketed coalesce over the cluster CSR (cached on the SelectOutput)
             csr = csr if csr is not None else build_csr(cluster_index, num_supernodes)
         else:
-            csr = None
-        ei, w, count = _RemapCoalesce.apply(w, row, col, cluster_index, num_nodes, num_supernodes,
-                                            L.OPS[reduce_op], flags, EPS, padded, csr)
+            csr = (None, None)
+        ei, w_out, _, _, _, count = O.remap_coalesce(row, col, w, cluster_index, csr[0], csr[1], num_nodes,
+                                                     num_supernodes, L.OPS[reduce_op], flags, EPS, padded, need_grad)
     else:
         raise RuntimeError
+    w = None if w is None else w_out
     w = edge_postprocess(ei, w, num_supernodes, degree_norm, edge_weight_norm, batch_pooled, num_graphs,
                          sorted_rows=out_sorted, count=count if padded else None)
     return ei, w, count
@@ -515,47 +300,6 @@ def sparse_connect_padded(
 LOSS_NONE, LOSS_MINCUT, LOSS_DIFFPOOL = 0, 1, 2
 
 
-class _DensePool(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, adj, s, flags, loss_kind, link_div, ent_div):
-        B, N, K = s.shape
-        F = x.size(-1) if x is not None else 0
-        dev = s.device
-        lib = L.load()
-        saved = L.workspace(lib.tgpb200_dense_pool_saved_bytes(B, N, K), dev)
-        x_pool = torch.empty((B, K, F), dtype=s.dtype, device=dev) if x is not None else None
-        adj_pool = torch.empty((B, K, K), dtype=s.dtype, device=dev) if adj is not None else None
-        losses = torch.zeros(4, dtype=torch.float32, device=dev)
-        L.call("tgpb200_dense_pool_fwd", L.ptr(adj), L.ptr(s), L.ptr(x), B, N, K, F, L.dtype_code(s.dtype), flags,
-               loss_kind, EPS, link_div, ent_div, L.ptr(x_pool), L.ptr(adj_pool), L.ptr(losses), L.ptr(saved),
-               saved.numel(), L.stream())
-        ctx.save_for_backward(x, adj, s, saved)
-        ctx.set_materialize_grads(False)
-        ctx.cfg = (B, N, K, F, flags, loss_kind, link_div, ent_div)
-        return x_pool, adj_pool, losses
-
-    @staticmethod
-    def backward(ctx, gx_pool, gadj_pool, glosses):
-        x, adj, s, saved = ctx.saved_tensors
-        B, N, K, F, flags, loss_kind, link_div, ent_div = ctx.cfg
-        dev = s.device
-        lib = L.load()
-        need_adj = adj is not None and ctx.needs_input_grad[1]
-        ws = L.workspace(lib.tgpb200_dense_pool_bwd_workspace_bytes(B, N, K, int(need_adj)), dev)
-        gs = torch.empty_like(s)
-        gx = torch.empty_like(x) if (x is not None and gx_pool is not None) else None
-        gadj = torch.empty_like(adj) if need_adj else None
-        gxp = None if gx_pool is None or x is None else gx_pool.contiguous()
-        gap = None if gadj_pool is None or adj is None else gadj_pool.contiguous()
-        gl = None if glosses is None else glosses.to(torch.float32).contiguous()
-        L.call("tgpb200_dense_pool_bwd", L.ptr(adj), L.ptr(s), L.ptr(x), L.ptr(gxp), L.ptr(gap), L.ptr(gl), B, N, K, F,
-               L.dtype_code(s.dtype), flags, loss_kind, EPS, link_div, ent_div, L.ptr(gs), L.ptr(gx), L.ptr(gadj),
-               L.ptr(saved), saved.numel(), L.ptr(ws), ws.numel(), L.stream())
-        if x is not None and gx is None:
-            gx = torch.zeros_like(x)
-        return gx, gadj, gs, None, None, None, None
-
-
 def dense_flags(remove_self_loops: bool, degree_norm: bool, adj_transpose: bool, edge_weight_norm: bool) -> int:
     return (
         (L.REMOVE_SELF_LOOPS if remove_self_loops else 0)
@@ -591,7 +335,8 @@ def dense_pool(
     if x is not None and x.dtype != s.dtype or adj is not None and adj.dtype != s.dtype:
         raise RuntimeError("tgp_b200.dense_pool: x, adj and s must share one dtype")
     flags = dense_flags(remove_self_loops, degree_norm, adj_transpose, edge_weight_norm)
-    return _DensePool.apply(x, adj, s, flags, loss_kind, float(link_div), float(ent_div))
+    x_pool, adj_pool, losses, _ = _T.stas_fused(x, adj, s, flags, loss_kind, float(link_div), float(ent_div))
+    return (x_pool if x is not None else None), (adj_pool if adj is not None else None), losses
 
 
 # --------------------------------------------------------------------------- #
