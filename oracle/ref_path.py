@@ -411,6 +411,54 @@ def entropy_loss(S: Tensor, num_nodes: int) -> Tensor:
     return (-(S2 * torch.log(S2 + EPS)).sum(dim=-1)).sum() / num_nodes
 
 
+def sparse_mincut_loss(edge_index: Tensor, S: Tensor, edge_weight: Optional[Tensor] = None,
+                       batch: Optional[Tensor] = None, batch_reduction: str = "mean") -> Tensor:
+    """tgp/utils/losses.py:126-215 (unbatched MinCutPooling): -sum_e w_e <S_i, S_j> / (sum_i d_i |S_i|^2 + eps) per
+    graph, d = row sums of the sparse adjacency."""
+    n = S.size(0)
+    w = torch.ones(edge_index.size(1), dtype=S.dtype) if edge_weight is None else edge_weight.view(-1)
+    if batch is None:
+        batch = torch.zeros(n, dtype=torch.long)
+    B = int(batch.max()) + 1
+    deg = pyg.scatter(w, edge_index[0], dim=0, dim_size=n, reduce="sum")
+    den = pyg.scatter(deg * (S * S).sum(-1), batch, dim=0, dim_size=B, reduce="sum")
+    contrib = w * (S[edge_index[0]] * S[edge_index[1]]).sum(-1)
+    num = pyg.scatter(contrib, batch[edge_index[0]], dim=0, dim_size=B, reduce="sum")
+    return _batch_reduce(-(num / (den + EPS)), batch_reduction)
+
+
+def unbatched_orthogonality_loss(S: Tensor, batch: Optional[Tensor] = None, batch_reduction: str = "mean") -> Tensor:
+    """tgp/utils/losses.py:319-389: per graph || S_g^T S_g / ||S_g^T S_g||_F - I / sqrt(K) ||_F."""
+    K = S.size(1)
+    if batch is None:
+        batch = torch.zeros(S.size(0), dtype=torch.long)
+    id_k = torch.eye(K, dtype=S.dtype) / math.sqrt(K)
+    out = []
+    for g in range(int(batch.max()) + 1):
+        sg = S[batch == g]
+        sts = sg.t() @ sg
+        out.append(torch.norm(sts / torch.norm(sts) - id_k))
+    return _batch_reduce(torch.stack(out), batch_reduction)
+
+
+def sparse_link_pred_loss(S: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor] = None,
+                          batch: Optional[Tensor] = None, normalize_loss: bool = True) -> Tensor:
+    """tgp/utils/losses.py:711-777: sqrt(sum_e (w - ss)^2 + sum_g ||S_g^T S_g||_F^2 - sum_e ss^2), ss = <S_i, S_j>."""
+    w = torch.ones(edge_index.size(1), dtype=S.dtype) if edge_weight is None else edge_weight.view(-1).to(S.dtype)
+    if batch is None:
+        batch = torch.zeros(S.size(0), dtype=torch.long)
+    ss = (S[edge_index[0]] * S[edge_index[1]]).sum(-1)
+    total, numel = S.new_zeros(()), 0
+    for g in range(int(batch.max()) + 1):
+        sg = S[batch == g]
+        sts = sg.t() @ sg
+        total = total + (sts * sts).sum()
+        numel += sg.size(0) ** 2
+    link = torch.sqrt(torch.clamp(((w - ss) ** 2).sum() + total - (ss ** 2).sum(), min=0.0))
+    return link / numel if (normalize_loss and numel > 0) else link
+
+
+
 # --------------------------------------------------------------------------- #
 # Orchestration (call order of the poolers)
 # --------------------------------------------------------------------------- #

@@ -497,3 +497,78 @@ def test_bucketed_coalesce_mul_gradient_with_zero_weights():
     assert torch.equal(eg.cpu(), eo)
     (wgo * coef.float().to(DEV)).sum().backward()
     torch.testing.assert_close(wg.grad.cpu().double(), wc.grad, rtol=1e-4, atol=1e-9)
+
+
+# --------------------------------------------------------------------------- #
+# unbatched dense mode: sparse adjacency, SpMM + batched product, sparse loss twins (reference-generated golden)
+# --------------------------------------------------------------------------- #
+def test_unbatched_sparse_path_matches_reference_golden():
+    from tgp_b200 import unbatched as U
+
+    cases = torch.load(os.path.join(ROOT, "tests", "golden", "ref_unbatched.pt"), weights_only=False)
+    for name, c in cases.items():
+        ei, ew, b = c["edge_index"].to(DEV), c["edge_weight"], c["batch"]
+        bg = None if b is None else b.to(DEV)
+        sr = c["s_raw"].to(DEV).requires_grad_(True)
+        wg = None if ew is None else ew.to(DEV).requires_grad_(True)
+        s = torch.softmax(sr, -1)
+        cut = U.sparse_mincut_loss(ei, s, wg, bg)
+        ortho = U.unbatched_orthogonality_loss(s, bg)
+        link = U.sparse_link_pred_loss(s, ei, wg, bg, normalize_loss=False)
+        link_n = U.sparse_link_pred_loss(s, ei, wg, bg, normalize_loss=True)
+        for got, key in ((cut, "cut"), (ortho, "ortho"), (link, "link"), (link_n, "link_norm")):
+            torch.testing.assert_close(got.detach().cpu(), c[key], rtol=1e-5, atol=1e-7, msg=f"{name}:{key}")
+        (cut + 0.5 * ortho + 0.25 * link).backward()
+        sc = float(c["grad_s_raw"].abs().max())
+        torch.testing.assert_close(sr.grad.cpu(), c["grad_s_raw"], rtol=1e-4, atol=1e-5 * sc, msg=name)
+        if wg is not None:
+            sc = float(c["grad_w"].abs().max())
+            torch.testing.assert_close(wg.grad.cpu(), c["grad_w"], rtol=1e-4, atol=1e-5 * sc, msg=name)
+        K = s.size(1)
+        nb = 1 if b is None else int(b.max()) + 1
+        bp = torch.arange(nb, device=DEV).repeat_interleave(K)
+        so = T.SelectOutput(s=torch.softmax(c["s_raw"], -1).to(DEV), batch=bg)
+        for so_flag in (False, True):
+            for dn in (False, True):
+                a_ref, w_ref = c[f"adj_so{int(so_flag)}_dn{int(dn)}"]
+                conn = T.B200DenseConnect(True, dn, False, False, so_flag)
+                a, w = conn(ei, so, edge_weight=None if ew is None else ew.to(DEV), batch=bg, batch_pooled=bp)
+                if so_flag:
+                    assert torch.equal(a.cpu(), a_ref), name
+                    torch.testing.assert_close(w.cpu(), w_ref, rtol=1e-5, atol=1e-6)
+                else:
+                    torch.testing.assert_close(a.cpu(), a_ref, rtol=1e-5, atol=1e-6, msg=f"{name} dn{dn}")
+
+
+def test_unbatched_mincut_pool_equals_batched_on_large_ragged_batch():
+    """tests/poolers/test_dense_poolers_batched_vs_unbatched.py:36-174 at a size where the padded adjacency would be
+    64x the edge list: the sparse path must agree with the batched tensor-core path (rtol 1e-5)."""
+    from tgp_b200 import unbatched as U
+
+    g = torch.Generator().manual_seed(13)
+    sizes = [int(v) for v in torch.randint(40, 400, (24,), generator=g)]
+    K, F = 12, 20
+    batch = torch.cat([torch.full((n,), i) for i, n in enumerate(sizes)])
+    N = batch.numel()
+    eis, off = [], 0
+    for n in sizes:
+        r = torch.randint(0, n, (2, 4 * n), generator=g)
+        r = r[:, r[0] != r[1]]
+        eis.append(torch.cat([r, r.flip(0)], 1) + off)
+        off += n
+    ei = torch.cat(eis, 1)
+    ei = torch.unique(ei, dim=1)  # distinct, row-sorted edges
+    ew = torch.rand(ei.size(1), generator=g) + 0.5
+    s = torch.softmax(torch.randn(N, K, generator=g), -1).to(DEV)
+    x = torch.randn(N, F, generator=g).to(DEV)
+    xp_u, ap_u, loss_u = U.mincut_pool_unbatched(x, ei.to(DEV), ew.to(DEV), s, batch.to(DEV), num_graphs=len(sizes))
+    B = len(sizes)
+    s3, _ = F_.to_dense_batch(s, batch.to(DEV), B)
+    x3, _ = F_.to_dense_batch(x, batch.to(DEV), B, s3.size(1))
+    adj = F_.to_dense_adj(ei.to(DEV), batch.to(DEV), ew.to(DEV), num_graphs=B, max_num_nodes=s3.size(1))
+    xp_b, ap_b, loss_b = T.mincut_pool(x3, adj, s3, adj_transpose=False)
+    sc = lambda t: float(t.abs().max())
+    torch.testing.assert_close(xp_u, xp_b, rtol=1e-5, atol=1e-5 * sc(xp_b))
+    torch.testing.assert_close(ap_u, ap_b, rtol=1e-5, atol=1e-5 * sc(ap_b))
+    for k in loss_b:
+        torch.testing.assert_close(loss_u[k], loss_b[k], rtol=2e-5, atol=1e-7, msg=k)

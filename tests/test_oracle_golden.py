@@ -113,3 +113,35 @@ def test_dense_cases(golden):
         torch.testing.assert_close(sr.grad, c["grad_s_raw"], rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(x.grad, c["grad_x"], rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(a.grad, c["grad_adj"], rtol=1e-5, atol=1e-6)
+
+
+def test_oracle_unbatched_losses_and_connect_match_reference_golden():
+    """tests/golden/ref_unbatched.pt was produced by the reference's own DenseConnect (unbatched) and sparse loss
+    functions (make_golden_unbatched.py); the oracle restatements must reproduce it."""
+    import os
+
+    import torch
+
+    from oracle import ref_path as R
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_unbatched.pt")
+    cases = torch.load(path, weights_only=False)
+    assert set(cases) == {"ragged_w", "ragged_now", "single_w"}
+    for name, c in cases.items():
+        s = torch.softmax(c["s_raw"], -1)
+        ei, ew, b = c["edge_index"], c["edge_weight"], c["batch"]
+        assert torch.equal(R.sparse_mincut_loss(ei, s, ew, b), c["cut"]), name
+        assert torch.equal(R.unbatched_orthogonality_loss(s, b), c["ortho"]), name
+        assert torch.equal(R.sparse_link_pred_loss(s, ei, ew, b, normalize_loss=False), c["link"]), name
+        assert torch.equal(R.sparse_link_pred_loss(s, ei, ew, b, normalize_loss=True), c["link_norm"]), name
+        K = s.size(1)
+        nb = 1 if b is None else int(b.max()) + 1
+        bp = torch.arange(nb).repeat_interleave(K)
+        for so_flag in (False, True):
+            for dn in (False, True):
+                a_ref, w_ref = c[f"adj_so{int(so_flag)}_dn{int(dn)}"]
+                a, w = R.dense_connect_forward_unbatched(ei, ew, b, s, bp, remove_self_loops=True, degree_norm=dn,
+                                                         edge_weight_norm=False, sparse_output=so_flag)
+                torch.testing.assert_close(a, a_ref, rtol=1e-6, atol=1e-7)
+                if w_ref is not None:
+                    torch.testing.assert_close(w, w_ref, rtol=1e-6, atol=1e-7)

@@ -184,9 +184,9 @@ class B200DenseConnect(Connect):
         return adj_pool, None
 
     def _forward_unbatched_inputs(self, edge_index, edge_weight, batch, s, batch_pooled):
-        """Sparse adjacency + dense ``[N, K]`` assignment (dense_conn.py:273-354).  The per-graph
-        ``sparse.mm`` loop of the reference becomes: scatter the edges into a padded ``[B, Nmax, Nmax]`` batch
-        (``to_dense_adj`` kernel) and run the batched tensor-core path; same values as the batched mode."""
+        """Sparse adjacency + dense ``[N, K]`` assignment (dense_conn.py:273-354).  The per-graph ``sparse.mm`` loop
+        of the reference becomes one SpMM kernel + one batched tensor-core product (``tgp_b200.unbatched``); memory
+        stays ``O(E + B Nmax K)``."""
         to_coo = isinstance(edge_index, Tensor) and edge_index.is_sparse
         if to_coo:
             coo = edge_index.coalesce()
@@ -203,23 +203,21 @@ class B200DenseConnect(Connect):
                 "[DenseConnect - unbatched]: SelectOutput.s must have shape "
                 f"[N, K] or [1, N, K], but got {s.size()}."
             )
+        from .unbatched import dense_connect_unbatched
+
         num_nodes, K = s.size()
-        B = 1 if batch is None else int(batch.max().item()) + 1
-        b0 = batch if batch is not None else torch.zeros(num_nodes, dtype=torch.long, device=s.device)
-        s3, _ = F_.to_dense_batch(s, b0, B)
-        adj = F_.to_dense_adj(edge_index, b0, edge_weight, num_graphs=B, max_num_nodes=s3.size(1)).to(s.dtype)
+        B = 1 if batch is None else int(batch.max().item()) + 1  # the reference's own sync (dense_conn.py:329)
+        # S^T (A S): one SpMM over the edge list + one batched product over [B, Nmax, K] -- no [B, Nmax, Nmax] tensor
+        raw = dense_connect_unbatched(edge_index, edge_weight, batch, s, B)
         if not self.sparse_output:
-            _, adj_pool, _ = F_.dense_pool(
-                None, adj, s3, remove_self_loops=self.remove_self_loops, degree_norm=self.degree_norm,
-                adj_transpose=False, edge_weight_norm=self.edge_weight_norm,
-            )
-            return adj_pool, None
+            return postprocess_adj_pool_dense(raw, remove_self_loops=self.remove_self_loops,
+                                              degree_norm=self.degree_norm, adj_transpose=False,
+                                              edge_weight_norm=self.edge_weight_norm), None
         if self.edge_weight_norm and batch_pooled is None:
             raise AssertionError(
                 "edge_weight_norm=True but batch_pooled=None. "
                 "batch_pooled parameter is required for per-graph normalization in DenseConnect."
             )
-        _, raw, _ = F_.dense_pool(None, adj, s3)
         ei, ew = F_.dense_to_block_diag(raw)
         n_super = B * K
         flags = F_.L.REMOVE_SELF_LOOPS if self.remove_self_loops else 0
