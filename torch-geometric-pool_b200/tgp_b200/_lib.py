@@ -178,5 +178,17 @@ def kernel_trace() -> list:
     return out
 
 
+_NVTX = os.environ.get("TGPB200_NVTX", "0") == "1"
+
+
 def call(name: str, *args) -> None:
+    """One C-ABI entry point.  ``TGPB200_NVTX=1`` brackets every call with an NVTX range named after the entry point
+    (the dispatcher ops of ``libtgp_b200_ops.so`` are visible to ``torch.autograd.profiler.emit_nvtx`` as usual)."""
+    if _NVTX:
+        torch.cuda.nvtx.range_push(name)
+        try:
+            check(getattr(load(), name)(*args), name)
+        finally:
+            torch.cuda.nvtx.range_pop()
+        return
     check(getattr(load(), name)(*args), name)
