@@ -87,7 +87,8 @@ int tgpb200_segment_reduce_fwd(const void* x, const int64_t* node_index, const f
  * gradient is split evenly among ties (torch scatter_reduce amax/amin rule, the PyG CPU path);
  * x_pool (forward output) is required for those ops.  node_index must be sorted ascending
  * (SelectOutput invariant, tgp/select/base_select.py:56-60). */
-size_t tgpb200_segment_reduce_bwd_workspace_bytes(int64_t nnz, int64_t num_clusters, int64_t F, int op);
+size_t tgpb200_segment_reduce_bwd_workspace_bytes(int64_t num_nodes, int64_t nnz, int64_t num_clusters, int64_t F,
+                                                  int op);
 int tgpb200_segment_reduce_bwd(const void* x, const int64_t* node_index, const int64_t* cluster_index,
                                const float* weight, const int32_t* order, const int32_t* ptr, const void* x_pool,
                                const void* grad_pool, int64_t num_nodes, int64_t nnz, int64_t num_clusters, int64_t F,

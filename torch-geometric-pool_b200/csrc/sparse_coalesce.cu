@@ -43,12 +43,26 @@ __device__ __forceinline__ float combine_w(int op, float acc, float v) {
 // rs[v] / re[v] = first / one-past-last edge of fine row v in the row-sorted edge list (0 / 0 when absent)
 static __global__ void k_fine_row_spans(const int64_t* __restrict__ row, int64_t E, int64_t N, int32_t* __restrict__ rs,
                                         int32_t* __restrict__ re) {
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  const int64_t r = row[e];
-  if (r < 0 || r >= N) return;
-  if (e == 0 || row[e - 1] != r) rs[r] = (int32_t)e;
-  if (e + 1 == E || row[e + 1] != r) re[r] = (int32_t)(e + 1);
+  // four consecutive edges per thread (two 128-bit loads), neighbours of the group from the adjacent lanes
+  const int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (e0 >= E) return;
+  int64_t r[6];
+  if (e0 + 4 <= E && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+    const longlong2 a = __ldcs(reinterpret_cast<const longlong2*>(row + e0));
+    const longlong2 b = __ldcs(reinterpret_cast<const longlong2*>(row + e0 + 2));
+    r[1] = a.x, r[2] = a.y, r[3] = b.x, r[4] = b.y;
+  } else {
+    for (int k = 0; k < 4; ++k) r[1 + k] = e0 + k < E ? row[e0 + k] : -1;
+  }
+  r[0] = e0 > 0 ? row[e0 - 1] : -1;
+  r[5] = e0 + 4 < E ? row[e0 + 4] : -1;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t e = e0 + k, v = r[1 + k];
+    if (e >= E || v < 0 || v >= N) continue;
+    if (r[k] != v) rs[v] = (int32_t)e;
+    if (r[k + 2] != v || e + 1 == E) re[v] = (int32_t)(e + 1);
+  }
 }
 
 // cost[m] = entries of CSR member m: its degree, or one placeholder for an isolated node (so that the number of
@@ -635,7 +649,7 @@ int tgpb200_bucket_coalesce_plan(const int64_t* row, int64_t E, const int64_t* c
   cudaMemsetAsync(pl.hubbits, 0, (size_t)(K / 32 + 1) * 4, st);
   cudaMemsetAsync(pl.plan, 0, 4 * sizeof(unsigned long long), st);
   if (E > 0)
-    launch("k_fine_row_spans", k_fine_row_spans, (unsigned)ceil_div(E, 256), 256, 0, st, row, E, N, pl.rs, pl.re);
+    launch("k_fine_row_spans", k_fine_row_spans, (unsigned)ceil_div(ceil_div(E, 4), 256), 256, 0, st, row, E, N, pl.rs, pl.re);
   launch("k_member_cost", k_member_cost, (unsigned)ceil_div(N + 1, 256), 256, 0, st, order, pl.rs, pl.re, N, pl.voff);
   int rc = exclusive_scan_i32(pl.voff, pl.voff, N + 1, nullptr, reinterpret_cast<int64_t*>(pl.plan), ws, st);
   if (rc != TGPB200_OK) return rc;

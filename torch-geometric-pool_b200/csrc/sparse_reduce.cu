@@ -264,6 +264,16 @@ static __global__ void k_count_ties(const XT* __restrict__ x, const int64_t* __r
   inv_ties[t] = cnt > 0 ? 1.f / (float)cnt : 0.f;
 }
 
+// first[n] = position of node n's first entry in the (sorted) node_index, -1 (pre-filled) if it has none
+static __global__ void k_first_entry(const int64_t* __restrict__ node_index, int64_t nnz, int64_t N,
+                                     int32_t* __restrict__ first) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  const int64_t n = node_index[i];
+  if (n < 0 || n >= N) return;
+  if (i == 0 || node_index[i - 1] != n) first[n] = (int32_t)i;
+}
+
 // ------------------------------------------------------------------------------------------
 // Backward: one lane-group per NODE (node_index is sorted, so a node's entries are adjacent):
 //   grad_x[n] = sum_{i in run(n)} w_i * gs_i,   grad_w[i] = <x[n], gs_i>,
@@ -273,7 +283,8 @@ template <typename XT, typename OT, bool kVec>
 static __global__ void __launch_bounds__(256)
     k_segment_reduce_bwd(const XT* __restrict__ x, const int64_t* __restrict__ node_index,
                          const int64_t* __restrict__ cluster_index, const float* __restrict__ weight,
-                         const int32_t* __restrict__ ptr, const OT* __restrict__ pool, const OT* __restrict__ gpool,
+                         const int32_t* __restrict__ ptr, const int32_t* __restrict__ first,
+                         const OT* __restrict__ pool, const OT* __restrict__ gpool,
                          const float* __restrict__ inv_ties, int64_t N, int64_t nnz, int64_t K, int64_t F, int op,
                          int lpr, XT* __restrict__ gx, float* __restrict__ gw) {
   constexpr int W = Vec<XT>::N;
@@ -283,30 +294,14 @@ static __global__ void __launch_bounds__(256)
   int lane = threadIdx.x & 31;
   unsigned gmask = lpr >= 32 ? kFull : (((1u << lpr) - 1u) << (lane & ~(lpr - 1)));
 
-  // Locate the entries of node n.  The probe loads (neighbouring node ids and the would-be cluster / weight of the
-  // identity layout) are independent of each other, so the common "every node selected once, node_index[n] == n"
-  // case costs one round trip instead of a chain of dependent loads; otherwise binary search + a linear run scan.
-  int64_t lo, hi;
-  {
-    const int64_t a = n < nnz ? node_index[n] : -1;
-    const int64_t pa = (n > 0 && n - 1 < nnz) ? node_index[n - 1] : -1;
-    const int64_t na = n + 1 < nnz ? node_index[n + 1] : -2;
-    if (a == n && pa != n) {
-      lo = n;
-      hi = n + 1;
-      if (na == n) {
-        while (hi < nnz && node_index[hi] == n) ++hi;
-      }
-    } else {
-      int64_t x0 = 0, x1 = nnz;
-      while (x0 < x1) {
-        int64_t mid = (x0 + x1) >> 1;
-        if (node_index[mid] < n) x0 = mid + 1; else x1 = mid;
-      }
-      lo = x0;
-      hi = lo;
-      while (hi < nnz && node_index[hi] == n) ++hi;
-    }
+  // Entries of node n: first[n] (inverse map built by k_first_entry, -1 for an unselected node) and the adjacent
+  // run behind it (node_index is sorted).  One dependent load instead of a log2(nnz)-step binary search.
+  int64_t lo = first[n], hi = 0;
+  if (lo < 0) {
+    lo = 0;
+  } else {
+    hi = lo + 1;
+    while (hi < nnz && node_index[hi] == n) ++hi;
   }
 
   const XT* xr = x + n * F;
@@ -379,8 +374,8 @@ template <typename XT, typename OT, int NPW>
 static __global__ void __launch_bounds__(256)
     k_segment_reduce_bwd_rows(const int64_t* __restrict__ node_index, const int64_t* __restrict__ cluster_index,
                               const float* __restrict__ weight, const int32_t* __restrict__ ptr,
-                              const OT* __restrict__ gpool, int64_t N, int64_t nnz, int64_t K, int64_t F, int op,
-                              XT* __restrict__ gx) {
+                              const int32_t* __restrict__ first, const OT* __restrict__ gpool, int64_t N, int64_t nnz,
+                              int64_t K, int64_t F, int op, XT* __restrict__ gx) {
   constexpr int W = Vec<XT>::N;
   const int lane = threadIdx.x & 31;
   const int64_t n0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * NPW;
@@ -389,23 +384,13 @@ static __global__ void __launch_bounds__(256)
   float coef = 0.f;
   if (lane < NPW && n0 + lane < N) {
     const int64_t n = n0 + lane;
-    const int64_t a = n < nnz ? node_index[n] : -1;
-    const int64_t pa = (n > 0 && n - 1 < nnz) ? node_index[n - 1] : -1;
-    const int64_t na = n + 1 < nnz ? node_index[n + 1] : -2;
-    if (a == n && pa != n) {
-      lo = n;
-      hi = n + 1;
-      if (na == n)
-        while (hi < nnz && node_index[hi] == n) ++hi;
+    lo = first[n];  // inverse map (k_first_entry): -1 for an unselected node
+    if (lo < 0) {
+      lo = 0;
     } else {
-      int64_t x0 = 0, x1 = nnz;
-      while (x0 < x1) {
-        int64_t mid = (x0 + x1) >> 1;
-        if (node_index[mid] < n) x0 = mid + 1; else x1 = mid;
-      }
-      lo = x0;
-      hi = lo;
-      while (hi < nnz && node_index[hi] == n) ++hi;
+      hi = lo + 1;
+      if (hi < nnz && node_index[hi] == n)
+        while (hi < nnz && node_index[hi] == n) ++hi;
     }
     if (hi == lo + 1) {
       c = cluster_index[lo];
@@ -503,6 +488,11 @@ static int launch_bwd(const void* x, const int64_t* node_index, const int64_t* c
                       int64_t nnz, int64_t K, int64_t F, int op, void* gx, float* gw, Workspace& ws, cudaStream_t st) {
   constexpr int W = Vec<XT>::N;
   bool vec = (F % W == 0) && Vec<OT>::N == W;
+  int32_t* first = ws.take<int32_t>((size_t)(N > 0 ? N : 1));
+  if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+  cudaMemsetAsync(first, 0xff, (size_t)(N > 0 ? N : 1) * sizeof(int32_t), st);
+  if (nnz > 0)
+    launch("k_first_entry", k_first_entry, (unsigned)ceil_div(nnz, 256), 256, 0, st, node_index, nnz, N, first);
   float* inv_ties = nullptr;
   if (op == TGPB200_MAX || op == TGPB200_MIN) {
     inv_ties = ws.take<float>((size_t)K * F);
@@ -521,16 +511,16 @@ static int launch_bwd(const void* x, const int64_t* node_index, const int64_t* c
     constexpr int NPW = 4;
     const int64_t warps = ceil_div(N, NPW);
     launch("k_segment_reduce_bwd", k_segment_reduce_bwd_rows<XT, OT, NPW>, (unsigned)ceil_div(warps * 32, 256), 256, 0, st,
-           node_index, cluster_index, weight, ptr, (const OT*)gpool, N, nnz, K, F, op, (XT*)gx);
+           node_index, cluster_index, weight, ptr, first, (const OT*)gpool, N, nnz, K, F, op, (XT*)gx);
     return launch_status();
   }
   if (vec)
     launch("k_segment_reduce_bwd", k_segment_reduce_bwd<XT, OT, true>, grid, 256, 0, st, (const XT*)x, node_index, cluster_index, weight, ptr,
-                                                             (const OT*)pool, (const OT*)gpool, inv_ties, N, nnz, K, F,
+                                                             first, (const OT*)pool, (const OT*)gpool, inv_ties, N, nnz, K, F,
                                                              op, lpr, (XT*)gx, gw);
   else
     launch("k_segment_reduce_bwd", k_segment_reduce_bwd<XT, OT, false>, grid, 256, 0, st, (const XT*)x, node_index, cluster_index, weight, ptr,
-                                                              (const OT*)pool, (const OT*)gpool, inv_ties, N, nnz, K,
+                                                              first, (const OT*)pool, (const OT*)gpool, inv_ties, N, nnz, K,
                                                               F, op, lpr, (XT*)gx, gw);
   return launch_status();
 }
@@ -592,10 +582,11 @@ int tgpb200_segment_reduce_fwd(const void* x, const int64_t* node_index, const f
   return TGPB200_ERR_UNSUPPORTED;
 }
 
-size_t tgpb200_segment_reduce_bwd_workspace_bytes(int64_t nnz, int64_t K, int64_t F, int op) {
+size_t tgpb200_segment_reduce_bwd_workspace_bytes(int64_t N, int64_t nnz, int64_t K, int64_t F, int op) {
   (void)nnz;
-  if (op == TGPB200_MAX || op == TGPB200_MIN) return align_up((size_t)(K * F > 0 ? K * F : 1) * sizeof(float)) + 256;
-  return 256;
+  size_t b = align_up((size_t)(N > 0 ? N : 1) * sizeof(int32_t)) + 256;  // node -> first entry
+  if (op == TGPB200_MAX || op == TGPB200_MIN) b += align_up((size_t)(K * F > 0 ? K * F : 1) * sizeof(float));
+  return b;
 }
 
 int tgpb200_segment_reduce_bwd(const void* x, const int64_t* node_index, const int64_t* cluster_index,

@@ -141,7 +141,7 @@ std::tuple<Tensor, Tensor> segment_reduce_bwd(const Tensor& x, const Tensor& nod
   const bool has_w = weight.has_value() && weight->defined();
   Tensor gw = (has_w && need_weight_grad) ? at::empty({nnz}, x.options().dtype(at::kFloat))
                                           : at::empty({0}, x.options().dtype(at::kFloat));
-  Tensor ws = workspace(tgpb200_segment_reduce_bwd_workspace_bytes(nnz, num_clusters, F, (int)op), x);
+  Tensor ws = workspace(tgpb200_segment_reduce_bwd_workspace_bytes(N, nnz, num_clusters, F, (int)op), x);
   check(tgpb200_segment_reduce_bwd(x.data_ptr(), node_index.data_ptr<int64_t>(), cluster_index.data_ptr<int64_t>(),
                                    has_w ? weight->data_ptr<float>() : nullptr, order.data_ptr<int32_t>(),
                                    p.data_ptr<int32_t>(), x_pool.data_ptr(), g.data_ptr(), N, nnz, num_clusters, F,

@@ -34,7 +34,7 @@ SIGNATURES = {
     "tgpb200_build_csr_workspace_bytes": (_SZ, [_I64, _I64]),
     "tgpb200_build_csr": (_INT, [_P, _I64, _I64, _P, _P, _P, _SZ, _P]),
     "tgpb200_segment_reduce_fwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _INT, _INT, _INT, _P, _P]),
-    "tgpb200_segment_reduce_bwd_workspace_bytes": (_SZ, [_I64, _I64, _I64, _INT]),
+    "tgpb200_segment_reduce_bwd_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64, _INT]),
     "tgpb200_segment_reduce_bwd": (
         _INT,
         [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _INT, _INT, _INT, _P, _P, _P, _SZ, _P],

@@ -10,6 +10,7 @@ static buffers can be captured once and replayed with a single ``cudaGraphLaunch
 """
 from __future__ import annotations
 
+import gc
 from typing import Any, Callable
 
 import torch
@@ -27,13 +28,19 @@ class GraphedStep:
     def __init__(self, fn: Callable[[], Any], warmup: int = 3):
         if not torch.cuda.is_available():
             raise RuntimeError("tgp_b200.GraphedStep needs a CUDA device (no CPU fallback by design)")
+        # Autograd graphs of earlier eager calls can sit in reference cycles until the cyclic collector runs; their
+        # AccumulateGrad nodes are bound to the stream they were created on (usually the legacy default stream) and
+        # would be reused inside the capture (cudaErrorStreamCaptureImplicit).  Collect before warm-up and capture.
+        gc.collect()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):  # lazy initialisation (TMA descriptors, smem opt-ins) outside capture
-                fn()
+                out = fn()
+                del out
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        gc.collect()
         self.graph = torch.cuda.CUDAGraph()
         n0 = L.kernel_launches()
         with torch.cuda.graph(self.graph):
