@@ -18,18 +18,6 @@ import torch
 from . import _lib as L
 
 
-def _release_stale_autograd_graphs() -> None:
-    """The autograd engine's device thread keeps the LAST graph it executed alive until it receives another task,
-    and with it the AccumulateGrad nodes of the leaves -- bound to the stream they were created on (usually the
-    legacy default stream of an earlier eager call).  A later forward would reuse them, also inside a capture
-    (cudaErrorStreamCaptureImplicit).  A throw-away backward hands the thread a new task; then the cyclic collector
-    can free the old graphs."""
-    t = torch.zeros(1, device="cuda", requires_grad=True)
-    (t * 1.0).sum().backward()
-    del t
-    gc.collect()
-
-
 class GraphedStep:
     """Capture ``fn()`` into one CUDA graph.  ``fn`` must read its inputs from tensors that stay alive (their
     storage is baked into the graph), may call ``torch.autograd.backward`` (set ``.grad = None`` first so the
@@ -42,14 +30,17 @@ class GraphedStep:
             raise RuntimeError("tgp_b200.GraphedStep needs a CUDA device (no CPU fallback by design)")
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        # Autograd graphs of earlier eager calls can sit in reference cycles until the cyclic collector runs; their
+        # AccumulateGrad nodes are bound to the stream they were created on (usually the legacy default stream) and
+        # would be reused inside the capture (cudaErrorStreamCaptureImplicit).  Collect before warm-up and capture.
+        gc.collect()
         with torch.cuda.stream(side):
-            _release_stale_autograd_graphs()
             for _ in range(max(warmup, 1)):  # lazy initialisation (TMA descriptors, smem opt-ins) outside capture
                 out = fn()
                 del out
-            _release_stale_autograd_graphs()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        gc.collect()
         self.graph = torch.cuda.CUDAGraph()
         n0 = L.kernel_launches()
         with torch.cuda.graph(self.graph):
