@@ -890,6 +890,34 @@ static __global__ void k_da_elementwise(const T* __restrict__ A, const float* __
   dA[i] = from_f32<T>(v);
 }
 
+// 128-bit form of the above (N a multiple of the vector width, 16-byte aligned pointers): one row / graph lookup per
+// vector, streaming loads and stores (dA and A are touched once)
+template <typename T>
+static __global__ void k_da_elementwise_vec(const T* __restrict__ A, const float* __restrict__ ss,
+                                            const float* __restrict__ coef, int64_t total_vec, int N,
+                                            T* __restrict__ dA) {
+  constexpr int V = 16 / sizeof(T);
+  int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (iv >= total_vec) return;
+  const int64_t i = iv * V;
+  const int64_t row = i / N;
+  const int b = (int)(row / N);
+  const float c_den = coef[b * 4 + 0], c_a2 = coef[b * 4 + 1];
+  if (c_den == 0.f && c_a2 == 0.f) return;
+  const float add = c_den != 0.f ? c_den * ss[row] : 0.f;
+  uint4 gv = __ldcs(reinterpret_cast<const uint4*>(dA + i));
+  uint4 av = c_a2 != 0.f ? __ldcs(reinterpret_cast<const uint4*>(A + i)) : make_uint4(0, 0, 0, 0);
+  T* g = reinterpret_cast<T*>(&gv);
+  const T* a = reinterpret_cast<const T*>(&av);
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    float v = to_f32<T>(g[k]) + add;
+    if (c_a2 != 0.f) v += c_a2 * 2.f * to_f32<T>(a[k]);
+    g[k] = from_f32<T>(v);
+  }
+  __stcs(reinterpret_cast<uint4*>(dA + i), gv);
+}
+
 template <typename T>
 static __global__ void k_cast_out(const float* __restrict__ in, T* __restrict__ out, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1180,9 +1208,15 @@ static int dense_bwd(const T* A, const T* S, const T* X, const T* gXpool, const 
     if (rc) return rc;
     rc = mm1<T, T>(B, N, N, K, Mat{U, NK, K, 0}, Mat{S, NK, K, 0}, dA_out, NN, N, 1, st, "k_tc_gemm:dA=USt");
     if (rc) return rc;
-    if (loss_kind != 0)
-      launch("k_da_elementwise", k_da_elementwise<T>, (unsigned)ceil_div((int64_t)B * NN, 256), 256, 0, st, A, pl.ss,
-             coef, (int64_t)B * NN, N, dA_out);
+    if (loss_kind != 0) {
+      constexpr int V = 16 / sizeof(T);
+      if (N % V == 0 && aligned16(A) && aligned16(dA_out))
+        launch("k_da_elementwise", k_da_elementwise_vec<T>, (unsigned)ceil_div((int64_t)B * NN / V, 256), 256, 0, st, A,
+               pl.ss, coef, (int64_t)B * NN / V, N, dA_out);
+      else
+        launch("k_da_elementwise", k_da_elementwise<T>, (unsigned)ceil_div((int64_t)B * NN, 256), 256, 0, st, A, pl.ss,
+               coef, (int64_t)B * NN, N, dA_out);
+    }
   }
   return launch_status();
 }

@@ -3,6 +3,8 @@
 #pragma once
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace tgp {
@@ -193,6 +195,13 @@ inline int compact_emit(Pred pred, Emit emit, int64_t n, const int* counts, cuda
 // exclusive offset by walking back over the published aggregates until they meet an inclusive prefix.
 // tile_state ([tiles] uint64) and ticket (int) must be zero before the launch.  Spins are bounded (trap).
 // ------------------------------------------------------------------------------------------
+// A predicate may split itself into stage0 (independent streaming loads) / stage1 / stage2 (dependent lookups) and
+// declare `static constexpr bool kStaged = true`.
+template <typename P, typename = void>
+struct pred_is_staged : std::false_type {};
+template <typename P>
+struct pred_is_staged<P, std::void_t<decltype(P::kStaged)>> : std::integral_constant<bool, P::kStaged> {};
+
 template <typename Pred, typename Emit>
 static __global__ void __launch_bounds__(kCompactThreads)
     k_compact_onepass(Pred pred, Emit emit, int64_t n, unsigned long long* __restrict__ tile_state,
@@ -207,12 +216,33 @@ static __global__ void __launch_bounds__(kCompactThreads)
   typename Pred::Payload pay[kCompactItems];
   unsigned ball[kCompactItems];
   int cnt = 0;
+  if constexpr (pred_is_staged<Pred>::value) {
+    // staged predicate: every stage is a separate fully unrolled loop, so the loads of all items of a stage are in
+    // flight together (a one-call predicate with early exits serialises row -> col -> mask -> table per item)
+    bool ok[kCompactItems];
 #pragma unroll
-  for (int j = 0; j < kCompactItems; ++j) {
-    int64_t i = base + j * 32 + lane;
-    bool f = (i < n) && pred(i, pay[j]);
-    ball[j] = __ballot_sync(kFull, f);
-    cnt += __popc(ball[j]);
+    for (int j = 0; j < kCompactItems; ++j) {
+      int64_t i = base + j * 32 + lane;
+      ok[j] = i < n;
+      if (ok[j]) pred.stage0(i, pay[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kCompactItems; ++j) ok[j] = ok[j] && pred.stage1(pay[j]);
+#pragma unroll
+    for (int j = 0; j < kCompactItems; ++j) ok[j] = ok[j] && pred.stage2(pay[j]);
+#pragma unroll
+    for (int j = 0; j < kCompactItems; ++j) {
+      ball[j] = __ballot_sync(kFull, ok[j]);
+      cnt += __popc(ball[j]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kCompactItems; ++j) {
+      int64_t i = base + j * 32 + lane;
+      bool f = (i < n) && pred(i, pay[j]);
+      ball[j] = __ballot_sync(kFull, f);
+      cnt += __popc(ball[j]);
+    }
   }
   if (lane == 0) warp_tot[w] = cnt;
   __syncthreads();

@@ -24,7 +24,9 @@ static __global__ void k_build_table(const int64_t* __restrict__ node_index, int
 }
 
 struct KeptPred {
+  static constexpr bool kStaged = true;
   struct Payload {
+    int64_t r64, c64;
     int32_t r, c;
     float w;
   };
@@ -36,19 +38,29 @@ struct KeptPred {
   int64_t N;
   bool rsl;
   float eps;
-  __device__ bool operator()(int64_t i, Payload& p) const {
-    // the edge list is touched once: streaming (evict-first) loads keep the mask / table lines in L2
-    int64_t r = __ldcs(row + i), c = __ldcs(col + i);
+  // stage 0: the three streaming loads of the edge (touched once: evict-first keeps the mask / table lines in L2)
+  __device__ void stage0(int64_t i, Payload& p) const {
+    p.r64 = __ldcs(row + i);
+    p.c64 = __ldcs(col + i);
+    p.w = w ? __ldcs(w + i) : 1.f;
+  }
+  // stage 1: range / self-loop / tiny-weight tests and the two membership bits
+  __device__ bool stage1(Payload& p) const {
+    const int64_t r = p.r64, c = p.c64;
     if (r < 0 || r >= N || c < 0 || c >= N) return false;
     if (rsl && r == c) return false;
-    if (!((__ldg(bits + (r >> 5)) >> (r & 31)) & 1u) || !((__ldg(bits + (c >> 5)) >> (c & 31)) & 1u)) return false;
-    p.r = __ldg(table + r);
-    p.c = __ldg(table + c);
-    if (w) {
-      p.w = __ldcs(w + i);
-      if (!(fabsf(p.w) > eps)) return false;
-    }
+    if (w && !(fabsf(p.w) > eps)) return false;
+    return ((__ldg(bits + (r >> 5)) >> (r & 31)) & 1u) && ((__ldg(bits + (c >> 5)) >> (c & 31)) & 1u);
+  }
+  // stage 2: relabel (only the surviving edges touch the table)
+  __device__ bool stage2(Payload& p) const {
+    p.r = __ldg(table + p.r64);
+    p.c = __ldg(table + p.c64);
     return true;
+  }
+  __device__ bool operator()(int64_t i, Payload& p) const {
+    stage0(i, p);
+    return stage1(p) && stage2(p);
   }
 };
 struct KeptEmit {
