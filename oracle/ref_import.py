@@ -10,8 +10,8 @@ The reference's control flow (``BaseReduce.forward``, ``sparse_connect``,
 ``DenseConnect``, ``postprocess_adj_pool_*``, the four losses, ``SelectOutput``,
 ``TopkSelect``) then executes verbatim on top of those primitives.
 
-Used by ``tests/golden/make_golden.py`` (to generate the committed fixtures) and by
-``tests/test_oracle_vs_reference.py`` (skipped when /root/reference is absent).
+Used by ``tests/golden/make_golden.py`` and ``tests/golden/make_golden_unbatched.py`` (to generate the committed
+fixtures; the latter also asserts that the oracle reproduces the reference bit for bit).
 Never imported by the product package, ``smoke()`` or ``bench.py``.
 """
 
