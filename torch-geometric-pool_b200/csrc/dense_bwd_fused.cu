@@ -1,0 +1,431 @@
+// Fused dense-pooling backward, fp32 (3xTF32): ONE launch per batch instead of three engine launches.
+//
+//   W  = A S                                              (never leaves the SM: accumulated in TMEM, split into hi / lo
+//                                                          in registers and fed back as the A operand of the next MMA)
+//   dS = X Gx^T + T^T Graw + S P + W Graw^T (+ element-wise loss terms)          [N, K]
+//   dX = S Gx                                                                    [N, F]
+//
+// (math: SURVEY Appendix B; reference autograd of tgp/connect/dense_conn.py:112-122 and tgp/utils/losses.py:39-123;
+//  Graw = d loss / d (S^T A S), P = d loss / d (S^T S) and the per-graph coefficients come from k_graph_bwd.)
+//
+// Work item = (graph, 128-row block of nodes).  Per item the MMA warp runs a fixed chain of "pairs" (A_p, B_p), each a
+// run of 32-wide k-blocks through the same shared-memory stage ring / TMEM operand ring as the fp32 engine
+// (tc_gemm.cu, k_tc_gemm_ts):
+//   pair 0          A rows x S                -> W accumulator          (contraction over all N nodes)
+//   pair 1          X rows x Gx^T             -> dS accumulator (first)
+//   pair 2          T^T rows x Graw           -> dS
+//   pair 3          S rows x P                -> dS                     (only with auxiliary losses)
+//   pair 4          W (from TMEM) x Graw^T    -> dS
+//   pair 5, 6       S rows x Gx[:, 64 j ..]   -> dX accumulators (one per 64 feature columns)
+// The dS / dX accumulators are single-buffered: the epilogue of item i drains them while pair 0 of item i+1 (40 % of an
+// item's MMA work) only touches the W accumulator.
+//
+// Tensor memory (512 columns): W [0, 128) | dS [128, 256) | dX [256, 384) | operand ring: 2 x 64 columns.
+// Warp roles (576 threads): 0 TMA, 1 MMA, 2-9 two split groups of four warps, 10-17 epilogue.
+#include <stdlib.h>
+#include <string.h>
+
+#include "dense.cuh"
+#include "tc_gemm.cuh"
+#include "tc_ptx.cuh"
+
+namespace tgp {
+namespace tc {
+
+extern long long* g_engine_dbg;
+
+namespace {
+
+#ifndef TGPB200_BWD_CONCAT
+#define TGPB200_BWD_CONCAT 1
+#endif
+// 3xTF32 of the W / dS pairs as TWO instructions per k-step: hi_a x [hi_b | lo_b] (N = 128: the lo tile of B directly
+// follows its hi tile in shared memory) + lo_a x hi_b (N = 64).  A tcgen05.mma costs ~57 cycles of dispatch whatever
+// its N <= 64 and 74 cycles at N = 128 (benchmarks/mma_rate.cu), so the instruction COUNT is what the MMA warp pays
+// for.  The accumulators of those pairs are 128 columns wide ([.. | hi_a lo_b], summed by whoever reads them).
+constexpr bool kConcat = TGPB200_BWD_CONCAT != 0;
+constexpr int kPairs = 7;
+constexpr int kGroups = kConcat ? 2 : 3;   // split groups = TMEM operand stages
+constexpr int kEpiW = 8;                   // epilogue warps (two per TMEM lane quadrant)
+constexpr int kThreadsBwd = 64 + kGroups * 128 + kEpiW * 32;
+constexpr int BK = 32, KSTEPS = 4;
+constexpr int BNB = 64;                    // MMA N of every pair
+constexpr uint32_t kAccW = kConcat ? 128 : 64;  // width of the W and dS accumulators
+constexpr uint32_t kColW = 0, kColS = kAccW, kColX = 2 * kAccW, kColRing = 2 * kAccW + 128, kRing = 64;
+constexpr uint32_t kABytes = BM * kStageRowBytes, kBBytes = BNB * kStageRowBytes;
+constexpr uint32_t kStage = kABytes + 2 * kBBytes;  // [A raw | B hi | B lo] = 32 KB
+constexpr uint32_t kEpiBytes = kEpiW * 4096;
+
+enum ASrc { kAKMajor = 0, kAMnPlain = 1, kATmem = 2 };
+
+struct BwdParams {
+  CUtensorMap map_a[kPairs], map_b[kPairs];
+  int kd[kPairs], a_src[kPairs], b_mn[kPairs], b_n0[kPairs], first[kPairs], wide[kPairs];
+  uint32_t acc_col[kPairs];
+  int num_pairs;
+  int batch, N, K, F;
+  int m_tiles, num_items, stages;
+  CUtensorMap map_ds, map_dx;
+  const float* S;      // element-wise terms (nullptr: none)
+  const float* d;
+  const float* coef;
+  float eps;
+  long long* dbg;
+};
+
+__global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid_constant__ BwdParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stages = P.stages;
+  // [stages][kStage] | epilogue staging | barriers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStage * stages + kEpiBytes);
+  const uint32_t bar_base = smem_u32(bars);
+  auto bar_full = [&](int s) { return bar_base + 8u * s; };
+  auto bar_lo = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto bar_empty = [&](int s) { return bar_base + 8u * (2 * stages + s); };
+  auto bar_tfree = [&](int g) { return bar_base + 8u * (3 * stages + g); };
+  const uint32_t bar_wfull = bar_base + 8u * (3 * stages + kGroups), bar_tfull = bar_wfull + 8u, bar_tempty = bar_wfull + 16u;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + kGroups + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_lo(s), 128);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int g = 0; g < kGroups; ++g) mbar_init(bar_tfree(g), 1);
+    mbar_init(bar_wfull, 1);
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tempty, kEpiW * 32);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int kblocks[kPairs];
+  for (int p = 0; p < kPairs; ++p) kblocks[p] = p < P.num_pairs ? (P.kd[p] + BK - 1) / BK : 0;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int item = blockIdx.x; item < P.num_items; item += gridDim.x) {
+      const int mt = item % P.m_tiles, b = item / P.m_tiles;
+      const int m0 = mt * BM;
+      for (int p = 0; p < P.num_pairs; ++p) {
+        const int src = P.a_src[p];
+        for (int kb = 0; kb < kblocks[p]; ++kb) {
+          mbar_wait(bar_empty(s), ph ^ 1);
+          const uint32_t sa = smem_base + (uint32_t)s * kStage, sb = sa + kABytes;
+          const int k0 = kb * BK;
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_full(s), (src == kATmem ? 0u : kABytes) + kBBytes);
+            if (src == kAMnPlain) tma_load_3d(sa, &P.map_a[p], bar_full(s), m0, k0, b);      // [32 k][128 m], no swizzle
+            else if (src == kAKMajor) tma_load_3d(sa, &P.map_a[p], bar_full(s), k0, m0, b);  // [128 m][32 k], 128B swizzle
+            if (P.b_mn[p]) {
+              for (int blk = 0; blk < BNB / 32; ++blk)
+                tma_load_3d(sb + blk * (BK * kStageRowBytes), &P.map_b[p], bar_full(s), P.b_n0[p] + blk * 32, k0, b);
+            } else {
+              tma_load_3d(sb, &P.map_b[p], bar_full(s), k0, P.b_n0[p], b);
+            }
+          }
+          __syncwarp();
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    const uint32_t tm = __shfl_sync(kFull, tmem_base, 0);
+    int s = 0;
+    uint32_t ph = 0, kc = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
+      for (int p = 0; p < P.num_pairs; ++p) {
+        if (p == 1) {  // first pair that writes the dS / dX accumulators: the previous item's epilogue has drained them
+          mbar_wait(bar_tempty, ((uint32_t)it & 1u) ^ 1u);
+          tc_fence_after();
+        }
+        const uint32_t d_tmem = tm + P.acc_col[p];
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)P.b_mn[p] << 16) |
+                               ((uint32_t)(BNB >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint32_t b_lbo = P.b_mn[p] ? BK * kStageRowBytes : 16;
+        const uint32_t b_step = P.b_mn[p] ? 8 * kStageRowBytes : 32;
+        const uint64_t desc_b0 = make_desc(smem_base, b_lbo, P.b_mn[p] ? 512 : 1024, P.b_mn[p] ? 1 : 2);
+        const uint32_t idesc2 = (idesc & ~(0x3fu << 17)) | ((uint32_t)((2 * BNB) >> 3) << 17);
+        const bool wide = kConcat && P.wide[p] != 0;
+        uint32_t accum = P.first[p] ? 0u : 1u;
+        for (int kb = 0; kb < kblocks[p]; ++kb, ++kc) {
+          mbar_wait(bar_lo(s), ph);
+          if (P.dbg && blockIdx.x == 0 && lane == 0 && kc < 128) P.dbg[kc * 8 + 5] = clock64();
+          tc_fence_after();
+          const uint32_t ts = kc % (uint32_t)kGroups;
+          const uint32_t a_stage = tm + kColRing + ts * kRing;
+          const uint64_t db0 = desc_b0 + (uint64_t)(((uint32_t)s * kStage + kABytes) >> 4);
+          if (P.dbg && blockIdx.x == 0 && lane == 0 && kc < 128) P.dbg[kc * 8 + 7] = clock64();
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+              const uint64_t db = db0 + (uint64_t)(kk * (b_step >> 4)), db_lo = db + (kBBytes >> 4);
+              const uint32_t a_hi = a_stage + (uint32_t)(kk * 16), a_lo = a_hi + 8;
+              if (wide) {
+                umma_ts_tf32(d_tmem, a_hi, db, idesc2, kk == 0 ? accum : 1u);  // hi_a x [hi_b | lo_b]
+                umma_ts_tf32(d_tmem, a_lo, db, idesc, 1u);                     // lo_a x hi_b
+              } else {
+                umma_ts_tf32(d_tmem, a_lo, db, idesc, kk == 0 ? accum : 1u);
+                umma_ts_tf32(d_tmem, a_hi, db_lo, idesc, 1u);
+                umma_ts_tf32(d_tmem, a_hi, db, idesc, 1u);
+              }
+            }
+            if (P.dbg && blockIdx.x == 0 && kc < 128) P.dbg[kc * 8 + 0] = clock64();
+            umma_commit(bar_empty(s));
+            umma_commit(bar_tfree(ts));
+          }
+          __syncwarp();
+          if (P.dbg && blockIdx.x == 0 && lane == 0 && kc < 128) P.dbg[kc * 8 + 6] = clock64();
+          accum = 1;
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+        if (p == 0) {  // W complete: the split warps may read it back
+          if (elect_one()) umma_commit(bar_wfull);
+          __syncwarp();
+        }
+      }
+      if (elect_one()) umma_commit(bar_tfull);
+      __syncwarp();
+    }
+  } else if (warp < 2 + kGroups * 4) {
+    // ===================== split: B hi / lo in shared memory, A hi / lo into the TMEM ring =====================
+    const int grp = (warp - 2) >> 2;
+    const int t = (threadIdx.x - 64) & 127;
+    const int q = warp & 3;             // TMEM lane quadrant of this warp
+    const int m_local = q * 32 + lane;  // row of the tile this thread stages
+    int s = 0;
+    uint32_t ph = 0, kc = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
+      for (int p = 0; p < P.num_pairs; ++p) {
+        const int src = P.a_src[p];
+        for (int kb = 0; kb < kblocks[p]; ++kb, ++kc) {
+          if ((int)(kc % (uint32_t)kGroups) != grp) {  // another group's k-block
+            if (++s == stages) { s = 0; ph ^= 1; }
+            continue;
+          }
+          mbar_wait(bar_full(s), ph);
+          const uint32_t sa = smem_base + (uint32_t)s * kStage, sb = sa + kABytes;
+          // B: hi in place, lo behind it
+          for (uint32_t ch = t; ch < kBBytes / 16; ch += 128) {
+            const float4 v = lds128(sb + ch * 16);
+            float4 h, l;
+            h.x = rna_tf32(v.x), h.y = rna_tf32(v.y), h.z = rna_tf32(v.z), h.w = rna_tf32(v.w);
+            l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
+            sts128(sb + ch * 16, h);
+            sts128(sb + kBBytes + ch * 16, l);
+          }
+          fence_proxy_async();
+          // A: this thread's row, 32 k values
+          float x[32];
+          if (src == kATmem) {
+            mbar_wait(bar_wfull, (uint32_t)it & 1u);
+            tc_fence_after();
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + kColW + (uint32_t)(kb * BK), x);
+            if (kConcat) {
+              float x2[32];
+              tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + kColW + 64u + (uint32_t)(kb * BK), x2);
+#pragma unroll
+              for (int k = 0; k < 32; ++k) x[k] += x2[k];
+            }
+          } else if (src == kAMnPlain) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) x[k] = lds32(sa + (uint32_t)k * (BM * 4) + (uint32_t)m_local * 4);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 v = lds128(sa + (uint32_t)m_local * kStageRowBytes + (uint32_t)((c ^ (m_local & 7)) << 4));
+              x[4 * c] = v.x, x[4 * c + 1] = v.y, x[4 * c + 2] = v.z, x[4 * c + 3] = v.w;
+            }
+          }
+          mbar_wait(bar_tfree(grp), ((kc / (uint32_t)kGroups) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t a_stage = tmem_base + ((uint32_t)(q * 32) << 16) + kColRing + (uint32_t)grp * kRing;
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS; ++kk) {
+            float hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              hi[i] = rna_tf32(x[kk * 8 + i]);
+              lo[i] = x[kk * 8 + i] - hi[i];
+            }
+            tmem_st16(a_stage + (uint32_t)(kk * 16), hi, lo);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(bar_lo(s));
+          if (P.dbg && blockIdx.x == 0 && lane == 0 && kc < 128) P.dbg[kc * 8 + 1 + q] = clock64();
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: dS (+ element-wise terms) and dX through TMA stores =====================
+    const int quad = warp & 3;
+    const int ew = warp - 2 - kGroups * 4;   // 0 .. 7
+    const int e2 = ew >> 2;                  // which of the quadrant's two warps
+    const uint32_t stg = smem_base + (uint32_t)kStage * stages + (uint32_t)ew * 4096u;
+    const int n_chunks = 2 + (P.F + 31) / 32;
+    int it = 0;
+    for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
+      const int mt = item % P.m_tiles, b = item / P.m_tiles;
+      mbar_wait(bar_tfull, (uint32_t)it & 1u);
+      if (P.dbg && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 32) P.dbg[(128 + it) * 8 + 0] = clock64();
+      tc_fence_after();
+      const int m_base = mt * BM + quad * 32;
+      const int m = m_base + lane;
+      for (int c = 0; c < n_chunks; ++c) {
+        if ((c & 1) != e2) continue;
+        const bool is_ds = c < 2;
+        const int n0 = is_ds ? c * 32 : (c - 2) * 32;
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (is_ds ? kColS : kColX) + (uint32_t)n0, v);
+        if (kConcat && is_ds) {  // + hi_a x lo_b
+          float v2[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + kColS + 64u + (uint32_t)n0, v2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += v2[j];
+        }
+        if (m_base >= P.N || n0 >= (is_ds ? P.K : P.F)) continue;  // warp-uniform
+        if (is_ds && P.S != nullptr && m < P.N) {
+          // element-wise gradient terms: mincut denominator (2 c_den d_i S) and entropy loss
+          const float c_den = P.coef[b * 4 + 0], c_ent = P.coef[b * 4 + 2];
+          if (c_den != 0.f || c_ent != 0.f) {
+            const float dd = 2.f * c_den * P.d[(int64_t)b * P.N + m];
+            const float* srow = P.S + ((int64_t)b * P.N + m) * P.K + n0;
+            float sv[32];
+            if (n0 + 32 <= P.K) {
+              const float4* s4 = reinterpret_cast<const float4*>(srow);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t4 = __ldg(s4 + j);
+                sv[4 * j] = t4.x, sv[4 * j + 1] = t4.y, sv[4 * j + 2] = t4.z, sv[4 * j + 3] = t4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sv[j] = n0 + j < P.K ? srow[j] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float add = dd * sv[j];
+              if (c_ent != 0.f) add += c_ent * (-__logf(sv[j] + P.eps) - __fdividef(sv[j], sv[j] + P.eps));
+              v[j] += add;
+            }
+          }
+        }
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+        const uint32_t row = stg + (uint32_t)lane * 128u;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4)
+          sts128(row + (uint32_t)((c4 ^ (lane & 7)) << 4), make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]));
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(is_ds ? &P.map_ds : &P.map_dx, stg, n0, m_base, b);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty);
+      if (P.dbg && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 32) P.dbg[(128 + it) * 8 + 1] = clock64();
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// row-major fp32 output [batch][rows][cols], box {32, 32, 1}, 128B swizzle (staged one row per lane)
+bool make_out_map(CUtensorMap* map, float* ptr, int64_t batch, int64_t rows, int64_t cols) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn || ((uintptr_t)ptr & 15) || (cols % 4)) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)rows * cols * 4};
+  cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+// fp32 only.  Graw / Pm: [B, K, K] from k_graph_bwd (Pm nullptr: no S P term); ew_*: element-wise terms (ew_S nullptr: none).
+// Returns TGPB200_ERR_UNSUPPORTED outside the envelope (K <= 64, F <= 128, 16-byte aligned rows): the caller then runs
+// the one-product-per-launch chain.
+int dense_bwd_fused(const float* A, const float* S, const float* X, const float* Tt, const float* Gx, const float* Graw,
+                    const float* Pm, int B, int N, int K, int F, const float* ew_S, const float* ew_d, const float* ew_coef,
+                    float eps, float* dS, float* dX, cudaStream_t stream) {
+  {
+    const char* e = getenv("TGPB200_BWD_FUSED");
+    if (e && e[0] == '0') return TGPB200_ERR_UNSUPPORTED;
+  }
+  if (!A || !S || !X || !Tt || !Gx || !Graw || !dS || !dX || B <= 0) return TGPB200_ERR_UNSUPPORTED;
+  if (K > BNB || F > 128 || (N % 4) || (K % 4) || (F % 4) || N < 1) return TGPB200_ERR_UNSUPPORTED;
+  const uintptr_t al = (uintptr_t)A | (uintptr_t)S | (uintptr_t)X | (uintptr_t)Tt | (uintptr_t)Gx | (uintptr_t)Graw |
+                       (uintptr_t)(Pm ? Pm : Graw);
+  if (al & 15) return TGPB200_ERR_UNSUPPORTED;
+  BwdParams P;
+  memset(&P, 0, sizeof(P));
+  P.batch = B, P.N = N, P.K = K, P.F = F;
+  P.m_tiles = (N + BM - 1) / BM;
+  P.num_items = B * P.m_tiles;
+  const int64_t NN = (int64_t)N * N, NK = (int64_t)N * K, NF = (int64_t)N * F, KK = (int64_t)K * K, KF = (int64_t)K * F;
+  int n = 0;
+  bool ok = true;
+  auto add = [&](int kd, int a_src, OperandDesc a, OperandDesc b, int b_n0, uint32_t acc, int first) {
+    P.kd[n] = kd, P.a_src[n] = a_src, P.b_mn[n] = b.mn_major, P.b_n0[n] = b_n0, P.acc_col[n] = acc, P.first[n] = first;
+    P.wide[n] = acc != kColX && acc != kColX + (uint32_t)BNB;
+    if (a_src == kAKMajor) ok = ok && make_operand_map(&P.map_a[n], a, false, B, N, kd, BM);
+    else if (a_src == kAMnPlain) ok = ok && make_operand_map_mn_plain(&P.map_a[n], a, B, N, kd);
+    // the N extent of a B operand is its full column / row count (b_n0 selects the 64-wide slice)
+    ok = ok && make_operand_map(&P.map_b[n], b, false, B, b.mn_major ? (int)b.row_stride : (int)(b.batch_stride / b.row_stride), kd, BNB);
+    ++n;
+  };
+  // pair 0: W = A S
+  add(N, kAKMajor, OperandDesc{A, NN, N, 0}, OperandDesc{S, NK, K, 1}, 0, kColW, 1);
+  // pair 1: dS = X Gx^T   (B = Gx [K rows][F], contraction over F: K-major)
+  add(F, kAKMajor, OperandDesc{X, NF, F, 0}, OperandDesc{Gx, KF, F, 0}, 0, kColS, 1);
+  // pair 2: dS += T^T Graw  (A = T [K][N]: node index contiguous -> MN-major; B = Graw [k1][k2]: MN-major)
+  add(K, kAMnPlain, OperandDesc{Tt, NK, N, 1}, OperandDesc{Graw, KK, K, 1}, 0, kColS, 0);
+  // pair 3: dS += S P
+  if (Pm) add(K, kAKMajor, OperandDesc{S, NK, K, 0}, OperandDesc{Pm, KK, K, 1}, 0, kColS, 0);
+  // pair 4: dS += W Graw^T  (A from the W accumulator; B = Graw [k2 rows][k1]: K-major)
+  add(K, kATmem, OperandDesc{nullptr, 0, 0, 0}, OperandDesc{Graw, KK, K, 0}, 0, kColS, 0);
+  // pairs 5..: dX[:, 64 j .. 64 j + 64) = S Gx[:, 64 j ..]   (B = Gx [K][F]: MN-major)
+  for (int j = 0; j * BNB < F; ++j)
+    add(K, kAKMajor, OperandDesc{S, NK, K, 0}, OperandDesc{Gx, KF, F, 1}, j * BNB, kColX + (uint32_t)(j * BNB), 1);
+  if (!ok) return TGPB200_ERR_UNSUPPORTED;
+  P.num_pairs = n;
+  if (!make_out_map(&P.map_ds, dS, B, N, K) || !make_out_map(&P.map_dx, dX, B, N, F)) return TGPB200_ERR_UNSUPPORTED;
+  P.S = ew_S, P.d = ew_d, P.coef = ew_coef, P.eps = eps;
+  P.stages = 6;
+  P.dbg = g_engine_dbg;
+  static bool attr_set = false;
+  if (!attr_set) {
+    attr_set = true;
+    cudaFuncSetAttribute(k_dense_bwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }
+  const size_t smem = (size_t)kStage * P.stages + kEpiBytes + (3 * P.stages + kGroups + 4) * 8 + 16 + 1024;
+  const int sms = device_sm_count();
+  const int grid = P.num_items < sms ? P.num_items : sms;
+  launch("k_dense_bwd_fused", k_dense_bwd_fused, grid, kThreadsBwd, smem, stream, P);
+  return launch_status();
+}
+
+}  // namespace tc
+}  // namespace tgp

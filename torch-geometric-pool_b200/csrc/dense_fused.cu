@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(320, 1) k_dense_fwd_fused(const __grid_constan
 }
 
 long long* g_fused_dbg = nullptr;
+long long* g_engine_dbg = nullptr;
 
 // Returns TGPB200_ERR_UNSUPPORTED when the shape does not fit (the caller then uses the per-product path).
 int dense_fwd_fused(const void* A, const void* S, const void* X, int B, int N, int K, int F, bool bf16, float eps,
@@ -417,3 +418,5 @@ int dense_fwd_fused(const void* A, const void* S, const void* X, int B, int N, i
 }  // namespace tgp
 
 extern "C" void tgpb200_debug_fused_timeline(long long* p) { tgp::tc::g_fused_dbg = p; }
+// same for the engine / fused backward (k_tc_gemm_ts, k_dense_bwd_fused): [160][8] clock64 stamps of block 0
+extern "C" void tgpb200_debug_engine_timeline(long long* p) { tgp::tc::g_engine_dbg = p; }

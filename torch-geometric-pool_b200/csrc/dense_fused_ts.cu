@@ -46,12 +46,13 @@ constexpr int kSplitWarps = TGPB200_TS_SPLIT_WARPS;     // per group; multiple o
 constexpr int kSplitThreads = kSplitWarps * 32;         // per group
 constexpr int kEpiWarps = 8;                            // two per TMEM lane quadrant, alternate 32-column chunks
 constexpr int kTsThreads = 64 + kSplitGroups * kSplitThreads + kEpiWarps * 32;  // TMA, MMA, split groups, epilogue
-constexpr int kTpr = kSplitThreads / 16;                // statistics: threads per node row
+constexpr int kTpr = kEpiWarps * 32 / 16;               // statistics (epilogue warps): threads per node row
 constexpr int kACols = 32;                           // TMEM columns per (tile, k-block): 2 k-steps x (8 hi + 8 lo)
 
 struct TsParams {
   CUtensorMap map_a, map_x, map_s;  // row-major boxes {extent, 16, 1}, no swizzle
   CUtensorMap map_sb;               // S as swizzled 128-byte column blocks (B operand)
+  CUtensorMap map_ot, map_ox, map_om;  // outputs Tt / Xp / Mm as [B][K rows][extent], box {32, 32, 1} (TMA stores)
   int B, N, K, F;
   int BN;                  // MMA N (K rounded up to 16)
   int t_a, t_x, t_s, nb_s;
@@ -73,7 +74,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
   const uint32_t stage_bytes = P.stage_bytes;
   // barriers: full[stages] (TMA landed), ready[stages] (split done: B operand in smem + A operand in TMEM),
   // empty[stages] (MMAs of the stage retired), tfree[2] (TMEM A stage retired), tfull, tempty (accumulators)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stage_bytes * stages);
+  // [stages][stage_bytes] | epilogue staging: kEpiWarps x 4 KB | barriers | lo flags
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stage_bytes * stages + kEpiWarps * 4096);
   const uint32_t bar_base = smem_u32(bars);
   auto bar_full = [&](int s) { return bar_base + 8u * s; };
   auto bar_ready = [&](int s) { return bar_base + 8u * (stages + s); };
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
     for (int s = 0; s < stages; ++s) {
       mbar_init(bar_full(s), 1);
       mbar_init(bar_ready(s), kSplitThreads);
-      mbar_init(bar_empty(s), 1);
+      mbar_init(bar_empty(s), 1 + kEpiWarps * 32);  // MMAs retired (commit) + statistics read (epilogue threads)
     }
     mbar_init(bar_tfree(0), 1);
     mbar_init(bar_tfree(1), 1);
@@ -188,7 +190,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
     const int t = (threadIdx.x - 64) % kSplitThreads;      // thread index inside the group
     const int q = warp & 3;                                // TMEM lane quadrant of this warp
     const int half = ((warp - 2) % kSplitWarps) >> 2;      // which of the quadrant's warps inside the group
-    const int r = t / kTpr, c16 = t % kTpr;
     int s = 0;
     uint32_t ph = 0, kc = 0;
     for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
@@ -200,35 +201,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
         mbar_wait(bar_full(s), ph);
         if (P.dbg && blockIdx.x == 0 && t == 0 && kc < 96) P.dbg[kc * 8 + 5] = clock64();
         const uint32_t base = smem_base + (uint32_t)s * stage_bytes;
-        // ---- pass 1a: row statistics (16 rows x 8 threads, 128-bit reads of the row-major tiles)
-        float sd = 0.f, sa2 = 0.f, s2 = 0.f, se = 0.f;
-        {
-          const uint32_t ra = base + (uint32_t)r * P.N * 4;
-          for (int col = c16 * 4; col < P.N; col += 4 * kTpr) {
-            const float4 v = lds128(ra + col * 4);
-            sd += (v.x + v.y) + (v.z + v.w);
-            sa2 += fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
-          }
-          const uint32_t rs = base + off_s + (uint32_t)r * P.K * 4;
-          for (int col = c16 * 4; col < P.K; col += 4 * kTpr) {
-            const float4 v = lds128(rs + col * 4);
-            s2 += fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
-            se -= fmaf(v.x, __logf(v.x + P.eps),
-                       fmaf(v.y, __logf(v.y + P.eps), fmaf(v.z, __logf(v.z + P.eps), v.w * __logf(v.w + P.eps))));
-          }
-        }
-#pragma unroll
-        for (int o = 1; o < kTpr; o <<= 1) {
-          sd += __shfl_xor_sync(kFull, sd, o);
-          sa2 += __shfl_xor_sync(kFull, sa2, o);
-          s2 += __shfl_xor_sync(kFull, s2, o);
-          se += __shfl_xor_sync(kFull, se, o);
-        }
-        const int node = kb * TBK + r;
-        if (c16 == 0 && node < P.N) {
-          const int64_t o = (int64_t)b * P.N + node;
-          P.d[o] = sd, P.a2[o] = sa2, P.ss[o] = s2, P.ent[o] = se;
-        }
         // ---- pass 1b: hi / lo of the B operand (swizzled S blocks), in place + next to it
         for (uint32_t ch = t; ch < (uint32_t)P.nb_s * 128; ch += kSplitThreads) {
           const uint32_t a = base + off_sb + ch * 16;
@@ -277,35 +249,82 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
   } else {
     // ===================== epilogue (accumulators single-buffered) =====================
     const int quad = warp & 3;
-    const int e2 = ((warp - 2 - kSplitGroups * kSplitWarps) >> 2) & 1;  // which of the quadrant's two epilogue warps
+    const int ew = warp - 2 - kSplitGroups * kSplitWarps;  // 0 .. kEpiWarps - 1
+    const int e2 = (ew >> 2) & 1;                          // which of the quadrant's two epilogue warps
+    const uint32_t stg = smem_base + (uint32_t)stage_bytes * stages + (uint32_t)ew * 4096u;  // this warp's staging tile
+    const int t = threadIdx.x - (kTsThreads - kEpiWarps * 32);  // 0 .. 255
+    const int r = t / kTpr, c16 = t % kTpr;
+    int s = 0;
+    uint32_t ph = 0;
     int it = 0;
     for (int b = blockIdx.x; b < P.B; b += gridDim.x, ++it) {
+      // ---- row statistics of every k-block of the graph (these warps are otherwise idle during the main loop; on the
+      //      split warps this pass was ~35 % of the work of the role that bounds the kernel)
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(bar_full(s), ph);
+        const uint32_t base = smem_base + (uint32_t)s * stage_bytes;
+        float sd = 0.f, sa2 = 0.f, s2 = 0.f, se = 0.f;
+        {
+          const uint32_t ra = base + (uint32_t)r * P.N * 4;
+          for (int col = c16 * 4; col < P.N; col += 4 * kTpr) {
+            const float4 v = lds128(ra + col * 4);
+            sd += (v.x + v.y) + (v.z + v.w);
+            sa2 += fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+          }
+          const uint32_t rs = base + off_s + (uint32_t)r * P.K * 4;
+          for (int col = c16 * 4; col < P.K; col += 4 * kTpr) {
+            const float4 v = lds128(rs + col * 4);
+            s2 += fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+            se -= fmaf(v.x, __logf(v.x + P.eps),
+                       fmaf(v.y, __logf(v.y + P.eps), fmaf(v.z, __logf(v.z + P.eps), v.w * __logf(v.w + P.eps))));
+          }
+        }
+#pragma unroll
+        for (int o = 1; o < kTpr; o <<= 1) {
+          sd += __shfl_xor_sync(kFull, sd, o);
+          sa2 += __shfl_xor_sync(kFull, sa2, o);
+          s2 += __shfl_xor_sync(kFull, s2, o);
+          se += __shfl_xor_sync(kFull, se, o);
+        }
+        const int node = kb * TBK + r;
+        if (c16 == 0 && node < P.N) {
+          const int64_t o = (int64_t)b * P.N + node;
+          P.d[o] = sd, P.a2[o] = sa2, P.ss[o] = s2, P.ent[o] = se;
+        }
+        mbar_arrive(bar_empty(s));  // this thread has read its share of the stage
+        if (++s == stages) { s = 0; ph ^= 1; }
+      }
       mbar_wait(bar_tfull, (uint32_t)it & 1u);
       tc_fence_after();
-      const int row = quad * 32 + lane;
       int chunk = 0;
       for (int g = 0; g < G; ++g) {
         const int seg = g < P.t_a ? 0 : (g < P.t_a + P.t_x ? 1 : 2);
-        const int m = (seg == 0 ? g : (seg == 1 ? g - P.t_a : g - P.t_a - P.t_x)) * BM + row;
+        const int m0 = (seg == 0 ? g : (seg == 1 ? g - P.t_a : g - P.t_a - P.t_x)) * BM + quad * 32;  // warp-uniform
         const int m_ext = seg == 0 ? P.N : (seg == 1 ? P.F : P.K);
         for (int c0 = 0; c0 < BN; c0 += 32, ++chunk) {
           if ((chunk & 1) != e2) continue;
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * BN + c0), v);
-          if (m >= m_ext || c0 >= P.K) continue;
-          // transposed stores: for a fixed accumulator column the 32 lanes hold 32 consecutive rows, which are the
-          // contiguous index of the destination (128-byte stores)
-          float* o = seg == 0 ? P.Tt + (int64_t)b * P.K * P.N + m
-                              : (seg == 1 ? P.Xp + (int64_t)b * P.K * P.F + m : P.Mm + (int64_t)b * P.K * P.K + m);
-          const int64_t ld = seg == 0 ? P.N : (seg == 1 ? P.F : P.K);
+          if (m0 >= m_ext || c0 >= P.K) continue;
+          // Transposed tile through shared memory: accumulator column j becomes row c0 + j of the destination, the 32
+          // lanes (rows of the MMA tile) its 32 contiguous elements -> conflict-free 128-byte rows, ONE TMA store per
+          // chunk (1024 scalar global stores per graph kept the LSU busy for most of the 7 k-cycle epilogue bubble).
+          if (lane == 0) tma_store_wait_read<0>();  // the previous store of this warp has read the staging tile
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < P.K) o[(int64_t)(c0 + j) * ld] = v[j];
+          for (int j = 0; j < 32; ++j) sts32(stg + (uint32_t)(j * 128 + lane * 4), __float_as_uint(v[j]));
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(seg == 0 ? &P.map_ot : (seg == 1 ? &P.map_ox : &P.map_om), stg, m0, c0, b);
+            tma_store_commit();
+          }
         }
       }
       tc_fence_before();
       mbar_arrive(bar_tempty);
     }
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -322,6 +341,19 @@ bool make_map_rows(CUtensorMap* map, const void* ptr, int64_t batch, int64_t row
   cuuint32_t box[3] = {(cuuint32_t)cols, (cuuint32_t)TBK, 1}, estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// output [batch][rows][cols] fp32, box {32 cols, 32 rows, 1}, no swizzle (TMA stores of the transposed chunks)
+bool make_map_out(CUtensorMap* map, const void* ptr, int64_t batch, int64_t rows, int64_t cols) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn || ((uintptr_t)ptr & 15)) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)rows * cols * 4};
+  cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -349,7 +381,7 @@ int dense_fwd_fused_ts(const float* A, const float* S, const float* X, int B, in
   const size_t rows_bytes = (size_t)TBK * (N + F + K) * 4;
   P.off_sb = (uint32_t)((rows_bytes + 1023) / 1024 * 1024);
   P.stage_bytes = P.off_sb + 2u * (uint32_t)P.nb_s * kSBlock;
-  int stages = (int)((size_t)(216 * 1024) / P.stage_bytes);
+  int stages = (int)((size_t)(216 * 1024 - kEpiWarps * 4096) / P.stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return TGPB200_ERR_UNSUPPORTED;
   P.stages = stages;
@@ -359,12 +391,14 @@ int dense_fwd_fused_ts(const float* A, const float* S, const float* X, int B, in
   if (!make_map_rows(&P.map_a, A, B, N, N) || !make_map_rows(&P.map_x, X, B, N, F) || !make_map_rows(&P.map_s, S, B, N, K))
     return TGPB200_ERR_UNSUPPORTED;
   if (!make_map_3d(&P.map_sb, S, false, B, N, K, K, (int64_t)N * K, TBK, true)) return TGPB200_ERR_UNSUPPORTED;
+  if (!make_map_out(&P.map_ot, Tt, B, K, N) || !make_map_out(&P.map_ox, Xp, B, K, F) || !make_map_out(&P.map_om, Mm, B, K, K))
+    return TGPB200_ERR_UNSUPPORTED;
   static bool attr_set = false;
   if (!attr_set) {
     attr_set = true;
     cudaFuncSetAttribute(k_dense_fwd_fused_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   }
-  const size_t smem = (size_t)P.stage_bytes * stages + (3 * stages + 4) * 8 + 16 + 1024;
+  const size_t smem = (size_t)P.stage_bytes * stages + kEpiWarps * 4096 + (3 * stages + 4) * 8 + 16 + 1024;
   if (smem > 227 * 1024) return TGPB200_ERR_UNSUPPORTED;
   const int sms = device_sm_count();
   const int grid = B < sms ? B : sms;

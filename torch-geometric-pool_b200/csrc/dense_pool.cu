@@ -1168,6 +1168,18 @@ static int dense_bwd(const T* A, const T* S, const T* X, const T* gXpool, const 
     }
   }
   const bool have_x = X && gXpool;
+  bool fused_bwd = false;
+  if constexpr (std::is_same<T, float>::value) {
+    if (have_a && have_x && dX_out && dS_out) {
+      // one launch: W = A S in tensor memory -> dS (all four products + element-wise terms) and dX
+      const bool ew = loss_kind != 0;
+      rc = tc::dense_bwd_fused(A, S, X, pl.Tt, gXpool, Graw, loss_kind != 0 ? P : (float*)nullptr, B, N, K, F,
+                               ew ? S : (const float*)nullptr, pl.d, coef, eps, dS_out, dX_out, st);
+      if (rc == TGPB200_OK) fused_bwd = true;
+      else if (rc != TGPB200_ERR_UNSUPPORTED) return rc;
+    }
+  }
+  if (!fused_bwd) {
   if (have_x && dX_out) {  // dX = S Gx  [N, F]
     rc = mm1<T, T>(B, N, F, K, Mat{S, NK, K, 0}, Mat{gXpool, KF, F, 1}, dX_out, NF, F, 1, st, "k_tc_gemm:dX=SGx");
     if (rc) return rc;
@@ -1203,6 +1215,7 @@ static int dense_bwd(const T* A, const T* S, const T* X, const T* gXpool, const 
   if (have_a && loss_kind != 0 && !ew_done)
     launch("k_ds_elementwise", k_ds_elementwise<T>, (unsigned)ceil_div((int64_t)B * NK, 256), 256, 0, st, S, pl.d, coef,
            (int64_t)B * NK, N, K, eps, dS_out);
+  }  // !fused_bwd
   if (have_a && dA_out) {  // dA = (S Graw) S^T + element-wise terms
     rc = mm1<T, T>(B, N, K, K, Mat{S, NK, K, 0}, Mat{Gt, KK, K, 1}, U, NK, K, 1, st, "k_tc_gemm:U=SG");
     if (rc) return rc;

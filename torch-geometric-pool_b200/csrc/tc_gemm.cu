@@ -31,19 +31,32 @@ struct KernelParams {
   const float* ew_d;
   const float* ew_coef;
   float ew_eps;
+  long long* dbg;  // optional clock64 timeline of block 0 ([128][8], benchmarks/engine_timeline.py)
+  // Row-major destinations leave through TMA stores: every epilogue warp stages its 32 x 32 chunk in shared memory
+  // (swizzled, one row per lane) and one lane issues cp.async.bulk.tensor.  Writing the rows straight from the
+  // registers costs 32 separate 128-byte lines per store instruction and kept the LSU busy for ~3 k cycles per
+  // 128 x 64 tile (benchmarks/engine_timeline.py), stalling the split warps that share it.
+  CUtensorMap map_out;
+  int tma_out;       // 1: use map_out
+  int epi_bufs;      // staging buffers per epilogue warp (1 or 2)
 };
+
+// Staging state of one epilogue warp for the TMA-store path
+struct EpiStage {
+  uint32_t smem;  // first staging buffer of this warp (1024-byte aligned, 4 KB per buffer)
+  int n;          // chunks staged so far
+};
+extern long long* g_engine_dbg;
 
 // Epilogue of one 32-column chunk: thread `lane` of a quadrant holds row m of the tile, v[0..32) = columns n0..n0+31.
 template <bool kF32>
 __device__ __forceinline__ void store_chunk(const KernelParams& P, float (&v)[32], int b, int m_base, int m, int n0,
-                                            int64_t obase) {
+                                            int64_t obase, EpiStage& es) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] *= P.alpha;
   if (P.out_cs == 1) {
-    // Row-major destination: every thread owns one row and moves its 32 values as 8 x 128-bit accesses
-    // (fewer instructions than a shared-memory transposition, which measured slower).
+    const bool full = n0 + 32 <= P.N;
     if (m < P.M) {
-      const bool full = n0 + 32 <= P.N;
       if (P.ew_S != nullptr) {
         // fused element-wise gradient terms of the dense backward (see GemmProblem::ew_*)
         const float c_den = P.ew_coef[b * 4 + 0], c_ent = P.ew_coef[b * 4 + 2];
@@ -86,6 +99,45 @@ __device__ __forceinline__ void store_chunk(const KernelParams& P, float (&v)[32
           }
         }
       }
+    }
+    if (P.tma_out) {
+      // stage (lane = row of the chunk) with the swizzle of the output map, then one TMA store; rows >= M and
+      // columns >= N are clipped by the map
+      const int lane = threadIdx.x & 31;
+      const int nb = P.epi_bufs;
+      const uint32_t buf = es.smem + (uint32_t)(es.n % nb) * 4096u;
+      if (lane == 0) {
+        if (nb == 2) tma_store_wait_read<1>();
+        else tma_store_wait_read<0>();
+      }
+      __syncwarp();
+      if (!P.out_bf16) {
+        const uint32_t row = buf + (uint32_t)lane * 128u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          sts128(row + (uint32_t)((c ^ (lane & 7)) << 4), make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+      } else {
+        const uint32_t row = buf + (uint32_t)lane * 64u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 pk;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) h2[q] = __floats2bfloat162_rn(v[8 * c + 2 * q], v[8 * c + 2 * q + 1]);
+          sts128u(row + (uint32_t)((c ^ ((lane >> 1) & 3)) << 4), pk);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&P.map_out, buf, n0, m_base, b);
+        tma_store_commit();
+      }
+      ++es.n;
+      return;
+    }
+    // every thread owns one row and moves its 32 values as 8 x 128-bit accesses
+    if (m < P.M) {
       if (!P.out_bf16 && full && (((obase + n0) & 3) == 0)) {
         float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + obase + n0);
 #pragma unroll
@@ -157,6 +209,7 @@ __device__ __forceinline__ void store_chunk(const KernelParams& P, float (&v)[32
 }
 
 constexpr int kThreads = 320;
+constexpr uint32_t kEpiStageBytes = 32 * 1024;  // 8 x 4 KB staging buffers of the TMA-store epilogue
 
 template <bool kF32>
 __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__ KernelParams P) {
@@ -172,7 +225,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
   const uint32_t a_bytes = BM * kStageRowBytes, b_bytes = (uint32_t)BN * kStageRowBytes;
   const uint32_t stage_bytes = (a_bytes + b_bytes) * (kF32 ? 2 : 1);
   const int stages = P.stages;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stage_bytes * stages);
+  // [stages][stage_bytes] | epilogue staging (kEpiStageBytes, TMA stores) | barriers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stage_bytes * stages + kEpiStageBytes);
   // barrier layout: full[stages], lo[stages], empty[stages], tmem_full[2], tmem_empty[2]
   const uint32_t bar_base = smem_u32(bars);
   auto bar_full = [&](int s) { return bar_base + 8u * s; };
@@ -347,6 +401,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
     // 32-column chunks (the fused element-wise epilogue of the backward is instruction-bound with four warps).
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int c_first = (!kF32 && warp < 6) ? 32 : 0, c_step = kF32 ? 32 : 64;
+    // fp32: four epilogue warps with two staging buffers each; bf16: eight warps with one
+    EpiStage es{smem_base + (uint32_t)stage_bytes * stages + (uint32_t)(kF32 ? (warp - 6) * 2 : (warp - 2)) * 4096u, 0};
     int it = 0;
     for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
       int nt = item % P.n_tiles, mt = (item / P.n_tiles) % P.m_tiles, b = item / (P.n_tiles * P.m_tiles);
@@ -369,11 +425,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
         }
         const int n0 = nt * BN + c0;
         if (n0 >= P.N || m_base >= P.M) continue;  // warp-uniform
-        store_chunk<kF32>(P, v, b, m_base, m, n0, obase);
+        store_chunk<kF32>(P, v, b, m_base, m, n0, obase, es);
       }
       tc_fence_before();
       mbar_arrive(bar_tempty(ab));
     }
+    if (P.tma_out && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -522,6 +579,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     // ===================== epilogue (both CTAs): own 128 TMEM lanes -> global =====================
     const int quad = warp & 3;
     const int c_first = warp < 6 ? 32 : 0;
+    EpiStage es{0u, 0};  // P.tma_out is never set for the pair engine
     int it = 0;
     for (int item = pair; item < P.num_items; item += npairs, ++it) {
       int nt = item % P.n_tiles, mt = (item / P.n_tiles) % P.m_tiles, b = item / (P.n_tiles * P.m_tiles);
@@ -537,7 +595,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN + c0), v);
         const int n0 = nt * BN + c0;
         if (n0 >= P.N || m_base >= P.M) continue;  // warp-uniform
-        store_chunk<false>(P, v, b, m_base, m, n0, obase);
+        store_chunk<false>(P, v, b, m_base, m, n0, obase, es);
       }
       tc_fence_before();
       mbar_arrive_cluster(mapa_shared(bar_tempty(ab), 0));
@@ -562,7 +620,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 //   * three MMAs per k-step (lo_a hi_b, hi_a lo_b, hi_a hi_b), accumulators BN wide, double-buffered.
 // Warp roles (448 threads): 0 TMA, 1 MMA, 2-5 split group 0, 6-9 epilogue, 10-13 split group 1.
 // ------------------------------------------------------------------------------------------
-constexpr int kThreadsTs = 448;
+#ifndef TGPB200_TS_GROUPS
+#define TGPB200_TS_GROUPS 2
+#endif
+constexpr int kTsGroups = TGPB200_TS_GROUPS;  // split groups = TMEM operand stages (k-block kc goes to group kc % G)
+constexpr int kThreadsTs = 320 + 128 * (kTsGroups - 1);  // TMA, MMA, split group 0, epilogue, split groups 1..
 constexpr int kRingCols = 64;  // TMEM columns per operand stage: 4 k-steps x (8 hi + 8 lo)
 
 __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_constant__ KernelParams P) {
@@ -573,7 +635,7 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
   const uint32_t a_bytes = BM * kStageRowBytes, b_bytes = (uint32_t)BN * kStageRowBytes;
   const uint32_t stage_bytes = a_bytes + 2 * b_bytes;  // [A raw | B hi | B lo]
   const int stages = P.stages;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stage_bytes * stages);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stage_bytes * stages + kEpiStageBytes);
   const uint32_t bar_base = smem_u32(bars);
   auto bar_full = [&](int s) { return bar_base + 8u * s; };
   auto bar_lo = [&](int s) { return bar_base + 8u * (stages + s); };
@@ -581,7 +643,7 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
   auto bar_tfull = [&](int i) { return bar_base + 8u * (3 * stages + i); };
   auto bar_tempty = [&](int i) { return bar_base + 8u * (3 * stages + 2 + i); };
   auto bar_tfree = [&](int i) { return bar_base + 8u * (3 * stages + 4 + i); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + 6);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + 4 + kTsGroups);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = smem_u32(smem);
@@ -596,8 +658,8 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull(i), 1);
       mbar_init(bar_tempty(i), 128);
-      mbar_init(bar_tfree(i), 1);
     }
+    for (int i = 0; i < kTsGroups; ++i) mbar_init(bar_tfree(i), 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
@@ -613,12 +675,15 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
     // ===================== TMA producer =====================
     int s = 0;
     uint32_t ph = 0;
+    int dbg_n = 0;
     for (int item = blockIdx.x; item < P.num_items; item += gridDim.x) {
       int nt = item % P.n_tiles, mt = (item / P.n_tiles) % P.m_tiles, b = item / (P.n_tiles * P.m_tiles);
       int m0 = mt * BM, n0 = nt * BN;
       for (int p = 0; p < P.num_pairs; ++p) {
         for (int kb = 0; kb < kblocks[p]; ++kb) {
           mbar_wait(bar_empty(s), ph ^ 1);
+          if (P.dbg && blockIdx.x == 0 && lane == 0 && dbg_n < 128) P.dbg[dbg_n * 8 + 0] = clock64();
+          ++dbg_n;
           const uint32_t sa = smem_base + (uint32_t)s * stage_bytes, sb = sa + a_bytes;
           const int k0 = kb * BK;
           if (elect_one()) {
@@ -659,8 +724,9 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
         const uint64_t desc_b0 = make_desc(smem_base, b_lbo, P.b_mn[p] ? 512 : 1024, P.b_mn[p] ? 1 : 2);
         for (int kb = 0; kb < kblocks[p]; ++kb, ++kc) {
           mbar_wait(bar_lo(s), ph);
+          if (P.dbg && blockIdx.x == 0 && lane == 0 && kc < 128) P.dbg[kc * 8 + 5] = clock64();
           tc_fence_after();
-          const uint32_t ts = kc & 1u;
+          const uint32_t ts = kc % (uint32_t)kTsGroups;
           const uint32_t a_stage = tm + ring0 + ts * kRingCols;
           const uint64_t db0 = desc_b0 + (uint64_t)(((uint32_t)s * stage_bytes + a_bytes) >> 4);
           if (elect_one()) {
@@ -676,6 +742,7 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
             umma_commit(bar_tfree(ts));
           }
           __syncwarp();
+          if (P.dbg && blockIdx.x == 0 && lane == 0 && kc < 128) P.dbg[kc * 8 + 6] = clock64();
           accum = 1;
           if (++s == stages) { s = 0; ph ^= 1; }
         }
@@ -685,7 +752,7 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
     }
   } else if (warp < 6 || warp >= 10) {
     // ===================== split: B hi/lo in shared memory, A hi/lo into the TMEM ring =====================
-    const int grp = warp >= 10 ? 1 : 0;
+    const int grp = warp >= 10 ? 1 + ((warp - 10) >> 2) : 0;
     const int t = (threadIdx.x - 64) & 127;
     const int q = warp & 3;            // TMEM lane quadrant of this warp
     const int m_local = q * 32 + lane; // output row of the tile this thread stages
@@ -694,11 +761,12 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
     for (int item = blockIdx.x; item < P.num_items; item += gridDim.x) {
       for (int p = 0; p < P.num_pairs; ++p) {
         for (int kb = 0; kb < kblocks[p]; ++kb, ++kc) {
-          if ((int)(kc & 1u) != grp) {  // the other group's k-block
+          if ((int)(kc % (uint32_t)kTsGroups) != grp) {  // another group's k-block
             if (++s == stages) { s = 0; ph ^= 1; }
             continue;
           }
           mbar_wait(bar_full(s), ph);
+          if (P.dbg && blockIdx.x == 0 && t == 0 && kc < 128) P.dbg[kc * 8 + 1] = clock64();
           const uint32_t sa = smem_base + (uint32_t)s * stage_bytes, sb = sa + a_bytes;
           // B: hi in place, lo behind it
           for (uint32_t ch = t; ch < b_bytes / 16; ch += 128) {
@@ -722,7 +790,9 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
               x[4 * c] = v.x, x[4 * c + 1] = v.y, x[4 * c + 2] = v.z, x[4 * c + 3] = v.w;
             }
           }
-          mbar_wait(bar_tfree(grp), ((kc >> 1) & 1u) ^ 1u);
+          if (P.dbg && blockIdx.x == 0 && t == 0 && kc < 128) P.dbg[kc * 8 + 2] = clock64();
+          mbar_wait(bar_tfree(grp), ((kc / (uint32_t)kTsGroups) & 1u) ^ 1u);
+          if (P.dbg && blockIdx.x == 0 && t == 0 && kc < 128) P.dbg[kc * 8 + 3] = clock64();
           tc_fence_after();
           const uint32_t a_stage = tmem_base + ((uint32_t)(q * 32) << 16) + ring0 + (uint32_t)grp * kRingCols;
 #pragma unroll
@@ -738,6 +808,7 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(bar_lo(s));
+          if (P.dbg && blockIdx.x == 0 && t == 0 && kc < 128) P.dbg[kc * 8 + 4] = clock64();
           if (++s == stages) { s = 0; ph ^= 1; }
         }
       }
@@ -745,12 +816,14 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
   } else {
     // ===================== epilogue (warps 6-9) =====================
     const int quad = warp & 3;
+    EpiStage es{smem_base + (uint32_t)stage_bytes * stages + (uint32_t)(warp - 6) * 2u * 4096u, 0};
     int it = 0;
     for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
       int nt = item % P.n_tiles, mt = (item / P.n_tiles) % P.m_tiles, b = item / (P.n_tiles * P.m_tiles);
       const int ab = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       mbar_wait(bar_tfull(ab), aph);
+      if (P.dbg && blockIdx.x == 0 && threadIdx.x == 192 && it < 32) P.dbg[(128 + it) * 8 + 0] = clock64();
       tc_fence_after();
       const int m_base = mt * BM + quad * 32;
       const int m = m_base + lane;
@@ -760,11 +833,13 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN + c0), v);
         const int n0 = nt * BN + c0;
         if (n0 >= P.N || m_base >= P.M) continue;  // warp-uniform
-        store_chunk<true>(P, v, b, m_base, m, n0, obase);
+        store_chunk<true>(P, v, b, m_base, m, n0, obase, es);
       }
       tc_fence_before();
       mbar_arrive(bar_tempty(ab));
+      if (P.dbg && blockIdx.x == 0 && threadIdx.x == 192 && it < 32) P.dbg[(128 + it) * 8 + 1] = clock64();
     }
+    if (P.tma_out && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -835,8 +910,8 @@ int device_sm_count() {
 
 // Operand [batch][rows][cols] (cols contiguous).  K-major: rows = MN extent, cols = K extent, box {BK, box_mn, 1}.
 // MN-major: rows = K extent, cols = MN extent, box {EPB, BK, 1} (one load per 128-byte block of the MN extent).
-static bool make_map(CUtensorMap* map, const OperandDesc& op, bool bf16, int batch, int mn_extent, int k_extent,
-                     int box_mn) {
+bool make_operand_map(CUtensorMap* map, const OperandDesc& op, bool bf16, int batch, int mn_extent, int k_extent,
+                      int box_mn) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   const int es = bf16 ? 2 : 4, epb = kStageRowBytes / es;
@@ -865,7 +940,7 @@ static bool make_map(CUtensorMap* map, const OperandDesc& op, bool bf16, int bat
 }
 
 // MN-major operand as ONE unswizzled box [BK k-rows][128 MN columns] (TMEM-operand engine: only the split warps read it)
-static bool make_map_mn_plain(CUtensorMap* map, const OperandDesc& op, int batch, int mn_extent, int k_extent) {
+bool make_operand_map_mn_plain(CUtensorMap* map, const OperandDesc& op, int batch, int mn_extent, int k_extent) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[3] = {(cuuint64_t)mn_extent, (cuuint64_t)k_extent, (cuuint64_t)batch};
@@ -944,29 +1019,50 @@ int gemm(const GemmProblem& p, cudaStream_t stream) {
     P.kd[i] = p.kd[i];
     P.a_mn[i] = p.a[i].mn_major, P.b_mn[i] = p.b[i].mn_major;
     if (ts && p.a[i].mn_major) {
-      if (!make_map_mn_plain(&P.map_a[i], p.a[i], p.batch, p.M, p.kd[i])) return TGPB200_ERR_UNSUPPORTED;
-    } else if (!make_map(&P.map_a[i], p.a[i], bf16, p.batch, p.M, p.kd[i], BM)) {
+      if (!make_operand_map_mn_plain(&P.map_a[i], p.a[i], p.batch, p.M, p.kd[i])) return TGPB200_ERR_UNSUPPORTED;
+    } else if (!make_operand_map(&P.map_a[i], p.a[i], bf16, p.batch, p.M, p.kd[i], BM)) {
       return TGPB200_ERR_UNSUPPORTED;
     }
-    if (!make_map(&P.map_b[i], p.b[i], bf16, p.batch, p.N, p.kd[i], pair ? P.BN / 2 : P.BN)) return TGPB200_ERR_UNSUPPORTED;
+    if (!make_operand_map(&P.map_b[i], p.b[i], bf16, p.batch, p.N, p.kd[i], pair ? P.BN / 2 : P.BN)) return TGPB200_ERR_UNSUPPORTED;
   }
   const size_t stage_bytes = pair ? (size_t)(BM + P.BN / 2) * kStageRowBytes
                              : ts ? (size_t)(BM + 2 * P.BN) * kStageRowBytes
                                   : (size_t)(BM + P.BN) * kStageRowBytes * (bf16 ? 1 : 2);
-  const size_t budget = 200 * 1024;
+  const size_t budget = 192 * 1024;  // + 32 KB of epilogue staging + barriers + alignment slack <= 227 KB
   int stages = (int)(budget / stage_bytes);
   if (stages > (pair ? 8 : 6)) stages = pair ? 8 : 6;
   if (stages < 2) return TGPB200_ERR_UNSUPPORTED;
   P.stages = stages;
   uint32_t cols = 32;
   // shared-memory fp32 accumulators are 2 BN wide ([.. | hi_a lo_b]); the TMEM-operand form adds a 2 x 64 column ring
-  while (cols < (uint32_t)(ts ? 2 * P.BN + 2 * kRingCols : (bf16 ? 2 : 4) * P.BN)) cols <<= 1;
+  while (cols < (uint32_t)(ts ? 2 * P.BN + kTsGroups * kRingCols : (bf16 ? 2 : 4) * P.BN)) cols <<= 1;
   P.tmem_cols = cols;
   P.out = p.out, P.out_bs = p.out_batch_stride, P.out_rs = p.out_row_stride, P.out_cs = p.out_col_stride;
   P.alpha = p.alpha, P.accumulate = p.accumulate, P.out_bf16 = p.out_bf16;
   P.skip_lo_b_mask = p.skip_lo_b_mask;
   P.ew_S = p.ew_S, P.ew_d = p.ew_d, P.ew_coef = p.ew_coef, P.ew_eps = p.ew_eps;
-  const size_t smem = stage_bytes * stages + (3 * stages + 4) * 8 + 16 + 1024;
+  P.dbg = ts ? g_engine_dbg : nullptr;
+  // TMA-store epilogue: row-major destination, no read-modify-write, 16-byte aligned rows
+  {
+    const int oes = p.out_bf16 ? 2 : 4;
+    const char* e = getenv("TGPB200_GEMM_TMA_STORE");
+    P.epi_bufs = bf16 ? 1 : 2;
+    P.tma_out = 0;
+    if (!(e && e[0] == '0') && !pair && p.out_col_stride == 1 && !p.accumulate && ((uintptr_t)p.out & 15) == 0 &&
+        (p.out_row_stride * oes) % 16 == 0 && (p.out_batch_stride * oes) % 16 == 0 && p.out_row_stride >= p.N) {
+      EncodeTiledFn fn = encode_fn();
+      cuuint64_t dims[3] = {(cuuint64_t)p.N, (cuuint64_t)p.M, (cuuint64_t)p.batch};
+      cuuint64_t bs = (cuuint64_t)(p.out_batch_stride > 0 ? p.out_batch_stride : p.out_row_stride * p.M) * oes;
+      cuuint64_t strides[2] = {(cuuint64_t)p.out_row_stride * oes, bs};
+      cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+      if (fn && fn(&P.map_out, p.out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.out,
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   p.out_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+        P.tma_out = 1;
+    }
+  }
+  const size_t smem = stage_bytes * stages + kEpiStageBytes + (3 * stages + 4) * 8 + 16 + 1024;
   if (pair) {
     int npairs = P.num_items < num_sms / 2 ? P.num_items : num_sms / 2;
     launch(p.tag ? p.tag : "k_tc_gemm_pair_bf16", k_tc_gemm_pair, 2 * npairs, kThreads, smem, stream, P);

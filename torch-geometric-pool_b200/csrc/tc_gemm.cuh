@@ -77,6 +77,13 @@ bool make_map_3d(CUtensorMap* map, const void* ptr, bool bf16, int64_t batch, in
 // canonical UMMA MN-major layout, with ONE TMA instruction per tile.  cols must be a multiple of the block width.
 bool make_map_blocked(CUtensorMap* map, const void* ptr, bool bf16, int64_t batch, int64_t rows, int64_t cols,
                       int64_t row_stride, int64_t batch_stride, int box_rows, int box_blocks, bool swizzle32);
+// Operand [batch][rows][cols] (cols contiguous) of the engine.  K-major: rows = MN extent, cols = K extent, box
+// {128 B of K, box_mn, 1}, 128B swizzle.  MN-major: rows = K extent, cols = MN extent, box {128 B of MN, 32 k-rows, 1}
+// (one load per 128-byte block of the MN extent; fp32 uses the 32-byte-atom swizzle).
+bool make_operand_map(CUtensorMap* map, const OperandDesc& op, bool bf16, int batch, int mn_extent, int k_extent,
+                      int box_mn);
+// fp32 MN-major operand as ONE unswizzled box [32 k-rows][128 MN columns] (read by the split warps only)
+bool make_operand_map_mn_plain(CUtensorMap* map, const OperandDesc& op, int batch, int mn_extent, int k_extent);
 int device_sm_count();
 bool gemm_supported(const GemmProblem& p);
 
