@@ -48,11 +48,11 @@ for _ in range(50):
     bwd()
 e1.record(); torch.cuda.synchronize()
 print(f"backward (k_graph_bwd + fused or 3 products): {e0.elapsed_time(e1) / 50 * 1000:.1f} us")
-dbg = torch.zeros(160 * 8, dtype=torch.long, device=dev)
+dbg = torch.zeros(360 * 8, dtype=torch.long, device=dev)
 lib.tgpb200_debug_engine_timeline(dbg.data_ptr())
 bwd(); torch.cuda.synchronize()
 lib.tgpb200_debug_engine_timeline(None)
-d = dbg.cpu().view(160, 8)
+d = dbg.cpu().view(360, 8)
 t0 = int(d[0, 1])
 print(" kc | arrive_q0 arrive_q1 arrive_q2 arrive_q3 | mma_ready fenced mmas_issued committed   (22 k-blocks per item: 8 W, 4 X, 2 T, 2 SP, 2 WG, 4 dX)")
 for i in range(0, 70):
@@ -62,3 +62,15 @@ print(" item  epi_start epi_end")
 for i in range(0, 8):
     r = [int(v) - t0 for v in d[128 + i, :2]]
     print(f"{i:3d} {r[0]:9d} {r[1]:9d}")
+
+# per-CTA start / end (global timer, ns)
+import statistics
+rows = [(int(d[200 + i, 0]), int(d[200 + i, 1]), int(d[200 + i, 2])) for i in range(148) if int(d[200 + i, 0]) > 0]
+g0 = min(r[0] for r in rows)
+starts = sorted(r[0] - g0 for r in rows); ends = sorted(r[1] - g0 for r in rows); durs = sorted(r[1] - r[0] for r in rows)
+print(f"CTAs: {len(rows)}  start ns min/med/max {starts[0]}/{statistics.median(starts)}/{starts[-1]}  end ns min/med/max {ends[0]}/{statistics.median(ends)}/{ends[-1]}")
+print(f"duration ns min/med/max {durs[0]}/{statistics.median(durs)}/{durs[-1]}")
+slow = sorted(rows, key=lambda r: r[0] - r[1])[:12]
+print("slowest CTAs (block, smid, dur ns):", [(rows.index(r), r[2], r[1] - r[0]) for r in slow])
+fast = sorted(rows, key=lambda r: r[1] - r[0])[:12]
+print("fastest CTAs (block, smid, dur ns):", [(rows.index(r), r[2], r[1] - r[0]) for r in fast])

@@ -7,11 +7,11 @@ lib = L.load(); lib.tgpb200_debug_fused_timeline.argtypes = [ctypes.c_void_p]
 B, N, K, F = 512, 256, 64, 128
 a = (torch.rand(B, N, N, device="cuda") < 0.05).float(); s = torch.softmax(torch.randn(B, N, K, device="cuda"), -1); x = torch.randn(B, N, F, device="cuda")
 for _ in range(3): T.mincut_pool(x, a, s)
-dbg = torch.zeros(96 * 8, dtype=torch.long, device="cuda")
+dbg = torch.zeros(160 * 8, dtype=torch.long, device="cuda")
 lib.tgpb200_debug_fused_timeline(dbg.data_ptr())
 T.mincut_pool(x, a, s); torch.cuda.synchronize()
 lib.tgpb200_debug_fused_timeline(None)
-d = dbg.cpu().view(96, 8)
+d = dbg.cpu().view(160, 8)
 t0 = int(d[0, 0])
 print("kb   tma_start tma_done | mma_ready ring_wait_done mma_done | split_start split_done pass1_done   (cycles since first TMA; TMEM-operand kernel)")
 for i in list(range(0, 24)) + list(range(40, 52)):

@@ -134,6 +134,43 @@ def test_dense_fp32_componentwise_bounds(B, N, K, F):
             torch.testing.assert_close(got[2][k].double(), exp[2][k].double(), rtol=1e-5, atol=0.0, msg=k)
 
 
+# --------------------------------------------------------------------------- #
+# fused dense backward (one launch, W = A S in tensor memory) against the one-product-per-launch chain
+@pytest.mark.parametrize("B,N,K,F", [(3, 256, 64, 128), (2, 384, 64, 128), (5, 200, 48, 100), (4, 128, 16, 64), (2, 96, 64, 36)])
+@pytest.mark.parametrize("kind", ["mincut", "diff", "plain"])
+def test_fused_dense_backward_matches_product_chain(B, N, K, F, kind, monkeypatch):
+    g = torch.Generator().manual_seed(7 * N + K)
+    a, s_raw, x = _dense_inputs(g, B, N, K, F)
+    a = a * (torch.rand(B, N, N, generator=g) + 0.5)  # weighted, not symmetric
+    s = torch.softmax(s_raw, -1)
+    gx, ga = torch.randn(B, K, F, generator=g).to(DEV), torch.randn(B, K, K, generator=g).to(DEV)
+
+    def run(fused):
+        monkeypatch.setenv("TGPB200_BWD_FUSED", "1" if fused else "0")
+        ss = s.to(DEV).requires_grad_(True)
+        xx = x.to(DEV).requires_grad_(True)
+        if kind == "mincut":
+            xp, ap, loss = T.mincut_pool(xx, a.to(DEV), ss)
+        elif kind == "diff":
+            xp, ap, loss = T.diff_pool(xx, a.to(DEV), ss)
+        else:
+            xp, ap, loss = T.mincut_pool(xx, a.to(DEV), ss, remove_self_loops=False, degree_norm=False)
+            loss = {}
+        total = (xp * gx).sum() + (ap * ga).sum()
+        for v in loss.values():
+            total = total + v
+        total.backward()
+        torch.cuda.synchronize()
+        return ss.grad.clone(), xx.grad.clone()
+
+    ds0, dx0 = run(False)
+    ds1, dx1 = run(True)
+    # same 3xTF32 products, different accumulation grouping: a few fp32 ulps of the largest partial sums
+    for got, ref, name in ((ds1, ds0, "dS"), (dx1, dx0, "dX")):
+        scale = float(ref.abs().max())
+        torch.testing.assert_close(got, ref, rtol=2e-6, atol=2e-6 * scale, msg=lambda m: f"{name}: {m}")
+
+
 def test_sparse_weights_gradients_rtol_1e5():
     """kept-node + cluster paths: pooled features bit-identical to the sequential CPU sums, edge weights and all
     gradients at rtol 1e-5 (component-wise floor for the degree-normalised sums)."""

@@ -89,6 +89,14 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = smem_u32(smem);
+  if (P.dbg && threadIdx.x == 0) {  // per-CTA start (global timer, ns) and SM id: rows 200.. of the debug buffer
+    unsigned long long t;
+    uint32_t smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    P.dbg[(200 + blockIdx.x) * 8 + 0] = (long long)t;
+    P.dbg[(200 + blockIdx.x) * 8 + 2] = (long long)smid;
+  }
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -348,6 +356,11 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
 
   tc_fence_before();
   __syncthreads();
+  if (P.dbg && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.dbg[(200 + blockIdx.x) * 8 + 1] = (long long)t;
+  }
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
