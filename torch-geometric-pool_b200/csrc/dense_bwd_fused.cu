@@ -21,7 +21,7 @@
 // item's MMA work) only touches the W accumulator.
 //
 // Tensor memory (512 columns): W [0, 128) | dS [128, 256) | dX [256, 384) | operand ring: 2 x 64 columns.
-// Warp roles (576 threads): 0 TMA, 1 MMA, 2-9 two split groups of four warps, 10-17 epilogue.
+// Warp roles (448 threads): 0 TMA, 1 MMA, 2-9 two split groups of four warps, 10-13 epilogue.
 #include <stdlib.h>
 #include <string.h>
 
@@ -36,6 +36,11 @@ extern long long* g_engine_dbg;
 
 namespace {
 
+// 4 epilogue warps keep the CTA at 448 threads: registers are allocated per 128 threads, so 576 threads are budgeted as
+// 640 (96 registers per thread, spills inside the pipeline loops) while 448 get 128 registers and no spill.
+#ifndef TGPB200_BWD_EPI_WARPS
+#define TGPB200_BWD_EPI_WARPS 4
+#endif
 #ifndef TGPB200_BWD_CONCAT
 #define TGPB200_BWD_CONCAT 1
 #endif
@@ -46,7 +51,7 @@ namespace {
 constexpr bool kConcat = TGPB200_BWD_CONCAT != 0;
 constexpr int kPairs = 7;
 constexpr int kGroups = kConcat ? 2 : 3;   // split groups = TMEM operand stages
-constexpr int kEpiW = 8;                   // epilogue warps (two per TMEM lane quadrant)
+constexpr int kEpiW = TGPB200_BWD_EPI_WARPS;  // epilogue warps (one or two per TMEM lane quadrant)
 constexpr int kThreadsBwd = 64 + kGroups * 128 + kEpiW * 32;
 constexpr int BK = 32, KSTEPS = 4;
 constexpr int BNB = 64;                    // MMA N of every pair
@@ -116,8 +121,8 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  int kblocks[kPairs];
-  for (int p = 0; p < kPairs; ++p) kblocks[p] = p < P.num_pairs ? (P.kd[p] + BK - 1) / BK : 0;
+  // (k-block counts come from the kernel parameters each time: a dynamically indexed local array lives in local
+  //  memory, and with 227 KB of the L1 carved out as shared memory those loads miss to L2 inside the hot loops)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
       const int m0 = mt * BM;
       for (int p = 0; p < P.num_pairs; ++p) {
         const int src = P.a_src[p];
-        for (int kb = 0; kb < kblocks[p]; ++kb) {
+        for (int kb = 0, nkb = (P.kd[p] + BK - 1) / BK; kb < nkb; ++kb) {
           mbar_wait(bar_empty(s), ph ^ 1);
           const uint32_t sa = smem_base + (uint32_t)s * kStage, sb = sa + kABytes;
           const int k0 = kb * BK;
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
         const uint32_t idesc2 = (idesc & ~(0x3fu << 17)) | ((uint32_t)((2 * BNB) >> 3) << 17);
         const bool wide = kConcat && P.wide[p] != 0;
         uint32_t accum = P.first[p] ? 0u : 1u;
-        for (int kb = 0; kb < kblocks[p]; ++kb, ++kc) {
+        for (int kb = 0, nkb = (P.kd[p] + BK - 1) / BK; kb < nkb; ++kb, ++kc) {
           mbar_wait(bar_lo(s), ph);
           if (P.dbg && blockIdx.x == 0 && lane == 0 && kc < 128) P.dbg[kc * 8 + 5] = clock64();
           tc_fence_after();
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
     for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
       for (int p = 0; p < P.num_pairs; ++p) {
         const int src = P.a_src[p];
-        for (int kb = 0; kb < kblocks[p]; ++kb, ++kc) {
+        for (int kb = 0, nkb = (P.kd[p] + BK - 1) / BK; kb < nkb; ++kb, ++kc) {
           if ((int)(kc % (uint32_t)kGroups) != grp) {  // another group's k-block
             if (++s == stages) { s = 0; ph ^= 1; }
             continue;
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
     // ===================== epilogue: dS (+ element-wise terms) and dX through TMA stores =====================
     const int quad = warp & 3;
     const int ew = warp - 2 - kGroups * 4;   // 0 .. 7
-    const int e2 = ew >> 2;                  // which of the quadrant's two warps
+    const int e2 = ew >> 2;                  // which of the quadrant's warps
     const uint32_t stg = smem_base + (uint32_t)kStage * stages + (uint32_t)ew * 4096u;
     const int n_chunks = 2 + (P.F + 31) / 32;
     int it = 0;
@@ -296,7 +301,7 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
       const int m_base = mt * BM + quad * 32;
       const int m = m_base + lane;
       for (int c = 0; c < n_chunks; ++c) {
-        if ((c & 1) != e2) continue;
+        if (kEpiW == 8 && (c & 1) != e2) continue;
         const bool is_ds = c < 2;
         const int n0 = is_ds ? c * 32 : (c - 2) * 32;
         float v[32];
@@ -314,23 +319,23 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
           if (c_den != 0.f || c_ent != 0.f) {
             const float dd = 2.f * c_den * P.d[(int64_t)b * P.N + m];
             const float* srow = P.S + ((int64_t)b * P.N + m) * P.K + n0;
-            float sv[32];
-            if (n0 + 32 <= P.K) {
-              const float4* s4 = reinterpret_cast<const float4*>(srow);
+            // eight columns at a time (32 live values of S on top of the 32 accumulator values spilled to local memory)
+#pragma unroll
+            for (int j8 = 0; j8 < 32; j8 += 8) {
+              float sv[8];
+              if (n0 + 32 <= P.K) {
+                const float4 t0 = __ldg(reinterpret_cast<const float4*>(srow + j8)), t1 = __ldg(reinterpret_cast<const float4*>(srow + j8 + 4));
+                sv[0] = t0.x, sv[1] = t0.y, sv[2] = t0.z, sv[3] = t0.w, sv[4] = t1.x, sv[5] = t1.y, sv[6] = t1.z, sv[7] = t1.w;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sv[j] = n0 + j8 + j < P.K ? srow[j8 + j] : 0.f;
+              }
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 t4 = __ldg(s4 + j);
-                sv[4 * j] = t4.x, sv[4 * j + 1] = t4.y, sv[4 * j + 2] = t4.z, sv[4 * j + 3] = t4.w;
+                float add = dd * sv[j];
+                if (c_ent != 0.f) add += c_ent * (-__logf(sv[j] + P.eps) - __fdividef(sv[j], sv[j] + P.eps));
+                v[j8 + j] += add;
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) sv[j] = n0 + j < P.K ? srow[j] : 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float add = dd * sv[j];
-              if (c_ent != 0.f) add += c_ent * (-__logf(sv[j] + P.eps) - __fdividef(sv[j], sv[j] + P.eps));
-              v[j] += add;
             }
           }
         }
