@@ -54,10 +54,10 @@ bwd(); torch.cuda.synchronize()
 lib.tgpb200_debug_engine_timeline(None)
 d = dbg.cpu().view(360, 8)
 t0 = int(d[0, 1])
-print(" kc | arrive_q0 arrive_q1 arrive_q2 arrive_q3 | mma_ready fenced mmas_issued committed   (22 k-blocks per item: 8 W, 4 X, 2 T, 2 SP, 2 WG, 4 dX)")
+print(" kc | arrive_q0 arrive_q1 arrive_q2 arrive_q3 | wait_start mma_ready mmas_issued committed   (22 k-blocks per item: 8 W, 4 X, 2 T, 2 SP, 2 WG, 4 dX)")
 for i in range(0, 70):
     r = [int(v) - t0 for v in d[i, :8]]
-    print(f"{i:3d} | {r[1]:9d} {r[2]:9d} {r[3]:9d} {r[4]:9d} | {r[5]:9d} {r[7]:9d} {r[0]:9d} {r[6]:9d}")
+    print(f"{i:3d} | {r[1]:9d} {r[2]:9d} {r[3]:9d} {r[4]:9d} | {r[7]:9d} {r[5]:9d} {r[0]:9d} {r[6]:9d}")
 print(" item  epi_start epi_end")
 for i in range(0, 8):
     r = [int(v) - t0 for v in d[128 + i, :2]]

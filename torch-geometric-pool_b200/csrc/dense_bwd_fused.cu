@@ -154,35 +154,37 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    // ===================== MMA issuer: ONE elected thread runs the whole loop =====================
+    // (electing per k-block and reconverging the warp afterwards costs ~150 cycles per iteration of the issue loop:
+    //  benchmarks/mma_rate.cu, k_loop modes 0 / 1)
     const uint32_t tm = __shfl_sync(kFull, tmem_base, 0);
-    int s = 0;
-    uint32_t ph = 0, kc = 0;
-    int it = 0;
-    for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
-      for (int p = 0; p < P.num_pairs; ++p) {
-        if (p == 1) {  // first pair that writes the dS / dX accumulators: the previous item's epilogue has drained them
-          mbar_wait(bar_tempty, ((uint32_t)it & 1u) ^ 1u);
-          tc_fence_after();
-        }
-        const uint32_t d_tmem = tm + P.acc_col[p];
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)P.b_mn[p] << 16) |
-                               ((uint32_t)(BNB >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        const uint32_t b_lbo = P.b_mn[p] ? BK * kStageRowBytes : 16;
-        const uint32_t b_step = P.b_mn[p] ? 8 * kStageRowBytes : 32;
-        const uint64_t desc_b0 = make_desc(smem_base, b_lbo, P.b_mn[p] ? 512 : 1024, P.b_mn[p] ? 1 : 2);
-        const uint32_t idesc2 = (idesc & ~(0x3fu << 17)) | ((uint32_t)((2 * BNB) >> 3) << 17);
-        const bool wide = kConcat && P.wide[p] != 0;
-        uint32_t accum = P.first[p] ? 0u : 1u;
-        for (int kb = 0, nkb = (P.kd[p] + BK - 1) / BK; kb < nkb; ++kb, ++kc) {
-          mbar_wait(bar_lo(s), ph);
-          if (P.dbg && blockIdx.x == 0 && lane == 0 && kc < 128) P.dbg[kc * 8 + 5] = clock64();
-          tc_fence_after();
-          const uint32_t ts = kc % (uint32_t)kGroups;
-          const uint32_t a_stage = tm + kColRing + ts * kRing;
-          const uint64_t db0 = desc_b0 + (uint64_t)(((uint32_t)s * kStage + kABytes) >> 4);
-          if (P.dbg && blockIdx.x == 0 && lane == 0 && kc < 128) P.dbg[kc * 8 + 7] = clock64();
-          if (elect_one()) {
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0, kc = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
+        for (int p = 0; p < P.num_pairs; ++p) {
+          if (p == 1) {  // first pair that writes the dS / dX accumulators: the previous item's epilogue has drained them
+            mbar_wait(bar_tempty, ((uint32_t)it & 1u) ^ 1u);
+            tc_fence_after();
+          }
+          const uint32_t d_tmem = tm + P.acc_col[p];
+          const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)P.b_mn[p] << 16) |
+                                 ((uint32_t)(BNB >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+          const uint32_t b_lbo = P.b_mn[p] ? BK * kStageRowBytes : 16;
+          const uint32_t b_step = P.b_mn[p] ? 8 * kStageRowBytes : 32;
+          const uint64_t desc_b0 = make_desc(smem_base, b_lbo, P.b_mn[p] ? 512 : 1024, P.b_mn[p] ? 1 : 2);
+          const uint32_t idesc2 = (idesc & ~(0x3fu << 17)) | ((uint32_t)((2 * BNB) >> 3) << 17);
+          const bool wide = kConcat && P.wide[p] != 0;
+          uint32_t accum = P.first[p] ? 0u : 1u;
+          for (int kb = 0, nkb = (P.kd[p] + BK - 1) / BK; kb < nkb; ++kb, ++kc) {
+            if (P.dbg && blockIdx.x == 0 && kc < 128) P.dbg[kc * 8 + 7] = clock64();
+            mbar_wait(bar_lo(s), ph);
+            if (P.dbg && blockIdx.x == 0 && kc < 128) P.dbg[kc * 8 + 5] = clock64();
+            tc_fence_after();
+            const uint32_t ts = kc % (uint32_t)kGroups;
+            const uint32_t a_stage = tm + kColRing + ts * kRing;
+            const uint64_t db0 = desc_b0 + (uint64_t)(((uint32_t)s * kStage + kABytes) >> 4);
 #pragma unroll
             for (int kk = 0; kk < KSTEPS; ++kk) {
               const uint64_t db = db0 + (uint64_t)(kk * (b_step >> 4)), db_lo = db + (kBBytes >> 4);
@@ -199,20 +201,16 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
             if (P.dbg && blockIdx.x == 0 && kc < 128) P.dbg[kc * 8 + 0] = clock64();
             umma_commit(bar_empty(s));
             umma_commit(bar_tfree(ts));
+            if (P.dbg && blockIdx.x == 0 && kc < 128) P.dbg[kc * 8 + 6] = clock64();
+            accum = 1;
+            if (++s == stages) { s = 0; ph ^= 1; }
           }
-          __syncwarp();
-          if (P.dbg && blockIdx.x == 0 && lane == 0 && kc < 128) P.dbg[kc * 8 + 6] = clock64();
-          accum = 1;
-          if (++s == stages) { s = 0; ph ^= 1; }
+          if (p == 0) umma_commit(bar_wfull);  // W complete: the split warps may read it back
         }
-        if (p == 0) {  // W complete: the split warps may read it back
-          if (elect_one()) umma_commit(bar_wfull);
-          __syncwarp();
-        }
+        umma_commit(bar_tfull);
       }
-      if (elect_one()) umma_commit(bar_tfull);
-      __syncwarp();
     }
+    __syncwarp();
   } else if (warp < 2 + kGroups * 4) {
     // ===================== split: B hi / lo in shared memory, A hi / lo into the TMEM ring =====================
     const int grp = (warp - 2) >> 2;

@@ -139,13 +139,14 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp, tcgen05 instructions on one elected lane) =====================
-    {
-      // tf32 x tf32 -> f32, A from TMEM (K-major by construction), B MN-major, N = BN, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
-                             ((uint32_t)(BM >> 4) << 24);
-      const uint64_t desc0 = make_desc(smem_base, kSBlock, 512, 1);  // 32-byte-atom swizzle, 4-row atoms
-      const uint32_t tm = __shfl_sync(kFull, tmem_base, 0);
+    // ===================== MMA issuer: ONE elected thread runs the whole loop =====================
+    // (electing per k-block and reconverging the warp afterwards costs ~150 cycles per iteration: mma_rate.cu, k_loop)
+    // tf32 x tf32 -> f32, A from TMEM (K-major by construction), B MN-major, N = BN, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)(BM >> 4) << 24);
+    const uint64_t desc0 = make_desc(smem_base, kSBlock, 512, 1);  // 32-byte-atom swizzle, 4-row atoms
+    const uint32_t tm = __shfl_sync(kFull, tmem_base, 0);
+    if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       uint32_t kc = 0;
@@ -155,35 +156,32 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
         tc_fence_after();
         for (int kb = 0; kb < kblocks; ++kb, ++kc) {
           mbar_wait(bar_ready(s), ph);
-          if (P.dbg && blockIdx.x == 0 && lane == 0 && kc < 96) P.dbg[kc * 8 + 2] = clock64();
+          if (P.dbg && blockIdx.x == 0 && kc < 96) P.dbg[kc * 8 + 2] = clock64();
           tc_fence_after();
           const uint32_t ts = kc & 1u;
           const uint32_t a_stage = tm + a_cols0 + ts * (uint32_t)(G * kACols);
           const uint64_t db0 = desc0 + (uint64_t)(((uint32_t)s * stage_bytes + off_sb) >> 4);
-          if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-              const uint64_t db = db0 + (uint64_t)(kk * ((8 * kStageRowBytes) >> 4)), db_lo = db + (sb_bytes >> 4);
-              const uint32_t acc0 = (kb > 0 || kk > 0) ? 1u : 0u;
-              for (int g = 0; g < G; ++g) {
-                const uint32_t a_hi = a_stage + (uint32_t)(g * kACols + kk * 16), a_lo = a_hi + 8;
-                const uint32_t dt = tm + (uint32_t)(g * BN);
-                umma_ts_tf32(dt, a_lo, db, idesc, acc0);
-                umma_ts_tf32(dt, a_hi, db_lo, idesc, 1u);
-                umma_ts_tf32(dt, a_hi, db, idesc, 1u);
-              }
+          for (int kk = 0; kk < 2; ++kk) {
+            const uint64_t db = db0 + (uint64_t)(kk * ((8 * kStageRowBytes) >> 4)), db_lo = db + (sb_bytes >> 4);
+            const uint32_t acc0 = (kb > 0 || kk > 0) ? 1u : 0u;
+            for (int g = 0; g < G; ++g) {
+              const uint32_t a_hi = a_stage + (uint32_t)(g * kACols + kk * 16), a_lo = a_hi + 8;
+              const uint32_t dt = tm + (uint32_t)(g * BN);
+              umma_ts_tf32(dt, a_lo, db, idesc, acc0);
+              umma_ts_tf32(dt, a_hi, db_lo, idesc, 1u);
+              umma_ts_tf32(dt, a_hi, db, idesc, 1u);
             }
-            umma_commit(bar_empty(s));    // the TMA producer may refill the shared-memory stage
-            umma_commit(bar_tfree(ts));   // the split warps may overwrite the TMEM operand stage
           }
-          __syncwarp();
-          if (P.dbg && blockIdx.x == 0 && lane == 0 && kc < 96) P.dbg[kc * 8 + 4] = clock64();
+          umma_commit(bar_empty(s));    // the TMA producer may refill the shared-memory stage
+          umma_commit(bar_tfree(ts));   // the split warps may overwrite the TMEM operand stage
+          if (P.dbg && blockIdx.x == 0 && kc < 96) P.dbg[kc * 8 + 4] = clock64();
           if (++s == stages) { s = 0; ph ^= 1; }
         }
-        if (elect_one()) umma_commit(bar_tfull);
-        __syncwarp();
+        umma_commit(bar_tfull);
       }
     }
+    __syncwarp();
   } else if (warp < 2 + kSplitGroups * kSplitWarps) {
     // ===================== split: statistics, B operand (smem), A operand (TMEM) =====================
     const int grp = (warp - 2) / kSplitWarps;              // which k-blocks this warp's group takes

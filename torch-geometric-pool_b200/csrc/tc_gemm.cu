@@ -703,33 +703,34 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    // ===================== MMA issuer: ONE elected thread runs the whole loop =====================
+    // (electing per k-block and reconverging the warp afterwards costs ~150 cycles per iteration: mma_rate.cu, k_loop)
     const uint32_t tm = __shfl_sync(kFull, tmem_base, 0);
-    int s = 0;
-    uint32_t ph = 0, kc = 0;
-    int it = 0;
-    for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
-      const int ab = it & 1;
-      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(bar_tempty(ab), aph ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tm + (uint32_t)(ab * BN);
-      uint32_t accum = 0;
-      for (int p = 0; p < P.num_pairs; ++p) {
-        // tf32 x tf32 -> f32; A from TMEM (K-major by construction), B as stored
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)P.b_mn[p] << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        const uint32_t b_lbo = P.b_mn[p] ? BK * kStageRowBytes : 16;
-        const uint32_t b_step = P.b_mn[p] ? 8 * kStageRowBytes : 32;
-        const uint64_t desc_b0 = make_desc(smem_base, b_lbo, P.b_mn[p] ? 512 : 1024, P.b_mn[p] ? 1 : 2);
-        for (int kb = 0, nkb = (P.kd[p] + BK - 1) / BK; kb < nkb; ++kb, ++kc) {
-          mbar_wait(bar_lo(s), ph);
-          if (P.dbg && blockIdx.x == 0 && lane == 0 && kc < 128) P.dbg[kc * 8 + 5] = clock64();
-          tc_fence_after();
-          const uint32_t ts = kc % (uint32_t)kTsGroups;
-          const uint32_t a_stage = tm + ring0 + ts * kRingCols;
-          const uint64_t db0 = desc_b0 + (uint64_t)(((uint32_t)s * stage_bytes + a_bytes) >> 4);
-          if (elect_one()) {
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0, kc = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
+        const int ab = it & 1;
+        const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(bar_tempty(ab), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tm + (uint32_t)(ab * BN);
+        uint32_t accum = 0;
+        for (int p = 0; p < P.num_pairs; ++p) {
+          // tf32 x tf32 -> f32; A from TMEM (K-major by construction), B as stored
+          const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)P.b_mn[p] << 16) |
+                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+          const uint32_t b_lbo = P.b_mn[p] ? BK * kStageRowBytes : 16;
+          const uint32_t b_step = P.b_mn[p] ? 8 * kStageRowBytes : 32;
+          const uint64_t desc_b0 = make_desc(smem_base, b_lbo, P.b_mn[p] ? 512 : 1024, P.b_mn[p] ? 1 : 2);
+          for (int kb = 0, nkb = (P.kd[p] + BK - 1) / BK; kb < nkb; ++kb, ++kc) {
+            mbar_wait(bar_lo(s), ph);
+            if (P.dbg && blockIdx.x == 0 && kc < 128) P.dbg[kc * 8 + 5] = clock64();
+            tc_fence_after();
+            const uint32_t ts = kc % (uint32_t)kTsGroups;
+            const uint32_t a_stage = tm + ring0 + ts * kRingCols;
+            const uint64_t db0 = desc_b0 + (uint64_t)(((uint32_t)s * stage_bytes + a_bytes) >> 4);
 #pragma unroll
             for (int kk = 0; kk < KSTEPS; ++kk) {
               const uint64_t db = db0 + (uint64_t)(kk * (b_step >> 4)), db_lo = db + (b_bytes >> 4);
@@ -740,16 +741,15 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
             }
             umma_commit(bar_empty(s));
             umma_commit(bar_tfree(ts));
+            if (P.dbg && blockIdx.x == 0 && kc < 128) P.dbg[kc * 8 + 6] = clock64();
+            accum = 1;
+            if (++s == stages) { s = 0; ph ^= 1; }
           }
-          __syncwarp();
-          if (P.dbg && blockIdx.x == 0 && lane == 0 && kc < 128) P.dbg[kc * 8 + 6] = clock64();
-          accum = 1;
-          if (++s == stages) { s = 0; ph ^= 1; }
         }
+        umma_commit(bar_tfull(ab));
       }
-      if (elect_one()) umma_commit(bar_tfull(ab));
-      __syncwarp();
     }
+    __syncwarp();
   } else if (warp < 6 || warp >= 10) {
     // ===================== split: B hi/lo in shared memory, A hi/lo into the TMEM ring =====================
     const int grp = warp >= 10 ? 1 + ((warp - 10) >> 2) : 0;
