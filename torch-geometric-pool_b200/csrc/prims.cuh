@@ -99,6 +99,40 @@ static __global__ void k_scan_down(const int* __restrict__ in, int* __restrict__
   }
 }
 
+// Small inputs (n <= kScanSmall): ONE block scans the whole array with a running carry -- one launch instead of three.
+// (The TopK step on 128 small graphs, BASELINE config 1, is a chain of ~20 launches of a few microseconds each; nine of
+// them were the three phases of three scans.)  Integer sums: the result is identical to the tiled path.
+constexpr int kScanSmall = 32768;
+constexpr int kScanSmallItems = 8;
+static __global__ void __launch_bounds__(1024) k_scan_small(const int* __restrict__ in, int* __restrict__ out, int n,
+                                                            int* __restrict__ total32, int64_t* __restrict__ total64) {
+  __shared__ int red[33];
+  int carry = 0;
+  for (int start = 0; start < n; start += 1024 * kScanSmallItems) {
+    const int base = start + (int)threadIdx.x * kScanSmallItems;
+    int v[kScanSmallItems];
+    int s = 0;
+#pragma unroll
+    for (int j = 0; j < kScanSmallItems; ++j) {
+      v[j] = base + j < n ? in[base + j] : 0;
+      s += v[j];
+    }
+    int tot;
+    int ex = carry + block_exclusive_scan_i(s, red, &tot);
+#pragma unroll
+    for (int j = 0; j < kScanSmallItems; ++j) {
+      if (base + j < n) out[base + j] = ex;
+      ex += v[j];
+    }
+    carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (total32) *total32 = carry;
+    if (total64) *total64 = carry;
+  }
+}
+
 inline size_t scan_workspace_bytes(int64_t n) { return align_up((size_t)ceil_div(n > 0 ? n : 1, kScanTile) * sizeof(int)); }
 
 // out may alias in.  total32/total64 (device) receive the grand total when non-null.
@@ -107,6 +141,10 @@ inline int exclusive_scan_i32(const int* in, int* out, int64_t n, int* total32, 
   int nt = (int)ceil_div(n > 0 ? n : 1, kScanTile);
   int* sums = ws.take<int>(nt);
   if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+  if (n <= kScanSmall) {
+    launch("k_scan_small", k_scan_small, 1, 1024, 0, stream, in, out, (int)n, total32, total64);
+    return launch_status();
+  }
   launch("k_scan_reduce", k_scan_reduce, nt, kScanThreads, 0, stream, in, n, sums);
   launch("k_scan_spine", k_scan_spine, 1, 1024, 0, stream, sums, nt, total32, total64);
   if (n > 0) launch("k_scan_down", k_scan_down, nt, kScanThreads, 0, stream, in, out, n, sums);
@@ -444,7 +482,7 @@ static __global__ void __launch_bounds__(kSortThreads)
       }
       dsum[q] = run;
       tsum += run;
-      g_base[d] = tile_off[(size_t)d * nt + blockIdx.x];
+      g_base[d] = tile_off ? tile_off[(size_t)d * nt + blockIdx.x] : 0;
     }
     int ex = block_exclusive_scan_i(tsum, scan_tmp, &tot);
 #pragma unroll
@@ -468,7 +506,8 @@ static __global__ void __launch_bounds__(kSortThreads)
   for (int lp = threadIdx.x; lp < tot; lp += kSortThreads) {
     KeyT k = s_keys[lp];
     int d = (int)((k >> shift) & (BINS - 1));
-    int64_t pos = (int64_t)g_base[d] + (lp - dig_base[d]);
+    // a single tile (tile_off == nullptr: no histogram / scan launches) is globally sorted once it is tile-sorted
+    int64_t pos = tile_off ? (int64_t)g_base[d] + (lp - dig_base[d]) : (int64_t)lp;
     keys_out[pos] = k;
     vals_out[pos] = s_vals[lp];
   }
@@ -499,9 +538,14 @@ static int radix_pass(const KeyT* kin, const uint32_t* vin, KeyT* kout, uint32_t
     cudaFuncSetAttribute(k_radix_scatter<KeyT, BITS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)radix_scatter_smem<KeyT, BITS>());
   }
-  launch("k_radix_hist", k_radix_hist<KeyT, BITS>, nt, kSortThreads, 0, stream, kin, n, n_dev, shift, hist, nt);
-  int rc = exclusive_scan_i32(hist, hist, (int64_t)nt * BINS, nullptr, nullptr, ws, stream);
-  if (rc != TGPB200_OK) return rc;
+  if (nt == 1) {
+    // one tile: the scatter kernel's own digit prefix is the global one -- one launch per pass instead of three
+    hist = nullptr;
+  } else {
+    launch("k_radix_hist", k_radix_hist<KeyT, BITS>, nt, kSortThreads, 0, stream, kin, n, n_dev, shift, hist, nt);
+    int rc = exclusive_scan_i32(hist, hist, (int64_t)nt * BINS, nullptr, nullptr, ws, stream);
+    if (rc != TGPB200_OK) return rc;
+  }
   if (vin == nullptr)
     launch("k_radix_scatter", k_radix_scatter<KeyT, BITS, true>, nt, kSortThreads, radix_scatter_smem<KeyT, BITS>(),
            stream, kin, (const uint32_t*)nullptr, kout, vout, n, n_dev, shift, hist, nt);
