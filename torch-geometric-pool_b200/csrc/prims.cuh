@@ -133,18 +133,118 @@ static __global__ void __launch_bounds__(1024) k_scan_small(const int* __restric
   }
 }
 
-inline size_t scan_workspace_bytes(int64_t n) { return align_up((size_t)ceil_div(n > 0 ? n : 1, kScanTile) * sizeof(int)); }
+// Large inputs: single-pass scan with decoupled look-back -- the input is read ONCE and there is one kernel (plus the
+// memset of the tile states) instead of three.  Tiles take a ticket, publish (flag, tile sum) packed in 64 bits and walk
+// back over the published aggregates until they meet an inclusive prefix (same protocol as k_compact_onepass).
+// tile_state ([tiles] uint64) and ticket (int) must be zero before the launch.  Sums are < 2^31 (contract of this scan).
+static __global__ void __launch_bounds__(kScanThreads)
+    k_scan_onepass(const int* __restrict__ in, int* __restrict__ out, int64_t n, unsigned long long* __restrict__ tile_state,
+                   int* __restrict__ ticket, int num_tiles, int* __restrict__ total32, int64_t* __restrict__ total64) {
+  __shared__ int red[33];
+  __shared__ int s_tile, s_excl;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
+  __syncthreads();
+  const int tile = s_tile;
+  const int64_t base = (int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int v[kScanItems];
+  int s = 0;
+  if (base + kScanItems <= n && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+#pragma unroll
+    for (int j = 0; j < kScanItems; j += 4) {
+      const int4 q = *reinterpret_cast<const int4*>(in + base + j);
+      v[j] = q.x, v[j + 1] = q.y, v[j + 2] = q.z, v[j + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) v[j] = base + j < n ? in[base + j] : 0;
+  }
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) s += v[j];
+  int total;
+  int ex = block_exclusive_scan_i(s, red, &total);
+  if (w == 0) {
+    unsigned long long excl = 0;
+    if (tile == 0) {
+      if (lane == 0) atomicExch(&tile_state[0], (2ull << 32) | (unsigned)total);
+    } else {
+      if (lane == 0) atomicExch(&tile_state[tile], (1ull << 32) | (unsigned)total);
+      int t = tile - 1;
+      while (true) {
+        const int idx = t - lane;
+        unsigned long long st = 2ull << 32;  // before tile 0: an inclusive prefix of 0
+        if (idx >= 0) {
+          long long spins = 0;
+          while (((st = *(volatile unsigned long long*)&tile_state[idx]) >> 32) == 0) {
+            if (++spins > (1ll << 26)) __trap();
+          }
+        }
+        const unsigned done = __ballot_sync(kFull, (st >> 32) == 2);
+        const int first = done ? __ffs(done) - 1 : 31;  // lanes up to the nearest inclusive prefix contribute
+        unsigned val = lane <= first ? (unsigned)(st & 0xffffffffull) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(kFull, val, o);
+        excl += val;
+        if (done) break;
+        t -= 32;
+      }
+      if (lane == 0) {
+        __threadfence();
+        atomicExch(&tile_state[tile], (2ull << 32) | (unsigned)(excl + (unsigned)total));
+      }
+    }
+    if (lane == 0) {
+      s_excl = (int)excl;
+      if (tile == num_tiles - 1) {
+        if (total32) *total32 = (int)excl + total;
+        if (total64) *total64 = (int64_t)excl + total;
+      }
+    }
+  }
+  __syncthreads();
+  ex += s_excl;
+  if (base + kScanItems <= n && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+#pragma unroll
+    for (int j = 0; j < kScanItems; j += 4) {
+      int4 q;
+      q.x = ex, q.y = ex + v[j], q.z = q.y + v[j + 1], q.w = q.z + v[j + 2];
+      ex = q.w + v[j + 3];
+      *reinterpret_cast<int4*>(out + base + j) = q;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      if (base + j < n) out[base + j] = ex;
+      ex += v[j];
+    }
+  }
+}
+
+// workspace: tile sums of the three-phase path, or tile states + ticket of the one-pass path (the larger of the two)
+inline size_t scan_workspace_bytes(int64_t n) {
+  return align_up(((size_t)ceil_div(n > 0 ? n : 1, kScanTile) + 2) * sizeof(unsigned long long));
+}
 
 // out may alias in.  total32/total64 (device) receive the grand total when non-null.
 inline int exclusive_scan_i32(const int* in, int* out, int64_t n, int* total32, int64_t* total64, Workspace& ws,
                               cudaStream_t stream) {
   int nt = (int)ceil_div(n > 0 ? n : 1, kScanTile);
-  int* sums = ws.take<int>(nt);
+  unsigned long long* state = ws.take<unsigned long long>((size_t)nt + 2);
   if (!ws.ok) return TGPB200_ERR_WORKSPACE;
   if (n <= kScanSmall) {
     launch("k_scan_small", k_scan_small, 1, 1024, 0, stream, in, out, (int)n, total32, total64);
     return launch_status();
   }
+  {
+    static const bool three_phase = [] { const char* e = getenv("TGPB200_SCAN_ONEPASS"); return e && e[0] == '0'; }();
+    if (!three_phase) {
+      cudaMemsetAsync(state, 0, ((size_t)nt + 2) * sizeof(unsigned long long), stream);
+      launch("k_scan_onepass", k_scan_onepass, nt, kScanThreads, 0, stream, in, out, n, state,
+             reinterpret_cast<int*>(state + nt), nt, total32, total64);
+      return launch_status();
+    }
+  }
+  int* sums = reinterpret_cast<int*>(state);
   launch("k_scan_reduce", k_scan_reduce, nt, kScanThreads, 0, stream, in, n, sums);
   launch("k_scan_spine", k_scan_spine, 1, 1024, 0, stream, sums, nt, total32, total64);
   if (n > 0) launch("k_scan_down", k_scan_down, nt, kScanThreads, 0, stream, in, out, n, sums);
