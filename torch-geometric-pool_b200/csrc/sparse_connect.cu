@@ -261,6 +261,27 @@ static __global__ void k_coalesce_ties(const float* __restrict__ w, const float*
   int s = slot[e];
   if (s >= 0 && w[e] == out_w[s]) atomicAdd(&ties[s], 1);
 }
+// sum / mean: four edges per thread (128-bit slot read and gradient write, the gathers of the four in flight together)
+static __global__ void k_coalesce_bwd4(const float* __restrict__ gout, const int32_t* __restrict__ slot,
+                                       const int32_t* __restrict__ run_len, int64_t E4, int mean,
+                                       float* __restrict__ gin) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= E4) return;
+  const int4 s = reinterpret_cast<const int4*>(slot)[q];
+  const int ss[4] = {s.x, s.y, s.z, s.w};
+  float g[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) g[j] = ss[j] >= 0 ? __ldg(gout + ss[j]) : 0.f;
+  if (mean) {
+    int len[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) len[j] = ss[j] >= 0 ? __ldg(run_len + ss[j]) : 1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[j] = g[j] / (float)len[j];
+  }
+  reinterpret_cast<float4*>(gin)[q] = make_float4(g[0], g[1], g[2], g[3]);
+}
+
 static __global__ void k_coalesce_bwd(const float* __restrict__ w, const float* __restrict__ out_w,
                                       const float* __restrict__ gout, const int32_t* __restrict__ slot,
                                       const int32_t* __restrict__ run_len, const float* __restrict__ run_aux,
@@ -802,6 +823,16 @@ int tgpb200_coalesce_bwd(const float* edge_weight, const float* out_weight, cons
     if (!ws.ok) return TGPB200_ERR_WORKSPACE;
     cudaMemsetAsync(ties, 0, (size_t)(num_out > 0 ? num_out : 1) * sizeof(int), st);
     launch("k_coalesce_ties", k_coalesce_ties, grid, 256, 0, st, edge_weight, out_weight, edge_slot, E, ties);
+  }
+  if ((op == TGPB200_SUM || op == TGPB200_MEAN) && E >= 4 &&
+      ((reinterpret_cast<uintptr_t>(edge_slot) | reinterpret_cast<uintptr_t>(grad_in)) & 15) == 0) {
+    const int64_t E4 = E / 4;
+    launch("k_coalesce_bwd", k_coalesce_bwd4, (unsigned)ceil_div(E4, 256), 256, 0, st, grad_out, edge_slot, run_len, E4,
+           op == TGPB200_MEAN ? 1 : 0, grad_in);
+    if (E % 4)  // tail through the general kernel
+      launch("k_coalesce_bwd", k_coalesce_bwd, 1, 256, 0, st, edge_weight ? edge_weight + E4 * 4 : nullptr, out_weight, grad_out, edge_slot + E4 * 4,
+             run_len, run_aux, ties, E - E4 * 4, op, grad_in + E4 * 4);
+    return launch_status();
   }
   launch("k_coalesce_bwd", k_coalesce_bwd, grid, 256, 0, st, edge_weight, out_weight, grad_out, edge_slot, run_len, run_aux, ties, E, op, grad_in);
   return launch_status();
