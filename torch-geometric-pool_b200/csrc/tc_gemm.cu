@@ -298,11 +298,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp; tcgen05 instructions on one elected lane) =====================
-    {
-      // instruction descriptor: c=F32 (1<<4), a/b format, a/b major, N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t fmt = kF32 ? 2u : 1u;  // TF32 : BF16
-      const uint32_t tm = __shfl_sync(kFull, tmem_base, 0);
+    // ===================== MMA issuer: ONE elected thread runs the whole loop =====================
+    // (electing per k-block and reconverging the warp afterwards costs ~150 cycles per iteration: mma_rate.cu, k_loop)
+    // instruction descriptor: c=F32 (1<<4), a/b format, a/b major, N>>3 at [17,23), M>>4 at [24,29)
+    const uint32_t fmt = kF32 ? 2u : 1u;  // TF32 : BF16
+    const uint32_t tm = __shfl_sync(kFull, tmem_base, 0);
+    if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -318,8 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
           const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)P.a_mn[p] << 15) |
                                  ((uint32_t)P.b_mn[p] << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
           // same with N = 2 BN: one instruction multiplies hi_a by [hi_b | lo_b] (the lo tile sits right behind the
-          // hi tile of B in shared memory).  An MMA costs ~43 + N/2 cycles (benchmarks/mma_rate.cu), so 3xTF32 as two
-          // instructions per k-step (N = 2 BN, N = BN) is cheaper than three N = BN ones.
+          // hi tile of B in shared memory): 3xTF32 as two instructions per k-step instead of three.
           const uint32_t idesc2 = (idesc & ~(0x3fu << 17)) | ((uint32_t)((2 * BN) >> 3) << 17);
           const uint32_t a_lbo = P.a_mn[p] ? BK * kStageRowBytes : 16, b_lbo = P.b_mn[p] ? BK * kStageRowBytes : 16;
           const uint32_t a_step = P.a_mn[p] ? UMMA_K * kStageRowBytes : 32, b_step = P.b_mn[p] ? UMMA_K * kStageRowBytes : 32;
@@ -334,28 +334,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
             const uint32_t so = ((uint32_t)s * stage_bytes) >> 4;
             const uint64_t da0 = desc_a0 + so, db0 = desc_b0 + so + (a_bytes >> 4);
             const uint32_t a_lo_off = (a_bytes + 2 * b_bytes) >> 4;  // stage = [A | B | B lo | A lo]
-            if (elect_one()) {
 #pragma unroll
-              for (int kk = 0; kk < KSTEPS; ++kk) {
-                const uint64_t da = da0 + (uint64_t)(kk * (a_step >> 4)), db = db0 + (uint64_t)(kk * (b_step >> 4));
-                if (kF32) {
-                  umma<true>(d_tmem, da, db, idesc2, kk == 0 ? accum : 1u);  // hi_a x [hi_b | lo_b]
-                  umma<true>(d_tmem, da + a_lo_off, db, idesc, 1u);          // lo_a x hi_b
-                } else {
-                  umma<false>(d_tmem, da, db, idesc, kk == 0 ? accum : 1u);
-                }
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+              const uint64_t da = da0 + (uint64_t)(kk * (a_step >> 4)), db = db0 + (uint64_t)(kk * (b_step >> 4));
+              if (kF32) {
+                umma<true>(d_tmem, da, db, idesc2, kk == 0 ? accum : 1u);  // hi_a x [hi_b | lo_b]
+                umma<true>(d_tmem, da + a_lo_off, db, idesc, 1u);          // lo_a x hi_b
+              } else {
+                umma<false>(d_tmem, da, db, idesc, kk == 0 ? accum : 1u);
               }
-              umma_commit(bar_empty(s));
             }
-            __syncwarp();
+            umma_commit(bar_empty(s));
             accum = 1;
             if (++s == stages) { s = 0; ph ^= 1; }
           }
         }
-        if (elect_one()) umma_commit(bar_tfull(ab));
-        __syncwarp();
+        umma_commit(bar_tfull(ab));
       }
     }
+    __syncwarp();
   } else if (kF32 && warp < 6) {
     // ===================== operand split (fp32 only): lo = x - trunc_tf32(x) =====================
     {
