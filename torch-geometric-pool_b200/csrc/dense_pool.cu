@@ -562,13 +562,16 @@ static __global__ void k_finalize_losses(const float* __restrict__ stats, int B,
 // trained assignment that reproduces A), so shape generality and a fixed reduction order matter, not speed.
 template <typename T>
 static __global__ void __launch_bounds__(256)
-    k_link_residual(const T* __restrict__ A, const T* __restrict__ S, int N, int K, int tiles_n,
+    k_link_residual(const T* __restrict__ A, const T* __restrict__ S, int N, int K, int tiles_n, int64_t total,
                     const float* __restrict__ losses, float* __restrict__ partial) {
   if (losses[5] == 0.f) return;
   __shared__ float si[16][65], sj[16][65];
   __shared__ float red[32];
   const int tiles = tiles_n * tiles_n;
-  const int tile = blockIdx.x % tiles, b = blockIdx.x / tiles;
+  // grid-stride over the (graph, tile) pairs: the launch is a few CTAs per SM, so the common case (flag clear, every
+  // CTA returns at once) costs microseconds instead of the scheduling of B * tiles CTAs (61 us per C3 step)
+  for (int64_t wid = blockIdx.x; wid < total; wid += gridDim.x) {
+  const int tile = (int)(wid % tiles), b = (int)(wid / tiles);
   const int i0 = (tile / tiles_n) * 64, j0 = (tile % tiles_n) * 64;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 4 x 4 micro-tile per thread
   const T* Sb = S + (int64_t)b * N * K;
@@ -610,7 +613,9 @@ static __global__ void __launch_bounds__(256)
       }
     }
   s = block_sum(s, red);
-  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  if (threadIdx.x == 0) partial[wid] = s;
+  __syncthreads();
+  }
 }
 static __global__ void k_link_fix(const float* __restrict__ partial, int64_t n, float link_div,
                                   float* __restrict__ losses) {
@@ -1124,8 +1129,10 @@ static int dense_fwd(const T* A, const T* S, const T* X, int B, int N, int K, in
            pl.losses);
     if (link_tau > 0.f) {
       const int tn = (N + 63) / 64;
-      launch("k_link_residual", k_link_residual<T>, (unsigned)(tn * tn * B), 256, 0, st, A, S, N, K, tn, pl.losses,
-             link_partial);
+      const int64_t total = (int64_t)tn * tn * B;
+      const int64_t cap = (int64_t)tc::device_sm_count() * 8;
+      launch("k_link_residual", k_link_residual<T>, (unsigned)(total < cap ? total : cap), 256, 0, st, A, S, N, K, tn, total,
+             pl.losses, link_partial);
       launch("k_link_fix", k_link_fix, 1, 1024, 0, st, link_partial, (int64_t)B * tn * tn, link_div, pl.losses);
     }
     if (losses_out) cudaMemcpyAsync(losses_out, pl.losses, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st);
