@@ -41,8 +41,12 @@ namespace {
 #ifndef TGPB200_BWD_EPI_WARPS
 #define TGPB200_BWD_EPI_WARPS 4
 #endif
+// Ablation switches (timing experiments only, results are wrong when any bit is set): benchmarks/ablate_bwd.sh
+#ifndef TGPB200_ABL
+#define TGPB200_ABL 0
+#endif
 #ifndef TGPB200_BWD_CONCAT
-#define TGPB200_BWD_CONCAT 1
+#define TGPB200_BWD_CONCAT 0
 #endif
 // 3xTF32 of the W / dS pairs as TWO instructions per k-step: hi_a x [hi_b | lo_b] (N = 128: the lo tile of B directly
 // follows its hi tile in shared memory) + lo_a x hi_b (N = 64).  A tcgen05.mma costs ~57 cycles of dispatch whatever
@@ -50,16 +54,25 @@ namespace {
 // for.  The accumulators of those pairs are 128 columns wide ([.. | hi_a lo_b], summed by whoever reads them).
 constexpr bool kConcat = TGPB200_BWD_CONCAT != 0;
 constexpr int kPairs = 7;
-constexpr int kGroups = kConcat ? 2 : 3;   // split groups = TMEM operand stages
+constexpr int kGroups = 2;                 // split groups (k-block kc goes to group kc % kGroups)
+// TMEM operand ring: the slot of k-block kc is kc % kSlots.  A slot is recycled when the MMAs that read it have
+// RETIRED (tcgen05.commit -> mbarrier -> the split warps' wait): with as many slots as split groups that round trip
+// (~1.8 k cycles: benchmarks/ablate_bwd.sh, every stage of the pipeline emptied) bounds the kernel at one k-block per
+// ~900 cycles whatever the k-block contains.  With more slots than groups the split warps never wait for it.
+constexpr int kSlots = kConcat ? 2 : 4;
 constexpr int kEpiW = TGPB200_BWD_EPI_WARPS;  // epilogue warps (one or two per TMEM lane quadrant)
 constexpr int kThreadsBwd = 64 + kGroups * 128 + kEpiW * 32;
 constexpr int BK = 32, KSTEPS = 4;
 constexpr int BNB = 64;                    // MMA N of every pair
 constexpr uint32_t kAccW = kConcat ? 128 : 64;  // width of the W and dS accumulators
 constexpr uint32_t kColW = 0, kColS = kAccW, kColX = 2 * kAccW, kColRing = 2 * kAccW + 128, kRing = 64;
+static_assert(kColRing + kSlots * kRing <= 512, "tensor memory budget");
 constexpr uint32_t kABytes = BM * kStageRowBytes, kBBytes = BNB * kStageRowBytes;
 constexpr uint32_t kStage = kABytes + 2 * kBBytes;  // [A raw | B hi | B lo] = 32 KB
-constexpr uint32_t kEpiBytes = kEpiW * 4096;
+constexpr uint32_t kEpiBufs = kEpiW == 4 ? 2 : 1;  // staging tiles per epilogue warp (32 KB in total)
+constexpr uint32_t kEpiBytes = kEpiW * kEpiBufs * 4096;
+// rows of S for the element-wise terms of dS: 128 rows x 64 columns fp32, prefetched with cp.async while the item's MMAs run
+constexpr uint32_t kHookBytes = BM * BNB * 4;
 
 enum ASrc { kAKMajor = 0, kAMnPlain = 1, kATmem = 2 };
 
@@ -82,15 +95,15 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int stages = P.stages;
-  // [stages][kStage] | epilogue staging | barriers
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStage * stages + kEpiBytes);
+  // [stages][kStage] | epilogue staging | S rows of the element-wise terms | barriers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStage * stages + kEpiBytes + kHookBytes);
   const uint32_t bar_base = smem_u32(bars);
   auto bar_full = [&](int s) { return bar_base + 8u * s; };
   auto bar_lo = [&](int s) { return bar_base + 8u * (stages + s); };
   auto bar_empty = [&](int s) { return bar_base + 8u * (2 * stages + s); };
   auto bar_tfree = [&](int g) { return bar_base + 8u * (3 * stages + g); };
-  const uint32_t bar_wfull = bar_base + 8u * (3 * stages + kGroups), bar_tfull = bar_wfull + 8u, bar_tempty = bar_wfull + 16u;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + kGroups + 3);
+  const uint32_t bar_wfull = bar_base + 8u * (3 * stages + kSlots), bar_tfull = bar_wfull + 8u, bar_tempty = bar_wfull + 16u;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + kSlots + 3);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = smem_u32(smem);
@@ -109,7 +122,7 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
       mbar_init(bar_lo(s), 128);
       mbar_init(bar_empty(s), 1);
     }
-    for (int g = 0; g < kGroups; ++g) mbar_init(bar_tfree(g), 1);
+    for (int g = 0; g < kSlots; ++g) mbar_init(bar_tfree(g), 1);
     mbar_init(bar_wfull, 1);
     mbar_init(bar_tfull, 1);
     mbar_init(bar_tempty, kEpiW * 32);
@@ -137,9 +150,12 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
           mbar_wait(bar_empty(s), ph ^ 1);
           const uint32_t sa = smem_base + (uint32_t)s * kStage, sb = sa + kABytes;
           const int k0 = kb * BK;
-          if (elect_one()) {
-            mbar_arrive_expect_tx(bar_full(s), (src == kATmem ? 0u : kABytes) + kBBytes);
-            if (src == kAMnPlain) tma_load_3d(sa, &P.map_a[p], bar_full(s), m0, k0, b);      // [32 k][128 m], no swizzle
+          if ((TGPB200_ABL & 64) && elect_one()) mbar_arrive(bar_full(s));
+          if (!(TGPB200_ABL & 64) && elect_one()) {
+            const bool load_a = src != kATmem && !(TGPB200_ABL & 32);
+            mbar_arrive_expect_tx(bar_full(s), (load_a ? kABytes : 0u) + kBBytes);
+            if (!load_a) {
+            } else if (src == kAMnPlain) tma_load_3d(sa, &P.map_a[p], bar_full(s), m0, k0, b);      // [32 k][128 m], no swizzle
             else if (src == kAKMajor) tma_load_3d(sa, &P.map_a[p], bar_full(s), k0, m0, b);  // [128 m][32 k], 128B swizzle
             if (P.b_mn[p]) {
               for (int blk = 0; blk < BNB / 32; ++blk)
@@ -182,11 +198,11 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
             mbar_wait(bar_lo(s), ph);
             if (P.dbg && blockIdx.x == 0 && kc < 128) P.dbg[kc * 8 + 5] = clock64();
             tc_fence_after();
-            const uint32_t ts = kc % (uint32_t)kGroups;
+            const uint32_t ts = kc % (uint32_t)kSlots;
             const uint32_t a_stage = tm + kColRing + ts * kRing;
             const uint64_t db0 = desc_b0 + (uint64_t)(((uint32_t)s * kStage + kABytes) >> 4);
 #pragma unroll
-            for (int kk = 0; kk < KSTEPS; ++kk) {
+            for (int kk = 0; kk < ((TGPB200_ABL & 128) ? 0 : KSTEPS); ++kk) {
               const uint64_t db = db0 + (uint64_t)(kk * (b_step >> 4)), db_lo = db + (kBBytes >> 4);
               const uint32_t a_hi = a_stage + (uint32_t)(kk * 16), a_lo = a_hi + 8;
               if (wide) {
@@ -231,7 +247,7 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
           mbar_wait(bar_full(s), ph);
           const uint32_t sa = smem_base + (uint32_t)s * kStage, sb = sa + kABytes;
           // B: hi in place, lo behind it
-          for (uint32_t ch = t; ch < kBBytes / 16; ch += 128) {
+          for (uint32_t ch = t; ch < ((TGPB200_ABL & 1) ? 0u : kBBytes / 16); ch += 128) {
             const float4 v = lds128(sb + ch * 16);
             float4 h, l;
             h.x = rna_tf32(v.x), h.y = rna_tf32(v.y), h.z = rna_tf32(v.z), h.w = rna_tf32(v.w);
@@ -239,10 +255,13 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
             sts128(sb + ch * 16, h);
             sts128(sb + kBBytes + ch * 16, l);
           }
-          fence_proxy_async();
+          if (!(TGPB200_ABL & 2)) fence_proxy_async();
           // A: this thread's row, 32 k values
           float x[32];
-          if (src == kATmem) {
+          if (TGPB200_ABL & 4) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) x[k] = (float)(k + lane);
+          } else if (src == kATmem) {
             mbar_wait(bar_wfull, (uint32_t)it & 1u);
             tc_fence_after();
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + kColW + (uint32_t)(kb * BK), x);
@@ -262,9 +281,10 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
               x[4 * c] = v.x, x[4 * c + 1] = v.y, x[4 * c + 2] = v.z, x[4 * c + 3] = v.w;
             }
           }
-          mbar_wait(bar_tfree(grp), ((kc / (uint32_t)kGroups) & 1u) ^ 1u);
+          const uint32_t slot = kc % (uint32_t)kSlots;
+          mbar_wait(bar_tfree(slot), ((kc / (uint32_t)kSlots) & 1u) ^ 1u);
           tc_fence_after();
-          const uint32_t a_stage = tmem_base + ((uint32_t)(q * 32) << 16) + kColRing + (uint32_t)grp * kRing;
+          const uint32_t a_stage = tmem_base + ((uint32_t)(q * 32) << 16) + kColRing + slot * kRing;
 #pragma unroll
           for (int kk = 0; kk < KSTEPS; ++kk) {
             float hi[8], lo[8];
@@ -273,7 +293,8 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
               hi[i] = rna_tf32(x[kk * 8 + i]);
               lo[i] = x[kk * 8 + i] - hi[i];
             }
-            tmem_st16(a_stage + (uint32_t)(kk * 16), hi, lo);
+            if (!(TGPB200_ABL & 8)) tmem_st16(a_stage + (uint32_t)(kk * 16), hi, lo);
+            else if (hi[0] == 123.456f && lo[7] == 3.f) P.dbg[0] = 1;  // keep the conversion alive
           }
           tmem_st_wait();
           tc_fence_before();
@@ -288,17 +309,38 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
     const int quad = warp & 3;
     const int ew = warp - 2 - kGroups * 4;   // 0 .. 7
     const int e2 = ew >> 2;                  // which of the quadrant's warps
-    const uint32_t stg = smem_base + (uint32_t)kStage * stages + (uint32_t)ew * 4096u;
+    const uint32_t stg0 = smem_base + (uint32_t)kStage * stages + (uint32_t)ew * kEpiBufs * 4096u;
+    uint32_t n_stored = 0;
+    const uint32_t hook0 = smem_base + (uint32_t)kStage * stages + kEpiBytes;
     const int n_chunks = 2 + (P.F + 31) / 32;
     int it = 0;
     for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
       const int mt = item % P.m_tiles, b = item / P.m_tiles;
+      const int m_base = mt * BM + quad * 32;
+      const int m = m_base + lane;
+      // Element-wise gradient terms of dS (mincut denominator 2 c_den d_i S, entropy loss): this thread's row of S is
+      // fetched NOW, asynchronously into shared memory, so that its latency sits behind the item's MMAs instead of in
+      // the drain (loading it per chunk after the accumulators were ready cost 21 us of the 115 us kernel).
+      float dd = 0.f, c_ent = 0.f;
+      bool hook = false;
+      const uint32_t hrow = hook0 + (uint32_t)(quad * 32 + lane) * (BNB * 4);
+      if (!(TGPB200_ABL & 256) && P.S != nullptr && m < P.N) {
+        const float c_den = P.coef[b * 4 + 0];
+        c_ent = P.coef[b * 4 + 2];
+        hook = c_den != 0.f || c_ent != 0.f;
+        if (hook) {
+          dd = 2.f * c_den * P.d[(int64_t)b * P.N + m];
+          const float* srow = P.S + ((int64_t)b * P.N + m) * P.K;
+          for (int j = 0; j * 4 < P.K; ++j) cp_async16(hrow + (uint32_t)((j ^ (lane & 7)) << 4), srow + j * 4);
+        }
+      }
+      cp_async_commit();
       mbar_wait(bar_tfull, (uint32_t)it & 1u);
       if (P.dbg && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 32) P.dbg[(128 + it) * 8 + 0] = clock64();
       tc_fence_after();
-      const int m_base = mt * BM + quad * 32;
-      const int m = m_base + lane;
-      for (int c = 0; c < n_chunks; ++c) {
+      cp_async_wait_all();
+      __syncwarp();
+      for (int c = 0; c < ((TGPB200_ABL & 16) ? 0 : n_chunks); ++c) {
         if (kEpiW == 8 && (c & 1) != e2) continue;
         const bool is_ds = c < 2;
         const int n0 = is_ds ? c * 32 : (c - 2) * 32;
@@ -311,33 +353,28 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
           for (int j = 0; j < 32; ++j) v[j] += v2[j];
         }
         if (m_base >= P.N || n0 >= (is_ds ? P.K : P.F)) continue;  // warp-uniform
-        if (is_ds && P.S != nullptr && m < P.N) {
-          // element-wise gradient terms: mincut denominator (2 c_den d_i S) and entropy loss
-          const float c_den = P.coef[b * 4 + 0], c_ent = P.coef[b * 4 + 2];
-          if (c_den != 0.f || c_ent != 0.f) {
-            const float dd = 2.f * c_den * P.d[(int64_t)b * P.N + m];
-            const float* srow = P.S + ((int64_t)b * P.N + m) * P.K + n0;
-            // eight columns at a time (32 live values of S on top of the 32 accumulator values spilled to local memory)
+        if (is_ds && hook) {
 #pragma unroll
-            for (int j8 = 0; j8 < 32; j8 += 8) {
-              float sv[8];
-              if (n0 + 32 <= P.K) {
-                const float4 t0 = __ldg(reinterpret_cast<const float4*>(srow + j8)), t1 = __ldg(reinterpret_cast<const float4*>(srow + j8 + 4));
-                sv[0] = t0.x, sv[1] = t0.y, sv[2] = t0.z, sv[3] = t0.w, sv[4] = t1.x, sv[5] = t1.y, sv[6] = t1.z, sv[7] = t1.w;
-              } else {
+          for (int c4 = 0; c4 < 8; ++c4) {
+            if (n0 + c4 * 4 < P.K) {  // K is a multiple of 4: whole 16-byte chunks
+              const float4 t4 = lds128(hrow + (uint32_t)((((n0 >> 2) + c4) ^ (lane & 7)) << 4));
+              const float sv[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) sv[j] = n0 + j8 + j < P.K ? srow[j8 + j] : 0.f;
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < 4; ++j) {
                 float add = dd * sv[j];
                 if (c_ent != 0.f) add += c_ent * (-__logf(sv[j] + P.eps) - __fdividef(sv[j], sv[j] + P.eps));
-                v[j8 + j] += add;
+                v[c4 * 4 + j] += add;
               }
             }
           }
         }
-        if (lane == 0) tma_store_wait_read<0>();
+        // two staging tiles per warp: the store of the previous chunk may still be reading the other one
+        const uint32_t stg = stg0 + (n_stored % kEpiBufs) * 4096u;
+        ++n_stored;
+        if (lane == 0) {
+          if (kEpiBufs == 2) tma_store_wait_read<1>();
+          else tma_store_wait_read<0>();
+        }
         __syncwarp();
         const uint32_t row = stg + (uint32_t)lane * 128u;
 #pragma unroll
@@ -345,7 +382,7 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
           sts128(row + (uint32_t)((c4 ^ (lane & 7)) << 4), make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]));
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !(TGPB200_ABL & 512)) {
           tma_store_3d(is_ds ? &P.map_ds : &P.map_dx, stg, n0, m_base, b);
           tma_store_commit();
         }
@@ -429,14 +466,14 @@ int dense_bwd_fused(const float* A, const float* S, const float* X, const float*
   P.num_pairs = n;
   if (!make_out_map(&P.map_ds, dS, B, N, K) || !make_out_map(&P.map_dx, dX, B, N, F)) return TGPB200_ERR_UNSUPPORTED;
   P.S = ew_S, P.d = ew_d, P.coef = ew_coef, P.eps = eps;
-  P.stages = 6;
+  P.stages = 5;
   P.dbg = g_engine_dbg;
   static bool attr_set = false;
   if (!attr_set) {
     attr_set = true;
     cudaFuncSetAttribute(k_dense_bwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   }
-  const size_t smem = (size_t)kStage * P.stages + kEpiBytes + (3 * P.stages + kGroups + 4) * 8 + 16 + 1024;
+  const size_t smem = (size_t)kStage * P.stages + kEpiBytes + kHookBytes + (3 * P.stages + kSlots + 4) * 8 + 16 + 1024;
   const int sms = device_sm_count();
   const int grid = P.num_items < sms ? P.num_items : sms;
   launch("k_dense_bwd_fused", k_dense_bwd_fused, grid, kThreadsBwd, smem, stream, P);
