@@ -30,16 +30,23 @@ for path in sys.argv[1:]:
     assert lib.tgpb200_dense_pool_fwd(a.data_ptr(), s.data_ptr(), x.data_ptr(), B, N, K, F, 0, 7, 1, 1e-8, 1.0, 1.0,
                                       xp.data_ptr(), ap.data_ptr(), losses.data_ptr(), saved.data_ptr(), saved.numel(), st) == 0
 
-    def bwd():
+    def bwd(stream):
         assert lib.tgpb200_dense_pool_bwd(a.data_ptr(), s.data_ptr(), x.data_ptr(), gxp.data_ptr(), gap.data_ptr(), gl.data_ptr(),
                                           B, N, K, F, 0, 7, 1, 1e-8, 1.0, 1.0, gs.data_ptr(), gx.data_ptr(), None,
-                                          saved.data_ptr(), saved.numel(), ws.data_ptr(), ws.numel(), st) == 0
+                                          saved.data_ptr(), saved.numel(), ws.data_ptr(), ws.numel(), stream) == 0
     for _ in range(5):
-        bwd()
+        bwd(st)
     torch.cuda.synchronize()
+    # one CUDA graph of 10 backward calls: the eager call is CPU-bound (~60 us of tensor-map encodes per call)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        cs = torch.cuda.current_stream().cuda_stream
+        for _ in range(10):
+            bwd(cs)
+    graph.replay(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(100):
-        bwd()
+    for _ in range(10):
+        graph.replay()
     e1.record(); torch.cuda.synchronize()
-    print(f"{os.path.basename(path):18s} backward {e0.elapsed_time(e1) / 100 * 1000:7.1f} us", flush=True)
+    print(f"{os.path.basename(path):18s} backward {e0.elapsed_time(e1) / 100 * 1000:7.1f} us (graph replay)", flush=True)

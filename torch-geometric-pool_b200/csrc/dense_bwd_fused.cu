@@ -119,13 +119,13 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_lo(s), 128);
+      mbar_init(bar_lo(s), 4);  // one arrival per split warp of the group (after __syncwarp), not one per thread
       mbar_init(bar_empty(s), 1);
     }
     for (int g = 0; g < kSlots; ++g) mbar_init(bar_tfree(g), 1);
     mbar_init(bar_wfull, 1);
     mbar_init(bar_tfull, 1);
-    mbar_init(bar_tempty, kEpiW * 32);
+    mbar_init(bar_tempty, kEpiW);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
             if (P.dbg && blockIdx.x == 0 && kc < 128) P.dbg[kc * 8 + 7] = clock64();
             mbar_wait(bar_lo(s), ph);
             if (P.dbg && blockIdx.x == 0 && kc < 128) P.dbg[kc * 8 + 5] = clock64();
-            tc_fence_after();
+            if (!(TGPB200_ABL & 1024)) tc_fence_after();
             const uint32_t ts = kc % (uint32_t)kSlots;
             const uint32_t a_stage = tm + kColRing + ts * kRing;
             const uint64_t db0 = desc_b0 + (uint64_t)(((uint32_t)s * kStage + kABytes) >> 4);
@@ -215,8 +215,8 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
               }
             }
             if (P.dbg && blockIdx.x == 0 && kc < 128) P.dbg[kc * 8 + 0] = clock64();
-            umma_commit(bar_empty(s));
-            umma_commit(bar_tfree(ts));
+            if (TGPB200_ABL & 4096) mbar_arrive(bar_empty(s)); else umma_commit(bar_empty(s));
+            if (TGPB200_ABL & 8192) mbar_arrive(bar_tfree(ts)); else umma_commit(bar_tfree(ts));
             if (P.dbg && blockIdx.x == 0 && kc < 128) P.dbg[kc * 8 + 6] = clock64();
             accum = 1;
             if (++s == stages) { s = 0; ph ^= 1; }
@@ -282,6 +282,12 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
             }
           }
           const uint32_t slot = kc % (uint32_t)kSlots;
+          if (TGPB200_ABL & 16384) {  // skeleton experiment: nothing between the two barriers
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_lo(s));
+            if (++s == stages) { s = 0; ph ^= 1; }
+            continue;
+          }
           mbar_wait(bar_tfree(slot), ((kc / (uint32_t)kSlots) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t a_stage = tmem_base + ((uint32_t)(q * 32) << 16) + kColRing + slot * kRing;
@@ -298,7 +304,8 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
           }
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(bar_lo(s));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_lo(s));  // 128 per-thread arrivals on one barrier word serialise
           if (P.dbg && blockIdx.x == 0 && lane == 0 && kc < 128) P.dbg[kc * 8 + 1 + q] = clock64();
           if (++s == stages) { s = 0; ph ^= 1; }
         }
@@ -388,7 +395,8 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) k_dense_bwd_fused(const __grid
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_tempty);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty);
       if (P.dbg && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 32) P.dbg[(128 + it) * 8 + 1] = clock64();
     }
     if (lane == 0) tma_store_wait_all();
@@ -467,6 +475,10 @@ int dense_bwd_fused(const float* A, const float* S, const float* X, const float*
   if (!make_out_map(&P.map_ds, dS, B, N, K) || !make_out_map(&P.map_dx, dX, B, N, F)) return TGPB200_ERR_UNSUPPORTED;
   P.S = ew_S, P.d = ew_d, P.coef = ew_coef, P.eps = eps;
   P.stages = 5;
+  {
+    const char* e = getenv("TGPB200_BWD_STAGES");  // experiment: fewer shared-memory stages
+    if (e && atoi(e) >= 2 && atoi(e) <= 5) P.stages = atoi(e);
+  }
   P.dbg = g_engine_dbg;
   static bool attr_set = false;
   if (!attr_set) {

@@ -623,6 +623,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 constexpr int kTsGroups = TGPB200_TS_GROUPS;  // split groups = TMEM operand stages (k-block kc goes to group kc % G)
 constexpr int kThreadsTs = 320 + 128 * (kTsGroups - 1);  // TMA, MMA, split group 0, epilogue, split groups 1..
 constexpr int kRingCols = 64;  // TMEM columns per operand stage: 4 k-steps x (8 hi + 8 lo)
+// TMEM operand slots: k-block kc uses slot kc % kTsSlots.  More slots than split groups, so that the split warps do not
+// wait for the retirement of the MMAs that read a slot two k-blocks ago (commit -> mbarrier -> wait is a long round trip).
+constexpr int kTsSlots = 4;  // 2 BN + 4 x 64 columns <= 512 for BN <= 128
 
 __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_constant__ KernelParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -640,7 +643,7 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
   auto bar_tfull = [&](int i) { return bar_base + 8u * (3 * stages + i); };
   auto bar_tempty = [&](int i) { return bar_base + 8u * (3 * stages + 2 + i); };
   auto bar_tfree = [&](int i) { return bar_base + 8u * (3 * stages + 4 + i); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + 4 + kTsGroups);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + 4 + kTsSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = smem_u32(smem);
@@ -656,7 +659,7 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
       mbar_init(bar_tfull(i), 1);
       mbar_init(bar_tempty(i), 128);
     }
-    for (int i = 0; i < kTsGroups; ++i) mbar_init(bar_tfree(i), 1);
+    for (int i = 0; i < kTsSlots; ++i) mbar_init(bar_tfree(i), 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
@@ -725,7 +728,7 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
             mbar_wait(bar_lo(s), ph);
             if (P.dbg && blockIdx.x == 0 && kc < 128) P.dbg[kc * 8 + 5] = clock64();
             tc_fence_after();
-            const uint32_t ts = kc % (uint32_t)kTsGroups;
+            const uint32_t ts = kc % (uint32_t)kTsSlots;
             const uint32_t a_stage = tm + ring0 + ts * kRingCols;
             const uint64_t db0 = desc_b0 + (uint64_t)(((uint32_t)s * stage_bytes + a_bytes) >> 4);
 #pragma unroll
@@ -788,10 +791,11 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
             }
           }
           if (P.dbg && blockIdx.x == 0 && t == 0 && kc < 128) P.dbg[kc * 8 + 2] = clock64();
-          mbar_wait(bar_tfree(grp), ((kc / (uint32_t)kTsGroups) & 1u) ^ 1u);
+          const uint32_t slot = kc % (uint32_t)kTsSlots;
+          mbar_wait(bar_tfree(slot), ((kc / (uint32_t)kTsSlots) & 1u) ^ 1u);
           if (P.dbg && blockIdx.x == 0 && t == 0 && kc < 128) P.dbg[kc * 8 + 3] = clock64();
           tc_fence_after();
-          const uint32_t a_stage = tmem_base + ((uint32_t)(q * 32) << 16) + ring0 + (uint32_t)grp * kRingCols;
+          const uint32_t a_stage = tmem_base + ((uint32_t)(q * 32) << 16) + ring0 + slot * kRingCols;
 #pragma unroll
           for (int kk = 0; kk < KSTEPS; ++kk) {
             float hi[8], lo[8];
@@ -1032,7 +1036,7 @@ int gemm(const GemmProblem& p, cudaStream_t stream) {
   P.stages = stages;
   uint32_t cols = 32;
   // shared-memory fp32 accumulators are 2 BN wide ([.. | hi_a lo_b]); the TMEM-operand form adds a 2 x 64 column ring
-  while (cols < (uint32_t)(ts ? 2 * P.BN + kTsGroups * kRingCols : (bf16 ? 2 : 4) * P.BN)) cols <<= 1;
+  while (cols < (uint32_t)(ts ? 2 * P.BN + kTsSlots * kRingCols : (bf16 ? 2 : 4) * P.BN)) cols <<= 1;
   P.tmem_cols = cols;
   P.out = p.out, P.out_bs = p.out_batch_stride, P.out_rs = p.out_row_stride, P.out_cs = p.out_col_stride;
   P.alpha = p.alpha, P.accumulate = p.accumulate, P.out_bf16 = p.out_bf16;
