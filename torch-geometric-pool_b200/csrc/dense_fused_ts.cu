@@ -47,6 +47,10 @@ constexpr int kSplitThreads = kSplitWarps * 32;         // per group
 constexpr int kEpiWarps = 8;                            // two per TMEM lane quadrant, alternate 32-column chunks
 constexpr int kTsThreads = 64 + kSplitGroups * kSplitThreads + kEpiWarps * 32;  // TMA, MMA, split groups, epilogue
 constexpr int kTpr = kEpiWarps * 32 / 16;               // statistics (epilogue warps): threads per node row
+// Ablation switches (timing experiments only; results are wrong when any bit is set): benchmarks/ablate_fwd.py
+#ifndef TGPB200_ABLF
+#define TGPB200_ABLF 0   // 1 no drain, 2 no statistics, 4 no B split, 8 no M-side staging, 16 no MMAs, 32 no TMA loads
+#endif
 constexpr int kACols = 32;                           // TMEM columns per (tile, k-block): 2 k-steps x (8 hi + 8 lo)
 
 struct TsParams {
@@ -124,7 +128,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
           if (P.dbg && blockIdx.x == 0 && lane == 0 && dbg_n < 96) P.dbg[dbg_n * 8 + 0] = clock64();
           const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
           const int k0 = kb * TBK;
-          if (elect_one()) {
+          if ((TGPB200_ABLF & 32) && elect_one()) mbar_arrive(bar_full(s));
+          if (!(TGPB200_ABLF & 32) && elect_one()) {
             mbar_arrive_expect_tx(bar_full(s), tx);
             tma_load_3d(dst, &P.map_a, bar_full(s), 0, k0, b);
             tma_load_3d(dst + off_x, &P.map_x, bar_full(s), 0, k0, b);
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
           const uint32_t a_stage = tm + a_cols0 + ts * (uint32_t)(G * kACols);
           const uint64_t db0 = desc0 + (uint64_t)(((uint32_t)s * stage_bytes + off_sb) >> 4);
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
+          for (int kk = 0; kk < ((TGPB200_ABLF & 16) ? 0 : 2); ++kk) {
             const uint64_t db = db0 + (uint64_t)(kk * ((8 * kStageRowBytes) >> 4)), db_lo = db + (sb_bytes >> 4);
             const uint32_t acc0 = (kb > 0 || kk > 0) ? 1u : 0u;
             for (int g = 0; g < G; ++g) {
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
         if (P.dbg && blockIdx.x == 0 && t == 0 && kc < 96) P.dbg[kc * 8 + 5] = clock64();
         const uint32_t base = smem_base + (uint32_t)s * stage_bytes;
         // ---- pass 1b: hi / lo of the B operand (swizzled S blocks), in place + next to it
-        for (uint32_t ch = t; ch < (uint32_t)P.nb_s * 128; ch += kSplitThreads) {
+        for (uint32_t ch = t; ch < ((TGPB200_ABLF & 4) ? 0u : (uint32_t)P.nb_s * 128); ch += kSplitThreads) {
           const uint32_t a = base + off_sb + ch * 16;
           const float4 v = lds128(a);
           float4 h, l;
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
         if (P.dbg && blockIdx.x == 0 && t == 0 && kc < 96) P.dbg[kc * 8 + 3] = clock64();
         tc_fence_after();
         const uint32_t a_stage = tmem_base + ((uint32_t)(q * 32) << 16) + a_cols0 + ts * (uint32_t)(G * kACols);
-        for (int g = half; g < G; g += kSplitWarps / 4) {
+        for (int g = half; g < ((TGPB200_ABLF & 8) ? 0 : G); g += kSplitWarps / 4) {
           const int seg = g < P.t_a ? 0 : (g < P.t_a + P.t_x ? 1 : 2);
           const int m = (seg == 0 ? g : (seg == 1 ? g - P.t_a : g - P.t_a - P.t_x)) * BM + q * 32 + lane;
           const int ext = seg == 0 ? P.N : (seg == 1 ? P.F : P.K);
@@ -262,7 +267,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
         mbar_wait(bar_full(s), ph);
         const uint32_t base = smem_base + (uint32_t)s * stage_bytes;
         float sd = 0.f, sa2 = 0.f, s2 = 0.f, se = 0.f;
-        {
+        if (!(TGPB200_ABLF & 2)) {
           const uint32_t ra = base + (uint32_t)r * P.N * 4;
           for (int col = c16 * 4; col < P.N; col += 4 * kTpr) {
             const float4 v = lds128(ra + col * 4);
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
           se += __shfl_xor_sync(kFull, se, o);
         }
         const int node = kb * TBK + r;
-        if (c16 == 0 && node < P.N) {
+        if (!(TGPB200_ABLF & 2) && c16 == 0 && node < P.N) {
           const int64_t o = (int64_t)b * P.N + node;
           P.d[o] = sd, P.a2[o] = sa2, P.ss[o] = s2, P.ent[o] = se;
         }
@@ -295,7 +300,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
       mbar_wait(bar_tfull, (uint32_t)it & 1u);
       tc_fence_after();
       int chunk = 0;
-      for (int g = 0; g < G; ++g) {
+      for (int g = 0; g < ((TGPB200_ABLF & 1) ? 0 : G); ++g) {
         const int seg = g < P.t_a ? 0 : (g < P.t_a + P.t_x ? 1 : 2);
         const int m0 = (seg == 0 ? g : (seg == 1 ? g - P.t_a : g - P.t_a - P.t_x)) * BM + quad * 32;  // warp-uniform
         const int m_ext = seg == 0 ? P.N : (seg == 1 ? P.F : P.K);
