@@ -39,6 +39,7 @@ struct KernelParams {
   CUtensorMap map_out;
   int tma_out;       // 1: use map_out
   int epi_bufs;      // staging buffers per epilogue warp (1 or 2)
+  int abl;           // timing experiments (TGPB200_ABL_GEMM): 1 no B loads, 2 no A loads, 4 no element-wise terms, 8 no stores
 };
 
 // Staging state of one epilogue warp for the TMA-store path
@@ -48,58 +49,89 @@ struct EpiStage {
 };
 extern long long* g_engine_dbg;
 
+// Element-wise gradient terms of the dense backward (GemmProblem::ew_*), software-pipelined: the per-row coefficients
+// are loaded once per item BEFORE the wait for the accumulators, and the values of S that chunk c needs are loaded
+// while chunk c - 1 is processed.  Loaded per chunk after the accumulators were ready, the four dependent global
+// round trips (two coefficients, the degree, the row of S) made the epilogue of `dS` the bottleneck of that product
+// (C3: 553 -> 354 us without the terms; benchmarks: TGPB200_ABL_GEMM=4).
+template <bool kF32>
+struct EwPre {
+  float dd = 0.f, c_ent = 0.f;
+  bool on = false;      // this row has element-wise terms
+  bool vec = false;     // raw[] holds the 32 values of the chunk (else: scalar loads at apply time)
+  uint4 raw[kF32 ? 8 : 4];
+};
+template <bool kF32>
+__device__ __forceinline__ void ew_item(const KernelParams& P, EwPre<kF32>& e, int b, int m) {
+  e.on = false;
+  if (P.ew_S == nullptr || (P.abl & 4) || m >= P.M || P.out_cs != 1) return;
+  const float c_den = P.ew_coef[b * 4 + 0];
+  e.c_ent = P.ew_coef[b * 4 + 2];
+  if (c_den == 0.f && e.c_ent == 0.f) return;
+  e.on = true;
+  e.dd = 2.f * c_den * P.ew_d[(int64_t)b * P.M + m];
+}
+template <bool kF32>
+__device__ __forceinline__ void ew_load(const KernelParams& P, EwPre<kF32>& e, int b, int m, int n0) {
+  e.vec = false;
+  if (!e.on || n0 >= P.N) return;
+  const int64_t si = ((int64_t)b * P.M + m) * P.N + n0;
+  if (n0 + 32 <= P.N && (si & (kF32 ? 3 : 7)) == 0) {
+    const uint4* s4 = kF32 ? reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(P.ew_S) + si)
+                           : reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(P.ew_S) + si);
+#pragma unroll
+    for (int j = 0; j < (kF32 ? 8 : 4); ++j) e.raw[j] = __ldg(s4 + j);
+    e.vec = true;
+  }
+}
+template <bool kF32>
+__device__ __forceinline__ void ew_apply(const KernelParams& P, const EwPre<kF32>& e, float (&v)[32], int b, int m, int n0) {
+  if (!e.on) return;
+  float sv[32];
+  if (e.vec) {
+    if (kF32) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sv[4 * j] = __uint_as_float(e.raw[j].x), sv[4 * j + 1] = __uint_as_float(e.raw[j].y);
+        sv[4 * j + 2] = __uint_as_float(e.raw[j].z), sv[4 * j + 3] = __uint_as_float(e.raw[j].w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&e.raw[j]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f2 = __bfloat1622float2(h2[q]);
+          sv[8 * j + 2 * q] = f2.x, sv[8 * j + 2 * q + 1] = f2.y;
+        }
+      }
+    }
+  } else {
+    const int64_t si = ((int64_t)b * P.M + m) * P.N + n0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      sv[j] = (n0 + j < P.N) ? (kF32 ? reinterpret_cast<const float*>(P.ew_S)[si + j]
+                                     : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.ew_S)[si + j]))
+                             : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float add = e.dd * sv[j];
+    if (e.c_ent != 0.f) add += e.c_ent * (-__logf(sv[j] + P.ew_eps) - __fdividef(sv[j], sv[j] + P.ew_eps));
+    v[j] += add;
+  }
+}
+
 // Epilogue of one 32-column chunk: thread `lane` of a quadrant holds row m of the tile, v[0..32) = columns n0..n0+31.
 template <bool kF32>
 __device__ __forceinline__ void store_chunk(const KernelParams& P, float (&v)[32], int b, int m_base, int m, int n0,
-                                            int64_t obase, EpiStage& es) {
+                                            int64_t obase, EpiStage& es, const EwPre<kF32>& ew) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] *= P.alpha;
   if (P.out_cs == 1) {
     const bool full = n0 + 32 <= P.N;
-    if (m < P.M) {
-      if (P.ew_S != nullptr) {
-        // fused element-wise gradient terms of the dense backward (see GemmProblem::ew_*)
-        const float c_den = P.ew_coef[b * 4 + 0], c_ent = P.ew_coef[b * 4 + 2];
-        if (c_den != 0.f || c_ent != 0.f) {
-          const float dd = 2.f * c_den * P.ew_d[(int64_t)b * P.M + m];
-          const int64_t si = ((int64_t)b * P.M + m) * P.N + n0;
-          float sv[32];
-          if (kF32 && full && ((si & 3) == 0)) {
-            const float4* s4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(P.ew_S) + si);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 t4 = __ldg(s4 + j);
-              sv[4 * j] = t4.x, sv[4 * j + 1] = t4.y, sv[4 * j + 2] = t4.z, sv[4 * j + 3] = t4.w;
-            }
-          } else if (!kF32 && full && ((si & 7) == 0)) {
-            const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(P.ew_S) + si);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 t4 = __ldg(s4 + j);
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t4);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float2 f2 = __bfloat1622float2(h2[q]);
-                sv[8 * j + 2 * q] = f2.x, sv[8 * j + 2 * q + 1] = f2.y;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              sv[j] = (n0 + j < P.N)
-                          ? (kF32 ? reinterpret_cast<const float*>(P.ew_S)[si + j]
-                                  : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.ew_S)[si + j]))
-                          : 0.f;
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float add = dd * sv[j];
-            if (c_ent != 0.f) add += c_ent * (-__logf(sv[j] + P.ew_eps) - __fdividef(sv[j], sv[j] + P.ew_eps));
-            v[j] += add;
-          }
-        }
-      }
-    }
+    ew_apply<kF32>(P, ew, v, b, m, n0);
+    if (P.abl & 8) return;
     if (P.tma_out) {
       // stage (lane = row of the chunk) with the swizzle of the output map, then one TMA store; rows >= M and
       // columns >= N are clipped by the map
@@ -275,16 +307,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
             uint32_t sa = smem_base + (uint32_t)s * stage_bytes, sb = sa + a_bytes;
             int k0 = kb * BK;
             if (elect_one()) {
-            mbar_arrive_expect_tx(bar_full(s), a_bytes + b_bytes);
+            mbar_arrive_expect_tx(bar_full(s), ((P.abl & 2) ? 0u : a_bytes) + ((P.abl & 1) ? 0u : b_bytes));
             // K-major: one box [rows x 128 B].  MN-major: one box [BK k-rows x 128 B] per 128-byte block of
             // the MN extent, laid out block after block (the canonical UMMA MN-major SW128 layout, LBO = BK*128 B).
-            if (P.a_mn[p]) {
+            if (P.abl & 2) {
+            } else if (P.a_mn[p]) {
               for (int blk = 0; blk < BM / EPB; ++blk)
                 tma_load_3d(sa + blk * (BK * kStageRowBytes), &P.map_a[p], bar_full(s), m0 + blk * EPB, k0, b);
             } else {
               tma_load_3d(sa, &P.map_a[p], bar_full(s), k0, m0, b);
             }
-            if (P.b_mn[p]) {
+            if (P.abl & 1) {
+            } else if (P.b_mn[p]) {
               for (int blk = 0; blk < BN / EPB; ++blk)
                 tma_load_3d(sb + blk * (BK * kStageRowBytes), &P.map_b[p], bar_full(s), n0 + blk * EPB, k0, b);
             } else {
@@ -405,12 +439,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
       int nt = item % P.n_tiles, mt = (item / P.n_tiles) % P.m_tiles, b = item / (P.n_tiles * P.m_tiles);
       int ab = it & 1;
       uint32_t aph = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(bar_tfull(ab), aph);
-      tc_fence_after();
       const int m_base = mt * BM + quad * 32;
       const int m = m_base + lane;
       const int64_t obase = (int64_t)b * P.out_bs + (int64_t)m * P.out_rs;
+      // element-wise terms: coefficients of this row and the S values of the first chunk before the accumulators are
+      // waited for, the values of chunk c + 1 while chunk c is processed
+      EwPre<kF32> ew, ew_next;
+      ew_item<kF32>(P, ew, b, m);
+      ew_load<kF32>(P, ew, b, m, nt * BN + c_first);
+      mbar_wait(bar_tfull(ab), aph);
+      tc_fence_after();
       for (int c0 = c_first; c0 < BN; c0 += c_step) {
+        ew_next = ew;
+        if (c0 + c_step < BN) ew_load<kF32>(P, ew_next, b, m, nt * BN + c0 + c_step);
         float v[32];
         uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * (kF32 ? 2 * BN : BN) + c0);
         tmem_ld32(taddr, v);
@@ -421,8 +462,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
           for (int j = 0; j < 32; ++j) v[j] += v2[j];
         }
         const int n0 = nt * BN + c0;
-        if (n0 >= P.N || m_base >= P.M) continue;  // warp-uniform
-        store_chunk<kF32>(P, v, b, m_base, m, n0, obase, es);
+        if (n0 < P.N && m_base < P.M) store_chunk<kF32>(P, v, b, m_base, m, n0, obase, es, ew);  // warp-uniform test
+        ew = ew_next;
       }
       tc_fence_before();
       mbar_arrive(bar_tempty(ab));
@@ -592,7 +633,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN + c0), v);
         const int n0 = nt * BN + c0;
         if (n0 >= P.N || m_base >= P.M) continue;  // warp-uniform
-        store_chunk<false>(P, v, b, m_base, m, n0, obase, es);
+        EwPre<false> ew;
+        ew_item<false>(P, ew, b, m);
+        ew_load<false>(P, ew, b, m, n0);
+        store_chunk<false>(P, v, b, m_base, m, n0, obase, es, ew);
       }
       tc_fence_before();
       mbar_arrive_cluster(mapa_shared(bar_tempty(ab), 0));
@@ -823,18 +867,23 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
       int nt = item % P.n_tiles, mt = (item / P.n_tiles) % P.m_tiles, b = item / (P.n_tiles * P.m_tiles);
       const int ab = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(bar_tfull(ab), aph);
-      if (P.dbg && blockIdx.x == 0 && threadIdx.x == 192 && it < 32) P.dbg[(128 + it) * 8 + 0] = clock64();
-      tc_fence_after();
       const int m_base = mt * BM + quad * 32;
       const int m = m_base + lane;
       const int64_t obase = (int64_t)b * P.out_bs + (int64_t)m * P.out_rs;
+      // element-wise terms (see EwPre): coefficients + the first chunk's S values before the accumulators are waited
+      // for, every later chunk's values issued before its TMEM read (one prefetch buffer: 128 registers per thread here)
+      EwPre<true> ew;
+      ew_item<true>(P, ew, b, m);
+      ew_load<true>(P, ew, b, m, nt * BN);
+      mbar_wait(bar_tfull(ab), aph);
+      if (P.dbg && blockIdx.x == 0 && threadIdx.x == 192 && it < 32) P.dbg[(128 + it) * 8 + 0] = clock64();
+      tc_fence_after();
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int n0 = nt * BN + c0;
+        if (c0 > 0) ew_load<true>(P, ew, b, m, n0);
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN + c0), v);
-        const int n0 = nt * BN + c0;
-        if (n0 >= P.N || m_base >= P.M) continue;  // warp-uniform
-        store_chunk<true>(P, v, b, m_base, m, n0, obase, es);
+        if (n0 < P.N && m_base < P.M) store_chunk<true>(P, v, b, m_base, m, n0, obase, es, ew);  // warp-uniform test
       }
       tc_fence_before();
       mbar_arrive(bar_tempty(ab));
@@ -1043,6 +1092,10 @@ int gemm(const GemmProblem& p, cudaStream_t stream) {
   P.skip_lo_b_mask = p.skip_lo_b_mask;
   P.ew_S = p.ew_S, P.ew_d = p.ew_d, P.ew_coef = p.ew_coef, P.ew_eps = p.ew_eps;
   P.dbg = ts ? g_engine_dbg : nullptr;
+  {
+    const char* e = getenv("TGPB200_ABL_GEMM");
+    P.abl = e ? atoi(e) : 0;
+  }
   // TMA-store epilogue: row-major destination, no read-modify-write, 16-byte aligned rows
   {
     const int oes = p.out_bf16 ? 2 : 4;
