@@ -137,7 +137,7 @@ __device__ __forceinline__ void store_chunk(const KernelParams& P, float (&v)[32
       // columns >= N are clipped by the map
       const int lane = threadIdx.x & 31;
       const int nb = P.epi_bufs;
-      const uint32_t buf = es.smem + (uint32_t)(es.n % nb) * 4096u;
+      const uint32_t buf = es.smem + (uint32_t)(es.n % nb) * (P.out_bf16 ? 2048u : 4096u);  // a bf16 chunk is 2 KB
       if (lane == 0) {
         if (nb == 2) tma_store_wait_read<1>();
         else tma_store_wait_read<0>();
@@ -1100,7 +1100,9 @@ int gemm(const GemmProblem& p, cudaStream_t stream) {
   {
     const int oes = p.out_bf16 ? 2 : 4;
     const char* e = getenv("TGPB200_GEMM_TMA_STORE");
-    P.epi_bufs = bf16 ? 1 : 2;
+    // staging tiles per epilogue warp: the fp32 engine's four warps own 8 KB each, the bf16 engine's eight warps 4 KB
+    // each -- room for two 2 KB bf16 chunks, so a store can still read one while the next chunk is staged
+    P.epi_bufs = bf16 ? (p.out_bf16 ? 2 : 1) : 2;
     P.tma_out = 0;
     if (!(e && e[0] == '0') && !pair && p.out_col_stride == 1 && !p.accumulate && ((uintptr_t)p.out & 15) == 0 &&
         (p.out_row_stride * oes) % 16 == 0 && (p.out_batch_stride * oes) % 16 == 0 && p.out_row_stride >= p.N) {
