@@ -84,11 +84,12 @@ __device__ __forceinline__ void ew_load(const KernelParams& P, EwPre<kF32>& e, i
     e.vec = true;
   }
 }
+// Called by ALL lanes of the warp (it votes): rows without terms (e.on false) take no part in the arithmetic.
 template <bool kF32>
 __device__ __forceinline__ void ew_apply(const KernelParams& P, const EwPre<kF32>& e, float (&v)[32], int b, int m, int n0) {
-  if (!e.on) return;
+  if (!__any_sync(0xffffffffu, e.on)) return;  // warp-uniform
   float sv[32];
-  if (e.vec) {
+  if (e.on && e.vec) {
     if (kF32) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -106,19 +107,39 @@ __device__ __forceinline__ void ew_apply(const KernelParams& P, const EwPre<kF32
         }
       }
     }
-  } else {
+  } else if (e.on) {
     const int64_t si = ((int64_t)b * P.M + m) * P.N + n0;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       sv[j] = (n0 + j < P.N) ? (kF32 ? reinterpret_cast<const float*>(P.ew_S)[si + j]
                                      : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.ew_S)[si + j]))
                              : 0.f;
-  }
+  } else {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float add = e.dd * sv[j];
-    if (e.c_ent != 0.f) add += e.c_ent * (-__logf(sv[j] + P.ew_eps) - __fdividef(sv[j], sv[j] + P.ew_eps));
-    v[j] += add;
+    for (int j = 0; j < 32; ++j) sv[j] = 1.f;  // inert row: keeps the vote below and the logarithm well defined
+  }
+  const float dd = e.on ? e.dd : 0.f, c_ent = e.on ? e.c_ent : 0.f;
+  if (!__any_sync(0xffffffffu, c_ent != 0.f)) {  // warp-uniform
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaf(dd, sv[j], v[j]);
+    return;
+  }
+  // entropy term -log(s + eps) - s / (s + eps).  With the reference's eps (1e-15) s + eps rounds to s for every s above
+  // ~1e-8, where the quotient is EXACTLY 1 (as the reference's IEEE division gives): the reciprocal is only evaluated
+  // when some element of the warp's chunk really needs it (the epilogue of dS is bound by the MUFU pipe: two
+  // transcendental operations per element).
+  bool need_div = false;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) need_div |= (sv[j] + P.ew_eps) != sv[j];
+  if (__any_sync(0xffffffffu, need_div)) {  // warp-uniform
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float se = sv[j] + P.ew_eps;
+      v[j] += dd * sv[j] + c_ent * (-__logf(se) - (se == sv[j] ? 1.f : __fdividef(sv[j], se)));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += dd * sv[j] + c_ent * (-__logf(sv[j]) - 1.f);
   }
 }
 
