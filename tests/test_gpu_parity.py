@@ -47,7 +47,11 @@ def test_native_library_is_loaded():
 # primitives through build_csr (scan + stable radix sort)
 # --------------------------------------------------------------------------- #
 @pytest.mark.parametrize("nnz,K", [(0, 3), (1, 1), (31, 5), (4096, 7), (4097, 300), (100_003, 65_537), (1_000_000, 17),
-                                   (2_000_000, 1_100_000)])
+                                   (2_000_000, 1_100_000),
+                                   # boundaries of the small-input paths: one-tile radix passes (2048 keys), the
+                                   # single-block scan (32768 counters) against the one-pass look-back scan
+                                   (2047, 3), (2048, 2048), (2049, 5), (50_000, 32_766), (50_000, 32_767),
+                                   (50_000, 32_768), (50_000, 40_000)])
 def test_build_csr_matches_stable_argsort(nnz, K):
     g = torch.Generator().manual_seed(nnz + K)
     c = torch.randint(0, K, (nnz,), generator=g)
