@@ -198,6 +198,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_dense_fwd_fused_ts(const __gr
     for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
       for (int kb = 0; kb < kblocks; ++kb, ++kc) {
         if (kSplitGroups > 1 && (int)(kc % kSplitGroups) != grp) {  // another group's k-block
+          // The group still OBSERVES the phase of a k-block it skips: with an odd number of stages a stage alternates
+          // between the groups, and a parity wait that has missed one completed phase of its barrier passes at once --
+          // before the data of the awaited phase has landed (seen as a hang with 3 stages).
+          mbar_wait(bar_full(s), ph);
           if (++s == stages) { s = 0; ph ^= 1; }
           continue;
         }

@@ -827,6 +827,10 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
       for (int p = 0; p < P.num_pairs; ++p) {
         for (int kb = 0, nkb = (P.kd[p] + BK - 1) / BK; kb < nkb; ++kb, ++kc) {
           if ((int)(kc % (uint32_t)kTsGroups) != grp) {  // another group's k-block
+            // The group still OBSERVES the phase of a k-block it skips: with an odd number of stages a stage alternates
+            // between the groups, and a parity wait that has missed one completed phase of its barrier passes at once --
+            // before the data of the awaited phase has landed (seen as a hang with 3 stages).
+            mbar_wait(bar_full(s), ph);
             if (++s == stages) { s = 0; ph ^= 1; }
             continue;
           }
