@@ -60,6 +60,7 @@ constexpr int kGroups = 2;                 // split groups (k-block kc goes to g
 // (~1.8 k cycles: benchmarks/ablate_bwd.sh, every stage of the pipeline emptied) bounds the kernel at one k-block per
 // ~900 cycles whatever the k-block contains.  With more slots than groups the split warps never wait for it.
 constexpr int kSlots = kConcat ? 2 : 4;
+static_assert(kSlots % kGroups == 0, "every operand slot must belong to ONE split group (its waiters see every phase)");
 constexpr int kEpiW = TGPB200_BWD_EPI_WARPS;  // epilogue warps (one or two per TMEM lane quadrant)
 constexpr int kThreadsBwd = 64 + kGroups * 128 + kEpiW * 32;
 constexpr int BK = 32, KSTEPS = 4;

@@ -691,6 +691,7 @@ constexpr int kRingCols = 64;  // TMEM columns per operand stage: 4 k-steps x (8
 // TMEM operand slots: k-block kc uses slot kc % kTsSlots.  More slots than split groups, so that the split warps do not
 // wait for the retirement of the MMAs that read a slot two k-blocks ago (commit -> mbarrier -> wait is a long round trip).
 constexpr int kTsSlots = 4;  // 2 BN + 4 x 64 columns <= 512 for BN <= 128
+static_assert(kTsSlots % kTsGroups == 0, "every operand slot must belong to ONE split group (its waiters see every phase)");
 
 __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_constant__ KernelParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
