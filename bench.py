@@ -128,6 +128,31 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------------------
 # timing helpers
 # --------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank (and first-touch its pinned host buffers) on the NUMA node its GPU hangs off: the end-to-end leg is
+    bound by host -> device DMA, and a pinned buffer on the other socket crosses the inter-socket link first.  Best
+    effort: returns a description, or None when the topology is not exposed (single node, container without sysfs)."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev_id = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 class Ctx:
     def __init__(self, args):
         self.args = args
@@ -137,6 +162,7 @@ class Ctx:
         self.dist = None
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
+        self.numa = bind_to_gpu_numa_node(self.local_rank) if self.world > 1 else None
         if self.world > 1:
             import torch.distributed as dist_
 
@@ -449,7 +475,8 @@ def dense_e2e(ctx, name):
             "d2h_bytes_per_step": 16, "ms_per_step": ms, "steps": steps,
             "inputs": "pinned host edge_index [2,E] int64 + x [B*N,F] fp32 + batch [B*N] int64 per step",
             "pipeline": "H2D of step i+1 on a copy stream overlaps the graph replay of step i; on-device "
-                        "to_dense_adj / to_dense_batch + linear-softmax select + fused pool fwd+bwd; losses read back"}
+                        "to_dense_adj / to_dense_batch + linear-softmax select + fused pool fwd+bwd; losses read back",
+            "host_numa_binding": ctx.numa}
 
 
 # --------------------------------------------------------------------------------------------------------------
