@@ -39,6 +39,7 @@ struct KernelParams {
   CUtensorMap map_out;
   int tma_out;       // 1: use map_out
   int epi_bufs;      // staging buffers per epilogue warp (1 or 2)
+  int pack2;         // fp32 TMEM-operand engine: one 128 x 128 tile holds the products of TWO batch items with M, N <= 64
   int abl;           // timing experiments (TGPB200_ABL_GEMM): 1 no B loads, 2 no A loads, 4 no element-wise terms, 8 no stores
 };
 
@@ -752,7 +753,18 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
           ++dbg_n;
           const uint32_t sa = smem_base + (uint32_t)s * stage_bytes, sb = sa + a_bytes;
           const int k0 = kb * BK;
-          if (elect_one()) {
+          if (P.pack2) {
+            // item = batch items (2 item, 2 item + 1): rows 0-63 / 64-127 of the A tile and columns 0-63 / 64-127 of the
+            // B tile come from the two items (a batch index past the end arrives as zeros)
+            if (elect_one()) {
+              mbar_arrive_expect_tx(bar_full(s), a_bytes + b_bytes);
+              for (int h = 0; h < 2; ++h) {
+                tma_load_3d(sa + h * (64 * kStageRowBytes), &P.map_a[p], bar_full(s), k0, 0, 2 * item + h);
+                for (int blk = 0; blk < 2; ++blk)
+                  tma_load_3d(sb + (2 * h + blk) * (BK * kStageRowBytes), &P.map_b[p], bar_full(s), blk * 32, k0, 2 * item + h);
+              }
+            }
+          } else if (elect_one()) {
             mbar_arrive_expect_tx(bar_full(s), a_bytes + b_bytes);
             if (P.a_mn[p]) tma_load_3d(sa, &P.map_a[p], bar_full(s), m0, k0, b);  // [32 k][128 m], no swizzle
             else tma_load_3d(sa, &P.map_a[p], bar_full(s), k0, m0, b);            // [128 m][32 k], 128B swizzle
@@ -893,6 +905,23 @@ __global__ void __launch_bounds__(kThreadsTs, 1) k_tc_gemm_ts(const __grid_const
       int nt = item % P.n_tiles, mt = (item / P.n_tiles) % P.m_tiles, b = item / (P.n_tiles * P.m_tiles);
       const int ab = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      if (P.pack2) {
+        // quadrants 0, 1 hold rows 0-63 of batch item 2 item (columns 0-63 of the accumulator), quadrants 2, 3 the
+        // rows of item 2 item + 1 (columns 64-127): the off-diagonal blocks of the 128 x 128 tile are not read
+        mbar_wait(bar_tfull(ab), aph);
+        tc_fence_after();
+        const int bb = 2 * item + (quad >> 1), mb = (quad & 1) * 32;
+        EwPre<true> none;
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN + (quad >> 1) * 64 + c0), v);
+          if (bb < P.batch && c0 < P.N && mb < P.M)  // warp-uniform
+            store_chunk<true>(P, v, bb, mb, mb + lane, c0, (int64_t)bb * P.out_bs + (int64_t)(mb + lane) * P.out_rs, es, none);
+        }
+        tc_fence_before();
+        mbar_arrive(bar_tempty(ab));
+        continue;
+      }
       const int m_base = mt * BM + quad * 32;
       const int m = m_base + lane;
       const int64_t obase = (int64_t)b * P.out_bs + (int64_t)m * P.out_rs;
@@ -1089,14 +1118,24 @@ int gemm(const GemmProblem& p, cudaStream_t stream) {
   const int tile_m = pair ? 2 * BM : BM;
   P.num_pairs = p.num_pairs;
   P.batch = p.batch, P.M = p.M, P.N = p.N;
+  // Small per-item products (M, N <= 64: the [K, K] products of the pooled graphs) leave three quarters of a 128 x 128
+  // tile empty and pay the per-k-block cost of the pipeline for it: TWO batch items share one tile -- A rows 0-63 /
+  // 64-127 and B columns 0-63 / 64-127 come from the two items, the diagonal 64 x 64 blocks of the accumulator are
+  // their products (the off-diagonal blocks are computed and dropped: the MMA costs N/2 cycles either way).
+  {
+    const char* e = getenv("TGPB200_GEMM_PACK2");
+    P.pack2 = ts && !pair && !(e && e[0] == '0') && p.num_pairs == 1 && p.M <= 64 && p.N <= 64 && p.batch >= 2 &&
+              !p.a[0].mn_major && p.b[0].mn_major && p.ew_S == nullptr && p.out_col_stride == 1;
+  }
+  if (P.pack2) P.BN = 128;
   P.m_tiles = (p.M + tile_m - 1) / tile_m, P.n_tiles = (p.N + P.BN - 1) / P.BN;
-  P.num_items = p.batch * P.m_tiles * P.n_tiles;
+  P.num_items = P.pack2 ? (p.batch + 1) / 2 : p.batch * P.m_tiles * P.n_tiles;
   for (int i = 0; i < p.num_pairs; ++i) {
     P.kd[i] = p.kd[i];
     P.a_mn[i] = p.a[i].mn_major, P.b_mn[i] = p.b[i].mn_major;
     if (ts && p.a[i].mn_major) {
       if (!make_operand_map_mn_plain(&P.map_a[i], p.a[i], p.batch, p.M, p.kd[i])) return TGPB200_ERR_UNSUPPORTED;
-    } else if (!make_operand_map(&P.map_a[i], p.a[i], bf16, p.batch, p.M, p.kd[i], BM)) {
+    } else if (!make_operand_map(&P.map_a[i], p.a[i], bf16, p.batch, p.M, p.kd[i], P.pack2 ? 64 : BM)) {
       return TGPB200_ERR_UNSUPPORTED;
     }
     if (!make_operand_map(&P.map_b[i], p.b[i], bf16, p.batch, p.N, p.kd[i], pair ? P.BN / 2 : P.BN)) return TGPB200_ERR_UNSUPPORTED;
