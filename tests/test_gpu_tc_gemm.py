@@ -62,6 +62,22 @@ def test_tc_gemm_fp32_ragged_shapes_both_engines(monkeypatch, ts, a_mn, b_mn, B,
     torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5 * scale)
 
 
+@pytest.mark.parametrize("pack", ["1", "0"])
+@pytest.mark.parametrize("B,M,N,Kd", [(2, 64, 64, 256), (5, 64, 64, 96), (7, 48, 40, 100), (3, 16, 16, 64), (1, 64, 64, 32),
+                                      (301, 64, 64, 64)])
+def test_tc_gemm_fp32_two_items_per_tile(monkeypatch, pack, B, M, N, Kd):
+    """Products with M, N <= 64 (K-major A, MN-major B: the A_raw = T S layout) share a 128 x 128 tile pairwise: odd
+    batch counts, ragged M / N / K, a single item (no packing), more tiles than SMs; against the unpacked engine's bound."""
+    monkeypatch.setenv("TGPB200_GEMM_PACK2", pack)
+    g = torch.Generator().manual_seed(3 * M + N + Kd + B)
+    a = torch.randn((B, M, Kd), generator=g).to(DEV)
+    b = torch.randn((B, Kd, N), generator=g).to(DEV)
+    out = _run(a, b, False, True, M, N, Kd)
+    ref = _ref(a, b, False, True)
+    scale = ref.abs().max().item()
+    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5 * scale)
+
+
 @pytest.mark.parametrize("a_mn", [False, True])
 @pytest.mark.parametrize("b_mn", [False, True])
 def test_tc_gemm_bf16(a_mn, b_mn):
