@@ -20,8 +20,11 @@
 // The dS / dX accumulators are single-buffered: the epilogue of item i drains them while pair 0 of item i+1 (40 % of an
 // item's MMA work) only touches the W accumulator.
 //
-// Tensor memory (512 columns): W [0, 128) | dS [128, 256) | dX [256, 384) | operand ring: 2 x 64 columns.
-// Warp roles (448 threads): 0 TMA, 1 MMA, 2-9 two split groups of four warps, 10-13 epilogue.
+// Tensor memory (512 columns): W [0, 64) | dS [64, 128) | dX [128, 256) | operand ring: FOUR slots of 64 columns
+// (two split groups: a slot is only reused after the MMAs that read it have retired, a round trip the split warps
+// must not wait for).  Shared memory: 5 stages x 32 KB | epilogue staging 32 KB | S rows of the element-wise terms 32 KB.
+// Warp roles (448 threads): 0 TMA, 1 MMA (one elected thread runs the issue loop), 2-9 two split groups of four
+// warps, 10-13 epilogue (element-wise terms prefetched with cp.async, double-buffered TMA stores).
 #include <stdlib.h>
 #include <string.h>
 
@@ -48,10 +51,10 @@ namespace {
 #ifndef TGPB200_BWD_CONCAT
 #define TGPB200_BWD_CONCAT 0
 #endif
-// 3xTF32 of the W / dS pairs as TWO instructions per k-step: hi_a x [hi_b | lo_b] (N = 128: the lo tile of B directly
-// follows its hi tile in shared memory) + lo_a x hi_b (N = 64).  A tcgen05.mma costs ~57 cycles of dispatch whatever
-// its N <= 64 and 74 cycles at N = 128 (benchmarks/mma_rate.cu), so the instruction COUNT is what the MMA warp pays
-// for.  The accumulators of those pairs are 128 columns wide ([.. | hi_a lo_b], summed by whoever reads them).
+// Optional (TGPB200_BWD_CONCAT=1): 3xTF32 of the W / dS pairs as TWO instructions per k-step, hi_a x [hi_b | lo_b]
+// (N = 128: the lo tile of B directly follows its hi tile in shared memory) + lo_a x hi_b (N = 64), with 128-column
+// accumulators ([.. | hi_a lo_b], summed by whoever reads them).  Fewer instructions, but the wider accumulators leave
+// room for two operand slots only; measured equal to the three-instruction form, which keeps four slots.
 constexpr bool kConcat = TGPB200_BWD_CONCAT != 0;
 constexpr int kPairs = 7;
 constexpr int kGroups = 2;                 // split groups (k-block kc goes to group kc % kGroups)
