@@ -2,8 +2,9 @@
 //
 // Same contraction as dense_fused.cu ([A | X | S]^T S per graph, one pass over A, X, S, row statistics on the way),
 // but the hi / lo halves of the M-side operand never go back to shared memory: the split warps read the TMA tile
-// once, round / subtract in registers and store both halves with tcgen05.st into a two-stage ring of TMEM columns;
-// tcgen05.mma then takes A from TMEM and only the small N-side operand (S, hi / lo) from shared memory.
+// once, round / subtract in registers and store both halves with tcgen05.st into a ring of TMEM operand stages (one
+// per split group); tcgen05.mma then takes A from TMEM and only the small N-side operand (S, hi / lo) from shared
+// memory.
 // The 3xTF32 kernels are bound by the shared-memory pipe (dense_fused.cu moves ~260 KB through it per 28 KB of
 // HBM data: TMA write, split read, hi + lo write back, three operand fetches); this form moves ~110 KB.
 //
@@ -13,9 +14,11 @@
 //   tensor memory: [0, G*BN) accumulators of the G = t_a + t_x + t_s M-tiles (single buffered),
 //     then 2 stages x G tiles x 2 k-steps x (8 hi + 8 lo) columns of A operand (lane = M row, column = k)
 //
-// Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, then kSplitWarps split / statistics / TMEM staging
-// warps (warp w owns TMEM lanes 32 (w & 3) .., the warps of a quadrant take the M-tiles round robin), then four
-// epilogue warps.
+// Roles: warp 0 TMA producer, warp 1 MMA issuer (one elected thread) + TMEM allocator, then kSplitGroups groups of
+// kSplitWarps split / TMEM staging warps (warp w owns TMEM lanes 32 (w & 3) .., the warps of a quadrant take the
+// M-tiles round robin; group g takes every kSplitGroups-th k-block), then kEpiWarps epilogue warps, which also
+// accumulate the row statistics from the stage's row-major tiles while the main loop runs and drain the accumulators
+// through transposed shared-memory tiles + TMA stores.
 #include <stdlib.h>
 #include <string.h>
 

@@ -674,10 +674,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 // ------------------------------------------------------------------------------------------
 // fp32 engine with the A operand in TENSOR MEMORY (3xTF32).  With both operands in shared memory the fp32 engine sits
 // on the shared-memory pipe (TMA write + split read + hi/lo write back + three operand fetches per k-step); here
-// the split warps read the A tile once, round / subtract in registers and tcgen05.st hi and lo into a two-stage
-// ring of TMEM columns (lane = output row, 8 columns = 8 k); only B (hi, lo) stays in shared memory.
-//   * two groups of four split warps take alternate k-blocks (the split of a stage is a latency chain); group g
-//     fills TMEM operand stage g,
+// the split warps read the A tile once, round / subtract in registers and tcgen05.st hi and lo into a ring of
+// kTsSlots TMEM operand slots (lane = output row, 8 columns = 8 k); only B (hi, lo) stays in shared memory.
+//   * two groups of four split warps take alternate k-blocks (the split of a stage is a latency chain); k-block kc
+//     goes to group kc % kTsGroups and to operand slot kc % kTsSlots,
 //   * K-major A tiles are read row-wise (128-bit, un-doing the 128B swizzle: conflict-free), MN-major A tiles are
 //     loaded UNswizzled ([k][128 m]) and read column-wise (32-bit, conflict-free),
 //   * three MMAs per k-step (lo_a hi_b, hi_a lo_b, hi_a hi_b), accumulators BN wide, double-buffered.

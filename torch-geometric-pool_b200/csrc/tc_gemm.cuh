@@ -9,10 +9,11 @@
 //   warps rewrite each fp32 tile in shared memory as hi = rna_tf32(x) (in place) and lo = x - hi (next to it);
 //   bf16 inputs are a single kind::f16 pass,
 // * either operand may be K-major or MN-major in global memory (no transposes are materialised),
-// * the epilogue reads TMEM with tcgen05.ld and writes fp32 or bf16 with arbitrary output strides.
+// * the epilogue reads TMEM with tcgen05.ld and writes fp32 or bf16 through swizzled shared-memory tiles and TMA
+//   stores when the output is row-contiguous and 16-byte aligned (per-thread stores with arbitrary strides otherwise).
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator (the whole warp runs the
-// loop, one elected lane issues), warps 2-5 = operand split (fp32) / extra epilogue warps (bf16), warps 6-9 = epilogue.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator (one elected thread runs the
+// issuing loop), warps 2-5 = operand split (fp32) / extra epilogue warps (bf16), warps 6-9 = epilogue.
 // (Eight split warps for fp32, data-parallel or as two groups on alternate stages, measured no faster: 53 us on the
 // C2-shaped products either way -- with operands in shared memory the engine sits on the shared-memory pipe.)
 #pragma once
