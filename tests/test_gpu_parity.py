@@ -51,7 +51,13 @@ def test_native_library_is_loaded():
                                    # boundaries of the small-input paths: one-tile radix passes (2048 keys), the
                                    # single-block scan (32768 counters) against the one-pass look-back scan
                                    (2047, 3), (2048, 2048), (2049, 5), (50_000, 32_766), (50_000, 32_767),
-                                   (50_000, 32_768), (50_000, 40_000)])
+                                   (50_000, 32_768), (50_000, 40_000),
+                                   # the same radix boundaries above the single-block build (K > 8192)
+                                   (2047, 9000), (2048, 9000), (2049, 9000),
+                                   # single-block build (nnz <= 8192 and K <= 8192): chunk / warp boundaries, one
+                                   # cluster holding everything, both limits and one past each
+                                   (32, 1), (33, 2), (1024, 1024), (1025, 2), (5000, 8192), (8192, 1), (8192, 8192),
+                                   (8193, 8192), (8192, 8193)])
 def test_build_csr_matches_stable_argsort(nnz, K):
     g = torch.Generator().manual_seed(nnz + K)
     c = torch.randint(0, K, (nnz,), generator=g)
@@ -61,6 +67,19 @@ def test_build_csr_matches_stable_argsort(nnz, K):
     exp_ptr[1:] = torch.bincount(c, minlength=K).cumsum(0)
     assert torch.equal(ptr.cpu(), exp_ptr)
     assert torch.equal(order.cpu()[:nnz], exp_order)
+
+
+@pytest.mark.parametrize("nnz,K", [(700, 40), (8192, 8192), (20_000, 300)])
+def test_build_csr_clamps_out_of_range_ids(nnz, K):
+    """Ids outside [0, K) are never dereferenced: both builds (single block / radix) file them under K - 1."""
+    g = torch.Generator().manual_seed(nnz)
+    c = torch.randint(-3, K + 3, (nnz,), generator=g)
+    order, ptr = F_.build_csr(c.to(DEV), K)
+    cc = torch.where((c < 0) | (c >= K), torch.full_like(c, K - 1), c)
+    exp_ptr = torch.zeros(K + 1, dtype=torch.int32)
+    exp_ptr[1:] = torch.bincount(cc, minlength=K).cumsum(0)
+    assert torch.equal(ptr.cpu(), exp_ptr)
+    assert torch.equal(order.cpu()[:nnz], torch.sort(cc, stable=True)[1].to(torch.int32))
 
 
 # --------------------------------------------------------------------------- #

@@ -438,12 +438,15 @@ inline size_t compact_onepass_workspace_bytes(int64_t n) {
   return align_up(((size_t)ceil_div(n > 0 ? n : 1, kCompactTile) + 2) * sizeof(unsigned long long));
 }
 
+inline size_t compact_onepass_state_words(int64_t n) { return (size_t)ceil_div(n > 0 ? n : 1, kCompactTile) + 2; }
+
+// `state` = compact_onepass_state_words(n) 64-bit words; the caller zeroes them when state_is_zero is set (small
+// inputs fold that into a kernel they launch anyway: one graph node less).
 template <typename Pred, typename Emit>
-static int compact_onepass(Pred pred, Emit emit, int64_t n, int64_t* count_out, Workspace& ws, cudaStream_t stream) {
+static int compact_onepass_on(Pred pred, Emit emit, int64_t n, int64_t* count_out, unsigned long long* state,
+                              bool state_is_zero, cudaStream_t stream) {
   int nt = (int)ceil_div(n > 0 ? n : 1, kCompactTile);
-  unsigned long long* state = ws.take<unsigned long long>((size_t)nt + 2);
-  if (!ws.ok) return TGPB200_ERR_WORKSPACE;
-  cudaMemsetAsync(state, 0, ((size_t)nt + 2) * sizeof(unsigned long long), stream);
+  if (!state_is_zero) cudaMemsetAsync(state, 0, ((size_t)nt + 2) * sizeof(unsigned long long), stream);
   int* ticket = reinterpret_cast<int*>(state + nt);
   if (n <= 0) {
     if (count_out) cudaMemsetAsync(count_out, 0, sizeof(int64_t), stream);
@@ -452,6 +455,13 @@ static int compact_onepass(Pred pred, Emit emit, int64_t n, int64_t* count_out, 
   launch("k_compact_onepass", k_compact_onepass<Pred, Emit>, nt, kCompactThreads, 0, stream, pred, emit, n, state, ticket,
          nt, count_out);
   return launch_status();
+}
+
+template <typename Pred, typename Emit>
+static int compact_onepass(Pred pred, Emit emit, int64_t n, int64_t* count_out, Workspace& ws, cudaStream_t stream) {
+  unsigned long long* state = ws.take<unsigned long long>(compact_onepass_state_words(n));
+  if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+  return compact_onepass_on(pred, emit, n, count_out, state, false, stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -23,6 +23,33 @@ static __global__ void k_build_table(const int64_t* __restrict__ node_index, int
   }
 }
 
+// Small graphs (one block): the -1 / 0 fills of the table, of the mask and of the compaction state and the table
+// build itself as ONE launch instead of three memsets and a kernel (a mini-batch step is launch-bound).
+constexpr int kSmallNodes = 32768;
+constexpr int kSmallThreads = 1024;
+
+inline bool small_paths_enabled() {
+  static const bool on = [] { const char* e = getenv("TGPB200_SMALL_PATHS"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+static __global__ void __launch_bounds__(kSmallThreads)
+    k_kept_init_small(const int64_t* __restrict__ node_index, int kept, int N, int32_t* __restrict__ table,
+                      uint32_t* __restrict__ bits, unsigned long long* __restrict__ state, int state_words) {
+  const int t = threadIdx.x;
+  for (int v = t; v < N; v += kSmallThreads) table[v] = -1;
+  for (int j = t; j < N / 32 + 1; j += kSmallThreads) bits[j] = 0u;
+  for (int j = t; j < state_words; j += kSmallThreads) state[j] = 0ull;
+  __syncthreads();
+  for (int j = t; j < kept; j += kSmallThreads) {
+    const int64_t v = node_index[j];
+    if (v >= 0 && v < N) {
+      table[v] = j;
+      atomicOr(&bits[v >> 5], 1u << (v & 31));
+    }
+  }
+}
+
 struct KeptPred {
   static constexpr bool kStaged = true;
   struct Payload {
@@ -771,13 +798,22 @@ int tgpb200_filter_relabel_onepass(const int64_t* row, const int64_t* col, const
   int32_t* table = ws.take<int32_t>((size_t)(N > 0 ? N : 1));
   uint32_t* bits = ws.take<uint32_t>((size_t)(N / 32 + 1));
   if (!ws.ok) return TGPB200_ERR_WORKSPACE;
-  cudaMemsetAsync(table, 0xff, (size_t)(N > 0 ? N : 1) * sizeof(int32_t), st);
-  cudaMemsetAsync(bits, 0, (size_t)(N / 32 + 1) * sizeof(uint32_t), st);
-  if (kept > 0)
-    launch("k_build_table", k_build_table, (unsigned)ceil_div(kept, 256), 256, 0, st, node_index, kept, N, table, bits);
+  const size_t state_words = compact_onepass_state_words(E);
+  unsigned long long* state = ws.take<unsigned long long>(state_words);
+  if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+  const bool small = small_paths_enabled() && N <= kSmallNodes && kept <= kSmallNodes && state_words <= 4096;
+  if (small) {
+    launch("k_kept_init_small", k_kept_init_small, 1, kSmallThreads, 0, st, node_index, (int)kept, (int)N, table, bits, state,
+           (int)state_words);
+  } else {
+    cudaMemsetAsync(table, 0xff, (size_t)(N > 0 ? N : 1) * sizeof(int32_t), st);
+    cudaMemsetAsync(bits, 0, (size_t)(N / 32 + 1) * sizeof(uint32_t), st);
+    if (kept > 0)
+      launch("k_build_table", k_build_table, (unsigned)ceil_div(kept, 256), 256, 0, st, node_index, kept, N, table, bits);
+  }
   KeptPred pred{row, col, edge_weight, table, bits, N, (flags & TGPB200_REMOVE_SELF_LOOPS) != 0, eps};
   KeptEmit emit{out_row, out_col, edge_weight ? out_weight : nullptr, src_edge};
-  return compact_onepass(pred, emit, E, count_out, ws, st);
+  return compact_onepass_on(pred, emit, E, count_out, state, small, st);
 }
 
 // grad_in[e] = grad_out[j] for the surviving edges (src_edge[j] == e), 0 elsewhere.
@@ -788,12 +824,26 @@ static __global__ void k_unfilter(const float* __restrict__ gout, const int32_t*
   if (j < cnt) gin[src[j]] = gout[j];
 }
 
+static __global__ void __launch_bounds__(kSmallThreads)
+    k_unfilter_small(const float* __restrict__ gout, const int32_t* __restrict__ src, int cnt,
+                     const int64_t* __restrict__ cnt_dev, int E, float* __restrict__ gin) {
+  if (cnt_dev) cnt = (int)min((int64_t)cnt, *cnt_dev);
+  for (int e = threadIdx.x; e < E; e += kSmallThreads) gin[e] = 0.f;
+  __syncthreads();
+  for (int j = threadIdx.x; j < cnt; j += kSmallThreads) gin[src[j]] = gout[j];
+}
+
 int tgpb200_filter_relabel_bwd(const float* grad_out, const int32_t* src_edge, int64_t num_out,
                                const int64_t* num_out_dev, int64_t E, float* grad_in, tgpb200_stream_t stream) {
   if (num_out < 0 || E < 0) return TGPB200_ERR_INVALID;
   if (E == 0) return TGPB200_OK;
   if (!grad_in || (num_out > 0 && (!grad_out || !src_edge))) return TGPB200_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  if (small_paths_enabled() && E <= kSmallNodes && num_out <= kSmallNodes) {  // zero fill + scatter as one launch
+    launch("k_unfilter_small", k_unfilter_small, 1, kSmallThreads, 0, st, grad_out, src_edge, (int)num_out, num_out_dev, (int)E,
+           grad_in);
+    return launch_status();
+  }
   cudaMemsetAsync(grad_in, 0, (size_t)E * sizeof(float), st);
   if (num_out > 0) launch("k_unfilter", k_unfilter, (unsigned)ceil_div(num_out, 256), 256, 0, st, grad_out, src_edge, num_out, num_out_dev, grad_in);
   return launch_status();

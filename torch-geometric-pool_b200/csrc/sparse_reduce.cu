@@ -17,6 +17,63 @@ static __global__ void k_cluster_keys_count(const int64_t* __restrict__ cluster,
   atomicAdd(&counts[c], 1);
 }
 
+// Small inputs (a mini-batch of small graphs: a few thousand kept nodes) are launch-bound: the generic build is a
+// memset + key / count kernel + one launch per radix pass + a scan.  ONE block does the same stable counting sort in
+// shared memory: per-cluster counts, exclusive scan (= ptr), then the members are placed in ascending entry order --
+// chunks of blockDim entries in order, the warps of a chunk in order, the lanes of a warp ranked with
+// __match_any_sync -- so `order` and `ptr` are bit-identical to the radix path.
+constexpr int kCsrSmallNnz = 8192;
+constexpr int kCsrSmallK = 8192;
+constexpr int kCsrSmallThreads = 1024;
+
+static __global__ void __launch_bounds__(kCsrSmallThreads)
+    k_build_csr_small(const int64_t* __restrict__ cluster, int nnz, int K, int32_t* __restrict__ order,
+                      int32_t* __restrict__ ptr) {
+  __shared__ int s_off[kCsrSmallK + 1];  // counts -> exclusive offsets -> next free position of every cluster
+  __shared__ int s_scan[33];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  auto cluster_of = [&](int i) {
+    const int64_t c = cluster[i];
+    return (int)((c < 0 || c >= K) ? (K - 1 > 0 ? K - 1 : 0) : c);  // same clamp as k_cluster_keys_count
+  };
+  for (int c = t; c <= K; c += kCsrSmallThreads) s_off[c] = 0;
+  __syncthreads();
+  for (int i = t; i < nnz; i += kCsrSmallThreads) atomicAdd(&s_off[cluster_of(i)], 1);
+  __syncthreads();
+  {  // exclusive scan over the K + 1 counters (the last one is zero and becomes the total)
+    const int per = (K + kCsrSmallThreads) / kCsrSmallThreads;  // ceil((K + 1) / threads)
+    const int lo = min(t * per, K + 1), hi = min(lo + per, K + 1);
+    int sum = 0;
+    for (int j = lo; j < hi; ++j) sum += s_off[j];
+    int base = block_exclusive_scan_i(sum, s_scan, nullptr);
+    for (int j = lo; j < hi; ++j) {
+      const int n = s_off[j];
+      s_off[j] = base;
+      ptr[j] = base;
+      base += n;
+    }
+  }
+  __syncthreads();
+  for (int i0 = 0; i0 < nnz; i0 += kCsrSmallThreads) {
+    const int i = i0 + t;
+    const bool on = i < nnz;
+    const int c = on ? cluster_of(i) : -1;
+    const unsigned peers = __match_any_sync(kFull, c);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    const bool last = lane == 31 - __clz((int)peers);  // the highest lane of the group advances the counter
+    const int warps = min(32, (nnz - i0 + 31) >> 5);
+    for (int ww = 0; ww < warps; ++ww) {
+      if (w == ww) {
+        const int p = on ? s_off[c] + rank : 0;
+        __syncwarp();
+        if (on && last) s_off[c] += __popc(peers);
+        if (on) order[p] = i;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 static int key_bits_for(int64_t max_value) {
   int b = 0;
   while (b < 63 && ((int64_t)1 << b) <= max_value) ++b;
@@ -274,6 +331,18 @@ static __global__ void k_first_entry(const int64_t* __restrict__ node_index, int
   if (i == 0 || node_index[i - 1] != n) first[n] = (int32_t)i;
 }
 
+// small inputs: the -1 fill and the map as one single-block launch
+static __global__ void __launch_bounds__(1024)
+    k_first_entry_small(const int64_t* __restrict__ node_index, int nnz, int N, int32_t* __restrict__ first) {
+  for (int n = threadIdx.x; n < N; n += 1024) first[n] = -1;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nnz; i += 1024) {
+    const int64_t n = node_index[i];
+    if (n < 0 || n >= N) continue;
+    if (i == 0 || node_index[i - 1] != n) first[n] = i;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Backward: one lane-group per NODE (node_index is sorted, so a node's entries are adjacent):
 //   grad_x[n] = sum_{i in run(n)} w_i * gs_i,   grad_w[i] = <x[n], gs_i>,
@@ -490,9 +559,14 @@ static int launch_bwd(const void* x, const int64_t* node_index, const int64_t* c
   bool vec = (F % W == 0) && Vec<OT>::N == W;
   int32_t* first = ws.take<int32_t>((size_t)(N > 0 ? N : 1));
   if (!ws.ok) return TGPB200_ERR_WORKSPACE;
-  cudaMemsetAsync(first, 0xff, (size_t)(N > 0 ? N : 1) * sizeof(int32_t), st);
-  if (nnz > 0)
-    launch("k_first_entry", k_first_entry, (unsigned)ceil_div(nnz, 256), 256, 0, st, node_index, nnz, N, first);
+  static const bool small_path = [] { const char* e = getenv("TGPB200_SMALL_PATHS"); return !(e && e[0] == '0'); }();
+  if (small_path && N > 0 && N <= 32768 && nnz <= 32768) {
+    launch("k_first_entry_small", k_first_entry_small, 1, 1024, 0, st, node_index, (int)nnz, (int)N, first);
+  } else {
+    cudaMemsetAsync(first, 0xff, (size_t)(N > 0 ? N : 1) * sizeof(int32_t), st);
+    if (nnz > 0)
+      launch("k_first_entry", k_first_entry, (unsigned)ceil_div(nnz, 256), 256, 0, st, node_index, nnz, N, first);
+  }
   float* inv_ties = nullptr;
   if (op == TGPB200_MAX || op == TGPB200_MIN) {
     inv_ties = ws.take<float>((size_t)K * F);
@@ -549,9 +623,14 @@ int tgpb200_build_csr(const int64_t* cluster_index, int64_t nnz, int64_t K, int3
   uint32_t* keys1 = ws.take<uint32_t>(n);
   uint32_t* valsA = ws.take<uint32_t>(n);
   if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+  if (nnz > 0 && K == 0) return TGPB200_ERR_INVALID;
+  static const bool small_path = [] { const char* e = getenv("TGPB200_SMALL_PATHS"); return !(e && e[0] == '0'); }();
+  if (small_path && nnz <= kCsrSmallNnz && K <= kCsrSmallK) {
+    launch("k_build_csr_small", k_build_csr_small, 1, kCsrSmallThreads, 0, st, cluster_index, (int)nnz, (int)K, order, ptr);
+    return launch_status();
+  }
   cudaMemsetAsync(ptr, 0, (size_t)(K + 1) * sizeof(int32_t), st);
   if (nnz > 0) {
-    if (K == 0) return TGPB200_ERR_INVALID;
     launch("k_cluster_keys_count", k_cluster_keys_count, (unsigned)ceil_div(nnz, 256), 256, 0, st, cluster_index, nnz, K, keys0, ptr);
     int bits = key_bits_for(K - 1);
     int passes = radix_passes(bits);
