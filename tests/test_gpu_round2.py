@@ -340,6 +340,51 @@ def test_c1_batch_topk_pool_parity_padded_and_graph_replay():
         assert graphed.kernels_per_replay > 0
 
 
+@pytest.mark.parametrize("op", ["sum", "mean"])
+def test_cluster_pool_padded_and_graph_replay(op):
+    """Cluster branch (row-bucketed coalesce incl. hub rows) in the no-host-read form: same coarse edges, weights and
+    gradients as the exact-size call in the first `count` columns, eagerly and replayed as one CUDA graph."""
+    g = torch.Generator().manual_seed(31)
+    n, spokes, K, F = 20_000, 3_000, 700, 32
+    hub = torch.zeros(spokes, dtype=torch.long)
+    leaves = torch.arange(1, spokes + 1)
+    rnd = torch.randint(0, n, (2, 80_000), generator=g)
+    ei = torch.cat([torch.stack([hub, leaves]), torch.stack([leaves, hub]), rnd], 1)
+    ei = ei[:, torch.argsort(ei[0] * n + ei[1], stable=True)].to(DEV)
+    cluster = torch.randint(2, K, (n,), generator=g)
+    cluster[0] = 0
+    cluster[1:spokes + 1] = 1
+    E = ei.size(1)
+    x0, w0 = torch.randn(n, F, generator=g).to(DEV), (torch.rand(E, generator=g) + 0.5).to(DEV)
+    so = T.SelectOutput(cluster_index=cluster.to(DEV), num_nodes=n, num_supernodes=K)
+    xg, wg = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+    xp, eo, wo, _ = T.sparse_pool(xg, ei, so, edge_weight=wg, reduce_op="mean", connect_op=op)
+    n_out = eo.size(1)
+    coef = torch.zeros(E, device=DEV)
+    coef[:n_out] = torch.arange(1, n_out + 1, device=DEV).float().sqrt()
+    torch.autograd.backward([xp, wo], [torch.ones_like(xp), coef[:n_out]])
+    xg2, wg2 = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+
+    def step():
+        xg2.grad = None
+        wg2.grad = None
+        xp2, e2, w2, _, cnt = T.sparse_pool_padded(xg2, ei, so, edge_weight=wg2, reduce_op="mean", connect_op=op)
+        torch.autograd.backward([xp2, w2], [torch.ones_like(xp2), coef])
+        return xp2, e2, w2, cnt
+
+    xp2, e2, w2, cnt = step()
+    assert int(cnt) == n_out and torch.equal(e2[:, :n_out], eo)
+    assert torch.equal(w2[:n_out].detach(), wo.detach()) and torch.equal(xp2.detach(), xp.detach())
+    assert torch.equal(wg2.grad, wg.grad) and torch.equal(xg2.grad, xg.grad)
+    del xp2, e2, w2, cnt
+    graphed = T.GraphedStep(step)
+    wg2.grad.zero_()
+    xp3, e3, w3, cnt3 = graphed.replay()
+    torch.cuda.synchronize()
+    assert int(cnt3) == n_out and torch.equal(e3[:, :n_out], eo) and torch.equal(w3[:n_out].detach(), wo.detach())
+    assert torch.equal(wg2.grad, wg.grad) and torch.equal(xg2.grad, xg.grad) and torch.equal(xp3.detach(), xp.detach())
+
+
 def test_dense_step_graph_replay_matches_eager():
     g = torch.Generator().manual_seed(2)
     B, N, K, F = 6, 256, 64, 128
