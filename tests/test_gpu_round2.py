@@ -49,7 +49,10 @@ def _dense_inputs(g, B, N, K, F, p=0.1):
 # --------------------------------------------------------------------------- #
 # (i) bf16 forward + backward, incl. the K = 256 shapes of C3 level 1
 # --------------------------------------------------------------------------- #
-@pytest.mark.parametrize("B,N,K,F", [(4, 512, 256, 256), (4, 256, 64, 256), (3, 128, 32, 64), (2, 64, 16, 256)])
+@pytest.mark.parametrize("B,N,K,F", [(4, 512, 256, 256), (4, 256, 64, 256), (3, 128, 32, 64), (2, 64, 16, 256),
+                                     # K = 256 with one A unit / two X units of the grouped fused forward (opt-in:
+                                     # test_grouped_fused_forward_k256 reruns these cases with the switch set)
+                                     (2, 256, 256, 256), (3, 512, 256, 512)])
 @pytest.mark.parametrize("kind", ["mincut", "diff"])
 def test_dense_pool_bf16_forward_backward(B, N, K, F, kind):
     g = torch.Generator().manual_seed(B * N + K + len(kind))
@@ -71,9 +74,32 @@ def test_dense_pool_bf16_forward_backward(B, N, K, F, kind):
         return [t.detach().float().cpu() for t in (xp, ap, *loss.values(), ss.grad, xx.grad, aa.grad)]
 
     exp = run(R, "cpu", torch.float32)
+    expect_grouped = bool(os.environ.get("TGPB200_EXPECT_GROUPED")) and K == 256
+    if expect_grouped:
+        from tgp_b200 import _lib
+
+        _lib.time_kernel("*")
     got = run(T, DEV, torch.bfloat16)
+    if expect_grouped:
+        torch.cuda.synchronize()
+        names = [n for n, _ in _lib.kernel_trace()]
+        _lib.time_kernel(None)
+        assert "k_dense_fwd_fused_bf16_grouped" in names, names
     for n_, e_, g_ in zip(["x_pool", "adj_pool", "loss0", "loss1", "grad_s", "grad_x", "grad_adj"], exp, got):
         close_bf16(g_, e_, f"{kind} bf16 {(B, N, K, F)} {n_}")
+
+
+def test_grouped_fused_forward_k256():
+    """The opt-in K = 256 fused forward (`TGPB200_FUSED_GROUPS=1`, read once per process): the K = 256 cases of the
+    bf16 parity test again in a child process with the switch set, and the kernel must be the one that ran."""
+    import subprocess
+
+    env = dict(os.environ, TGPB200_FUSED_GROUPS="1", TGPB200_EXPECT_GROUPED="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        "test_dense_pool_bf16_forward_backward and (256-256 or 256-512)"], env=env, cwd=ROOT, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
 
 
 # --------------------------------------------------------------------------- #
