@@ -533,6 +533,14 @@ static void prefix_run_sums(KeyF key, ValF val, int64_t n, const int64_t* n_dev,
   launch("k_dsum_finish", k_dsum_finish, (unsigned)ceil_div(K, 256), 256, 0, st, pb, pe, K, out);
 }
 
+// A value functor that gathers (`static constexpr bool kCostly = true`) is evaluated ONCE into a float array and the
+// two prefix passes read the array: the degree backward's dependent gather deg[other[e]] otherwise runs in both the
+// tile-sum and the down-sweep pass (ncu: down-sweep 1.37 ms against 0.45 ms for the plain-array form on 100 M edges).
+template <typename V, typename = void>
+struct val_is_costly : std::false_type {};
+template <typename V>
+struct val_is_costly<V, std::void_t<decltype(V::kCostly)>> : std::integral_constant<bool, V::kCostly> {};
+
 template <typename KeyF, typename ValF>
 static int det_segment_sum(KeyF key, ValF val, int64_t n, const int64_t* n_dev, int64_t K, bool keys_sorted, float* out,
                            Workspace& ws, cudaStream_t st) {
@@ -547,7 +555,14 @@ static int det_segment_sum(KeyF key, ValF val, int64_t n, const int64_t* n_dev, 
     return launch_status();
   }
   if (keys_sorted) {
-    prefix_run_sums(key, val, n, n_dev, K, pb, pe, tiles, out, st);
+    if constexpr (val_is_costly<ValF>::value) {
+      float* ev = ws.take<float>(m);
+      if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+      launch("k_eval_vals", k_eval_vals<ValF>, (unsigned)ceil_div(n, 256), 256, 0, st, val, n, n_dev, ev);
+      prefix_run_sums(key, ValOfArray{ev}, n, n_dev, K, pb, pe, tiles, out, st);
+    } else {
+      prefix_run_sums(key, val, n, n_dev, K, pb, pe, tiles, out, st);
+    }
     return launch_status();
   }
   uint32_t* keys0 = ws.take<uint32_t>(m);
@@ -585,6 +600,7 @@ struct DegVal {
 };
 // gradient w.r.t. dinv: row side sum_{e: row = v} g w dinv[col], column side sum_{e: col = v} g w dinv[row]
 struct DegBwdVal {
+  static constexpr bool kCostly = true;  // dependent gather: evaluated once into an array (det_segment_sum)
   const int64_t* other;  // the opposite endpoint of the key
   const float* w;
   const float* deg;
