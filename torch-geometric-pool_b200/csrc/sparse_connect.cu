@@ -535,6 +535,25 @@ struct val_is_costly : std::false_type {};
 template <typename V>
 struct val_is_costly<V, std::void_t<decltype(V::kCostly)>> : std::integral_constant<bool, V::kCostly> {};
 
+// keys0 (32-bit, invalid keys = K) and ev (values in position order) are ready: group by key, then prefix sums.
+// The values themselves ride through the stable sort as its 32-bit payload: no index payload, no gather afterwards
+// (a random 4-byte gather over 100 M values cost 1.5 ms, as much as two sort passes).  keys0 is overwritten.
+static int grouped_sums_of(uint32_t* keys0, float* ev, int64_t n, const int64_t* n_dev, int64_t K, double* pb, double* pe,
+                           double* tiles, float* out, Workspace& ws, cudaStream_t st) {
+  const size_t m = (size_t)(n > 0 ? n : 1);
+  uint32_t* keys1 = ws.take<uint32_t>(m);
+  uint32_t* vals0 = ws.take<uint32_t>(m);
+  uint32_t* vals1 = ws.take<uint32_t>(m);
+  if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+  bool in1 = false;
+  int rc = radix_sort_pairs<uint32_t>(keys0, reinterpret_cast<uint32_t*>(ev), vals0, keys1, vals1, n,
+                                      key_bits_for_u64((uint64_t)K), &in1, ws, st, n_dev);
+  if (rc != TGPB200_OK) return rc;
+  const float* sv = reinterpret_cast<const float*>(in1 ? vals1 : vals0);
+  prefix_run_sums(KeyOfArray32{in1 ? keys1 : keys0}, ValOfArray{sv}, n, n_dev, K, pb, pe, tiles, out, st);
+  return launch_status();
+}
+
 template <typename KeyF, typename ValF>
 static int det_segment_sum(KeyF key, ValF val, int64_t n, const int64_t* n_dev, int64_t K, bool keys_sorted, float* out,
                            Workspace& ws, cudaStream_t st) {
@@ -560,23 +579,12 @@ static int det_segment_sum(KeyF key, ValF val, int64_t n, const int64_t* n_dev, 
     return launch_status();
   }
   uint32_t* keys0 = ws.take<uint32_t>(m);
-  uint32_t* keys1 = ws.take<uint32_t>(m);
-  uint32_t* vals0 = ws.take<uint32_t>(m);
-  uint32_t* vals1 = ws.take<uint32_t>(m);
   float* ev = ws.take<float>(m);
   if (!ws.ok) return TGPB200_ERR_WORKSPACE;
   const unsigned grid = (unsigned)ceil_div(n, 256);
   launch("k_fill_keys32", k_fill_keys32<KeyF>, grid, 256, 0, st, key, n, n_dev, K, keys0);
   launch("k_eval_vals", k_eval_vals<ValF>, grid, 256, 0, st, val, n, n_dev, ev);
-  // the values themselves ride through the stable sort as its 32-bit payload: no index payload, no gather afterwards
-  // (a random 4-byte gather over 100 M values cost 1.5 ms, as much as two sort passes)
-  bool in1 = false;
-  int rc = radix_sort_pairs<uint32_t>(keys0, reinterpret_cast<uint32_t*>(ev), vals0, keys1, vals1, n,
-                                      key_bits_for_u64((uint64_t)K), &in1, ws, st, n_dev);
-  if (rc != TGPB200_OK) return rc;
-  const float* sv = reinterpret_cast<const float*>(in1 ? vals1 : vals0);
-  prefix_run_sums(KeyOfArray32{in1 ? keys1 : keys0}, ValOfArray{sv}, n, n_dev, K, pb, pe, tiles, out, st);
-  return launch_status();
+  return grouped_sums_of(keys0, ev, n, n_dev, K, pb, pe, tiles, out, ws, st);
 }
 
 static __global__ void k_rows_sorted(const int64_t* __restrict__ row, int64_t E, int32_t* __restrict__ sorted_out) {
@@ -617,6 +625,25 @@ struct ArrVal {
   const float* a;
   __device__ float operator()(int64_t i) const { return a[i]; }
 };
+
+// Both sides of the degree backward from ONE pass over the edges (row-sorted input): the row-side values
+// g w dinv[col], the column-side values g w dinv[row] and the 32-bit column keys of the grouped sum.  Same products in
+// the same order as DegBwdVal, so the sums are bit-identical to the two-functor form (3 kernels, each edge read 3 x).
+static __global__ void k_deg_bwd_prepare(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
+                                         const float* __restrict__ w, const float* __restrict__ deg,
+                                         const float* __restrict__ gout, int64_t E, const int64_t* __restrict__ E_dev,
+                                         int64_t K, float eps, float* __restrict__ ev_row, float* __restrict__ ev_col,
+                                         uint32_t* __restrict__ keys_col) {
+  if (E_dev) E = min(E, *E_dev);
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int64_t r = row[e], c = col[e];
+  const bool okr = r >= 0 && r < K, okc = c >= 0 && c < K;
+  const float g = gout[e] * (w ? w[e] : 1.f);
+  ev_row[e] = okc ? g * dinv_of(deg[c], eps) : 0.f;  // keyed by row, opposite endpoint = col
+  ev_col[e] = okr ? g * dinv_of(deg[r], eps) : 0.f;  // keyed by col, opposite endpoint = row
+  keys_col[e] = okc ? (uint32_t)c : (uint32_t)K;
+}
 
 static __global__ void k_deg_apply(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
                                    const float* __restrict__ w, const float* __restrict__ deg, int64_t E,
@@ -957,12 +984,30 @@ int tgpb200_degree_bwd_accumulate(const int64_t* row, const int64_t* col, const 
   float* part_row = ws.take<float>((size_t)K);
   float* part_col = ws.take<float>((size_t)K);
   if (!ws.ok) return TGPB200_ERR_WORKSPACE;
-  int rc = det_segment_sum(KeyOfArray64{row}, DegBwdVal{col, w, deg, grad_out, K, eps}, E, E_dev, K, rows_sorted != 0,
-                           part_row, ws, st);
-  if (rc != TGPB200_OK) return rc;
-  // the column side is a scatter by `col`: always grouped through the stable sort
-  rc = det_segment_sum(KeyOfArray64{col}, DegBwdVal{row, w, deg, grad_out, K, eps}, E, E_dev, K, false, part_col, ws, st);
-  if (rc != TGPB200_OK) return rc;
+  int rc;
+  if (rows_sorted && E > 0) {
+    const size_t m = (size_t)E;
+    double* pb = ws.take<double>((size_t)K + 1);
+    double* pe = ws.take<double>((size_t)K + 1);
+    double* tiles = ws.take<double>(m / kDsTile + 2);
+    float* ev_row = ws.take<float>(m);
+    float* ev_col = ws.take<float>(m);
+    uint32_t* keys0 = ws.take<uint32_t>(m);
+    if (!ws.ok) return TGPB200_ERR_WORKSPACE;
+    launch("k_deg_bwd_prepare", k_deg_bwd_prepare, (unsigned)ceil_div(E, 256), 256, 0, st, row, col, w, deg, grad_out, E,
+           E_dev, K, eps, ev_row, ev_col, keys0);
+    prefix_run_sums(KeyOfArray64{row}, ValOfArray{ev_row}, E, E_dev, K, pb, pe, tiles, part_row, st);
+    // the column side is a scatter by `col`: grouped through the stable sort (pb / pe / tiles are reused in stream order)
+    rc = grouped_sums_of(keys0, ev_col, E, E_dev, K, pb, pe, tiles, part_col, ws, st);
+    if (rc != TGPB200_OK) return rc;
+  } else {
+    rc = det_segment_sum(KeyOfArray64{row}, DegBwdVal{col, w, deg, grad_out, K, eps}, E, E_dev, K, rows_sorted != 0,
+                         part_row, ws, st);
+    if (rc != TGPB200_OK) return rc;
+    // the column side is a scatter by `col`: always grouped through the stable sort
+    rc = det_segment_sum(KeyOfArray64{col}, DegBwdVal{row, w, deg, grad_out, K, eps}, E, E_dev, K, false, part_col, ws, st);
+    if (rc != TGPB200_OK) return rc;
+  }
   launch("k_add_vec", k_add_vec, (unsigned)ceil_div(K, 256), 256, 0, st, part_row, part_col, K, grad_dinv);
   return launch_status();
 }
