@@ -516,12 +516,14 @@ static size_t det_segment_sum_workspace_bytes(int64_t n, int64_t K) {
          2 * align_up((size_t)(K + 1) * sizeof(double)) + align_up((m / kDsTile + 2) * sizeof(double)) + 1024;
 }
 
+// tiles_ready: `tiles` already holds the per-tile sums (a producer kernel with the tile layout of k_dsum_reduce)
 template <typename KeyF, typename ValF>
 static void prefix_run_sums(KeyF key, ValF val, int64_t n, const int64_t* n_dev, int64_t K, double* pb, double* pe,
-                            double* tiles, float* out, cudaStream_t st) {
+                            double* tiles, float* out, cudaStream_t st, bool tiles_ready = false) {
   const int nt = (int)ceil_div(n, kDsTile);
   cudaMemsetAsync(pb, 0xff, (size_t)K * sizeof(double), st);
-  launch("k_dsum_reduce", k_dsum_reduce<KeyF, ValF>, nt, kDsThreads, 0, st, key, val, n, n_dev, K, tiles);
+  if (!tiles_ready)
+    launch("k_dsum_reduce", k_dsum_reduce<KeyF, ValF>, nt, kDsThreads, 0, st, key, val, n, n_dev, K, tiles);
   launch("k_dsum_spine", k_dsum_spine, 1, 1024, 0, st, tiles, nt);
   launch("k_dsum_down", k_dsum_down<KeyF, ValF>, nt, kDsThreads, 0, st, key, val, n, n_dev, K, tiles, pb, pe);
   launch("k_dsum_finish", k_dsum_finish, (unsigned)ceil_div(K, 256), 256, 0, st, pb, pe, K, out);
@@ -629,20 +631,47 @@ struct ArrVal {
 // Both sides of the degree backward from ONE pass over the edges (row-sorted input): the row-side values
 // g w dinv[col], the column-side values g w dinv[row] and the 32-bit column keys of the grouped sum.  Same products in
 // the same order as DegBwdVal, so the sums are bit-identical to the two-functor form (3 kernels, each edge read 3 x).
-static __global__ void k_deg_bwd_prepare(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
-                                         const float* __restrict__ w, const float* __restrict__ deg,
-                                         const float* __restrict__ gout, int64_t E, const int64_t* __restrict__ E_dev,
-                                         int64_t K, float eps, float* __restrict__ ev_row, float* __restrict__ ev_col,
-                                         uint32_t* __restrict__ keys_col) {
+// It also leaves the row-side tile sums behind (one k_dsum_reduce pass less).
+static __global__ void __launch_bounds__(kDsThreads)
+    k_deg_bwd_prepare(const int64_t* __restrict__ row, const int64_t* __restrict__ col, const float* __restrict__ w,
+                      const float* __restrict__ deg, const float* __restrict__ gout, int64_t E,
+                      const int64_t* __restrict__ E_dev, int64_t K, float eps, float* __restrict__ ev_row,
+                      float* __restrict__ ev_col, uint32_t* __restrict__ keys_col, double* __restrict__ tile_sums) {
+  // tile layout and summation order of k_dsum_reduce, so tile_sums are the row-side tile sums bit for bit
+  __shared__ double red[33];
   if (E_dev) E = min(E, *E_dev);
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  const int64_t r = row[e], c = col[e];
-  const bool okr = r >= 0 && r < K, okc = c >= 0 && c < K;
-  const float g = gout[e] * (w ? w[e] : 1.f);
-  ev_row[e] = okc ? g * dinv_of(deg[c], eps) : 0.f;  // keyed by row, opposite endpoint = col
-  ev_col[e] = okr ? g * dinv_of(deg[r], eps) : 0.f;  // keyed by col, opposite endpoint = row
-  keys_col[e] = okc ? (uint32_t)c : (uint32_t)K;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int64_t wbase = (int64_t)blockIdx.x * kDsTile + (int64_t)wp * (32 * kDsItems);
+  int64_t r[kDsItems], c[kDsItems];
+  float g[kDsItems];
+#pragma unroll
+  for (int k = 0; k < kDsItems; ++k) {
+    const int64_t e = wbase + k * 32 + lane;
+    r[k] = e < E ? row[e] : -1;
+    c[k] = e < E ? col[e] : -1;
+    g[k] = e < E ? gout[e] * (w ? w[e] : 1.f) : 0.f;
+  }
+  float dr[kDsItems], dc[kDsItems];
+#pragma unroll
+  for (int k = 0; k < kDsItems; ++k) {
+    dr[k] = (r[k] >= 0 && r[k] < K) ? __ldg(deg + r[k]) : 0.f;
+    dc[k] = (c[k] >= 0 && c[k] < K) ? __ldg(deg + c[k]) : 0.f;
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < kDsItems; ++k) {
+    const int64_t e = wbase + k * 32 + lane;
+    if (e >= E) continue;
+    const bool okr = r[k] >= 0 && r[k] < K, okc = c[k] >= 0 && c[k] < K;
+    const float vr = okc ? g[k] * dinv_of(dc[k], eps) : 0.f;  // keyed by row, opposite endpoint = col
+    ev_row[e] = vr;
+    ev_col[e] = okr ? g[k] * dinv_of(dr[k], eps) : 0.f;       // keyed by col, opposite endpoint = row
+    keys_col[e] = okc ? (uint32_t)c[k] : (uint32_t)K;
+    if (okr) s += (double)vr;
+  }
+  double tot;
+  block_exclusive_scan_d(s, red, &tot);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
 }
 
 static __global__ void k_deg_apply(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
@@ -994,9 +1023,9 @@ int tgpb200_degree_bwd_accumulate(const int64_t* row, const int64_t* col, const 
     float* ev_col = ws.take<float>(m);
     uint32_t* keys0 = ws.take<uint32_t>(m);
     if (!ws.ok) return TGPB200_ERR_WORKSPACE;
-    launch("k_deg_bwd_prepare", k_deg_bwd_prepare, (unsigned)ceil_div(E, 256), 256, 0, st, row, col, w, deg, grad_out, E,
-           E_dev, K, eps, ev_row, ev_col, keys0);
-    prefix_run_sums(KeyOfArray64{row}, ValOfArray{ev_row}, E, E_dev, K, pb, pe, tiles, part_row, st);
+    launch("k_deg_bwd_prepare", k_deg_bwd_prepare, (unsigned)ceil_div(E, kDsTile), kDsThreads, 0, st, row, col, w, deg,
+           grad_out, E, E_dev, K, eps, ev_row, ev_col, keys0, tiles);
+    prefix_run_sums(KeyOfArray64{row}, ValOfArray{ev_row}, E, E_dev, K, pb, pe, tiles, part_row, st, true);
     // the column side is a scatter by `col`: grouped through the stable sort (pb / pe / tiles are reused in stream order)
     rc = grouped_sums_of(keys0, ev_col, E, E_dev, K, pb, pe, tiles, part_col, ws, st);
     if (rc != TGPB200_OK) return rc;
