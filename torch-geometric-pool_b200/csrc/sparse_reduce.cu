@@ -472,18 +472,19 @@ static __global__ void __launch_bounds__(256)
       }
     }
   }
-  int64_t lo_j[NPW], hi_j[NPW], c_j[NPW];
+  int lo_j[NPW], hi_j[NPW], c_j[NPW];  // nnz, K < 2^31 (checked by the entry point): 32-bit copies keep NPW = 8 in registers
   float coef_j[NPW];
 #pragma unroll
   for (int j = 0; j < NPW; ++j) {
-    lo_j[j] = __shfl_sync(kFull, lo, j), hi_j[j] = __shfl_sync(kFull, hi, j), c_j[j] = __shfl_sync(kFull, c, j);
+    lo_j[j] = __shfl_sync(kFull, (int)lo, j), hi_j[j] = __shfl_sync(kFull, (int)hi, j);
+    c_j[j] = __shfl_sync(kFull, (int)c, j);
     coef_j[j] = __shfl_sync(kFull, coef, j);
   }
   for (int64_t f = (int64_t)lane * W; f < F; f += 32 * W) {
     float g[NPW][W];
 #pragma unroll
     for (int j = 0; j < NPW; ++j)
-      if (c_j[j] >= 0) load_chunk<OT, W, true>(gpool + c_j[j] * F, f, F, g[j]);
+      if (c_j[j] >= 0) load_chunk<OT, W, true>(gpool + (int64_t)c_j[j] * F, f, F, g[j]);
 #pragma unroll
     for (int j = 0; j < NPW; ++j) {
       const int64_t n = n0 + j;
@@ -496,7 +497,7 @@ static __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int k = 0; k < W; ++k) acc[k] = 0.f;
         if (hi_j[j] > lo_j[j] + 1) {
-          for (int64_t i = lo_j[j]; i < hi_j[j]; ++i) {  // a node assigned to several clusters (soft sparse S)
+          for (int64_t i = lo_j[j]; i < (int64_t)hi_j[j]; ++i) {  // a node assigned to several clusters (soft sparse S)
             const int64_t ci = cluster_index[i];
             if (ci < 0 || ci >= K) continue;
             const float wi = weight ? weight[i] : 1.f;
@@ -582,7 +583,10 @@ static int launch_bwd(const void* x, const int64_t* node_index, const int64_t* c
   if (threads == 0) return TGPB200_OK;
   dim3 grid((unsigned)ceil_div(threads, 256));
   if (vec && gw == nullptr && (op == TGPB200_SUM || op == TGPB200_MEAN)) {
-    constexpr int NPW = 4;
+#ifndef TGPB200_BWD_NPW
+#define TGPB200_BWD_NPW 8  // rows in flight per warp: 4 left the kernel bound by its four dependent lookups (3.8 TB/s)
+#endif
+    constexpr int NPW = TGPB200_BWD_NPW;
     const int64_t warps = ceil_div(N, NPW);
     launch("k_segment_reduce_bwd", k_segment_reduce_bwd_rows<XT, OT, NPW>, (unsigned)ceil_div(warps * 32, 256), 256, 0, st,
            node_index, cluster_index, weight, ptr, first, (const OT*)gpool, N, nnz, K, F, op, (XT*)gx);
@@ -674,6 +678,7 @@ int tgpb200_segment_reduce_bwd(const void* x, const int64_t* node_index, const i
                                int x_dtype, int out_dtype, void* grad_x, float* grad_weight, void* workspace,
                                size_t workspace_bytes, tgpb200_stream_t stream) {
   if (N < 0 || nnz < 0 || K < 0 || F < 0 || op < TGPB200_SUM || op > TGPB200_MIN) return TGPB200_ERR_INVALID;
+  if (nnz >= INT32_MAX || K >= INT32_MAX) return TGPB200_ERR_INVALID;  // the CSR (ptr / order) is 32-bit
   if (N * F == 0 && nnz == 0) return TGPB200_OK;
   if (!grad_x || !ptr || !grad_pool || (nnz > 0 && (!x || !node_index || !cluster_index))) return TGPB200_ERR_INVALID;
   if ((op == TGPB200_MAX || op == TGPB200_MIN) && (!x_pool || !order)) return TGPB200_ERR_INVALID;
