@@ -200,11 +200,13 @@ static __global__ void __launch_bounds__(256)
   }
 }
 
-// Vector-row fast path of the forward: a warp takes NPW clusters at once.  Lanes 0..2*NPW-1 resolve the first two
+// Vector-row fast path of the forward: a warp takes NPW clusters at once.  Lanes 0..MPL*NPW-1 resolve the first MPL
 // members of each cluster side by side (ptr -> order -> node_index / weight are dependent loads), then all lanes
-// gather up to 2*NPW member rows with every load in flight; members beyond the second follow in the generic
-// two-at-a-time loop.  Members are combined in CSR order exactly as in k_segment_reduce_fwd (bit-identical sums).
-template <typename XT, typename OT, int NPW>
+// gather up to MPL*NPW member rows with every load in flight; later members follow in the generic two-at-a-time
+// loop.  Members are combined in CSR order exactly as in k_segment_reduce_fwd (bit-identical sums).  (NPW, MPL) =
+// (4, 2) for clusters of about two members, (8, 1) when almost every cluster has one (TopK: nnz == K) -- eight rows
+// in flight per warp either way; node ids travel as 32-bit (the launcher checks N < 2^31).
+template <typename XT, typename OT, int NPW, int MPL>
 static __global__ void __launch_bounds__(256)
     k_segment_reduce_fwd_rows(const XT* __restrict__ x, const int64_t* __restrict__ node_index,
                               const float* __restrict__ weight, const int32_t* __restrict__ order,
@@ -217,10 +219,10 @@ static __global__ void __launch_bounds__(256)
   int beg = 0, end = 0;
   int64_t node = -1;
   float wt = 0.f;
-  if (lane < 2 * NPW && c0 + (lane >> 1) < K) {
-    const int64_t c = c0 + (lane >> 1);
+  if (lane < MPL * NPW && c0 + lane / MPL < K) {
+    const int64_t c = c0 + lane / MPL;
     beg = ptr[c], end = ptr[c + 1];
-    const int m = beg + (lane & 1);
+    const int m = beg + lane % MPL;
     if (m < end) {
       const int i = order[m];
       node = node_index[i];
@@ -229,24 +231,24 @@ static __global__ void __launch_bounds__(256)
     }
   }
   int beg_j[NPW], end_j[NPW];
-  int64_t n_j[NPW][2];
-  float w_j[NPW][2];
+  int n_j[NPW][MPL];
+  float w_j[NPW][MPL];
 #pragma unroll
   for (int j = 0; j < NPW; ++j) {
-    beg_j[j] = __shfl_sync(kFull, beg, 2 * j), end_j[j] = __shfl_sync(kFull, end, 2 * j);
+    beg_j[j] = __shfl_sync(kFull, beg, MPL * j), end_j[j] = __shfl_sync(kFull, end, MPL * j);
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      n_j[j][k] = __shfl_sync(kFull, node, 2 * j + k);
-      w_j[j][k] = __shfl_sync(kFull, wt, 2 * j + k);
+    for (int k = 0; k < MPL; ++k) {
+      n_j[j][k] = __shfl_sync(kFull, (int)node, MPL * j + k);
+      w_j[j][k] = __shfl_sync(kFull, wt, MPL * j + k);
     }
   }
   for (int64_t f = (int64_t)lane * W; f < F; f += 32 * W) {
-    float v[NPW][2][W];
+    float v[NPW][MPL][W];
 #pragma unroll
     for (int j = 0; j < NPW; ++j)
 #pragma unroll
-      for (int k = 0; k < 2; ++k)
-        if (n_j[j][k] >= 0) load_chunk<XT, W, true>(x + n_j[j][k] * F, f, F, v[j][k]);
+      for (int k = 0; k < MPL; ++k)
+        if (n_j[j][k] >= 0) load_chunk<XT, W, true>(x + (int64_t)n_j[j][k] * F, f, F, v[j][k]);
 #pragma unroll
     for (int j = 0; j < NPW; ++j) {
       const int64_t c = c0 + j;
@@ -256,14 +258,14 @@ static __global__ void __launch_bounds__(256)
 #pragma unroll
       for (int k = 0; k < W; ++k) acc[k] = 0.f;
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < MPL; ++k) {
         if (b + k < e) {
 #pragma unroll
           for (int q = 0; q < W; ++q)
             acc[q] = combine(op, acc[q], n_j[j][k] >= 0 ? __fmul_rn(v[j][k][q], w_j[j][k]) : 0.f, k == 0);
         }
       }
-      int m = b + 2;
+      int m = b + MPL;
       for (; m + 1 < e; m += 2) {  // larger clusters: two members in flight
         int i0 = order[m], i1 = order[m + 1];
         int64_t n0 = node_index[i0], n1 = node_index[i1];
@@ -528,7 +530,8 @@ static __global__ void k_reduce_batch(const int64_t* __restrict__ batch, const i
 
 template <typename XT, typename OT>
 static int launch_fwd(const void* x, const int64_t* node_index, const float* weight, const int32_t* order,
-                      const int32_t* ptr, int64_t N, int64_t K, int64_t F, int op, void* out, cudaStream_t st) {
+                      const int32_t* ptr, int64_t N, int64_t nnz, int64_t K, int64_t F, int op, void* out,
+                      cudaStream_t st) {
   constexpr int W = Vec<XT>::N;
   bool vec = (F % W == 0) && (F % Vec<OT>::N == 0) && Vec<OT>::N == W;
   int64_t chunks = ceil_div(F, W);
@@ -537,10 +540,13 @@ static int launch_fwd(const void* x, const int64_t* node_index, const float* wei
   int64_t threads = K * lpr;
   if (threads == 0) return TGPB200_OK;
   dim3 grid((unsigned)ceil_div(threads, 256));
-  if (vec && lpr == 32) {  // rows of at least 32 vector chunks: several clusters per warp (latency-bound otherwise)
-    constexpr int NPW = 4;
-    launch("k_segment_reduce_fwd", k_segment_reduce_fwd_rows<XT, OT, NPW>, (unsigned)ceil_div(ceil_div(K, NPW) * 32, 256), 256, 0,
-           st, (const XT*)x, node_index, weight, order, ptr, N, K, F, op, (OT*)out);
+  if (vec && lpr == 32 && N < INT32_MAX) {  // rows of >= 32 vector chunks: several clusters per warp (latency-bound otherwise)
+    if (nnz <= K + K / 4)  // almost every cluster has one member (TopK): eight clusters per warp, one member preloaded
+      launch("k_segment_reduce_fwd", k_segment_reduce_fwd_rows<XT, OT, 8, 1>, (unsigned)ceil_div(ceil_div(K, 8) * 32, 256),
+             256, 0, st, (const XT*)x, node_index, weight, order, ptr, N, K, F, op, (OT*)out);
+    else
+      launch("k_segment_reduce_fwd", k_segment_reduce_fwd_rows<XT, OT, 4, 2>, (unsigned)ceil_div(ceil_div(K, 4) * 32, 256),
+             256, 0, st, (const XT*)x, node_index, weight, order, ptr, N, K, F, op, (OT*)out);
     return launch_status();
   }
   if (vec)
@@ -657,11 +663,11 @@ int tgpb200_segment_reduce_fwd(const void* x, const int64_t* node_index, const f
   if (!x_pool || !ptr || (nnz > 0 && (!x || !node_index || !order))) return TGPB200_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   if (x_dtype == TGPB200_F32 && out_dtype == TGPB200_F32)
-    return launch_fwd<float, float>(x, node_index, weight, order, ptr, N, K, F, op, x_pool, st);
+    return launch_fwd<float, float>(x, node_index, weight, order, ptr, N, nnz, K, F, op, x_pool, st);
   if (x_dtype == TGPB200_BF16 && out_dtype == TGPB200_BF16)
-    return launch_fwd<__nv_bfloat16, __nv_bfloat16>(x, node_index, weight, order, ptr, N, K, F, op, x_pool, st);
+    return launch_fwd<__nv_bfloat16, __nv_bfloat16>(x, node_index, weight, order, ptr, N, nnz, K, F, op, x_pool, st);
   if (x_dtype == TGPB200_BF16 && out_dtype == TGPB200_F32)
-    return launch_fwd<__nv_bfloat16, float>(x, node_index, weight, order, ptr, N, K, F, op, x_pool, st);
+    return launch_fwd<__nv_bfloat16, float>(x, node_index, weight, order, ptr, N, nnz, K, F, op, x_pool, st);
   return TGPB200_ERR_UNSUPPORTED;
 }
 
