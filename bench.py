@@ -581,6 +581,8 @@ def run_sparse(ctx, name):
         reduce_op, fresh_so, degree_norm = "sum", True, w["kind"] == "topk_big"
     torch.cuda.synchronize()
     e_out_box = [0]
+    # upstream gradients (what the next layer hands back) live outside the step, as in the dense workloads
+    up = {"xp": torch.ones(K, F, device=dev), "w": None}
 
     def eager():
         x.grad = None
@@ -589,7 +591,9 @@ def run_sparse(ctx, name):
             so._b200_csr = None
         xp, eo, wo, _ = T.sparse_pool(x, ei, so, edge_weight=ew, batch=batch, reduce_op=reduce_op,
                                       degree_norm=degree_norm)
-        torch.autograd.backward([xp, wo], [torch.ones_like(xp), torch.ones_like(wo)])
+        if up["w"] is None or up["w"].numel() != wo.numel():
+            up["w"] = torch.ones_like(wo)
+        torch.autograd.backward([xp, wo], [up["xp"], up["w"]])
         e_out_box[0] = eo.size(1)
 
     warm = max(args.warmup, 3)
@@ -607,7 +611,7 @@ def run_sparse(ctx, name):
     if w["kind"] in ("topk", "cluster"):
         # the no-host-read form captured as one CUDA graph (launch-bound batch; for the 20 M-edge cluster connect it
         # removes the two host reads and the launch gaps of ~40 kernels, at the price of capacity-sized launches)
-        g_xp = torch.ones(K, F, device=dev)
+        g_xp = up["xp"]
         g_w = torch.ones(E, device=dev)
 
         def padded():
