@@ -333,16 +333,15 @@ static __global__ void k_first_entry(const int64_t* __restrict__ node_index, int
   if (i == 0 || node_index[i - 1] != n) first[n] = (int32_t)i;
 }
 
-// small inputs: the -1 fill and the map as one single-block launch
-static __global__ void __launch_bounds__(1024)
-    k_first_entry_small(const int64_t* __restrict__ node_index, int nnz, int N, int32_t* __restrict__ first) {
-  for (int n = threadIdx.x; n < N; n += 1024) first[n] = -1;
-  __syncthreads();
-  for (int i = threadIdx.x; i < nnz; i += 1024) {
-    const int64_t n = node_index[i];
-    if (n < 0 || n >= N) continue;
-    if (i == 0 || node_index[i - 1] != n) first[n] = i;
+// first entry of node n without the inverse map: lower bound in the sorted node_index (small inputs only: ~log2(nnz)
+// cache-resident steps per node are cheaper than a separate map-building launch), -1 when the node has no entry
+__device__ __forceinline__ int64_t first_entry_of(const int64_t* __restrict__ node_index, int64_t nnz, int64_t n) {
+  int64_t lo = 0, hi = nnz;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (node_index[mid] < n) lo = mid + 1; else hi = mid;
   }
+  return (lo < nnz && node_index[lo] == n) ? lo : -1;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -367,7 +366,7 @@ static __global__ void __launch_bounds__(256)
 
   // Entries of node n: first[n] (inverse map built by k_first_entry, -1 for an unselected node) and the adjacent
   // run behind it (node_index is sorted).  One dependent load instead of a log2(nnz)-step binary search.
-  int64_t lo = first[n], hi = 0;
+  int64_t lo = first ? (int64_t)first[n] : first_entry_of(node_index, nnz, n), hi = 0;
   if (lo < 0) {
     lo = 0;
   } else {
@@ -455,7 +454,7 @@ static __global__ void __launch_bounds__(256)
   float coef = 0.f;
   if (lane < NPW && n0 + lane < N) {
     const int64_t n = n0 + lane;
-    lo = first[n];  // inverse map (k_first_entry): -1 for an unselected node
+    lo = first ? (int64_t)first[n] : first_entry_of(node_index, nnz, n);  // -1 for an unselected node
     if (lo < 0) {
       lo = 0;
     } else {
@@ -568,7 +567,7 @@ static int launch_bwd(const void* x, const int64_t* node_index, const int64_t* c
   if (!ws.ok) return TGPB200_ERR_WORKSPACE;
   static const bool small_path = [] { const char* e = getenv("TGPB200_SMALL_PATHS"); return !(e && e[0] == '0'); }();
   if (small_path && N > 0 && N <= 32768 && nnz <= 32768) {
-    launch("k_first_entry_small", k_first_entry_small, 1, 1024, 0, st, node_index, (int)nnz, (int)N, first);
+    first = nullptr;  // the backward kernels search the (cache-resident) sorted node_index themselves: one launch less
   } else {
     cudaMemsetAsync(first, 0xff, (size_t)(N > 0 ? N : 1) * sizeof(int32_t), st);
     if (nnz > 0)
